@@ -1,0 +1,192 @@
+/* scgpu.h -- C ABI of libscgpu.so: the B200-native (sm_100a) Scan Context loop-closure hot path.
+ *
+ * This is the drop-in boundary for SC-LeGO-LOAM's SCManager.  Every entry point names the reference
+ * interface it replaces ("SC.h" = SC-LeGO-LOAM/LeGO-LOAM/include/Scancontext.h, "SC.cpp" =
+ * .../src/Scancontext.cpp, "mapOpt.cpp" = .../src/mapOptmization.cpp).  The C++ class the reference's
+ * caller compiles against (same name, same six public methods, same constants) is include/Scancontext.h;
+ * its inline methods marshal into the functions below and do nothing else.
+ *
+ * Conventions
+ *   - plain C types, caller-owned buffers, no C++/torch types across the boundary;
+ *   - every function returns SCGPU_OK (0) or a negative SCGPU_E_* code; scgpu_last_error() gives the text;
+ *   - there is NO CPU fallback: without a CUDA device (or with a failing launch) calls return an error;
+ *   - a handle is not thread-safe (the reference is not either: SURVEY.md 8(b)); calls may come from
+ *     different host threads as long as they are serialised by the caller (mapOpt.cpp:844,1683).  Every call
+ *     sets its CUDA device explicitly and uses the handle's own stream -- no thread-local CUDA state;
+ *   - descriptors ("SC") cross the boundary as R*S values in COLUMN-major order (element (ring r, sector c)
+ *     at c*R + r), which is the memory layout of the reference's Eigen::MatrixXd;
+ *   - points cross the boundary as n records `stride` bytes apart, each beginning with float x, y, z
+ *     (stride 32 = pcl::PointXYZI, 16 = float4, 12 = packed xyz).
+ *
+ * Results are bit-identical to the reference for bins / SC / ring key / candidate indices / shifts /
+ * loop id / yaw and within 1e-5 relative for SC distances (tests/ compare against the reference compiled
+ * verbatim); retrieval is exact brute force in the canonical (squared ring-key distance, index) order.
+ */
+#ifndef SCGPU_H
+#define SCGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCGPU_OK 0
+#define SCGPU_E_INVALID (-1)  /* bad argument / configuration */
+#define SCGPU_E_CUDA (-2)     /* CUDA runtime error (see scgpu_last_error) */
+#define SCGPU_E_NODEVICE (-3) /* no usable CUDA device: there is no CPU path */
+#define SCGPU_E_EMPTY (-4)    /* detect on an empty database (reference: undefined behaviour, SC.cpp:251-252) */
+#define SCGPU_E_IO (-5)       /* save / load failure */
+
+/* flags */
+#define SCGPU_FLAG_FRESH_TREE 1u /* search keys [0, size - exclude_recent) on EVERY detect instead of emulating the
+                                    reference's periodically rebuilt KD-tree snapshot (SC.cpp:264-276) */
+
+/* The reference's compile-time constants (SC.h:77-96) as run-time configuration, plus placement. */
+typedef struct scgpu_config {
+  int32_t num_ring;        /* PC_NUM_RING              SC.h:79  (20) */
+  int32_t num_sector;      /* PC_NUM_SECTOR            SC.h:80  (60) */
+  double lidar_height;     /* LIDAR_HEIGHT             SC.h:77  (2.0) */
+  double max_radius;       /* PC_MAX_RADIUS            SC.h:81  (80.0) */
+  int32_t exclude_recent;  /* NUM_EXCLUDE_RECENT       SC.h:86  (50) */
+  int32_t num_candidates;  /* NUM_CANDIDATES_FROM_TREE SC.h:87  (10) */
+  double search_ratio;     /* SEARCH_RATIO             SC.h:90  (0.1) */
+  double dist_thres;       /* SC_DIST_THRES            SC.h:92  (0.5) */
+  int32_t tree_period;     /* TREE_MAKING_PERIOD_      SC.h:95  (10) */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t shard_rank;      /* this handle stores database entries i with i % shard_count == shard_rank */
+  int32_t shard_count;     /* 1 = whole database on this device */
+  uint64_t capacity_hint;  /* database entries (global) to reserve up front; storage grows on demand */
+  uint32_t flags;          /* SCGPU_FLAG_* */
+  uint32_t reserved;
+} scgpu_config;
+
+typedef struct scgpu_handle scgpu_handle;
+
+/* Fills *cfg with the reference's constants (SC.h:77-96), device 0, one shard. */
+int scgpu_default_config(scgpu_config* cfg);
+/* SCManager() (SC.h:61) + the storage behind SC.h:99-106, resident in HBM. */
+int scgpu_create(const scgpu_config* cfg, scgpu_handle** out);
+int scgpu_destroy(scgpu_handle* h);
+const char* scgpu_last_error(void);
+/* Library / build identification (sm target, kernels compiled). */
+const char* scgpu_version(void);
+
+/* ---- the reference's public methods, one call each --------------------------------------------------- */
+
+/* SCManager::makeScancontext (SC.h:63, SC.cpp:151-195): out = R*S doubles, column-major. */
+int scgpu_make_sc(scgpu_handle* h, const void* pts, size_t n, size_t stride_bytes, double* out_sc);
+/* SCManager::makeRingkeyFromScancontext (SC.h:64, SC.cpp:198-211): row means, out = R doubles. */
+int scgpu_ringkey(scgpu_handle* h, const double* sc, double* out_ring);
+/* SCManager::makeSectorkeyFromScancontext (SC.h:65, SC.cpp:214-227): column means, out = S doubles. */
+int scgpu_sectorkey(scgpu_handle* h, const double* sc, double* out_sector);
+/* SCManager::fastAlignUsingVkey (SC.h:67, SC.cpp:93-113): vkey1, vkey2 = S doubles. */
+int scgpu_fast_align(scgpu_handle* h, const double* vkey1, const double* vkey2, int* out_shift);
+/* SCManager::distDirectSC (SC.h:68, SC.cpp:69-90). */
+int scgpu_dist_direct(scgpu_handle* h, const double* sc1, const double* sc2, double* out_dist);
+/* SCManager::distanceBtnScanContext (SC.h:69, SC.cpp:116-148). */
+int scgpu_distance(scgpu_handle* h, const double* sc1, const double* sc2, double* out_dist, int* out_shift);
+/* SCManager::makeAndSaveScancontextAndKeys (SC.h:72, SC.cpp:230-244; call site mapOpt.cpp:1630).
+ * Asynchronous: returns once the scan has been staged; the scan buffer is not retained. */
+int scgpu_append_scan(scgpu_handle* h, const void* pts, size_t n, size_t stride_bytes);
+/* SCManager::detectLoopClosureID (SC.h:73, SC.cpp:247-338; call site mapOpt.cpp:916).
+ * *loop_id / *yaw_rad are the pair the reference returns.  The optional outputs carry what the reference
+ * prints (SC.cpp:322-329): the nearest distance, nearest index and its shift. */
+int scgpu_detect(scgpu_handle* h, int* loop_id, float* yaw_rad, double* nearest_dist, int* nearest_idx,
+                 int* nearest_shift);
+/* xy2theta (SC.h:53, SC.cpp:23-36) evaluated on the current device: azimuth in degrees. */
+int scgpu_xy2theta(float x, float y, float* out_deg);
+/* polarcontexts_.size() (SC.h:100). */
+int scgpu_size(scgpu_handle* h, uint64_t* out_n);
+
+/* ---- batched / bench / parity extras (no reference counterpart: the reference is one scan at a time) ---- */
+
+/* n_scans scans of pts_per_scan points each, contiguous, appended in order (= n_scans calls of
+ * scgpu_append_scan).  location: 0 = host memory (pinned or pageable), 1 = device memory on cfg.device. */
+int scgpu_append_scans_batched(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan,
+                               size_t stride_bytes, int location);
+/* Appends n ready-made descriptors (float, column-major R*S each; host memory): the keys are derived on
+ * the device exactly as SC.cpp:233-235 would.  Used to load / pre-fill a database. */
+int scgpu_append_descs(scgpu_handle* h, const float* sc, size_t n);
+/* The bench "step": append n_scans scans (as above) and run one detect after each append, exactly as the
+ * sequence { makeAndSaveScancontextAndKeys; detectLoopClosureID } x n_scans would, including the periodic
+ * tree-snapshot state.  Outputs are host arrays of n_scans entries (nearest_* optional). */
+int scgpu_replay_batched(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan,
+                         size_t stride_bytes, int location, int* loop_id, float* yaw_rad, double* nearest_dist,
+                         int* nearest_idx, int* nearest_shift);
+/* Detect for n_queries already-stored entries [first, first+n_queries) as if each had just been appended
+ * (database truncated to first+i+1 for query i) with a FRESH snapshot (n_search = first+i+1-exclude_recent). */
+int scgpu_query_batched(scgpu_handle* h, uint64_t first, size_t n_queries, int* loop_id, float* yaw_rad,
+                        double* nearest_dist, int* nearest_idx, int* nearest_shift);
+/* What the last scgpu_detect saw (parity dumps): K candidates in retrieval order, their squared ring-key
+ * distances, per-candidate SC distance and shift, and the number of keys that were searchable. */
+int scgpu_get_candidates(scgpu_handle* h, uint64_t* cand_idx, float* cand_d2, double* cand_dist, int* cand_shift,
+                         uint64_t* n_search);
+/* Same for query q of the last scgpu_replay_batched / scgpu_query_batched call. */
+int scgpu_get_batch_candidates(scgpu_handle* h, size_t q, uint64_t* cand_idx, float* cand_d2, double* cand_dist,
+                               int* cand_shift, uint64_t* n_search);
+/* Entry i as stored: SC (float R*S), ring key (float R = polarcontext_invkeys_mat_), sector key (double S). */
+int scgpu_get_entry(scgpu_handle* h, uint64_t i, float* sc, float* ring, double* sector);
+/* Forget entries >= n (bench resets; never called by the reference) and reset the tree-snapshot state, so the
+ * next detect takes a fresh snapshot exactly like the first detect of a new SCManager. */
+int scgpu_truncate(scgpu_handle* h, uint64_t n);
+/* Exhaustive search (BASELINE config 4/5): score query entry q against EVERY entry [0, n_search) with
+ * distanceBtnScanContext semantics; strict-min in index order.  flipped != 0 also scores each candidate with
+ * its columns reversed (forward first).  Outputs are for the global winner. */
+int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped, double* best_dist,
+                     int* best_shift, int64_t* best_idx, int* best_flip);
+/* Flat binary save / load of the descriptor database. */
+int scgpu_save(scgpu_handle* h, const char* path);
+int scgpu_load(scgpu_handle* h, const char* path);
+
+/* ---- staged device-side API (used by the sharded multi-GPU path; all pointers are DEVICE pointers on
+ *      cfg.device; `stream` is a cudaStream_t, 0 = the handle's own stream) ------------------------------ */
+
+/* Bytes of one packed descriptor record: float sc[R*S] | float ring[R] | double sector[S] | double colnorm[S],
+ * padded to 16 bytes. */
+int scgpu_record_bytes(scgpu_handle* h, size_t* out);
+/* Stage 1+2: scans -> records (descriptor + keys). */
+int scgpu_stage_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_per_scan, size_t stride_bytes,
+                      void* d_records, void* stream);
+/* Store records [0, n) as global entries first_global + i*global_step; only those with index % shard_count ==
+ * shard_rank are kept by this handle (global_step = shard_count, first_global % shard_count == shard_rank:
+ * a rank storing the entries it built itself).  Global size becomes max(size, first_global + (n-1)*global_step + 1). */
+int scgpu_stage_append(scgpu_handle* h, const void* d_records, uint64_t first_global, uint64_t global_step, size_t n,
+                       void* stream);
+/* Declares the global database size (all shards) after appends made through other handles / ranks. */
+int scgpu_stage_set_size(scgpu_handle* h, uint64_t n_global);
+/* Stage 3 (local): for each query record, the K best (dist2 bits << 32 | global idx) keys among this shard's
+ * entries with global idx < d_n_search[q], ascending; unfilled slots = UINT64_MAX. */
+int scgpu_stage_topk(scgpu_handle* h, const void* d_query_records, size_t n_queries, const uint64_t* d_n_search,
+                     uint64_t* d_keys_out, void* stream);
+/* Merge `parts` key lists per query (layout [parts][n_queries][K]) into one [n_queries][K]. */
+int scgpu_stage_merge(scgpu_handle* h, const uint64_t* d_keys_parts, int parts, size_t n_queries,
+                      uint64_t* d_keys_out, void* stream);
+/* Stage 4 (local): score the candidates this shard owns; per query the shard's best in retrieval order as
+ * {double dist; int32 rank_in_list; int32 shift; int64 global_idx} (24 bytes), dist = +inf when none. */
+int scgpu_stage_score(scgpu_handle* h, const void* d_query_records, size_t n_queries, const uint64_t* d_keys,
+                      const uint64_t* d_n_search, void* d_best_out, void* stream);
+/* Reduce `parts` per-shard bests (layout [parts][n_queries]) to the reference's result per query
+ * (d_n_search[q] == 0 marks a query that took the early return of SC.cpp:257-261). */
+int scgpu_stage_finalize(scgpu_handle* h, const void* d_best_parts, int parts, size_t n_queries,
+                         const uint64_t* d_n_search, int32_t* d_loop_id, float* d_yaw, double* d_nearest_dist,
+                         int32_t* d_nearest_idx, int32_t* d_nearest_shift, void* stream);
+/* Host helper: the n_search sequence a run of n consecutive detects produces (one detect after each append,
+ * database size first_size, first_size+1, ...), advancing the handle's snapshot state (SC.cpp:257-276). */
+int scgpu_plan_n_search(scgpu_handle* h, uint64_t first_size, size_t n, uint64_t* out_n_search);
+/* Parity probes (host arrays in, host arrays out): the device's atanf restatement for n values, and for n points
+ * (xyz packed, 12 bytes each) the 0-based bin sector*R+ring of SC.cpp:178-179 (-1 = not binned), the stored height
+ * of SC.cpp:168 and the azimuth of SC.cpp:172. */
+int scgpu_probe_atanf(const float* x, size_t n, float* out);
+int scgpu_probe_bins(scgpu_handle* h, const float* xyz, size_t n, int32_t* bin, float* height, float* theta_deg);
+/* Device time (CUDA events on the handle's stream) of the last scgpu_replay_batched / scgpu_append_scans_batched /
+ * scgpu_query_batched call: whole call, its k_build launches only, and everything after them. */
+int scgpu_get_timing(scgpu_handle* h, double* ms_total, double* ms_build, double* ms_query);
+/* Number of kernels launched by this handle so far (bench.py's gpu_launches). */
+int scgpu_launch_count(scgpu_handle* h, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCGPU_H */

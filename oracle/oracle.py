@@ -83,6 +83,8 @@ class Port:
                                     C.POINTER(C.c_uint64)]
         L.sco_db_exhaustive.argtypes = [_vp, _pd, _sz, _i, C.POINTER(_d), C.POINTER(_i), C.POINTER(C.c_int64),
                                         C.POINTER(_i)]
+        L.sco_atanf_many.argtypes = [_pf, _sz, _vp, _vp]
+        L.sco_bin_points.argtypes = [pp, _pf, _sz, _pi32, _pf, _pf]
         self.db = L.sco_db_create(C.byref(self.p))
 
     def __del__(self):
@@ -97,6 +99,20 @@ class Port:
 
     def xy2theta(self, x, y):
         return self.L.sco_xy2theta(float(x), float(y))
+
+    def atanf_many(self, x):
+        """(restatement, host libm) atanf of every element."""
+        x = np.ascontiguousarray(x, np.float32).ravel()
+        a, b = np.empty_like(x), np.empty_like(x)
+        self.L.sco_atanf_many(x, x.size, a.ctypes.data, b.ctypes.data)
+        return a, b
+
+    def bin_points(self, xyz):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        n = xyz.shape[0]
+        b, h, t = np.empty(n, np.int32), np.empty(n, np.float32), np.empty(n, np.float32)
+        self.L.sco_bin_points(C.byref(self.p), xyz.ravel(), n, b, h, t)
+        return b, h, t
 
     def bin_point(self, x, y, z):
         r, s, h = _i(), _i(), _f()

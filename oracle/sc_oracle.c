@@ -468,3 +468,27 @@ void sco_db_exhaustive(const sco_db* db, const double* query_sc, size_t n, int f
   *best_idx = bi;
   *best_flip = bf;
 }
+
+/* ---- vectorised helpers for the parity tests ------------------------------------------------ */
+void sco_atanf_many(const float* x, size_t n, float* out_port, float* out_libm) {
+  for (size_t i = 0; i < n; ++i) {
+    if (out_port) out_port[i] = sco_atanf(x[i]);
+    if (out_libm) out_libm[i] = atanf(x[i]);
+  }
+}
+
+/* bin = (sector-1)*R + (ring-1), or -1 when the point is not binned (outside the ROI / NaN coordinate or height,
+ * which the product kernel also drops); height / theta as SC.cpp:168 / 172. */
+void sco_bin_points(const sco_params* p, const float* xyz, size_t n, int32_t* bin, float* height, float* theta) {
+  for (size_t i = 0; i < n; ++i) {
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    int ring, sector;
+    float h = (float)((double)z + p->lidar_height);
+    int ok = 0;
+    if (x == x && y == y) ok = sco_bin_point(p, x, y, z, &ring, &sector, &h);
+    if (ok && !(h == h)) ok = 0;
+    bin[i] = ok ? (sector - 1) * p->R + (ring - 1) : -1;
+    height[i] = h;
+    theta[i] = sco_xy2theta(x, y);
+  }
+}

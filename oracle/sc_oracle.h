@@ -77,6 +77,10 @@ int sco_db_detect(sco_db* db, int* loop_id, float* yaw, double* min_dist, uint64
 void sco_db_exhaustive(const sco_db* db, const double* query_sc, size_t n, int flipped, double* best_dist,
                        int* best_shift, int64_t* best_idx, int* best_flip);
 
+/* vectorised helpers for the parity tests */
+void sco_atanf_many(const float* x, size_t n, float* out_port, float* out_libm);
+void sco_bin_points(const sco_params* p, const float* xyz, size_t n, int32_t* bin, float* height, float* theta);
+
 #ifdef __cplusplus
 }
 #endif

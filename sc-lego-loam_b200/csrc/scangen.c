@@ -121,17 +121,23 @@ void scangen_desc(const scangen_cfg* c, uint64_t scan_index, int R, int S, float
   float yaw, dx, dy;
   scangen_pose(c, scan_index, &place, &yaw, &dx, &dy);
   const int shift = (int)(yaw / 6.2831853f * (float)S) % S;
+  const int kr = 40 / R > 0 ? 40 / R : 1, ks = SG_CELLS_A / S > 0 ? SG_CELLS_A / S : 1; /* world cells per bin */
   for (int col = 0; col < S; ++col) {
-    const int ws = ((col + shift) % S) * SG_CELLS_A / S;
+    const int ws0 = ((col + shift) % S) * SG_CELLS_A / S;
     for (int r = 0; r < R; ++r) {
-      const int wk = r * 40 / R; /* 80 m = 40 world cells */
-      float v = place_height(c->seed, place, wk, ws);
+      const int wk0 = r * 40 / R; /* 80 m = 40 world cells */
+      float v = 0.f;
+      for (int a = 0; a < kr; ++a)
+        for (int b = 0; b < ks; ++b) {
+          const float hcell = place_height(c->seed, place, wk0 + a, (ws0 + b) % SG_CELLS_A);
+          if (hcell > v) v = hcell;
+        }
       const uint64_t h = h4(c->seed ^ 0xde5cull, scan_index, (uint64_t)col, (uint64_t)r);
       if (v > 0.f) {
-        if (u01(h) < 0.5f) v += 0.2f * (u01(mix64(h)) - 0.5f);
-        if (u01(mix64(h ^ 1)) < 0.03f) v = 0.f; /* occasionally missed */
-      } else if (u01(h) < 0.02f) {
-        v = 0.3f * u01(mix64(h)); /* occasional clutter */
+        v += 2.0f - 0.3f * u01(mix64(h));          /* max over the bin's returns + LIDAR_HEIGHT-like offset */
+        if (u01(mix64(h ^ 1)) < 0.03f) v = 0.27f;  /* structure occasionally missed */
+      } else {
+        v = (u01(h) < 0.75f) ? 0.27f : 0.f;        /* ground return, or an empty bin (zeros ~ 15 % overall) */
       }
       out[(size_t)col * R + r] = v;
     }

@@ -1,0 +1,1101 @@
+// scgpu.cu -- host side of libscgpu.so: the C ABI of include/scgpu.h over the sm_100a kernels in
+// scgpu_kernels.cuh.  No CPU implementation of any stage lives here: every entry point either launches the
+// kernels or fails.
+#include "scgpu.h"
+
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "scgpu_kernels.cuh"
+
+using namespace scgpu;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return fail(SCGPU_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));     \
+  } while (0)
+#define RET(call)              \
+  do {                         \
+    int r_ = (call);           \
+    if (r_ != SCGPU_OK) return r_; \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t want, bool zero = false, cudaStream_t st = 0) {
+    if (want <= bytes) return SCGPU_OK;
+    if (p) CK(cudaFree(p));
+    p = nullptr;
+    bytes = 0;
+    size_t cap = want + want / 4 + 256;
+    CK(cudaMalloc(&p, cap));
+    if (zero) CK(cudaMemsetAsync(p, 0, cap, st));
+    bytes = cap;
+    return SCGPU_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t want) {
+    if (want <= bytes) return SCGPU_OK;
+    if (p) CK(cudaFreeHost(p));
+    p = nullptr;
+    bytes = 0;
+    CK(cudaHostAlloc(&p, want + want / 4 + 256, cudaHostAllocDefault));
+    bytes = want + want / 4 + 256;
+    return SCGPU_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+}  // namespace
+
+struct scgpu_handle {
+  scgpu_config cfg;
+  Layout L;
+  int K, radius, W, slots;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_pin[2] = {nullptr, nullptr};
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;  // call start / builds done / call end
+  bool timing_valid = false;
+  // database shard
+  Db db{};
+  uint64_t n_global = 0;
+  // build workspace
+  DevBuf gbins, btickets;
+  size_t build_cap = 0;
+  // point staging
+  DevBuf d_pts[2];
+  PinBuf h_pts[2];
+  int pin_turn = 0;
+  // query workspace
+  DevBuf records, rec_single, nsearch, keys, partial, ttickets, pair_dist, pair_shift, best, o_loop, o_yaw, o_dist, o_idx, o_shift;
+  DevBuf api_in, api_out;
+  PinBuf h_out, h_ns;
+  size_t ttickets_cap = 0;
+  // snapshot state (SC.h:96, SC.cpp:264-276)
+  long long counter = 0;
+  uint64_t n_tree = 0;
+  // last pipeline (candidate dumps)
+  size_t last_nq = 0;
+  std::vector<uint64_t> last_nsearch;
+  uint64_t launches = 0;
+};
+
+namespace {
+
+uint64_t local_count(const scgpu_handle* h, uint64_t n_global) {
+  const uint64_t G = (uint64_t)h->cfg.shard_count, r = (uint64_t)h->cfg.shard_rank;
+  return n_global > r ? (n_global - 1 - r) / G + 1 : 0;
+}
+
+int db_reserve(scgpu_handle* h, uint64_t want_local) {
+  if (want_local <= h->db.cap) return SCGPU_OK;
+  CK(cudaDeviceSynchronize());  // rare: the shard moves to a larger allocation; nothing may still be reading the old one
+  uint64_t cap = h->db.cap ? h->db.cap * 2 : 1024;
+  while (cap < want_local) cap *= 2;
+  const Layout& L = h->L;
+  Db nd = h->db;
+  nd.cap = cap;
+  CK(cudaMalloc(&nd.sc, cap * L.RS * sizeof(float)));
+  CK(cudaMalloc(&nd.ringT, cap * L.R * sizeof(float)));
+  CK(cudaMalloc(&nd.sector, cap * L.S * sizeof(double)));
+  CK(cudaMalloc(&nd.colnorm, cap * L.S * sizeof(double)));
+  const uint64_t n = local_count(h, h->n_global);
+  if (h->db.cap && n) {
+    CK(cudaMemcpyAsync(nd.sc, h->db.sc, n * L.RS * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpy2DAsync(nd.ringT, cap * sizeof(float), h->db.ringT, h->db.cap * sizeof(float), n * sizeof(float), L.R,
+                         cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(nd.sector, h->db.sector, n * L.S * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(nd.colnorm, h->db.colnorm, n * L.S * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->db.cap) {
+    cudaFree(h->db.sc);
+    cudaFree(h->db.ringT);
+    cudaFree(h->db.sector);
+    cudaFree(h->db.colnorm);
+  }
+  h->db = nd;
+  return SCGPU_OK;
+}
+
+int build_reserve(scgpu_handle* h, size_t n_scans, cudaStream_t st) {
+  if (n_scans <= h->build_cap) return SCGPU_OK;
+  CK(cudaStreamSynchronize(st));
+  const size_t cap = n_scans + n_scans / 2 + 8;
+  h->build_cap = 0;
+  RET(h->gbins.reserve(cap * h->L.RS * sizeof(int)));
+  RET(h->btickets.reserve(cap * sizeof(unsigned)));
+  const size_t n = h->gbins.bytes / sizeof(int);
+  k_fill_int<<<256, 256, 0, st>>>(h->gbins.as<int>(), n, SCGPU_ENC_NOPOINT);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(h->btickets.p, 0, h->btickets.bytes, st));
+  h->build_cap = cap;
+  return SCGPU_OK;
+}
+
+// Stage 1+2 on device-resident points.
+int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_per_scan, size_t stride, void* d_records,
+                 cudaStream_t st) {
+  if (n_scans == 0) return SCGPU_OK;
+  if (stride < 12 || (stride & 3) || ((uintptr_t)d_pts & 3)) return fail(SCGPU_E_INVALID, "points must be 4-byte aligned, stride >= 12 and a multiple of 4");
+  if (pts_per_scan > 0xfffffff0ull || n_scans > 65535ull * 1024) return fail(SCGPU_E_INVALID, "scan too large");
+  RET(build_reserve(h, n_scans, st));
+  BuildParams p;
+  p.pts = static_cast<const unsigned char*>(d_pts);
+  p.scan_pitch = (unsigned long long)pts_per_scan * stride;
+  p.n_pts = (unsigned)pts_per_scan;
+  p.stride = (unsigned)stride;
+  // tile: few scans -> many tiles per scan (latency); many scans -> large tiles (fewer global atomics)
+  unsigned ppb;
+  if (n_scans >= 296) ppb = 16384;
+  else if (n_scans >= 32) ppb = 8192;
+  else ppb = 2048;
+  if (pts_per_scan == 0) ppb = 256;
+  p.pts_per_block = ppb;
+  p.bc.R = h->L.R;
+  p.bc.S = h->L.S;
+  p.bc.lidar_height = h->cfg.lidar_height;
+  p.bc.max_radius = h->cfg.max_radius;
+  p.L = h->L;
+  p.gbins = h->gbins.as<int>();
+  p.tickets = h->btickets.as<unsigned>();
+  p.records = static_cast<unsigned char*>(d_records);
+  const unsigned tiles = pts_per_scan ? (unsigned)((pts_per_scan + ppb - 1) / ppb) : 1;
+  const size_t smem = (size_t)h->L.RS * sizeof(int);
+  for (size_t s0 = 0; s0 < n_scans; s0 += 65535) {  // gridDim.y limit
+    const size_t ns = n_scans - s0 < 65535 ? n_scans - s0 : 65535;
+    BuildParams q = p;
+    q.pts = p.pts + s0 * p.scan_pitch;
+    q.records = p.records + s0 * h->L.rec_bytes;
+    q.gbins = p.gbins;  // per-launch scan index restarts at 0: workspace rows [0, ns)
+    dim3 grid(tiles, (unsigned)ns);
+    const bool al16 = (((uintptr_t)q.pts & 15) == 0);
+    if (stride == 16 && al16) k_build<16><<<grid, 256, smem, st>>>(q);
+    else if (stride == 32 && al16) k_build<32><<<grid, 256, smem, st>>>(q);
+    else k_build<0><<<grid, 256, smem, st>>>(q);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  return SCGPU_OK;
+}
+
+int launch_append(scgpu_handle* h, const void* d_records, uint64_t first_global, uint64_t step, size_t n, cudaStream_t st) {
+  if (n == 0) return SCGPU_OK;
+  if (step < 1) return fail(SCGPU_E_INVALID, "global_step must be >= 1");
+  const uint64_t new_size = first_global + (n - 1) * step + 1;
+  if (new_size > 0xffffffffull) return fail(SCGPU_E_INVALID, "database index space is 32 bits");
+  RET(db_reserve(h, local_count(h, new_size)));
+  k_append<<<(unsigned)n, 128, 0, st>>>(static_cast<const unsigned char*>(d_records), h->L, h->db, first_global, step);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (new_size > h->n_global) h->n_global = new_size;
+  return SCGPU_OK;
+}
+
+void choose_chunks(uint64_t n_local, size_t nq, unsigned& chunk, unsigned& chunks) {
+  if (n_local == 0) {
+    chunk = 256;
+    chunks = 1;
+    return;
+  }
+  uint64_t by_size = (n_local + 255) / 256;
+  uint64_t by_grid = (592 + nq - 1) / nq;
+  uint64_t c = by_size < by_grid ? by_size : by_grid;
+  if (c < 1) c = 1;
+  uint64_t ch = (n_local + c - 1) / c;
+  ch = (ch + 255) / 256 * 256;
+  chunk = (unsigned)ch;
+  chunks = (unsigned)((n_local + ch - 1) / ch);
+}
+
+int query_reserve(scgpu_handle* h, size_t nq, unsigned chunks, cudaStream_t st) {
+  const int K = h->K;
+  RET(h->keys.reserve(nq * K * sizeof(uint64_t)));
+  RET(h->partial.reserve(nq * (size_t)chunks * K * sizeof(uint64_t)));
+  if (nq > h->ttickets_cap) {
+    CK(cudaStreamSynchronize(st));
+    h->ttickets_cap = 0;
+    RET(h->ttickets.reserve(nq * sizeof(unsigned)));
+    CK(cudaMemsetAsync(h->ttickets.p, 0, h->ttickets.bytes, st));
+    h->ttickets_cap = h->ttickets.bytes / sizeof(unsigned);
+  }
+  RET(h->pair_dist.reserve(nq * K * sizeof(double)));
+  RET(h->pair_shift.reserve(nq * K * sizeof(int)));
+  RET(h->best.reserve(nq * sizeof(Best)));
+  RET(h->o_loop.reserve(nq * sizeof(int)));
+  RET(h->o_yaw.reserve(nq * sizeof(float)));
+  RET(h->o_dist.reserve(nq * sizeof(double)));
+  RET(h->o_idx.reserve(nq * sizeof(int)));
+  RET(h->o_shift.reserve(nq * sizeof(int)));
+  return SCGPU_OK;
+}
+
+int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* d_ns, uint64_t* d_keys_out, cudaStream_t st) {
+  if (nq == 0) return SCGPU_OK;
+  if (nq > 65535) return fail(SCGPU_E_INVALID, "at most 65535 queries per call");
+  unsigned chunk, chunks;
+  const uint64_t n_local = local_count(h, h->n_global);
+  choose_chunks(n_local, nq, chunk, chunks);
+  RET(query_reserve(h, nq, chunks, st));
+  TopkParams p;
+  p.qrecords = static_cast<const unsigned char*>(d_qrec);
+  p.L = h->L;
+  p.db = h->db;
+  p.n_search = reinterpret_cast<const unsigned long long*>(d_ns);
+  p.n_local = n_local;
+  p.chunk = chunk;
+  p.K = h->K;
+  p.partial = h->partial.as<unsigned long long>();
+  p.tickets = h->ttickets.as<unsigned>();
+  p.keys_out = reinterpret_cast<unsigned long long*>(d_keys_out);
+  dim3 grid(chunks, (unsigned)nq);
+  if (h->slots == 1) k_topk<1><<<grid, TOPK_THREADS, 0, st>>>(p);
+  else if (h->slots == 2) k_topk<2><<<grid, TOPK_THREADS, 0, st>>>(p);
+  else k_topk<4><<<grid, TOPK_THREADS, 0, st>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
+
+int launch_merge(scgpu_handle* h, const uint64_t* d_parts, int parts, size_t nq, uint64_t* d_out, cudaStream_t st) {
+  if (nq == 0) return SCGPU_OK;
+  const unsigned blocks = (unsigned)((nq + 3) / 4);
+  const unsigned long long* in = reinterpret_cast<const unsigned long long*>(d_parts);
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(d_out);
+  if (h->slots == 1) k_merge<1><<<blocks, 128, 0, st>>>(in, parts, (unsigned)nq, h->K, out);
+  else if (h->slots == 2) k_merge<2><<<blocks, 128, 0, st>>>(in, parts, (unsigned)nq, h->K, out);
+  else k_merge<4><<<blocks, 128, 0, st>>>(in, parts, (unsigned)nq, h->K, out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
+
+// candidates -> per (query, slot) distance/shift in h->pair_*; K_eff slots per query
+int launch_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* d_keys, const uint64_t* d_ns, int K_eff,
+                 double* d_pair_dist, int* d_pair_shift, int flip, cudaStream_t st) {
+  if (nq == 0 || K_eff == 0) return SCGPU_OK;
+  ScoreParams p;
+  p.qrecords = static_cast<const unsigned char*>(d_qrec);
+  p.L = h->L;
+  p.db = h->db;
+  p.keys = reinterpret_cast<const unsigned long long*>(d_keys);
+  p.n_search = reinterpret_cast<const unsigned long long*>(d_ns);
+  p.K = K_eff;
+  p.radius = h->radius;
+  p.pair_dist = d_pair_dist;
+  p.pair_shift = d_pair_shift;
+  p.flip = flip;
+  const size_t smem = pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float));
+  dim3 grid((unsigned)K_eff, (unsigned)nq);
+  k_score<<<grid, 128, smem, st>>>(p);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
+
+int launch_best(scgpu_handle* h, size_t nq, const uint64_t* d_keys, Best* d_best, cudaStream_t st) {
+  if (nq == 0) return SCGPU_OK;
+  k_best<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(h->pair_dist.as<double>(), h->pair_shift.as<int>(),
+                                                       reinterpret_cast<const unsigned long long*>(d_keys), (unsigned)nq, h->K, d_best);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
+
+int launch_finalize(scgpu_handle* h, const Best* d_parts, int parts, size_t nq, const uint64_t* d_ns, int* d_loop, float* d_yaw,
+                    double* d_dist, int* d_idx, int* d_shift, cudaStream_t st) {
+  if (nq == 0) return SCGPU_OK;
+  k_finalize<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(d_parts, parts, (unsigned)nq, reinterpret_cast<const unsigned long long*>(d_ns),
+                                                           h->K, h->L.S, h->cfg.dist_thres, d_loop, d_yaw, d_dist, d_idx, d_shift);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
+
+// n_search plan on the host; advances the snapshot state exactly like SC.cpp:257-276
+void plan(scgpu_handle* h, uint64_t first_size, size_t n, uint64_t* out) {
+  const uint64_t excl = (uint64_t)h->cfg.exclude_recent;
+  const bool fresh = (h->cfg.flags & SCGPU_FLAG_FRESH_TREE) || h->cfg.tree_period <= 0;
+  for (size_t i = 0; i < n; ++i) {
+    const uint64_t size = first_size + i;
+    if (size < excl + 1) {
+      out[i] = 0;
+      continue;
+    }
+    if (fresh || (h->counter % h->cfg.tree_period) == 0) h->n_tree = size - excl;
+    h->counter++;
+    out[i] = h->n_tree;
+  }
+}
+
+// full single-shard query pipeline for nq query records already on the device; results land in h->o_*.
+int run_pipeline(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* h_ns) {
+  cudaStream_t st = h->stream;
+  RET(h->nsearch.reserve(nq * sizeof(uint64_t)));
+  RET(h->h_ns.reserve(nq * sizeof(uint64_t)));
+  memcpy(h->h_ns.p, h_ns, nq * sizeof(uint64_t));
+  CK(cudaMemcpyAsync(h->nsearch.p, h->h_ns.p, nq * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  unsigned chunk, chunks;
+  choose_chunks(local_count(h, h->n_global), nq, chunk, chunks);
+  RET(query_reserve(h, nq, chunks, st));
+  const uint64_t* d_ns = h->nsearch.as<uint64_t>();
+  RET(launch_topk(h, d_qrec, nq, d_ns, h->keys.as<uint64_t>(), st));
+  RET(launch_score(h, d_qrec, nq, h->keys.as<uint64_t>(), d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
+  RET(launch_best(h, nq, h->keys.as<uint64_t>(), h->best.as<Best>(), st));
+  RET(launch_finalize(h, h->best.as<Best>(), 1, nq, d_ns, h->o_loop.as<int>(), h->o_yaw.as<float>(), h->o_dist.as<double>(),
+                      h->o_idx.as<int>(), h->o_shift.as<int>(), st));
+  h->last_nq = nq;
+  h->last_nsearch.assign(h_ns, h_ns + nq);
+  return SCGPU_OK;
+}
+
+// device results -> caller arrays (one packed D2H through pinned memory)
+int fetch_results(scgpu_handle* h, size_t nq, int* loop_id, float* yaw, double* dist, int* idx, int* shift) {
+  const size_t per = sizeof(int) + sizeof(float) + sizeof(double) + 2 * sizeof(int);
+  RET(h->h_out.reserve(nq * per + 64));
+  unsigned char* b = static_cast<unsigned char*>(h->h_out.p);
+  double* hd = reinterpret_cast<double*>(b);
+  int* hl = reinterpret_cast<int*>(b + nq * 8);
+  float* hy = reinterpret_cast<float*>(b + nq * 12);
+  int* hi = reinterpret_cast<int*>(b + nq * 16);
+  int* hs = reinterpret_cast<int*>(b + nq * 20);
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(hl, h->o_loop.p, nq * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hy, h->o_yaw.p, nq * 4, cudaMemcpyDeviceToHost, st));
+  if (dist) CK(cudaMemcpyAsync(hd, h->o_dist.p, nq * 8, cudaMemcpyDeviceToHost, st));
+  if (idx) CK(cudaMemcpyAsync(hi, h->o_idx.p, nq * 4, cudaMemcpyDeviceToHost, st));
+  if (shift) CK(cudaMemcpyAsync(hs, h->o_shift.p, nq * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (loop_id) memcpy(loop_id, hl, nq * 4);
+  if (yaw) memcpy(yaw, hy, nq * 4);
+  if (dist) memcpy(dist, hd, nq * 8);
+  if (idx) memcpy(idx, hi, nq * 4);
+  if (shift) memcpy(shift, hs, nq * 4);
+  return SCGPU_OK;
+}
+
+bool is_pinned_or_device(const void* p, int* is_device) {
+  cudaPointerAttributes a;
+  *is_device = 0;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) {
+    *is_device = 1;
+    return true;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Host points -> records, double-buffered H2D on the copy stream overlapped with k_build on the compute stream.
+int build_from_host(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, void* d_records) {
+  const size_t scan_bytes = pts_per_scan * stride;
+  if (scan_bytes == 0) return launch_build(h, h->d_pts[0].p ? h->d_pts[0].p : d_records, n_scans, 0, stride ? stride : 16, d_records, h->stream);
+  size_t per_chunk = (size_t)(32u << 20) / scan_bytes;
+  if (per_chunk < 1) per_chunk = 1;
+  if (per_chunk > n_scans) per_chunk = n_scans;
+  RET(h->d_pts[0].reserve(per_chunk * scan_bytes));
+  if (per_chunk < n_scans) RET(h->d_pts[1].reserve(per_chunk * scan_bytes));
+  int dev;
+  const bool pinned = is_pinned_or_device(pts, &dev) && !dev;
+  const unsigned char* src = static_cast<const unsigned char*>(pts);
+  int turn = 0;
+  for (size_t s0 = 0; s0 < n_scans; s0 += per_chunk, turn ^= 1) {
+    const size_t ns = n_scans - s0 < per_chunk ? n_scans - s0 : per_chunk;
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[turn], 0));
+    if (pinned) {
+      CK(cudaMemcpyAsync(h->d_pts[turn].p, src + s0 * scan_bytes, ns * scan_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    } else {
+      // pageable source: stage through our own pinned buffer so the copy is truly asynchronous
+      RET(h->h_pts[turn].reserve(per_chunk * scan_bytes));
+      CK(cudaEventSynchronize(h->ev_pin[turn]));
+      memcpy(h->h_pts[turn].p, src + s0 * scan_bytes, ns * scan_bytes);
+      CK(cudaMemcpyAsync(h->d_pts[turn].p, h->h_pts[turn].p, ns * scan_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+      CK(cudaEventRecord(h->ev_pin[turn], h->copy_stream));
+    }
+    CK(cudaEventRecord(h->ev_copied[turn], h->copy_stream));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_copied[turn], 0));
+    RET(launch_build(h, h->d_pts[turn].p, ns, pts_per_scan, stride, static_cast<unsigned char*>(d_records) + s0 * h->L.rec_bytes, h->stream));
+    CK(cudaEventRecord(h->ev_consumed[turn], h->stream));
+  }
+  return SCGPU_OK;
+}
+
+int build_any(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location, void* d_records) {
+  if (location == 1) return launch_build(h, pts, n_scans, pts_per_scan, stride, d_records, h->stream);
+  return build_from_host(h, pts, n_scans, pts_per_scan, stride, d_records);
+}
+
+int pair_api(scgpu_handle* h, const double* a, size_t na, const double* b, size_t nb, int mode, double* out_d, size_t nd, int* out_i) {
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  RET(h->api_in.reserve((na + nb) * sizeof(double)));
+  RET(h->api_out.reserve((nd + 2) * sizeof(double) + 16));
+  double* d_a = h->api_in.as<double>();
+  double* d_b = d_a + na;
+  CK(cudaMemcpyAsync(d_a, a, na * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (nb) CK(cudaMemcpyAsync(d_b, b, nb * sizeof(double), cudaMemcpyHostToDevice, st));
+  double* d_od = h->api_out.as<double>();
+  int* d_oi = reinterpret_cast<int*>(d_od + nd + 1);
+  const int W = (mode == 0) ? h->W : 1;
+  const size_t smem = pair_smem_bytes(h->L.R, h->L.S, W, sizeof(double));
+  k_pair_api<<<1, 128, smem, st>>>(d_a, d_b, h->L.R, h->L.S, h->radius, mode, d_od, d_oi);
+  h->launches++;
+  CK(cudaGetLastError());
+  std::vector<double> hd(nd + 2);
+  CK(cudaMemcpyAsync(hd.data(), d_od, (nd + 2) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (out_d) memcpy(out_d, hd.data(), nd * sizeof(double));
+  if (out_i) memcpy(out_i, reinterpret_cast<int*>(hd.data() + nd + 1), sizeof(int));
+  return SCGPU_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* scgpu_last_error(void) { return g_err; }
+const char* scgpu_version(void) { return "scgpu 0.1 (sm_100a; kernels: k_build k_append k_topk k_merge k_score k_best k_finalize k_pair_api)"; }
+
+int scgpu_default_config(scgpu_config* c) {
+  if (!c) return fail(SCGPU_E_INVALID, "null config");
+  memset(c, 0, sizeof *c);
+  c->num_ring = 20;
+  c->num_sector = 60;
+  c->lidar_height = 2.0;
+  c->max_radius = 80.0;
+  c->exclude_recent = 50;
+  c->num_candidates = 10;
+  c->search_ratio = 0.1;
+  c->dist_thres = 0.5;
+  c->tree_period = 10;
+  c->device = 0;
+  c->shard_rank = 0;
+  c->shard_count = 1;
+  c->capacity_hint = 8192;
+  return SCGPU_OK;
+}
+
+int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
+  if (!cfg || !out) return fail(SCGPU_E_INVALID, "null argument");
+  *out = nullptr;
+  if (cfg->num_ring < 1 || cfg->num_ring > 64 || cfg->num_sector < 1 || cfg->num_sector > 1024)
+    return fail(SCGPU_E_INVALID, "num_ring must be in [1,64], num_sector in [1,1024]");
+  if (cfg->num_candidates < 1 || cfg->num_candidates > 128) return fail(SCGPU_E_INVALID, "num_candidates must be in [1,128]");
+  if (cfg->exclude_recent < 0 || cfg->shard_count < 1 || cfg->shard_rank < 0 || cfg->shard_rank >= cfg->shard_count)
+    return fail(SCGPU_E_INVALID, "bad exclude_recent / shard placement");
+  if (!(cfg->search_ratio >= 0.0) || !(cfg->search_ratio <= 2.0)) return fail(SCGPU_E_INVALID, "search_ratio must be in [0,2]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SCGPU_E_NODEVICE, "no CUDA device: libscgpu has no CPU path");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SCGPU_E_INVALID, "device %d out of range (%d devices)", cfg->device, ndev);
+  CK(cudaSetDevice(cfg->device));
+  scgpu_handle* h = new scgpu_handle();
+  h->cfg = *cfg;
+  h->L = make_layout(cfg->num_ring, cfg->num_sector);
+  h->K = cfg->num_candidates;
+  h->slots = h->K <= 32 ? 1 : (h->K <= 64 ? 2 : 4);
+  h->radius = (int)llround(0.5 * cfg->search_ratio * cfg->num_sector);  // SC.cpp:123
+  h->W = 2 * h->radius + 1;
+  h->db.rank = cfg->shard_rank;
+  h->db.G = cfg->shard_count;
+  const size_t smem_f = pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float));
+  const size_t smem_d = pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(double));
+  if (smem_d > 220 * 1024) {
+    delete h;
+    return fail(SCGPU_E_INVALID, "descriptor %dx%d does not fit shared memory", cfg->num_ring, cfg->num_sector);
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pin[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t0);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t1);
+  if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t2);
+  if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+  if (e == cudaSuccess && smem_d > 48 * 1024) e = cudaFuncSetAttribute(k_pair_api, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(SCGPU_E_CUDA, "handle setup: %s", cudaGetErrorString(e));
+  }
+  uint64_t cap = cfg->capacity_hint / (uint64_t)cfg->shard_count + 1;
+  if (cap < 1024) cap = 1024;
+  int r = db_reserve(h, cap);
+  if (r == SCGPU_OK) r = h->rec_single.reserve(h->L.rec_bytes);
+  if (r != SCGPU_OK) {
+    delete h;
+    return r;
+  }
+  *out = h;
+  return SCGPU_OK;
+}
+
+int scgpu_destroy(scgpu_handle* h) {
+  if (!h) return SCGPU_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  DevBuf* bufs[] = {&h->gbins, &h->btickets, &h->d_pts[0], &h->d_pts[1], &h->records, &h->rec_single, &h->nsearch, &h->keys, &h->partial,
+                    &h->ttickets, &h->pair_dist, &h->pair_shift, &h->best, &h->o_loop, &h->o_yaw, &h->o_dist, &h->o_idx, &h->o_shift,
+                    &h->api_in, &h->api_out};
+  for (DevBuf* b : bufs) b->release();
+  h->h_pts[0].release();
+  h->h_pts[1].release();
+  h->h_out.release();
+  h->h_ns.release();
+  if (h->db.cap) {
+    cudaFree(h->db.sc);
+    cudaFree(h->db.ringT);
+    cudaFree(h->db.sector);
+    cudaFree(h->db.colnorm);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+    if (h->ev_pin[i]) cudaEventDestroy(h->ev_pin[i]);
+  }
+  if (h->ev_t0) cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1) cudaEventDestroy(h->ev_t1);
+  if (h->ev_t2) cudaEventDestroy(h->ev_t2);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  delete h;
+  return SCGPU_OK;
+}
+
+int scgpu_size(scgpu_handle* h, uint64_t* out_n) {
+  if (!h || !out_n) return fail(SCGPU_E_INVALID, "null argument");
+  *out_n = h->n_global;
+  return SCGPU_OK;
+}
+
+int scgpu_launch_count(scgpu_handle* h, uint64_t* out) {
+  if (!h || !out) return fail(SCGPU_E_INVALID, "null argument");
+  *out = h->launches;
+  return SCGPU_OK;
+}
+
+int scgpu_get_timing(scgpu_handle* h, double* ms_total, double* ms_build, double* ms_query) {
+  if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (!h->timing_valid) return fail(SCGPU_E_INVALID, "no timed call yet");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->ev_t2));
+  float a = 0, b = 0, c = 0;
+  CK(cudaEventElapsedTime(&a, h->ev_t0, h->ev_t2));
+  CK(cudaEventElapsedTime(&b, h->ev_t0, h->ev_t1));
+  CK(cudaEventElapsedTime(&c, h->ev_t1, h->ev_t2));
+  if (ms_total) *ms_total = a;
+  if (ms_build) *ms_build = b;
+  if (ms_query) *ms_query = c;
+  return SCGPU_OK;
+}
+
+int scgpu_record_bytes(scgpu_handle* h, size_t* out) {
+  if (!h || !out) return fail(SCGPU_E_INVALID, "null argument");
+  *out = h->L.rec_bytes;
+  return SCGPU_OK;
+}
+
+// ---- reference surface ----------------------------------------------------------------------------
+
+int scgpu_make_sc(scgpu_handle* h, const void* pts, size_t n, size_t stride, double* out_sc) {
+  if (!h || !out_sc || (!pts && n)) return fail(SCGPU_E_INVALID, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  RET(build_from_host(h, pts, 1, n, stride ? stride : 16, h->rec_single.p));
+  std::vector<float> sc(h->L.RS);
+  CK(cudaMemcpyAsync(sc.data(), h->rec_single.p, sizeof(float) * h->L.RS, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < h->L.RS; ++i) out_sc[i] = (double)sc[i];
+  return SCGPU_OK;
+}
+
+int scgpu_ringkey(scgpu_handle* h, const double* sc, double* out_ring) {
+  if (!h || !sc || !out_ring) return fail(SCGPU_E_INVALID, "null argument");
+  std::vector<double> o(h->L.R + h->L.S);
+  RET(pair_api(h, sc, h->L.RS, nullptr, 0, 3, o.data(), o.size(), nullptr));
+  memcpy(out_ring, o.data(), sizeof(double) * h->L.R);
+  return SCGPU_OK;
+}
+
+int scgpu_sectorkey(scgpu_handle* h, const double* sc, double* out_sector) {
+  if (!h || !sc || !out_sector) return fail(SCGPU_E_INVALID, "null argument");
+  std::vector<double> o(h->L.R + h->L.S);
+  RET(pair_api(h, sc, h->L.RS, nullptr, 0, 3, o.data(), o.size(), nullptr));
+  memcpy(out_sector, o.data() + h->L.R, sizeof(double) * h->L.S);
+  return SCGPU_OK;
+}
+
+int scgpu_fast_align(scgpu_handle* h, const double* v1, const double* v2, int* out_shift) {
+  if (!h || !v1 || !v2 || !out_shift) return fail(SCGPU_E_INVALID, "null argument");
+  return pair_api(h, v1, h->L.S, v2, h->L.S, 2, nullptr, 1, out_shift);
+}
+
+int scgpu_dist_direct(scgpu_handle* h, const double* sc1, const double* sc2, double* out_dist) {
+  if (!h || !sc1 || !sc2 || !out_dist) return fail(SCGPU_E_INVALID, "null argument");
+  return pair_api(h, sc1, h->L.RS, sc2, h->L.RS, 1, out_dist, 1, nullptr);
+}
+
+int scgpu_distance(scgpu_handle* h, const double* sc1, const double* sc2, double* out_dist, int* out_shift) {
+  if (!h || !sc1 || !sc2 || !out_dist || !out_shift) return fail(SCGPU_E_INVALID, "null argument");
+  return pair_api(h, sc1, h->L.RS, sc2, h->L.RS, 0, out_dist, 1, out_shift);
+}
+
+int scgpu_append_scans_batched(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location) {
+  if (!h || (!pts && n_scans && pts_per_scan)) return fail(SCGPU_E_INVALID, "null argument");
+  if (n_scans == 0) return SCGPU_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  RET(h->records.reserve(n_scans * h->L.rec_bytes));
+  CK(cudaEventRecord(h->ev_t0, h->stream));
+  RET(build_any(h, pts, n_scans, pts_per_scan, stride, location, h->records.p));
+  CK(cudaEventRecord(h->ev_t1, h->stream));
+  RET(launch_append(h, h->records.p, h->n_global, 1, n_scans, h->stream));
+  CK(cudaEventRecord(h->ev_t2, h->stream));
+  h->timing_valid = true;
+  if (location == 0) CK(cudaStreamSynchronize(h->copy_stream));  // the caller's buffer is not retained
+  return SCGPU_OK;
+}
+
+int scgpu_append_scan(scgpu_handle* h, const void* pts, size_t n, size_t stride) {
+  return scgpu_append_scans_batched(h, pts, 1, n, stride, 0);
+}
+
+int scgpu_append_descs(scgpu_handle* h, const float* sc, size_t n) {
+  if (!h || (!sc && n)) return fail(SCGPU_E_INVALID, "null argument");
+  if (n == 0) return SCGPU_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t batch = 8192;
+  DevBuf tmp;
+  RET(tmp.reserve(batch * h->L.RS * sizeof(float)));
+  int rc = SCGPU_OK;
+  for (size_t s0 = 0; s0 < n && rc == SCGPU_OK; s0 += batch) {
+    const size_t m = n - s0 < batch ? n - s0 : batch;
+    rc = h->records.reserve(m * h->L.rec_bytes);
+    if (rc != SCGPU_OK) break;
+    cudaError_t e = cudaMemcpyAsync(tmp.p, sc + s0 * h->L.RS, m * h->L.RS * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) {
+      rc = fail(SCGPU_E_CUDA, "H2D descriptors: %s", cudaGetErrorString(e));
+      break;
+    }
+    k_records_from_sc<<<(unsigned)m, 128, h->L.RS * sizeof(float), h->stream>>>(tmp.as<float>(), h->L, h->records.as<unsigned char>());
+    h->launches++;
+    rc = launch_append(h, h->records.p, h->n_global, 1, m, h->stream);
+    if (rc == SCGPU_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(SCGPU_E_CUDA, "append_descs sync failed");
+  }
+  tmp.release();
+  return rc;
+}
+
+int scgpu_detect(scgpu_handle* h, int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift) {
+  if (!h || !loop_id || !yaw) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "scgpu_detect needs the whole database on one device; use the staged API for shards");
+  if (h->n_global == 0) return fail(SCGPU_E_EMPTY, "detect on an empty database");
+  CK(cudaSetDevice(h->cfg.device));
+  uint64_t ns;
+  plan(h, h->n_global, 1, &ns);
+  if (ns == 0) {  // SC.cpp:257-261
+    *loop_id = -1;
+    *yaw = 0.0f;
+    if (nearest_dist) *nearest_dist = 10000000.0;
+    if (nearest_idx) *nearest_idx = 0;
+    if (nearest_shift) *nearest_shift = 0;
+    h->last_nq = 0;
+    return SCGPU_OK;
+  }
+  k_gather<<<1, 128, 0, h->stream>>>(h->rec_single.as<unsigned char>(), h->L, h->db, h->n_global - 1);
+  h->launches++;
+  CK(cudaGetLastError());
+  RET(run_pipeline(h, h->rec_single.p, 1, &ns));
+  return fetch_results(h, 1, loop_id, yaw, nearest_dist, nearest_idx, nearest_shift);
+}
+
+int scgpu_replay_batched(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location,
+                         int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift) {
+  if (!h || (!pts && n_scans && pts_per_scan) || !loop_id || !yaw) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "scgpu_replay_batched is single-shard; use the staged API for shards");
+  if (n_scans == 0) return SCGPU_OK;
+  if (n_scans > 65535) return fail(SCGPU_E_INVALID, "at most 65535 scans per call");
+  CK(cudaSetDevice(h->cfg.device));
+  const uint64_t first = h->n_global;
+  std::vector<uint64_t> ns(n_scans);
+  plan(h, first + 1, n_scans, ns.data());
+  RET(h->records.reserve(n_scans * h->L.rec_bytes));
+  CK(cudaEventRecord(h->ev_t0, h->stream));
+  RET(build_any(h, pts, n_scans, pts_per_scan, stride, location, h->records.p));
+  CK(cudaEventRecord(h->ev_t1, h->stream));
+  RET(launch_append(h, h->records.p, first, 1, n_scans, h->stream));
+  RET(run_pipeline(h, h->records.p, n_scans, ns.data()));
+  CK(cudaEventRecord(h->ev_t2, h->stream));
+  h->timing_valid = true;
+  RET(fetch_results(h, n_scans, loop_id, yaw, nearest_dist, nearest_idx, nearest_shift));
+  if (location == 0) CK(cudaStreamSynchronize(h->copy_stream));
+  return SCGPU_OK;
+}
+
+int scgpu_query_batched(scgpu_handle* h, uint64_t first, size_t nq, int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx,
+                        int* nearest_shift) {
+  if (!h || !loop_id || !yaw) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "scgpu_query_batched is single-shard; use the staged API for shards");
+  if (nq == 0) return SCGPU_OK;
+  if (first + nq > h->n_global || nq > 65535) return fail(SCGPU_E_INVALID, "query range outside the database");
+  CK(cudaSetDevice(h->cfg.device));
+  std::vector<uint64_t> ns(nq);
+  const uint64_t excl = (uint64_t)h->cfg.exclude_recent;
+  for (size_t i = 0; i < nq; ++i) {
+    const uint64_t size = first + i + 1;
+    ns[i] = size >= excl + 1 ? size - excl : 0;
+  }
+  RET(h->records.reserve(nq * h->L.rec_bytes));
+  CK(cudaEventRecord(h->ev_t0, h->stream));
+  CK(cudaEventRecord(h->ev_t1, h->stream));
+  k_gather<<<(unsigned)nq, 128, 0, h->stream>>>(h->records.as<unsigned char>(), h->L, h->db, first);
+  h->launches++;
+  CK(cudaGetLastError());
+  RET(run_pipeline(h, h->records.p, nq, ns.data()));
+  CK(cudaEventRecord(h->ev_t2, h->stream));
+  h->timing_valid = true;
+  return fetch_results(h, nq, loop_id, yaw, nearest_dist, nearest_idx, nearest_shift);
+}
+
+int scgpu_get_batch_candidates(scgpu_handle* h, size_t q, uint64_t* cand_idx, float* cand_d2, double* cand_dist, int* cand_shift,
+                               uint64_t* n_search) {
+  if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (q >= h->last_nq) return fail(SCGPU_E_INVALID, "no such query in the last call");
+  CK(cudaSetDevice(h->cfg.device));
+  const int K = h->K;
+  std::vector<uint64_t> keys(K);
+  std::vector<double> pd(K);
+  std::vector<int> ps(K);
+  CK(cudaMemcpy(keys.data(), h->keys.as<uint64_t>() + q * K, K * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pd.data(), h->pair_dist.as<double>() + q * K, K * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ps.data(), h->pair_shift.as<int>() + q * K, K * sizeof(int), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < K; ++k) {
+    const bool none = keys[k] == ~0ull;
+    // unfilled slots keep the reference's initial state: index 0, distance 0, last slot FLT_MAX (SC.cpp:283-284, nf.hpp:159-165)
+    if (cand_idx) cand_idx[k] = none ? 0 : (keys[k] & 0xffffffffull);
+    if (cand_d2) {
+      uint32_t bits = (uint32_t)(keys[k] >> 32);
+      float f;
+      memcpy(&f, &bits, 4);
+      cand_d2[k] = none ? (k == K - 1 ? FLT_MAX : 0.0f) : f;
+    }
+    if (cand_dist) cand_dist[k] = pd[k];
+    if (cand_shift) cand_shift[k] = ps[k];
+  }
+  if (n_search) *n_search = h->last_nsearch[q];
+  return SCGPU_OK;
+}
+
+int scgpu_get_candidates(scgpu_handle* h, uint64_t* cand_idx, float* cand_d2, double* cand_dist, int* cand_shift, uint64_t* n_search) {
+  return scgpu_get_batch_candidates(h, 0, cand_idx, cand_d2, cand_dist, cand_shift, n_search);
+}
+
+int scgpu_get_entry(scgpu_handle* h, uint64_t i, float* sc, float* ring, double* sector) {
+  if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (i >= h->n_global) return fail(SCGPU_E_INVALID, "entry out of range");
+  if ((int)(i % (uint64_t)h->cfg.shard_count) != h->cfg.shard_rank) return fail(SCGPU_E_INVALID, "entry lives on another shard");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  const uint64_t l = i / (uint64_t)h->cfg.shard_count;
+  if (sc) CK(cudaMemcpy(sc, h->db.sc + l * h->L.RS, sizeof(float) * h->L.RS, cudaMemcpyDeviceToHost));
+  if (ring) CK(cudaMemcpy2D(ring, sizeof(float), h->db.ringT + l, h->db.cap * sizeof(float), sizeof(float), h->L.R, cudaMemcpyDeviceToHost));
+  if (sector) CK(cudaMemcpy(sector, h->db.sector + l * h->L.S, sizeof(double) * h->L.S, cudaMemcpyDeviceToHost));
+  return SCGPU_OK;
+}
+
+int scgpu_truncate(scgpu_handle* h, uint64_t n) {
+  if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (n < h->n_global) h->n_global = n;
+  // the snapshot may reference forgotten entries: the next detect takes a fresh one (counter % period == 0)
+  h->counter = 0;
+  h->n_tree = 0;
+  return SCGPU_OK;
+}
+
+int scgpu_plan_n_search(scgpu_handle* h, uint64_t first_size, size_t n, uint64_t* out) {
+  if (!h || (!out && n)) return fail(SCGPU_E_INVALID, "null argument");
+  plan(h, first_size, n, out);
+  return SCGPU_OK;
+}
+
+// Exhaustive scoring with the exact FP64 pair kernel (every entry is a "candidate").
+int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped, double* best_dist, int* best_shift, int64_t* best_idx,
+                     int* best_flip) {
+  if (!h || !best_dist || !best_shift || !best_idx) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "scgpu_exhaustive is single-shard; use the staged API for shards");
+  if (q >= h->n_global || n_search > h->n_global) return fail(SCGPU_E_INVALID, "range outside the database");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  *best_dist = 10000000.0;
+  *best_shift = 0;
+  *best_idx = 0;
+  if (best_flip) *best_flip = 0;
+  if (n_search == 0) return SCGPU_OK;
+  k_gather<<<1, 128, 0, st>>>(h->rec_single.as<unsigned char>(), h->L, h->db, q);
+  h->launches++;
+  const size_t n = (size_t)n_search;
+  DevBuf keys, pd, ps, ns;
+  RET(keys.reserve(n * 8));
+  RET(pd.reserve(n * 8 * 2));
+  RET(ps.reserve(n * 4 * 2));
+  RET(ns.reserve(8));
+  std::vector<uint64_t> hk(n);
+  for (size_t i = 0; i < n; ++i) hk[i] = i;
+  uint64_t one = n_search;
+  CK(cudaMemcpyAsync(keys.p, hk.data(), n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ns.p, &one, 8, cudaMemcpyHostToDevice, st));
+  int rc = SCGPU_OK;
+  const size_t slab = 1u << 20;
+  for (int f = 0; f <= (flipped ? 1 : 0) && rc == SCGPU_OK; ++f)
+    for (size_t s0 = 0; s0 < n && rc == SCGPU_OK; s0 += slab) {
+      const size_t m = n - s0 < slab ? n - s0 : slab;
+      // one "query" with m candidate slots per launch (grid.x = slots)
+      ScoreParams p;
+      p.qrecords = h->rec_single.as<unsigned char>();
+      p.L = h->L;
+      p.db = h->db;
+      p.keys = keys.as<unsigned long long>() + s0;
+      p.n_search = ns.as<unsigned long long>();
+      p.K = (int)m;
+      p.radius = h->radius;
+      p.pair_dist = pd.as<double>() + f * n + s0;
+      p.pair_shift = ps.as<int>() + f * n + s0;
+      p.flip = f;
+      k_score<<<dim3((unsigned)m, 1), 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p);
+      h->launches++;
+      if (cudaGetLastError() != cudaSuccess) rc = fail(SCGPU_E_CUDA, "k_score launch failed");
+    }
+  std::vector<double> hd(n * (flipped ? 2 : 1));
+  std::vector<int> hs(n * (flipped ? 2 : 1));
+  if (rc == SCGPU_OK && cudaMemcpyAsync(hd.data(), pd.p, hd.size() * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail(SCGPU_E_CUDA, "D2H failed");
+  if (rc == SCGPU_OK && cudaMemcpyAsync(hs.data(), ps.p, hs.size() * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = fail(SCGPU_E_CUDA, "D2H failed");
+  if (rc == SCGPU_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(SCGPU_E_CUDA, "exhaustive sync failed");
+  keys.release();
+  pd.release();
+  ps.release();
+  ns.release();
+  if (rc != SCGPU_OK) return rc;
+  // strict-min in (index, forward-before-flipped) order: the argmin reduction of SC.cpp:296-311 over all entries
+  for (size_t i = 0; i < n; ++i)
+    for (int f = 0; f <= (flipped ? 1 : 0); ++f) {
+      const double d = hd[f * n + i];
+      if (d < *best_dist) {
+        *best_dist = d;
+        *best_shift = hs[f * n + i];
+        *best_idx = (int64_t)i;
+        if (best_flip) *best_flip = f;
+      }
+    }
+  return SCGPU_OK;
+}
+
+int scgpu_save(scgpu_handle* h, const char* path) {
+  if (!h || !path) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "save is single-shard");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaStreamSynchronize(h->stream));
+  const uint64_t n = h->n_global;
+  std::vector<float> sc((size_t)n * h->L.RS);
+  if (n) CK(cudaMemcpy(sc.data(), h->db.sc, sc.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(SCGPU_E_IO, "cannot open %s for writing", path);
+  const char magic[8] = {'S', 'C', 'G', 'P', 'U', 'D', 'B', '1'};
+  uint64_t hdr[4] = {(uint64_t)h->L.R, (uint64_t)h->L.S, n, 0};
+  bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(hdr, 8, 4, f) == 4 && fwrite(&h->cfg, sizeof h->cfg, 1, f) == 1 &&
+            (sc.empty() || fwrite(sc.data(), sizeof(float), sc.size(), f) == sc.size());
+  ok = (fclose(f) == 0) && ok;
+  return ok ? SCGPU_OK : fail(SCGPU_E_IO, "short write to %s", path);
+}
+
+int scgpu_load(scgpu_handle* h, const char* path) {
+  if (!h || !path) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "load is single-shard");
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(SCGPU_E_IO, "cannot open %s", path);
+  char magic[8];
+  uint64_t hdr[4];
+  scgpu_config saved;
+  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "SCGPUDB1", 8) != 0 || fread(hdr, 8, 4, f) != 4 || fread(&saved, sizeof saved, 1, f) != 1) {
+    fclose(f);
+    return fail(SCGPU_E_IO, "%s is not a scgpu database", path);
+  }
+  if ((int)hdr[0] != h->L.R || (int)hdr[1] != h->L.S) {
+    fclose(f);
+    return fail(SCGPU_E_INVALID, "database is %llux%llu, handle is %dx%d", (unsigned long long)hdr[0], (unsigned long long)hdr[1], h->L.R, h->L.S);
+  }
+  std::vector<float> sc((size_t)hdr[2] * h->L.RS);
+  const bool ok = sc.empty() || fread(sc.data(), sizeof(float), sc.size(), f) == sc.size();
+  fclose(f);
+  if (!ok) return fail(SCGPU_E_IO, "short read from %s", path);
+  return scgpu_append_descs(h, sc.data(), (size_t)hdr[2]);
+}
+
+int scgpu_probe_atanf(const float* x, size_t n, float* out) {
+  if ((!x || !out) && n) return fail(SCGPU_E_INVALID, "null argument");
+  if (n == 0) return SCGPU_OK;
+  float *dx = nullptr, *dy = nullptr;
+  CK(cudaMalloc(&dx, n * 4));
+  CK(cudaMalloc(&dy, n * 4));
+  CK(cudaMemcpy(dx, x, n * 4, cudaMemcpyHostToDevice));
+  k_probe_atanf<<<(unsigned)((n + 255) / 256), 256>>>(dx, dy, n);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(out, dy, n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dy);
+  if (e != cudaSuccess) return fail(SCGPU_E_CUDA, "probe_atanf: %s", cudaGetErrorString(e));
+  return SCGPU_OK;
+}
+
+int scgpu_probe_bins(scgpu_handle* h, const float* xyz, size_t n, int32_t* bin, float* height, float* theta) {
+  if (!h || ((!xyz || !bin || !height || !theta) && n)) return fail(SCGPU_E_INVALID, "null argument");
+  if (n == 0) return SCGPU_OK;
+  CK(cudaSetDevice(h->cfg.device));
+  float *dx = nullptr, *dh = nullptr, *dt = nullptr;
+  int* db = nullptr;
+  CK(cudaMalloc(&dx, n * 12));
+  CK(cudaMalloc(&dh, n * 4));
+  CK(cudaMalloc(&dt, n * 4));
+  CK(cudaMalloc(&db, n * 4));
+  CK(cudaMemcpy(dx, xyz, n * 12, cudaMemcpyHostToDevice));
+  BinConst bc;
+  bc.R = h->L.R;
+  bc.S = h->L.S;
+  bc.lidar_height = h->cfg.lidar_height;
+  bc.max_radius = h->cfg.max_radius;
+  k_probe_bins<<<(unsigned)((n + 255) / 256), 256>>>(dx, n, bc, db, dh, dt);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(bin, db, n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(height, dh, n * 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(theta, dt, n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dh);
+  cudaFree(dt);
+  cudaFree(db);
+  if (e != cudaSuccess) return fail(SCGPU_E_CUDA, "probe_bins: %s", cudaGetErrorString(e));
+  return SCGPU_OK;
+}
+
+int scgpu_xy2theta(float x, float y, float* out_deg) {
+  if (!out_deg) return fail(SCGPU_E_INVALID, "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SCGPU_E_NODEVICE, "no CUDA device: libscgpu has no CPU path");
+  }
+  float xyz[3] = {x, y, 0.f}, *dx = nullptr, *dh = nullptr, *dt = nullptr;
+  int* db = nullptr;
+  CK(cudaMalloc(&dx, 12));
+  CK(cudaMalloc(&dh, 4));
+  CK(cudaMalloc(&dt, 4));
+  CK(cudaMalloc(&db, 4));
+  CK(cudaMemcpy(dx, xyz, 12, cudaMemcpyHostToDevice));
+  BinConst bc{20, 60, 2.0, 80.0};
+  k_probe_bins<<<1, 32>>>(dx, 1, bc, db, dh, dt);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(out_deg, dt, 4, cudaMemcpyDeviceToHost);
+  cudaFree(dx);
+  cudaFree(dh);
+  cudaFree(dt);
+  cudaFree(db);
+  if (e != cudaSuccess) return fail(SCGPU_E_CUDA, "xy2theta: %s", cudaGetErrorString(e));
+  return SCGPU_OK;
+}
+
+// ---- staged API -------------------------------------------------------------------------------------
+
+#define ST(s) ((s) ? static_cast<cudaStream_t>(s) : h->stream)
+
+int scgpu_stage_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_per_scan, size_t stride, void* d_records, void* stream) {
+  if (!h || !d_records) return fail(SCGPU_E_INVALID, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  return launch_build(h, d_pts, n_scans, pts_per_scan, stride, d_records, ST(stream));
+}
+
+int scgpu_stage_append(scgpu_handle* h, const void* d_records, uint64_t first_global, uint64_t global_step, size_t n, void* stream) {
+  if (!h || !d_records) return fail(SCGPU_E_INVALID, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  return launch_append(h, d_records, first_global, global_step, n, ST(stream));
+}
+
+int scgpu_stage_set_size(scgpu_handle* h, uint64_t n_global) {
+  if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (local_count(h, n_global) > h->db.cap) return fail(SCGPU_E_INVALID, "size beyond this shard's stored entries");
+  h->n_global = n_global;
+  return SCGPU_OK;
+}
+
+int scgpu_stage_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* d_ns, uint64_t* d_keys_out, void* stream) {
+  if (!h || !d_qrec || !d_ns || !d_keys_out) return fail(SCGPU_E_INVALID, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  return launch_topk(h, d_qrec, nq, d_ns, d_keys_out, ST(stream));
+}
+
+int scgpu_stage_merge(scgpu_handle* h, const uint64_t* d_parts, int parts, size_t nq, uint64_t* d_out, void* stream) {
+  if (!h || !d_parts || !d_out || parts < 1) return fail(SCGPU_E_INVALID, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  return launch_merge(h, d_parts, parts, nq, d_out, ST(stream));
+}
+
+int scgpu_stage_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* d_keys, const uint64_t* d_ns, void* d_best_out,
+                      void* stream) {
+  if (!h || !d_qrec || !d_keys || !d_ns || !d_best_out) return fail(SCGPU_E_INVALID, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = ST(stream);
+  RET(query_reserve(h, nq, 1, st));
+  RET(launch_score(h, d_qrec, nq, d_keys, d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
+  return launch_best(h, nq, d_keys, static_cast<Best*>(d_best_out), st);
+}
+
+int scgpu_stage_finalize(scgpu_handle* h, const void* d_best_parts, int parts, size_t nq, const uint64_t* d_ns, int32_t* d_loop_id,
+                         float* d_yaw, double* d_nearest_dist, int32_t* d_nearest_idx, int32_t* d_nearest_shift, void* stream) {
+  if (!h || !d_best_parts || !d_ns || !d_loop_id || !d_yaw || parts < 1) return fail(SCGPU_E_INVALID, "bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  return launch_finalize(h, static_cast<const Best*>(d_best_parts), parts, nq, d_ns, d_loop_id, d_yaw, d_nearest_dist, d_nearest_idx,
+                         d_nearest_shift, ST(stream));
+}
+
+}  // extern "C"

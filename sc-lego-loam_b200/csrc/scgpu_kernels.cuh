@@ -1,0 +1,944 @@
+// scgpu_kernels.cuh -- hand-written sm_100a kernels of the Scan Context loop-closure hot path.
+//
+// One kernel per reference stage (citations: "SC.cpp" = SC-LeGO-LOAM/LeGO-LOAM/src/Scancontext.cpp,
+// "SC.h" = include/Scancontext.h, "nf.hpp" = include/nanoflann.hpp):
+//   k_build      stage 1+2  SC.cpp:151-195 (polar max-height binning) fused with SC.cpp:198-227 (keys)
+//   k_append     records -> HBM-resident database (SC.cpp:237-240)
+//   k_topk       stage 3    exact brute-force ring-key top-K replacing SC.cpp:283-289 / nf.hpp kd-tree
+//   k_score      stage 4    SC.cpp:116-148 column-shifted cosine distance (FP64, reference order)
+//   k_best/k_finalize       SC.cpp:296-336 candidate loop, threshold, yaw
+//
+// Bit-exactness rules used throughout: every arithmetic step of the reference is one IEEE operation here
+// (__fmul_rn/__fadd_rn/__dmul_rn/... never contract into FMA; the file is also compiled with --fmad=false);
+// FP64 reductions follow Eigen 3.3's SSE2 redux order (4 interleaved partial sums); the ring-key distance
+// follows nanoflann's grouped-by-4 FP32 accumulation.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace scgpu {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr unsigned long long KEY_NONE = ~0ull;
+
+// ------------------------------------------------------------------------------------------------
+// Packed descriptor record (one per scan): float sc[R*S] (column-major) | float ring[R] | double sector[S]
+// | double colnorm[S]; padded to 16 bytes.
+// ------------------------------------------------------------------------------------------------
+struct Layout {
+  int R, S, RS;
+  unsigned off_ring, off_sector, off_norm, rec_bytes;
+};
+
+__host__ __device__ inline Layout make_layout(int R, int S) {
+  Layout L;
+  L.R = R;
+  L.S = S;
+  L.RS = R * S;
+  L.off_ring = 4u * (unsigned)L.RS;
+  L.off_sector = (L.off_ring + 4u * (unsigned)R + 7u) & ~7u;
+  L.off_norm = L.off_sector + 8u * (unsigned)S;
+  L.rec_bytes = (L.off_norm + 8u * (unsigned)S + 15u) & ~15u;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact scalar pieces
+// ------------------------------------------------------------------------------------------------
+
+// glibc 2.39 atanf == fdlibm s_atanf.c evaluated in plain binary32 (verified over every float against the
+// host libm by tests/test_atanf.py on the oracle restatement, and against this device function on the GPU).
+// The reference reaches it through SC.cpp:26-35 (atan -> atanf: <math.h> is in scope in the ROS build).
+__device__ __forceinline__ float atanf_fdlibm(float x) {
+  const unsigned hx = __float_as_uint(x), ix = hx & 0x7fffffffu;
+  int id;
+  if (ix >= 0x4c000000u) {  // |x| >= 2^25, inf, NaN
+    if (ix > 0x7f800000u) return __fadd_rn(x, x);
+    const float r = __fadd_rn(__uint_as_float(0x3fc90fdau), __uint_as_float(0x33a22168u));
+    return (hx >> 31) ? -r : r;
+  }
+  float hi = 0.f, lo = 0.f;
+  if (ix < 0x3ee00000u) {  // |x| < 7/16
+    if (ix < 0x31000000u) return x;
+    id = -1;
+  } else {
+    x = fabsf(x);
+    if (ix < 0x3f980000u) {
+      if (ix < 0x3f300000u) {
+        id = 0;
+        hi = __uint_as_float(0x3eed6338u);
+        lo = __uint_as_float(0x31ac3769u);
+        x = __fdiv_rn(__fsub_rn(__fmul_rn(2.0f, x), 1.0f), __fadd_rn(2.0f, x));
+      } else {
+        id = 1;
+        hi = __uint_as_float(0x3f490fdau);
+        lo = __uint_as_float(0x33222168u);
+        x = __fdiv_rn(__fsub_rn(x, 1.0f), __fadd_rn(x, 1.0f));
+      }
+    } else {
+      if (ix < 0x401c0000u) {
+        id = 2;
+        hi = __uint_as_float(0x3f7b985eu);
+        lo = __uint_as_float(0x33140fb4u);
+        x = __fdiv_rn(__fsub_rn(x, 1.5f), __fadd_rn(1.0f, __fmul_rn(1.5f, x)));
+      } else {
+        id = 3;
+        hi = __uint_as_float(0x3fc90fdau);
+        lo = __uint_as_float(0x33a22168u);
+        x = __fdiv_rn(-1.0f, x);
+      }
+    }
+  }
+  const float aT0 = __uint_as_float(0x3eaaaaabu), aT1 = __uint_as_float(0xbe4ccccdu), aT2 = __uint_as_float(0x3e124925u),
+              aT3 = __uint_as_float(0xbde38e38u), aT4 = __uint_as_float(0x3dba2e6eu), aT5 = __uint_as_float(0xbd9d8795u),
+              aT6 = __uint_as_float(0x3d886b35u), aT7 = __uint_as_float(0xbd6ef16bu), aT8 = __uint_as_float(0x3d4bda59u),
+              aT9 = __uint_as_float(0xbd15a221u), aT10 = __uint_as_float(0x3c8569d7u);
+  const float z = __fmul_rn(x, x);
+  const float w = __fmul_rn(z, z);
+  float s1 = __fadd_rn(aT8, __fmul_rn(w, aT10));
+  s1 = __fadd_rn(aT6, __fmul_rn(w, s1));
+  s1 = __fadd_rn(aT4, __fmul_rn(w, s1));
+  s1 = __fadd_rn(aT2, __fmul_rn(w, s1));
+  s1 = __fadd_rn(aT0, __fmul_rn(w, s1));
+  s1 = __fmul_rn(z, s1);
+  float s2 = __fadd_rn(aT7, __fmul_rn(w, aT9));
+  s2 = __fadd_rn(aT5, __fmul_rn(w, s2));
+  s2 = __fadd_rn(aT3, __fmul_rn(w, s2));
+  s2 = __fadd_rn(aT1, __fmul_rn(w, s2));
+  s2 = __fmul_rn(w, s2);
+  const float xs = __fmul_rn(x, __fadd_rn(s1, s2));
+  if (id < 0) return __fsub_rn(x, xs);
+  const float r = __fsub_rn(hi, __fsub_rn(__fsub_rn(xs, lo), x));
+  return (hx >> 31) ? -r : r;
+}
+
+// SC.cpp:23-36.  (180/M_PI) is a double constant; the float atanf result is widened, scaled and offset in
+// double and narrowed by the float return.  NaN coordinates are rejected by the caller (reference: UB).
+__device__ __forceinline__ float xy2theta_exact(float x, float y) {
+  const double k = 180.0 / 3.14159265358979323846;
+  if ((x >= 0.f) & (y >= 0.f)) return __double2float_rn(__dmul_rn(k, (double)atanf_fdlibm(__fdiv_rn(y, x))));
+  if ((x < 0.f) & (y >= 0.f)) return __double2float_rn(__dsub_rn(180.0, __dmul_rn(k, (double)atanf_fdlibm(__fdiv_rn(y, -x)))));
+  if ((x < 0.f) & (y < 0.f)) return __double2float_rn(__dadd_rn(180.0, __dmul_rn(k, (double)atanf_fdlibm(__fdiv_rn(y, x)))));
+  return __double2float_rn(__dsub_rn(360.0, __dmul_rn(k, (double)atanf_fdlibm(__fdiv_rn(-y, x)))));
+}
+
+struct BinConst {
+  int R, S;
+  double lidar_height, max_radius;
+};
+
+// SC.cpp:166-183 for one point.  Returns the 0-based bin (sector*R + ring) or -1 when the point does not
+// contribute (outside the ROI, NaN coordinate, or a height that can never win the max).
+__device__ __forceinline__ int bin_point_exact(const BinConst& c, float x, float y, float z, float& height) {
+  height = __double2float_rn(__dadd_rn((double)z, c.lidar_height));                 // SC.cpp:168
+  const float range = __fsqrt_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));     // SC.cpp:171
+  if (!(x == x) || !(y == y)) return -1;                                            // reference: undefined
+  if ((double)range > c.max_radius) return -1;                                      // SC.cpp:175
+  if (!(height == height)) return -1;                                               // NaN never passes SC.cpp:182
+  const float theta = xy2theta_exact(x, y);                                         // SC.cpp:172
+  const double qr = ceil(__dmul_rn(__ddiv_rn((double)range, c.max_radius), (double)c.R));  // SC.cpp:178
+  const double qs = ceil(__dmul_rn(__ddiv_rn((double)theta, 360.0), (double)c.S));         // SC.cpp:179
+  // int(): NaN -> INT_MIN on x86, 0 here; both clamp to 1.  Values are otherwise far inside int range.
+  const int ring = max(min(c.R, __double2int_rz(qr)), 1);
+  const int sector = max(min(c.S, __double2int_rz(qs)), 1);
+  return (sector - 1) * c.R + (ring - 1);
+}
+
+// order-preserving float <-> int map so that atomicMax on ints is max on floats (SC.cpp:182-183)
+__device__ __forceinline__ int enc_float(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float dec_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+#define SCGPU_ENC_NOPOINT (-1148846081) /* enc_float(-1000.0f): bits 0xc47a0000 ^ 0x7fffffff = 0xbb85ffff */
+
+// Eigen 3.3 Core/Redux.h (LinearVectorizedTraversal, NoUnrolling, Packet2d, alignedStart 0): the order in which
+// the reference's sum()/mean()/norm()/dot() add their terms.  coeff(i) returns the i-th (transformed) scalar.
+template <class Coeff>
+__device__ __forceinline__ double redux_eigen(int size, Coeff coeff) {
+  const int alignedSize2 = (size / 4) * 4;
+  const int alignedSize = (size / 2) * 2;
+  if (size == 0) return 0.0;
+  double res;
+  if (alignedSize) {
+    double p00 = coeff(0), p01 = coeff(1);
+    if (alignedSize > 2) {
+      double p10 = coeff(2), p11 = coeff(3);
+      for (int i = 4; i < alignedSize2; i += 4) {
+        p00 = __dadd_rn(p00, coeff(i));
+        p01 = __dadd_rn(p01, coeff(i + 1));
+        p10 = __dadd_rn(p10, coeff(i + 2));
+        p11 = __dadd_rn(p11, coeff(i + 3));
+      }
+      p00 = __dadd_rn(p00, p10);
+      p01 = __dadd_rn(p01, p11);
+      if (alignedSize > alignedSize2) {
+        p00 = __dadd_rn(p00, coeff(alignedSize2));
+        p01 = __dadd_rn(p01, coeff(alignedSize2 + 1));
+      }
+    }
+    res = __dadd_rn(p00, p01);
+    for (int i = alignedSize; i < size; ++i) res = __dadd_rn(res, coeff(i));
+  } else {
+    res = coeff(0);
+    for (int i = 1; i < size; ++i) res = __dadd_rn(res, coeff(i));
+  }
+  return res;
+}
+
+template <class T>
+struct CoeffStrided {
+  const T* p;
+  int stride;
+  __device__ __forceinline__ double operator()(int i) const { return (double)p[i * stride]; }
+};
+template <class T>
+struct CoeffSquare {
+  const T* p;
+  __device__ __forceinline__ double operator()(int i) const {
+    const double v = (double)p[i];
+    return __dmul_rn(v, v);
+  }
+};
+template <class T>
+struct CoeffProduct {
+  const T* a;
+  const T* b;
+  __device__ __forceinline__ double operator()(int i) const { return __dmul_rn((double)a[i], (double)b[i]); }
+};
+// (vkey1[j] - vkey2[(j - s) mod S])^2  -- SC.cpp:99-103 with circshift SC.cpp:39-59
+struct CoeffShiftDiffSq {
+  const double* v1;
+  const double* v2;
+  int s, S;
+  __device__ __forceinline__ double operator()(int j) const {
+    int jj = j - s;
+    if (jj < 0) jj += S;
+    const double d = __dsub_rn(v1[j], v2[jj]);
+    return __dmul_rn(d, d);
+  }
+};
+
+// Keys of one descriptor held in shared memory (T = float from binning, or double from the public API):
+// ring key (SC.cpp:198-211), sector key (SC.cpp:214-227), column norms (SC.cpp:78).  Whole block cooperates.
+template <class T>
+__device__ __forceinline__ void keys_from_sc(const T* s_sc, int R, int S, double* ring_d, float* ring_f, double* sector,
+                                             double* colnorm) {
+  for (int t = threadIdx.x; t < R + S; t += blockDim.x) {
+    if (t < R) {
+      const double m = __ddiv_rn(redux_eigen(S, CoeffStrided<T>{s_sc + t, R}), (double)S);
+      if (ring_d) ring_d[t] = m;
+      if (ring_f) ring_f[t] = __double2float_rn(m);  // eig2stdvec, SC.cpp:62-66
+    } else {
+      const int c = t - R;
+      const T* col = s_sc + c * R;
+      if (sector) sector[c] = __ddiv_rn(redux_eigen(R, CoeffStrided<T>{col, 1}), (double)R);
+      if (colnorm) colnorm[c] = __dsqrt_rn(redux_eigen(R, CoeffSquare<T>{col}));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 1+2: k_build
+//   grid = (tiles per scan, scans), block = 256.  Each block bins a tile of consecutive points into a
+//   shared-memory R*S grid of order-encoded ints (warp-aggregated atomicMax), merges its non-empty bins into
+//   the scan's global grid, and the last block of a scan (ticket counter) decodes the grid, derives the keys
+//   and writes the packed record.  The global grid and the ticket are left reset for the next launch.
+// ------------------------------------------------------------------------------------------------
+struct BuildParams {
+  const unsigned char* pts;  // scans contiguous: scan s at pts + s * scan_pitch
+  unsigned long long scan_pitch;
+  unsigned n_pts;     // points per scan
+  unsigned stride;    // bytes between points
+  unsigned pts_per_block;
+  BinConst bc;
+  Layout L;
+  int* gbins;         // [scans][RS], pre-set to SCGPU_ENC_NOPOINT
+  unsigned* tickets;  // [scans], pre-set to 0
+  unsigned char* records;
+};
+
+template <int STRIDE>  // 16 / 32: one aligned 16-byte load per point; 0: three 4-byte loads (any 4-aligned stride)
+__device__ __forceinline__ void load_point(const unsigned char* p, float& x, float& y, float& z) {
+  if (STRIDE == 16 || STRIDE == 32) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+    x = v.x;
+    y = v.y;
+    z = v.z;
+  } else {
+    const float* f = reinterpret_cast<const float*>(p);
+    x = __ldcs(f);
+    y = __ldcs(f + 1);
+    z = __ldcs(f + 2);
+  }
+}
+
+// One atomicMax per distinct bin per warp: consecutive points of a scan share a beam and neighbouring
+// azimuths, so a warp usually touches one or two bins.
+__device__ __forceinline__ void warp_bin_max(int* s_bins, int bin, int enc) {
+  unsigned todo = __ballot_sync(FULL, bin >= 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int b = __shfl_sync(FULL, bin, leader);
+    const bool mine = (bin == b);
+    const int m = __reduce_max_sync(FULL, mine ? enc : INT_MIN);
+    if ((threadIdx.x & 31) == leader) atomicMax(&s_bins[b], m);
+    todo &= ~__ballot_sync(FULL, mine);
+  }
+}
+
+template <int STRIDE>
+__global__ void __launch_bounds__(256) k_build(const BuildParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* s_bins = reinterpret_cast<int*>(smem_raw);
+  __shared__ bool s_last;
+  const int RS = p.L.RS;
+  const unsigned scan = blockIdx.y;
+  for (int i = threadIdx.x; i < RS; i += blockDim.x) s_bins[i] = SCGPU_ENC_NOPOINT;
+  __syncthreads();
+
+  const unsigned start = blockIdx.x * p.pts_per_block;
+  const unsigned end = min(start + p.pts_per_block, p.n_pts);
+  const unsigned char* base = p.pts + (unsigned long long)scan * p.scan_pitch;
+  // whole warps iterate together (the aggregation uses full-mask warp primitives)
+  for (unsigned i0 = start + (threadIdx.x & ~31u); i0 < end; i0 += blockDim.x) {
+    const unsigned i = i0 + (threadIdx.x & 31u);
+    int bin = -1, enc = INT_MIN;
+    if (i < end) {
+      float x, y, z, h;
+      load_point<STRIDE>(base + (unsigned long long)i * p.stride, x, y, z);
+      bin = bin_point_exact(p.bc, x, y, z, h);
+      enc = enc_float(h);
+    }
+    warp_bin_max(s_bins, bin, enc);
+  }
+  __syncthreads();
+
+  if (gridDim.x > 1) {
+    int* g = p.gbins + (unsigned long long)scan * RS;
+    for (int i = threadIdx.x; i < RS; i += blockDim.x) {
+      const int v = s_bins[i];
+      if (v != SCGPU_ENC_NOPOINT) atomicMax(&g[i], v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&p.tickets[scan], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < RS; i += blockDim.x) {
+      s_bins[i] = __ldcg(&g[i]);
+      g[i] = SCGPU_ENC_NOPOINT;
+    }
+    if (threadIdx.x == 0) p.tickets[scan] = 0;
+    __syncthreads();
+  }
+
+  // decode (SC.cpp:187-190: cells still at NO_POINT become 0) and write the record
+  unsigned char* rec = p.records + (unsigned long long)scan * p.L.rec_bytes;
+  float* s_sc = reinterpret_cast<float*>(smem_raw);
+  float* rec_sc = reinterpret_cast<float*>(rec);
+  for (int i = threadIdx.x; i < RS; i += blockDim.x) {
+    float f = dec_float(s_bins[i]);
+    if (f == -1000.0f) f = 0.0f;
+    s_sc[i] = f;
+    rec_sc[i] = f;
+  }
+  __syncthreads();
+  keys_from_sc<float>(s_sc, p.L.R, p.L.S, nullptr, reinterpret_cast<float*>(rec + p.L.off_ring),
+                      reinterpret_cast<double*>(rec + p.L.off_sector), reinterpret_cast<double*>(rec + p.L.off_norm));
+}
+
+__global__ void k_fill_int(int* p, size_t n, int v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// Records from ready-made float descriptors (database load / pre-fill): keys as SC.cpp:233-235.
+__global__ void __launch_bounds__(128) k_records_from_sc(const float* sc, Layout L, unsigned char* records) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_sc = reinterpret_cast<float*>(smem_raw);
+  const float* src = sc + (size_t)blockIdx.x * L.RS;
+  unsigned char* rec = records + (size_t)blockIdx.x * L.rec_bytes;
+  for (int i = threadIdx.x; i < L.RS; i += blockDim.x) {
+    const float f = src[i];
+    s_sc[i] = f;
+    reinterpret_cast<float*>(rec)[i] = f;
+  }
+  __syncthreads();
+  keys_from_sc<float>(s_sc, L.R, L.S, nullptr, reinterpret_cast<float*>(rec + L.off_ring),
+                      reinterpret_cast<double*>(rec + L.off_sector), reinterpret_cast<double*>(rec + L.off_norm));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Database (one shard): sc[cap][RS] float | ringT[R][cap] float (dimension-major: coalesced streaming in
+// k_topk) | sector[cap][S] double | colnorm[cap][S] double.  Global entry g lives on shard g % G at g / G.
+// ------------------------------------------------------------------------------------------------
+struct Db {
+  float* sc;
+  float* ringT;
+  double* sector;
+  double* colnorm;
+  unsigned long long cap;  // local capacity
+  int rank, G;
+};
+
+// records [0,n) -> entries first_global + i*step (kept when owned)
+__global__ void __launch_bounds__(128) k_append(const unsigned char* records, Layout L, Db db, unsigned long long first_global,
+                                                unsigned long long step) {
+  const unsigned long long g = first_global + blockIdx.x * step;
+  if ((int)(g % (unsigned long long)db.G) != db.rank) return;
+  const unsigned long long l = g / (unsigned long long)db.G;
+  const unsigned char* rec = records + (size_t)blockIdx.x * L.rec_bytes;
+  const float4* src4 = reinterpret_cast<const float4*>(rec);
+  float4* dst4 = reinterpret_cast<float4*>(db.sc + l * L.RS);
+  if ((L.RS & 3) == 0) {
+    for (int i = threadIdx.x; i < L.RS / 4; i += blockDim.x) dst4[i] = src4[i];
+  } else {
+    for (int i = threadIdx.x; i < L.RS; i += blockDim.x) db.sc[l * L.RS + i] = reinterpret_cast<const float*>(rec)[i];
+  }
+  const float* ring = reinterpret_cast<const float*>(rec + L.off_ring);
+  const double* sector = reinterpret_cast<const double*>(rec + L.off_sector);
+  const double* norm = reinterpret_cast<const double*>(rec + L.off_norm);
+  for (int i = threadIdx.x; i < L.R; i += blockDim.x) db.ringT[(size_t)i * db.cap + l] = ring[i];
+  for (int i = threadIdx.x; i < L.S; i += blockDim.x) {
+    db.sector[l * L.S + i] = sector[i];
+    db.colnorm[l * L.S + i] = norm[i];
+  }
+}
+
+// entries first_global + i -> records (single shard only): query records for stored entries
+__global__ void __launch_bounds__(128) k_gather(unsigned char* records, Layout L, Db db, unsigned long long first_global) {
+  const unsigned long long l = first_global + blockIdx.x;
+  unsigned char* rec = records + (size_t)blockIdx.x * L.rec_bytes;
+  for (int i = threadIdx.x; i < L.RS; i += blockDim.x) reinterpret_cast<float*>(rec)[i] = db.sc[l * L.RS + i];
+  for (int i = threadIdx.x; i < L.R; i += blockDim.x) reinterpret_cast<float*>(rec + L.off_ring)[i] = db.ringT[(size_t)i * db.cap + l];
+  for (int i = threadIdx.x; i < L.S; i += blockDim.x) {
+    reinterpret_cast<double*>(rec + L.off_sector)[i] = db.sector[l * L.S + i];
+    reinterpret_cast<double*>(rec + L.off_norm)[i] = db.colnorm[l * L.S + i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 3: exact brute-force ring-key top-K (replaces the nanoflann KD-tree and its rebuild).
+//   Keys are (dist2 bits << 32 | global index): squared distances are non-negative floats, so unsigned
+//   64-bit order == (dist2, index) order -- the deterministic tie-break.
+//   Each warp keeps a sorted list of 32*SLOTS keys spread over its lanes (slot s lives in lane s%32,
+//   register s/32); a candidate is inserted only if it beats the current K-th key.
+// ------------------------------------------------------------------------------------------------
+template <int SLOTS>
+struct WarpList {
+  unsigned long long v[SLOTS];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) v[s] = KEY_NONE;
+  }
+  __device__ __forceinline__ unsigned long long kth(int K) const {  // value of slot K-1 (warp-uniform)
+    unsigned long long r = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const unsigned long long t = __shfl_sync(FULL, v[s], (K - 1) & 31);
+      if (((K - 1) >> 5) == s) r = t;
+    }
+    return r;
+  }
+  __device__ __forceinline__ void insert(unsigned long long c) {  // c is warp-uniform
+    const int lane = threadIdx.x & 31;
+    int pos = 0;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(FULL, v[s] < c));
+    unsigned long long carry = 0;  // last element of the previous register row
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      unsigned long long up = __shfl_up_sync(FULL, v[s], 1);
+      const unsigned long long last = __shfl_sync(FULL, v[s], 31);
+      if (lane == 0) up = carry;
+      carry = last;
+      const int slot = s * 32 + lane;
+      if (slot > pos) v[s] = up;
+      else if (slot == pos) v[s] = c;
+    }
+  }
+  // offer one key per lane (KEY_NONE = nothing)
+  __device__ __forceinline__ void offer(unsigned long long key, int K) {
+    unsigned long long w = kth(K);
+    unsigned cand = __ballot_sync(FULL, key < w);
+    while (cand) {
+      const int src = __ffs(cand) - 1;
+      cand &= cand - 1;
+      const unsigned long long c = __shfl_sync(FULL, key, src);
+      if (c < w) {
+        insert(c);
+        w = kth(K);
+      }
+    }
+  }
+  // offer `count` keys from memory
+  __device__ __forceinline__ void offer_from(const unsigned long long* src, int count, int K) {
+    const int lane = threadIdx.x & 31;
+    for (int b = 0; b < count; b += 32) {
+      const int i = b + lane;
+      offer(i < count ? src[i] : KEY_NONE, K);
+    }
+  }
+  __device__ __forceinline__ void store(unsigned long long* dst, int K) const {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s)
+      if (s * 32 + lane < K) dst[s * 32 + lane] = v[s];
+  }
+};
+
+// nf.hpp:383-408: four squared differences added left to right, then added to the running sum; FP32, no FMA.
+template <int RMAX>
+__device__ __forceinline__ float ringkey_dist2(const float* q, const float* ringT, unsigned long long cap, unsigned long long l, int R) {
+  float result = 0.f;
+  int d = 0;
+  for (; d + 3 < R; d += 4) {
+    const float d0 = __fsub_rn(q[d], __ldg(ringT + (size_t)d * cap + l));
+    const float d1 = __fsub_rn(q[d + 1], __ldg(ringT + (size_t)(d + 1) * cap + l));
+    const float d2 = __fsub_rn(q[d + 2], __ldg(ringT + (size_t)(d + 2) * cap + l));
+    const float d3 = __fsub_rn(q[d + 3], __ldg(ringT + (size_t)(d + 3) * cap + l));
+    const float t = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
+    result = __fadd_rn(result, t);
+  }
+  for (; d < R; ++d) {
+    const float d0 = __fsub_rn(q[d], __ldg(ringT + (size_t)d * cap + l));
+    result = __fadd_rn(result, __fmul_rn(d0, d0));
+  }
+  return result;
+}
+
+struct TopkParams {
+  const unsigned char* qrecords;     // query records
+  Layout L;
+  Db db;
+  const unsigned long long* n_search;  // per query: global entries [0, n_search) are searchable
+  unsigned long long n_local;          // local entries stored
+  unsigned chunk;                      // local entries per block
+  int K;
+  unsigned long long* partial;         // [nq][chunks][K]
+  unsigned* tickets;                   // [nq], pre-set to 0
+  unsigned long long* keys_out;        // [nq][K]
+};
+
+constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_WARPS = TOPK_THREADS / 32;
+
+template <int SLOTS>
+__global__ void __launch_bounds__(TOPK_THREADS) k_topk(const TopkParams p) {
+  __shared__ float s_q[64];
+  __shared__ unsigned long long s_lists[TOPK_WARPS * 32 * SLOTS];
+  __shared__ bool s_last;
+  const int q = blockIdx.y, K = p.K, R = p.L.R;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* qring = reinterpret_cast<const float*>(p.qrecords + (size_t)q * p.L.rec_bytes + p.L.off_ring);
+  if (threadIdx.x < R) s_q[threadIdx.x] = qring[threadIdx.x];
+  __syncthreads();
+  const unsigned long long ns = p.n_search[q];
+  // local entries l with l*G + rank < ns
+  unsigned long long vis = 0;
+  if (ns > (unsigned long long)p.db.rank) vis = (ns - 1 - p.db.rank) / p.db.G + 1;
+  if (vis > p.n_local) vis = p.n_local;
+  const unsigned long long start = (unsigned long long)blockIdx.x * p.chunk;
+  unsigned long long end = start + p.chunk;
+  if (end > vis) end = vis;
+
+  WarpList<SLOTS> list;
+  list.init();
+  for (unsigned long long base = start + (unsigned long long)warp * 32; base < end; base += TOPK_THREADS) {
+    const unsigned long long l = base + lane;
+    unsigned long long key = KEY_NONE;
+    if (l < end) {
+      const float d2 = ringkey_dist2<64>(s_q, p.db.ringT, p.db.cap, l, R);
+      key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(l * p.db.G + p.db.rank);
+    }
+    list.offer(key, K);
+  }
+  // block merge: warps > 0 publish, warp 0 absorbs
+  if (warp > 0) list.store(s_lists + warp * 32 * SLOTS, K);
+  __syncthreads();
+  unsigned long long* part = p.partial + ((size_t)q * gridDim.x + blockIdx.x) * K;
+  if (warp == 0) {
+    for (int w = 1; w < TOPK_WARPS; ++w) list.offer_from(s_lists + w * 32 * SLOTS, K, K);
+    if (gridDim.x == 1) {
+      list.store(p.keys_out + (size_t)q * K, K);
+      return;
+    }
+    list.store(part, K);
+    __threadfence();
+  }
+  if (gridDim.x == 1) return;
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&p.tickets[q], 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last || warp != 0) return;
+  __threadfence();
+  // last block of this query: merge every chunk's list (volatile-ish reads through L2)
+  list.init();
+  const unsigned long long* all = p.partial + (size_t)q * gridDim.x * K;
+  const int total = (int)gridDim.x * K;
+  for (int b = 0; b < total; b += 32) {
+    const int i = b + lane;
+    list.offer(i < total ? __ldcg(all + i) : KEY_NONE, K);
+  }
+  list.store(p.keys_out + (size_t)q * K, K);
+  if (lane == 0) p.tickets[q] = 0;
+}
+
+// merge `parts` lists per query: in [parts][nq][K] -> out [nq][K]; one warp per query
+template <int SLOTS>
+__global__ void __launch_bounds__(128) k_merge(const unsigned long long* in, int parts, unsigned nq, int K, unsigned long long* out) {
+  const unsigned q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= nq) return;
+  WarpList<SLOTS> list;
+  list.init();
+  for (int p = 0; p < parts; ++p) list.offer_from(in + ((size_t)p * nq + q) * K, K, K);
+  list.store(out + (size_t)q * K, K);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage 4: SC distance of one (query, candidate) pair -- SC.cpp:116-148 in FP64, reference order.
+//   T = float for database descriptors (bins are exact floats), double for the public pairwise API.
+// ------------------------------------------------------------------------------------------------
+struct PairSmem {
+  double* vk1;   // [S] sector key of sc1
+  double* vk2;   // [S]
+  double* n1;    // [S] column norms of sc1
+  double* n2;    // [S]
+  double* work;  // [max(S, WB*S)] per-shift norms, then per (shift, column) similarities
+  int* shifts;   // [W]
+  double* dist;  // [W]
+};
+
+constexpr int SCORE_WB = 16;  // shifts evaluated per pass (bounds the shared-memory footprint)
+
+__host__ __device__ inline size_t pair_smem_bytes(int R, int S, int W, size_t elem) {
+  size_t b = 2 * (size_t)R * S * elem;         // the two descriptors
+  b = (b + 7) & ~(size_t)7;
+  b += 4 * (size_t)S * 8;                      // vk1 vk2 n1 n2
+  const int wb = W < SCORE_WB ? W : SCORE_WB;
+  b += (size_t)(wb > 1 ? wb : 1) * S * 8;      // work
+  b += (size_t)W * 8;                          // dist
+  b += (size_t)W * 4;                          // shifts
+  return (b + 15) & ~(size_t)15;
+}
+
+template <class T>
+__device__ __forceinline__ PairSmem carve_pair_smem(unsigned char* raw, int R, int S, int W, T*& a, T*& b) {
+  a = reinterpret_cast<T*>(raw);
+  b = a + (size_t)R * S;
+  size_t off = 2 * (size_t)R * S * sizeof(T);
+  off = (off + 7) & ~(size_t)7;
+  PairSmem m;
+  m.vk1 = reinterpret_cast<double*>(raw + off);
+  m.vk2 = m.vk1 + S;
+  m.n1 = m.vk2 + S;
+  m.n2 = m.n1 + S;
+  m.work = m.n2 + S;
+  const int wb = W < SCORE_WB ? W : SCORE_WB;
+  m.dist = m.work + (size_t)(wb > 1 ? wb : 1) * S;
+  m.shifts = reinterpret_cast<int*>(m.dist + W);
+  return m;
+}
+
+// SC.cpp:93-113.  Needs m.vk1/m.vk2; returns the argmin shift to every thread.  Strict '<' in ascending shift
+// order == lexicographic min of (norm, shift) over norms < 1e7.
+__device__ __forceinline__ int fast_align_block(const PairSmem& m, int S) {
+  __shared__ int s_arg;
+  for (int s = threadIdx.x; s < S; s += blockDim.x)
+    m.work[s] = __dsqrt_rn(redux_eigen(S, CoeffShiftDiffSq{m.vk1, m.vk2, s, S}));
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double best = 10000000.0;
+    int arg = 0x7fffffff;
+    for (int s = threadIdx.x; s < S; s += 32) {
+      const double v = m.work[s];
+      if (v < best) {  // ascending s within a lane: strict '<' keeps the smallest s
+        best = v;
+        arg = s;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(FULL, best, o);
+      const int oa = __shfl_xor_sync(FULL, arg, o);
+      if (ob < best || (ob == best && oa < arg)) {
+        best = ob;
+        arg = oa;
+      }
+    }
+    if (threadIdx.x == 0) s_arg = (arg == 0x7fffffff) ? 0 : arg;
+  }
+  __syncthreads();
+  const int r = s_arg;
+  __syncthreads();
+  return r;
+}
+
+// SC.cpp:69-90 for the shifts m.shifts[0..W): m.dist[w] = distDirectSC(sc1, circshift(sc2, shift_w)).
+// Needs a, b (descriptors) and m.n1/m.n2 (column norms).
+template <class T>
+__device__ __forceinline__ void dist_direct_block(const PairSmem& m, const T* a, const T* b, int R, int S, int W) {
+  for (int w0 = 0; w0 < W; w0 += SCORE_WB) {
+    const int wn = min(SCORE_WB, W - w0);
+    for (int t = threadIdx.x; t < wn * S; t += blockDim.x) {
+      const int w = t / S, j = t - w * S;
+      int jb = j - m.shifts[w0 + w];
+      if (jb < 0) jb += S;
+      const double na = m.n1[j], nb = m.n2[jb];
+      double sim = 0.0;
+      if (!((na == 0.0) | (nb == 0.0))) {
+        const double dot = redux_eigen(R, CoeffProduct<T>{a + (size_t)j * R, b + (size_t)jb * R});
+        sim = __ddiv_rn(dot, __dmul_rn(na, nb));
+      }
+      m.work[t] = sim;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < wn; w += blockDim.x) {
+      const int s = m.shifts[w0 + w];
+      double sum = 0.0;
+      int num = 0;
+      for (int j = 0; j < S; ++j) {
+        int jb = j - s;
+        if (jb < 0) jb += S;
+        if ((m.n1[j] == 0.0) | (m.n2[jb] == 0.0)) continue;
+        sum = __dadd_rn(sum, m.work[w * S + j]);
+        ++num;
+      }
+      m.dist[w0 + w] = __dsub_rn(1.0, __ddiv_rn(sum, (double)num));  // 0/0 -> NaN like the reference
+    }
+    __syncthreads();
+  }
+}
+
+// SC.cpp:123-144: the shift search space around `a` and the strict-min over it in ascending shift order
+// (== lexicographic min of (dist, shift) over dist < 1e7; default (1e7, 0)).
+__device__ __forceinline__ void fill_shifts(const PairSmem& m, int a, int radius, int S) {
+  if (threadIdx.x == 0) {
+    m.shifts[0] = a;
+    for (int ii = 1; ii <= radius; ++ii) {
+      m.shifts[2 * ii - 1] = (a + ii + S) % S;
+      m.shifts[2 * ii] = ((a - ii + S) % S + S) % S;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void pick_min(const PairSmem& m, int W, double& dist, int& shift) {
+  dist = 10000000.0;
+  shift = 0;
+  bool any = false;
+  for (int w = 0; w < W; ++w) {
+    const double d = m.dist[w];
+    const int s = m.shifts[w];
+    if (d < 10000000.0 && (!any || d < dist || (d == dist && s < shift))) {
+      dist = d;
+      shift = s;
+      any = true;
+    }
+  }
+}
+
+struct ScoreParams {
+  const unsigned char* qrecords;
+  Layout L;
+  Db db;
+  const unsigned long long* keys;      // [nq][K] candidate keys (KEY_NONE = unfilled slot -> entry 0, SC.cpp:283-284)
+  const unsigned long long* n_search;  // [nq]; 0 = query took the early return (SC.cpp:257-261)
+  int K, radius;
+  double* pair_dist;  // [nq][K]
+  int* pair_shift;    // [nq][K]; -1 = candidate not owned by this shard
+  int flip;           // score the candidate with its columns reversed (composed "reverse loop" search)
+};
+
+__global__ void __launch_bounds__(128) k_score(const ScoreParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int k = blockIdx.x, q = blockIdx.y;
+  const int R = p.L.R, S = p.L.S, W = 2 * p.radius + 1;
+  const size_t o = (size_t)q * p.K + k;
+  if (p.n_search[q] == 0) {
+    if (threadIdx.x == 0) {
+      p.pair_dist[o] = 10000000.0;
+      p.pair_shift[o] = -1;
+    }
+    return;
+  }
+  const unsigned long long key = p.keys[o];
+  const unsigned long long g = (key == KEY_NONE) ? 0ull : (key & 0xffffffffull);
+  if ((int)(g % (unsigned long long)p.db.G) != p.db.rank) {
+    if (threadIdx.x == 0) {
+      p.pair_dist[o] = 10000000.0;
+      p.pair_shift[o] = -1;
+    }
+    return;
+  }
+  const unsigned long long l = g / (unsigned long long)p.db.G;
+  float *a, *b;
+  PairSmem m = carve_pair_smem<float>(smem_raw, R, S, W, a, b);
+  const unsigned char* qrec = p.qrecords + (size_t)q * p.L.rec_bytes;
+  const float* qsc = reinterpret_cast<const float*>(qrec);
+  const float* csc = p.db.sc + l * p.L.RS;
+  for (int i = threadIdx.x; i < p.L.RS; i += blockDim.x) {
+    a[i] = qsc[i];
+    int src = i;
+    if (p.flip) src = (S - 1 - i / R) * R + (i % R);
+    b[i] = csc[src];
+  }
+  const double* qv = reinterpret_cast<const double*>(qrec + p.L.off_sector);
+  const double* qn = reinterpret_cast<const double*>(qrec + p.L.off_norm);
+  for (int i = threadIdx.x; i < S; i += blockDim.x) {
+    const int ci = p.flip ? (S - 1 - i) : i;
+    m.vk1[i] = qv[i];
+    m.n1[i] = qn[i];
+    m.vk2[i] = p.db.sector[l * S + ci];
+    m.n2[i] = p.db.colnorm[l * S + ci];
+  }
+  __syncthreads();
+  const int align = fast_align_block(m, S);
+  fill_shifts(m, align, p.radius, S);
+  dist_direct_block<float>(m, a, b, R, S, W);
+  if (threadIdx.x == 0) {
+    double d;
+    int s;
+    pick_min(m, W, d, s);
+    p.pair_dist[o] = d;
+    p.pair_shift[o] = s;
+  }
+}
+
+// The public pairwise functions on caller-provided double matrices (SC.h:64-69).
+//   mode 0: distanceBtnScanContext -> out_d[0] = dist, out_i[0] = shift
+//   mode 1: distDirectSC           -> out_d[0]
+//   mode 2: fastAlignUsingVkey on keys passed in sc1/sc2 (S doubles each) -> out_i[0]
+//   mode 3: ring key + sector key of sc1 -> out_d[0..R) ring, out_d[R..R+S) sector
+__global__ void __launch_bounds__(128) k_pair_api(const double* sc1, const double* sc2, int R, int S, int radius, int mode,
+                                                  double* out_d, int* out_i) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int W = (mode == 0) ? 2 * radius + 1 : 1;
+  double *a, *b;
+  PairSmem m = carve_pair_smem<double>(smem_raw, R, S, W, a, b);
+  if (mode == 2) {
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+      m.vk1[i] = sc1[i];
+      m.vk2[i] = sc2[i];
+    }
+    __syncthreads();
+    const int al = fast_align_block(m, S);
+    if (threadIdx.x == 0) out_i[0] = al;
+    return;
+  }
+  for (int i = threadIdx.x; i < R * S; i += blockDim.x) {
+    a[i] = sc1[i];
+    if (mode != 3) b[i] = sc2[i];
+  }
+  __syncthreads();
+  if (mode == 3) {
+    keys_from_sc<double>(a, R, S, out_d, nullptr, out_d + R, nullptr);
+    return;
+  }
+  keys_from_sc<double>(a, R, S, nullptr, nullptr, m.vk1, m.n1);
+  keys_from_sc<double>(b, R, S, nullptr, nullptr, m.vk2, m.n2);
+  __syncthreads();
+  if (mode == 1) {
+    if (threadIdx.x == 0) m.shifts[0] = 0;
+    __syncthreads();
+    dist_direct_block<double>(m, a, b, R, S, 1);
+    if (threadIdx.x == 0) out_d[0] = m.dist[0];
+    return;
+  }
+  const int align = fast_align_block(m, S);
+  fill_shifts(m, align, radius, S);
+  dist_direct_block<double>(m, a, b, R, S, W);
+  if (threadIdx.x == 0) {
+    double d;
+    int s;
+    pick_min(m, W, d, s);
+    out_d[0] = d;
+    out_i[0] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SC.cpp:296-311: per query, strict-min over this shard's candidates in retrieval order.
+// ------------------------------------------------------------------------------------------------
+struct Best {
+  double dist;
+  int rank;   // position in the candidate list; K = none
+  int shift;
+  long long idx;
+};
+
+__global__ void k_best(const double* pair_dist, const int* pair_shift, const unsigned long long* keys, unsigned nq, int K, Best* out) {
+  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  Best b;
+  b.dist = 10000000.0;
+  b.rank = K;
+  b.shift = 0;
+  b.idx = 0;
+  for (int k = 0; k < K; ++k) {
+    const size_t o = (size_t)q * K + k;
+    if (pair_shift[o] < 0) continue;
+    const double d = pair_dist[o];
+    if (d < b.dist) {
+      b.dist = d;
+      b.rank = k;
+      b.shift = pair_shift[o];
+      const unsigned long long key = keys[o];
+      b.idx = (key == KEY_NONE) ? 0 : (long long)(key & 0xffffffffull);
+    }
+  }
+  out[q] = b;
+}
+
+// SC.cpp:317-336 over `parts` shard results: threshold and yaw.  yaw = deg2rad(float(shift * 360/S)) with
+// deg2rad(d) = float(double(d) * M_PI / 180.0) (SC.cpp:17-20, 333).
+__global__ void k_finalize(const Best* parts_in, int parts, unsigned nq, const unsigned long long* n_search, int K, int S,
+                           double thres, int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift) {
+  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  double dist = 10000000.0;
+  int rank = K, shift = 0;
+  long long idx = 0;
+  if (n_search[q] != 0) {
+    for (int p = 0; p < parts; ++p) {
+      const Best b = parts_in[(size_t)p * nq + q];
+      if (b.rank >= K) continue;
+      if (b.dist < dist || (b.dist == dist && b.rank < rank)) {
+        dist = b.dist;
+        rank = b.rank;
+        shift = b.shift;
+        idx = b.idx;
+      }
+    }
+  }
+  int lid = -1;
+  float y = 0.0f;
+  if (n_search[q] != 0) {
+    if (dist < thres) lid = (int)idx;
+    const double unit = __ddiv_rn(360.0, (double)S);                               // SC.h:82
+    const float deg = __double2float_rn(__dmul_rn((double)shift, unit));           // SC.cpp:333 argument narrowing
+    y = __double2float_rn(__ddiv_rn(__dmul_rn((double)deg, 3.14159265358979323846), 180.0));  // SC.cpp:17-20
+  }
+  loop_id[q] = lid;
+  yaw[q] = y;
+  if (nearest_dist) nearest_dist[q] = dist;
+  if (nearest_idx) nearest_idx[q] = (int)idx;
+  if (nearest_shift) nearest_shift[q] = shift;
+}
+
+// device-side probes used by the parity tests (tests/test_gpu_parity.py): atanf / xy2theta / bin of many points
+__global__ void k_probe_atanf(const float* x, float* out, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = atanf_fdlibm(x[i]);
+}
+__global__ void k_probe_bins(const float* xyz, size_t n, BinConst bc, int* bin, float* height, float* theta) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float h;
+  const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+  bin[i] = bin_point_exact(bc, x, y, z, h);
+  height[i] = h;
+  theta[i] = xy2theta_exact(x, y);
+}
+
+}  // namespace scgpu

@@ -1,0 +1,328 @@
+"""ctypes binding of the C ABI (include/scgpu.h) and a Python mirror of the reference's SCManager surface.
+
+The class below keeps the reference's method names and argument meaning (Scancontext.h:63-73) so that parity
+tests read like calls on the reference object.  Every method goes through libscgpu.so; there is no Python or
+CPU implementation of any stage -- if the library or a CUDA device is missing, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+OK = 0
+FLAG_FRESH_TREE = 1
+
+
+class ScgpuError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    """scgpu_config: the reference's constants (Scancontext.h:77-96) + placement."""
+    _fields_ = [("num_ring", C.c_int32), ("num_sector", C.c_int32), ("lidar_height", C.c_double),
+                ("max_radius", C.c_double), ("exclude_recent", C.c_int32), ("num_candidates", C.c_int32),
+                ("search_ratio", C.c_double), ("dist_thres", C.c_double), ("tree_period", C.c_int32),
+                ("device", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
+                ("capacity_hint", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+_vp, _sz, _i, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
+_pi, _pf, _pd = C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double)
+
+# name -> (argtypes); every function returns int status unless noted
+_SIGNATURES = {
+    "scgpu_default_config": [C.POINTER(Config)],
+    "scgpu_create": [C.POINTER(Config), C.POINTER(_vp)],
+    "scgpu_destroy": [_vp],
+    "scgpu_make_sc": [_vp, _vp, _sz, _sz, _vp],
+    "scgpu_ringkey": [_vp, _vp, _vp],
+    "scgpu_sectorkey": [_vp, _vp, _vp],
+    "scgpu_fast_align": [_vp, _vp, _vp, _pi],
+    "scgpu_dist_direct": [_vp, _vp, _vp, _pd],
+    "scgpu_distance": [_vp, _vp, _vp, _pd, _pi],
+    "scgpu_append_scan": [_vp, _vp, _sz, _sz],
+    "scgpu_detect": [_vp, _pi, _pf, _pd, _pi, _pi],
+    "scgpu_size": [_vp, C.POINTER(_u64)],
+    "scgpu_append_scans_batched": [_vp, _vp, _sz, _sz, _sz, _i],
+    "scgpu_append_descs": [_vp, _vp, _sz],
+    "scgpu_replay_batched": [_vp, _vp, _sz, _sz, _sz, _i, _vp, _vp, _vp, _vp, _vp],
+    "scgpu_query_batched": [_vp, _u64, _sz, _vp, _vp, _vp, _vp, _vp],
+    "scgpu_get_candidates": [_vp, _vp, _vp, _vp, _vp, C.POINTER(_u64)],
+    "scgpu_get_batch_candidates": [_vp, _sz, _vp, _vp, _vp, _vp, C.POINTER(_u64)],
+    "scgpu_get_entry": [_vp, _u64, _vp, _vp, _vp],
+    "scgpu_truncate": [_vp, _u64],
+    "scgpu_exhaustive": [_vp, _u64, _u64, _i, _pd, _pi, C.POINTER(C.c_int64), _pi],
+    "scgpu_save": [_vp, C.c_char_p],
+    "scgpu_load": [_vp, C.c_char_p],
+    "scgpu_record_bytes": [_vp, C.POINTER(_sz)],
+    "scgpu_stage_build": [_vp, _vp, _sz, _sz, _sz, _vp, _vp],
+    "scgpu_stage_append": [_vp, _vp, _u64, _u64, _sz, _vp],
+    "scgpu_stage_set_size": [_vp, _u64],
+    "scgpu_get_timing": [_vp, _pd, _pd, _pd],
+    "scgpu_stage_topk": [_vp, _vp, _sz, _vp, _vp, _vp],
+    "scgpu_stage_merge": [_vp, _vp, _i, _sz, _vp, _vp],
+    "scgpu_stage_score": [_vp, _vp, _sz, _vp, _vp, _vp, _vp],
+    "scgpu_stage_finalize": [_vp, _vp, _i, _sz, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "scgpu_plan_n_search": [_vp, _u64, _sz, _vp],
+    "scgpu_launch_count": [_vp, C.POINTER(_u64)],
+    "scgpu_xy2theta": [C.c_float, C.c_float, _pf],
+    "scgpu_probe_atanf": [_vp, _sz, _vp],
+    "scgpu_probe_bins": [_vp, _vp, _sz, _vp, _vp, _vp],
+}
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["scgpu_last_error", "scgpu_version"])
+
+_lib = None
+
+
+def load_library(build_if_missing=False):
+    """dlopen libscgpu.so (built in-tree by build.py).  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_SCGPU
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise ScgpuError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)")
+        _build.build_scgpu()
+    lib = C.CDLL(path)
+    for name, args in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = args
+    lib.scgpu_last_error.restype = C.c_char_p
+    lib.scgpu_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _check(rc):
+    if rc != OK:
+        raise ScgpuError(f"scgpu error {rc}: {load_library().scgpu_last_error().decode()}")
+
+
+def _pts(pts):
+    pts = np.ascontiguousarray(pts, dtype=np.float32)
+    if pts.ndim != 2 or pts.shape[1] < 3:
+        raise ValueError("points must be (n, k>=3) float32")
+    return pts, pts.ctypes.data, pts.shape[0], pts.shape[1] * 4
+
+
+def _d(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.float64).ravel()
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} values, got {a.size}")
+    return a
+
+
+class SCManager:
+    """Mirror of the reference's ``class SCManager`` (Scancontext.h:58-108) on one B200.
+
+    Matrices are numpy float64 arrays in the reference's memory layout (column-major R x S, i.e. a flat array
+    with element (ring r, sector c) at c*R + r); ``as_matrix`` reshapes to (R, S).
+    """
+
+    def __init__(self, **cfg):
+        self.lib = load_library()
+        self.cfg = Config()
+        _check(self.lib.scgpu_default_config(C.byref(self.cfg)))
+        for k, v in cfg.items():
+            if not hasattr(self.cfg, k):
+                raise TypeError(f"unknown config field {k}")
+            setattr(self.cfg, k, v)
+        self.h = _vp()
+        _check(self.lib.scgpu_create(C.byref(self.cfg), C.byref(self.h)))
+        self.R, self.S, self.K = self.cfg.num_ring, self.cfg.num_sector, self.cfg.num_candidates
+        # the reference's public constants, same names
+        self.LIDAR_HEIGHT = self.cfg.lidar_height
+        self.PC_NUM_RING, self.PC_NUM_SECTOR = self.R, self.S
+        self.PC_MAX_RADIUS = self.cfg.max_radius
+        self.PC_UNIT_SECTORANGLE = 360.0 / float(self.S)
+        self.PC_UNIT_RINGGAP = self.cfg.max_radius / float(self.R)
+        self.NUM_EXCLUDE_RECENT = self.cfg.exclude_recent
+        self.NUM_CANDIDATES_FROM_TREE = self.K
+        self.SEARCH_RATIO = self.cfg.search_ratio
+        self.SC_DIST_THRES = self.cfg.dist_thres
+        self.TREE_MAKING_PERIOD_ = self.cfg.tree_period
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.scgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def as_matrix(self, flat):
+        return np.asarray(flat).reshape(self.S, self.R).T
+
+    # ---- the reference's eight methods ---------------------------------------------------------
+    def makeScancontext(self, scan):
+        pts, ptr, n, stride = _pts(scan)
+        out = np.empty(self.R * self.S, np.float64)
+        _check(self.lib.scgpu_make_sc(self.h, ptr, n, stride, out.ctypes.data))
+        return out
+
+    def makeRingkeyFromScancontext(self, desc):
+        desc = _d(desc, self.R * self.S)
+        out = np.empty(self.R, np.float64)
+        _check(self.lib.scgpu_ringkey(self.h, desc.ctypes.data, out.ctypes.data))
+        return out
+
+    def makeSectorkeyFromScancontext(self, desc):
+        desc = _d(desc, self.R * self.S)
+        out = np.empty(self.S, np.float64)
+        _check(self.lib.scgpu_sectorkey(self.h, desc.ctypes.data, out.ctypes.data))
+        return out
+
+    def fastAlignUsingVkey(self, vkey1, vkey2):
+        a, b = _d(vkey1, self.S), _d(vkey2, self.S)
+        s = C.c_int()
+        _check(self.lib.scgpu_fast_align(self.h, a.ctypes.data, b.ctypes.data, C.byref(s)))
+        return s.value
+
+    def distDirectSC(self, sc1, sc2):
+        a, b = _d(sc1, self.R * self.S), _d(sc2, self.R * self.S)
+        d = C.c_double()
+        _check(self.lib.scgpu_dist_direct(self.h, a.ctypes.data, b.ctypes.data, C.byref(d)))
+        return d.value
+
+    def distanceBtnScanContext(self, sc1, sc2):
+        a, b = _d(sc1, self.R * self.S), _d(sc2, self.R * self.S)
+        d, s = C.c_double(), C.c_int()
+        _check(self.lib.scgpu_distance(self.h, a.ctypes.data, b.ctypes.data, C.byref(d), C.byref(s)))
+        return d.value, s.value
+
+    def makeAndSaveScancontextAndKeys(self, scan):
+        pts, ptr, n, stride = _pts(scan)
+        _check(self.lib.scgpu_append_scan(self.h, ptr, n, stride))
+
+    def detectLoopClosureID(self, details=False):
+        lid, yaw, nd, ni, ns = C.c_int(), C.c_float(), C.c_double(), C.c_int(), C.c_int()
+        _check(self.lib.scgpu_detect(self.h, C.byref(lid), C.byref(yaw), C.byref(nd), C.byref(ni), C.byref(ns)))
+        if not details:
+            return lid.value, np.float32(yaw.value)
+        return dict(loop_id=lid.value, yaw=np.float32(yaw.value), min_dist=nd.value, nn_idx=ni.value,
+                    nn_shift=ns.value)
+
+    # ---- extras ------------------------------------------------------------------------------------
+    def size(self):
+        n = _u64()
+        _check(self.lib.scgpu_size(self.h, C.byref(n)))
+        return n.value
+
+    def launch_count(self):
+        n = _u64()
+        _check(self.lib.scgpu_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    @staticmethod
+    def _scans(scans):
+        """(n_scans, pts, k) float32 numpy array, or (ptr, n_scans, pts, stride, location) tuple."""
+        if isinstance(scans, tuple):
+            return None, scans
+        scans = np.ascontiguousarray(scans, dtype=np.float32)
+        if scans.ndim != 3 or scans.shape[2] < 3:
+            raise ValueError("scans must be (n_scans, pts, k>=3) float32")
+        return scans, (scans.ctypes.data, scans.shape[0], scans.shape[1], scans.shape[2] * 4, 0)
+
+    def append_scans(self, scans):
+        keep, (ptr, n, pts, stride, loc) = self._scans(scans)
+        _check(self.lib.scgpu_append_scans_batched(self.h, ptr, n, pts, stride, loc))
+
+    def append_descs(self, descs):
+        descs = np.ascontiguousarray(descs, dtype=np.float32)
+        n = descs.size // (self.R * self.S)
+        _check(self.lib.scgpu_append_descs(self.h, descs.ctypes.data, n))
+
+    def replay(self, scans, out=None):
+        """The bench step: append each scan and detect after it; returns dict of arrays (n_scans,)."""
+        keep, (ptr, n, pts, stride, loc) = self._scans(scans)
+        if out is None:
+            out = dict(loop_id=np.empty(n, np.int32), yaw=np.empty(n, np.float32), min_dist=np.empty(n, np.float64),
+                       nn_idx=np.empty(n, np.int32), nn_shift=np.empty(n, np.int32))
+        _check(self.lib.scgpu_replay_batched(self.h, ptr, n, pts, stride, loc, out["loop_id"].ctypes.data,
+                                             out["yaw"].ctypes.data, out["min_dist"].ctypes.data,
+                                             out["nn_idx"].ctypes.data, out["nn_shift"].ctypes.data))
+        return out
+
+    def query_batched(self, first, n):
+        out = dict(loop_id=np.empty(n, np.int32), yaw=np.empty(n, np.float32), min_dist=np.empty(n, np.float64),
+                   nn_idx=np.empty(n, np.int32), nn_shift=np.empty(n, np.int32))
+        _check(self.lib.scgpu_query_batched(self.h, first, n, out["loop_id"].ctypes.data, out["yaw"].ctypes.data,
+                                            out["min_dist"].ctypes.data, out["nn_idx"].ctypes.data,
+                                            out["nn_shift"].ctypes.data))
+        return out
+
+    def candidates(self, q=0):
+        K = self.K
+        ci, cd = np.zeros(K, np.uint64), np.zeros(K, np.float32)
+        sd, ss = np.zeros(K, np.float64), np.zeros(K, np.int32)
+        ns = _u64()
+        _check(self.lib.scgpu_get_batch_candidates(self.h, q, ci.ctypes.data, cd.ctypes.data, sd.ctypes.data,
+                                                   ss.ctypes.data, C.byref(ns)))
+        return dict(cand_idx=ci, cand_d2=cd, cand_dist=sd, cand_shift=ss, n_tree=ns.value)
+
+    def get_entry(self, i):
+        sc, rk, sk = np.empty(self.R * self.S, np.float32), np.empty(self.R, np.float32), np.empty(self.S, np.float64)
+        _check(self.lib.scgpu_get_entry(self.h, i, sc.ctypes.data, rk.ctypes.data, sk.ctypes.data))
+        return sc, rk, sk
+
+    def truncate(self, n):
+        _check(self.lib.scgpu_truncate(self.h, n))
+
+    def exhaustive(self, q, n_search, flipped=False):
+        d, s, i, f = C.c_double(), C.c_int(), C.c_int64(), C.c_int()
+        _check(self.lib.scgpu_exhaustive(self.h, q, n_search, int(flipped), C.byref(d), C.byref(s), C.byref(i),
+                                         C.byref(f)))
+        return d.value, s.value, i.value, f.value
+
+    def save(self, path):
+        _check(self.lib.scgpu_save(self.h, os.fsencode(path)))
+
+    def load(self, path):
+        _check(self.lib.scgpu_load(self.h, os.fsencode(path)))
+
+    def plan_n_search(self, first_size, n):
+        out = np.empty(n, np.uint64)
+        _check(self.lib.scgpu_plan_n_search(self.h, first_size, n, out.ctypes.data))
+        return out
+
+    def probe_bins(self, xyz):
+        """Per point: 0-based bin (sector*R + ring, -1 = not binned), stored height, azimuth [deg] -- device side."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        n = xyz.shape[0]
+        b, hh, th = np.empty(n, np.int32), np.empty(n, np.float32), np.empty(n, np.float32)
+        _check(self.lib.scgpu_probe_bins(self.h, xyz.ctypes.data, n, b.ctypes.data, hh.ctypes.data, th.ctypes.data))
+        return b, hh, th
+
+    def timing(self):
+        """(ms_total, ms_build, ms_query) of the last batched call, from CUDA events on the library's stream."""
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _check(self.lib.scgpu_get_timing(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def record_bytes(self):
+        n = _sz()
+        _check(self.lib.scgpu_record_bytes(self.h, C.byref(n)))
+        return n.value
+
+
+def probe_atanf(x):
+    """The device's atanf restatement (glibc/fdlibm algorithm in plain binary32) for an array of floats."""
+    lib = load_library()
+    x = np.ascontiguousarray(x, dtype=np.float32).ravel()
+    out = np.empty_like(x)
+    _check(lib.scgpu_probe_atanf(x.ctypes.data, x.size, out.ctypes.data))
+    return out
+
+
+def xy2theta(x, y):
+    out = C.c_float()
+    _check(load_library().scgpu_xy2theta(float(x), float(y), C.byref(out)))
+    return np.float32(out.value)

@@ -1,0 +1,139 @@
+"""Keyframe database sharded over the ranks of one box.
+
+Entry i lives on rank i % G.  One process per GPU; torch.distributed supplies the communicator (NCCL over
+NVLink on the GPU box, gloo in the CPU tests).  The path has exactly three exchange steps per batch of queries
+and nothing else crosses ranks:
+
+    1. all_gather of the freshly built descriptor records (each rank bins its own scans)       ~5.8 KB / scan
+    2. all_gather of the per-shard top-K ring-key candidates  (K x 8 B per query per rank)
+    3. all_gather of the per-shard best (distance, position, shift, index) (24 B per query per rank)
+
+followed by a deterministic merge that reproduces the single-device result bit for bit: candidate lists merge in
+(squared distance, index) order, and the final argmin is the strict-min in candidate order (Scancontext.cpp:296-311).
+
+``ShardedSearch`` is backend-agnostic: ``stages`` provides build / append / topk / merge / score / finalize on
+torch tensors.  ``GpuStages`` (below) is the product backend -- the staged C ABI of include/scgpu.h on the
+current CUDA stream.  The CPU tests drive the same orchestration over gloo with a stand-in backend built on
+the oracle (tests/test_sharded_gloo.py).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class ShardedSearch:
+    def __init__(self, stages, rank=None, world=None, group=None):
+        self.st = stages
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.size = 0  # global number of entries
+
+    def _all_gather(self, t):
+        """[...]-> [G, ...] (same shape on every rank)."""
+        if self.world == 1:
+            return t.unsqueeze(0)
+        t = t.contiguous()
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t, group=self.group)     # rank-major concatenation along dim 0
+        return out.view((self.world,) + tuple(t.shape))
+
+    def prefill_descs(self, descs):
+        """Every rank passes the SAME (n, R*S) float32 descriptors; each keeps the entries it owns."""
+        self.st.prefill(descs)          # ownership (i % G == rank) is applied by the backend
+        self.size = self.st.size()
+
+    def step(self, scans_local):
+        """scans_local: this rank's B scans ([B, P, k] float32 on the stage device).  Scan j of rank r becomes
+        global entry size + j*G + r.  Returns the detect results of all G*B new entries in global order
+        (identical on every rank): dict(loop_id, yaw, min_dist, nn_idx, nn_shift)."""
+        G, B = self.world, scans_local.shape[0]
+        rec_local = self.st.build(scans_local)                                   # [B, rec]
+        gathered = self._all_gather(rec_local)                                   # [G, B, rec]   exchange 1
+        rec_global = gathered.transpose(0, 1).reshape(G * B, -1).contiguous()    # query q = j*G + r
+        first = self.size
+        self.st.append(rec_global, first, 1, G * B)
+        self.size = first + G * B
+        self.st.set_size(self.size)
+        n_search = self.st.plan_n_search(first + 1, G * B)                       # same on every rank
+        keys_local = self.st.topk(rec_global, n_search)                          # [GB, K]
+        keys = self.st.merge(self._all_gather(keys_local))                       # exchange 2
+        best_local = self.st.score(rec_global, keys, n_search)                   # [GB, 3] int64
+        return self.st.finalize(self._all_gather(best_local), n_search)          # exchange 3
+
+
+class GpuStages:
+    """The staged C ABI (scgpu_stage_*) on torch CUDA tensors, launched on torch's current stream so that the
+    kernels and the NCCL collectives are ordered without host synchronisation."""
+
+    def __init__(self, manager, device):
+        self.m = manager
+        self.lib = manager.lib
+        self.h = manager.h
+        self.device = torch.device(device)
+        self.rec_bytes = manager.record_bytes()
+        self.K = manager.K
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        from .scgpu import _check
+        _check(rc)
+
+    def build(self, scans):
+        assert scans.is_cuda and scans.dtype == torch.float32 and scans.is_contiguous()
+        B, P, k = scans.shape
+        rec = torch.empty((B, self.rec_bytes), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.scgpu_stage_build(self.h, scans.data_ptr(), B, P, k * 4, rec.data_ptr(), self._stream()))
+        return rec
+
+    def prefill(self, descs):
+        self.m.append_descs(descs)      # scgpu_append_descs keeps the entries this shard owns
+
+    def size(self):
+        return self.m.size()
+
+    def append(self, rec, first, step, n):
+        self._check(self.lib.scgpu_stage_append(self.h, rec.data_ptr(), first, step, n, self._stream()))
+
+    def set_size(self, n):
+        self._check(self.lib.scgpu_stage_set_size(self.h, n))
+
+    def plan_n_search(self, first_size, n):
+        ns = self.m.plan_n_search(first_size, n)
+        return torch.from_numpy(ns.astype(np.int64)).to(self.device, non_blocking=False)
+
+    def topk(self, qrec, n_search):
+        nq = qrec.shape[0]
+        keys = torch.empty((nq, self.K), dtype=torch.int64, device=self.device)
+        self._check(self.lib.scgpu_stage_topk(self.h, qrec.data_ptr(), nq, n_search.data_ptr(), keys.data_ptr(), self._stream()))
+        return keys
+
+    def merge(self, parts):
+        G, nq, K = parts.shape
+        if G == 1:
+            return parts[0]
+        out = torch.empty((nq, K), dtype=torch.int64, device=self.device)
+        self._check(self.lib.scgpu_stage_merge(self.h, parts.data_ptr(), G, nq, out.data_ptr(), self._stream()))
+        return out
+
+    def score(self, qrec, keys, n_search):
+        nq = qrec.shape[0]
+        best = torch.empty((nq, 3), dtype=torch.int64, device=self.device)   # {f64 dist, i32 rank, i32 shift, i64 idx}
+        self._check(self.lib.scgpu_stage_score(self.h, qrec.data_ptr(), nq, keys.data_ptr(), n_search.data_ptr(),
+                                               best.data_ptr(), self._stream()))
+        return best
+
+    def finalize(self, parts, n_search):
+        G, nq, _ = parts.shape
+        dev = self.device
+        out = dict(loop_id=torch.empty(nq, dtype=torch.int32, device=dev), yaw=torch.empty(nq, dtype=torch.float32, device=dev),
+                   min_dist=torch.empty(nq, dtype=torch.float64, device=dev), nn_idx=torch.empty(nq, dtype=torch.int32, device=dev),
+                   nn_shift=torch.empty(nq, dtype=torch.int32, device=dev))
+        self._check(self.lib.scgpu_stage_finalize(self.h, parts.contiguous().data_ptr(), G, nq, n_search.data_ptr(),
+                                                  out["loop_id"].data_ptr(), out["yaw"].data_ptr(), out["min_dist"].data_ptr(),
+                                                  out["nn_idx"].data_ptr(), out["nn_shift"].data_ptr(), self._stream()))
+        return out
