@@ -4,12 +4,13 @@ makeAndSaveScancontextAndKeys + detectLoopClosureID), next to the reference CPU 
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl scgpu|reference] [--sweep]
 
-Workload (BASELINE.json configs[1]): KITTI-00-shaped synthetic run -- a database of 4,541 keyframes, HDL-64
-scans (64 x 1875 = 120,000 points, float4 records), 20x60 descriptor, 10 candidates, exclude-recent 50.  One
-"step" replays the LAST `batch` keyframes of that run: for each of them descriptor build (k_build) + keys +
-append + exact ring-key top-10 (k_topk) + column-shifted cosine distance of the 10 candidates (k_score) + argmin,
-threshold and yaw, with the reference's periodic tree-snapshot semantics.  The database is truncated back to
-4,541 - batch before every step, so every step does identical work.
+Workload (BASELINE.json configs[1]): KITTI-00-shaped synthetic run -- 4,541 keyframes, HDL-64 scans (64 x 1875 =
+120,000 points, float4 records), 20x60 descriptor, 10 candidates, exclude-recent 50.  One "step" replays the
+WHOLE run from an empty database: for every keyframe descriptor build (k_build) + keys + append + exact ring-key
+top-10 over the keyframes visible at that moment (k_topk) + column-shifted cosine distance of the 10 candidates
+(k_score) + argmin, threshold and yaw -- with the reference's periodic tree-snapshot semantics, i.e. exactly the
+results of 4,541 x { makeAndSaveScancontextAndKeys; detectLoopClosureID }.  (--batch N replays only the last N
+keyframes on top of a pre-filled database; used for quick runs.)
 
   value   : keyframes(queries)/s with the scans already resident in HBM (device leg)
   e2e     : the same through the C ABI with HOST (pinned) scan buffers: H2D of the scans and D2H of the results
@@ -47,30 +48,37 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="scgpu", choices=["scgpu", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="keyframes replayed per step (per GPU)")
+    ap.add_argument("--batch", type=int, default=DB_SIZE, help="keyframes replayed per step (per GPU); default = the whole run")
     ap.add_argument("--sweep", action="store_true", help="also time query-only throughput vs database size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every ~2 ms DURING the timed regions."""
 
     def __init__(self, index=0):
-        self.index, self.samples, self._stop, self._t, self.active = index, [], threading.Event(), None, False
+        self.index, self.sm, self.reasons, self._stop, self._t, self.active = index, [], 0, threading.Event(), None, False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
     def _run(self):
+        nv = self.nv
         while not self._stop.is_set():
-            if self.active:
+            if self.active and nv is not None:
                 try:
-                    o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                       capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                    self.samples.append([x.strip() for x in o])
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)))
+                    self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.dev))
                 except Exception:
                     pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002)
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -79,15 +87,13 @@ class ClockSampler:
     def stop(self):
         self._stop.set()
         if self._t:
-            self._t.join(timeout=6)
+            self._t.join(timeout=2)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for bit, n in names.items() if self.reasons & bit), "samples": len(self.sm),
+                "source": "nvml, sampled during the timed regions"}
 
 
 def measured_peak():
@@ -98,14 +104,14 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def make_inputs(batch, first_scan, n_db_prefill, stride_floats=4, scan_step=1, scan_offset=0):
+def gen_scans(indices, out):
+    """out[j] = scan indices[j] (float4 records); scangen releases the GIL, so threads scale over the host cores."""
+    from concurrent.futures import ThreadPoolExecutor
     from sc_lego_loam_b200.synth import ScanGen
     gen = ScanGen("hdl64", seed=SEED, n_places=3500)
-    descs = gen.descs(0, n_db_prefill, R, S)
-    scans = np.empty((batch, PTS, stride_floats), np.float32)
-    for j in range(batch):
-        gen.scan(first_scan + j * scan_step + scan_offset, stride_floats, scans[j])
-    return descs, scans
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(lambda j: gen.scan(int(indices[j]), out.shape[2], out[j]), range(len(indices))))
+    return gen
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -167,7 +173,7 @@ def run_reference_arm(args):
     val = n / dt
     line = {"metric": "sc_loop_queries_per_sec", "value": val, "unit": "queries/s", "impl": "reference", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "db_keyframes": DB_SIZE, "replicas": cores, "keyframes_per_replica_per_step": per},
             "cpu_baseline": {"value": val, "unit": "queries/s", "cores": cores, "kind": kind,
                              "sample": f"{cores} independent SCManager replicas x {per} keyframes/step x {args.steps} steps; "
@@ -177,32 +183,42 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def cpu_baseline_single(n_prefill, scans, passes):
-    """One thread of the reference (kind 'reference') or the oracle port on a bounded sample of the workload."""
+def cpu_baseline_single(m, scans, gpu_res, n0, budget_keyframes=1491):
+    """One thread of the reference itself (oracle/_ref; else the oracle port) on a bounded sample of the SAME run:
+    its database is pre-filled with the descriptors of keyframes [0, i0) exactly as the GPU run stored them, then
+    keyframes [i0, end) go through makeAndSaveScancontextAndKeys + detectLoopClosureID.  i0 is chosen so that the
+    reference's first timed detect rebuilds its tree ((i0 - 50) % 10 == 0), i.e. both sides see the same
+    snapshots, and the loop ids / yaws of the sample are compared with the GPU's."""
     from oracle import oracle as orc
-    from sc_lego_loam_b200.synth import ScanGen
     kind = "reference" if orc.ref_available("default") else "port"
     obj = orc.Ref("default") if kind == "reference" else orc.Port()
-    for d in ScanGen("hdl64", seed=SEED, n_places=3500).descs(0, n_prefill, R, S):
-        obj.append_desc(d.astype(np.float64))
-    tb = td = 0.0
-    n = 0
-    for _ in range(passes):
-        if kind == "reference":
-            a, b = obj.time_run(scans)
-        else:
-            a = b = 0.0
-            for s in scans:
-                t0 = time.perf_counter()
-                obj.append_scan(s)
-                t1 = time.perf_counter()
-                obj.detect()
-                a += t1 - t0
-                b += time.perf_counter() - t1
-        tb, td, n = tb + a, td + b, n + len(scans)
+    total = n0 + len(scans)
+    i0 = max(n0, total - budget_keyframes)
+    while i0 < total - 1 and (i0 < 50 or (i0 - 50) % 10 != 0):
+        i0 += 1
+    for i in range(i0):
+        obj.append_desc(m.get_entry(i)[0].astype(np.float64))
+    sample = scans[i0 - n0:]
+    if kind == "reference":
+        tb, td, ids, yaws = obj.time_run(sample, want_results=True)
+    else:
+        tb = td = 0.0
+        ids, yaws = np.empty(len(sample), np.int32), np.empty(len(sample), np.float32)
+        for j, s in enumerate(sample):
+            t0 = time.perf_counter()
+            obj.append_scan(s)
+            t1 = time.perf_counter()
+            d = obj.detect()
+            tb, td = tb + (t1 - t0), td + (time.perf_counter() - t1)
+            ids[j], yaws[j] = d["loop_id"], d["yaw"]
+    n = len(sample)
+    match = bool(np.array_equal(ids, gpu_res["loop_id"][i0 - n0:]) and
+                 np.array_equal(yaws.view(np.uint32), gpu_res["yaw"][i0 - n0:].view(np.uint32)))
     return {"value": n / (tb + td), "unit": "queries/s", "cores": 1, "kind": kind,
-            "sample": f"{n} keyframes (the step's first {len(scans)} scans x {passes} passes), DB {n_prefill}->{n_prefill + n}; "
-                      f"build {1e3 * tb / n:.2f} ms + detect {1e3 * td / n:.2f} ms per keyframe; host has {os.cpu_count()} cores"}
+            "sample": f"keyframes [{i0}, {total}) of the same run ({n} keyframes, database {i0}->{total}, pre-filled with the "
+                      f"descriptors the GPU run stored); build {1e3 * tb / n:.2f} ms + detect {1e3 * td / n:.2f} ms per keyframe; "
+                      f"host has {os.cpu_count()} cores",
+            "loop_ids_and_yaws_equal_gpu": match}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -211,14 +227,16 @@ def run_single_gpu(args):
     from sc_lego_loam_b200.scgpu import SCManager
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the scgpu path has no CPU fallback")
-    B = args.batch
-    n0 = DB_SIZE - B
-    descs, scans = make_inputs(B, n0, n0)
-    m = SCManager(device=0, capacity_hint=DB_SIZE + 64)
-    m.append_descs(descs)
     torch.cuda.set_device(0)
-    d_scans = torch.from_numpy(scans).cuda()
-    h_scans = torch.from_numpy(scans).pin_memory()
+    B = min(args.batch, DB_SIZE)
+    n0 = DB_SIZE - B
+    h_scans = torch.empty((B, PTS, 4), dtype=torch.float32, pin_memory=True)
+    scans = h_scans.numpy()
+    gen = gen_scans(np.arange(n0, DB_SIZE), scans)
+    m = SCManager(device=0, capacity_hint=DB_SIZE + 64)
+    if n0:
+        m.append_descs(gen.descs(0, n0, R, S))
+    d_scans = h_scans.cuda()
     out = dict(loop_id=np.empty(B, np.int32), yaw=np.empty(B, np.float32), min_dist=np.empty(B, np.float64),
                nn_idx=np.empty(B, np.int32), nn_shift=np.empty(B, np.int32))
 
@@ -257,12 +275,13 @@ def run_single_gpu(args):
     line = {
         "metric": "sc_loop_queries_per_sec", "value": B * args.steps / dt_dev, "unit": "queries/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 binning + f64 keys/distance", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32 binning + f64 keys/distance", "data": "synthetic",
         "config": {"workload": WORKLOAD, "db_keyframes": DB_SIZE, "keyframes_per_step": B, "points_per_scan": PTS,
                    "point_stride_bytes": 16, "l2": f"inputs larger than L2 ({B * PTS * 16 >> 20} MiB of points per step)",
                    "parallelism": "1 gpu"},
         "e2e": {"value": B * args.steps / dt_e2e, "unit": "queries/s", "h2d_bytes_per_step": B * PTS * 16 + B * 8,
-                "d2h_bytes_per_step": B * 24, "ms_per_step": 1e3 * dt_e2e / args.steps, "results_equal_device_leg": bool(same)},
+                "d2h_bytes_per_step": B * 24, "ms_per_step": 1e3 * dt_e2e / args.steps, "results_equal_device_leg": bool(same),
+                "h2d_gbs": (B * PTS * 16) / (dt_e2e / args.steps) / 1e9},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_build", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SCAN * B,
@@ -271,10 +290,10 @@ def run_single_gpu(args):
                    "queries_only_per_sec": B / (ms_query * 1e-3), "loops_found": int((res_dev["loop_id"] >= 0).sum())},
         "clocks": clocks.summary(),
     }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_single(m, scans, res_dev, n0)
     if args.sweep:
         line["sweep"] = db_size_sweep(m, torch)
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_single(n0, scans[:64], 3)
     print(json.dumps(line))
 
 
@@ -302,6 +321,8 @@ def db_size_sweep(m, torch):
 
 
 def run_multi_gpu(args):
+    """STRONG scaling of the same job: the 4,541-keyframe run (rounded up to a multiple of G) replayed from an
+    empty database, keyframe i built by and stored on rank i % G; every query searches all shards."""
     import torch
     import torch.distributed as dist
     from sc_lego_loam_b200.scgpu import SCManager
@@ -309,14 +330,17 @@ def run_multi_gpu(args):
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    G, B = world, args.batch
-    n0 = (DB_SIZE - B) // G * G       # database before the step (a multiple of G keeps shards equal)
-    descs, scans = make_inputs(B, n0, n0, scan_step=G, scan_offset=rank)
-    m = SCManager(device=local, shard_rank=rank, shard_count=G, capacity_hint=DB_SIZE + G * B + 64)
+    G = world
+    total = min(args.batch, DB_SIZE)
+    B = (total + G - 1) // G                     # keyframes per rank per step
+    n0 = (DB_SIZE - total) // G * G              # pre-filled part when --batch < the whole run
+    h_scans = torch.empty((B, PTS, 4), dtype=torch.float32, pin_memory=True)
+    gen = gen_scans(n0 + np.arange(B) * G + rank, h_scans.numpy())
+    m = SCManager(device=local, shard_rank=rank, shard_count=G, capacity_hint=n0 + G * B + 64)
     search = ShardedSearch(GpuStages(m, f"cuda:{local}"), rank, world)
-    search.prefill_descs(descs)
-    d_scans = torch.from_numpy(scans).cuda()
-    h_scans = torch.from_numpy(scans).pin_memory()
+    if n0:
+        search.prefill_descs(gen.descs(0, n0, R, S))
+    d_scans = h_scans.cuda()
     d_stage = torch.empty_like(d_scans)
 
     def step(e2e):
@@ -356,18 +380,19 @@ def run_multi_gpu(args):
 
     dt_dev, launches, r = timed(False)
     dt_e2e, _, r2 = timed(True)
+    same = all(torch.equal(r[k].cpu(), r2[k]) for k in ("loop_id", "nn_idx", "nn_shift"))
     if rank == 0:
         clocks.stop()
         nq = G * B
         line = {
             "metric": "sc_loop_queries_per_sec", "value": nq * args.steps / dt_dev, "unit": "queries/s", "n_gpus": G,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 binning + f64 keys/distance", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 binning + f64 keys/distance", "data": "synthetic",
             "config": {"workload": WORKLOAD, "db_keyframes": n0 + nq, "keyframes_per_step": nq, "keyframes_per_gpu_per_step": B,
                        "points_per_scan": PTS, "point_stride_bytes": 16, "l2": "inputs larger than L2",
-                       "parallelism": f"database sharded i%{G} over {G} gpus; 3 NCCL all_gathers per step"},
+                       "parallelism": f"database sharded i%{G} over {G} gpus; each rank bins its own scans; 3 NCCL all_gathers per step"},
             "e2e": {"value": nq * args.steps / dt_e2e, "unit": "queries/s", "h2d_bytes_per_step": nq * PTS * 16 + nq * 8,
-                    "d2h_bytes_per_step": nq * 24 * G, "ms_per_step": 1e3 * dt_e2e / args.steps},
+                    "d2h_bytes_per_step": nq * 24 * G, "ms_per_step": 1e3 * dt_e2e / args.steps, "results_equal_device_leg": bool(same)},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
             "stages": {"loops_found": int((r["loop_id"] >= 0).sum().item())},
         }

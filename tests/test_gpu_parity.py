@@ -98,7 +98,9 @@ def test_device_bins_match_oracle(variant):
     assert np.array_equal(gb, ob), f"{(gb != ob).sum()} bins differ"
     assert np.array_equal(gh.view(np.uint32), oh.view(np.uint32))
     fin = np.isfinite(pts[:, 0]) & np.isfinite(pts[:, 1])
-    assert np.array_equal(gt[fin].view(np.uint32), ot[fin].view(np.uint32))
+    nan = np.isnan(ot[fin])                      # x = y = 0: theta is NaN on both sides (payload bits are not compared)
+    assert np.array_equal(np.isnan(gt[fin]), nan) and nan.any()
+    assert np.array_equal(gt[fin][~nan].view(np.uint32), ot[fin][~nan].view(np.uint32))
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
