@@ -141,7 +141,8 @@ int scgpu_save(scgpu_handle* h, const char* path);
 int scgpu_load(scgpu_handle* h, const char* path);
 
 /* ---- staged device-side API (used by the sharded multi-GPU path; all pointers are DEVICE pointers on
- *      cfg.device; `stream` is a cudaStream_t, 0 = the handle's own stream) ------------------------------ */
+ *      cfg.device; `stream` is the caller's cudaStream_t, used as given -- NULL is the CUDA default stream --
+ *      so the launches are ordered with the caller's own work, e.g. torch's current stream and NCCL) --------- */
 
 /* Bytes of one packed descriptor record: float sc[R*S] | float ring[R] | double sector[S] | double colnorm[S],
  * padded to 16 bytes. */

@@ -1047,7 +1047,9 @@ int scgpu_xy2theta(float x, float y, float* out_deg) {
 
 // ---- staged API -------------------------------------------------------------------------------------
 
-#define ST(s) ((s) ? static_cast<cudaStream_t>(s) : h->stream)
+// the caller's stream exactly as given: NULL is the CUDA legacy default stream (what torch uses unless told otherwise),
+// NOT the handle's private stream -- the staged calls must be ordered with the caller's own work
+#define ST(s) (static_cast<cudaStream_t>(s))
 
 int scgpu_stage_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_per_scan, size_t stride, void* d_records, void* stream) {
   if (!h || !d_records) return fail(SCGPU_E_INVALID, "null argument");
