@@ -40,6 +40,8 @@ extern "C" {
 #define SCGPU_E_IO (-5)       /* save / load failure */
 
 /* flags */
+#define SCGPU_FLAG_EXACT_BINNING 2u /* disable the FP32 front end of the binning kernel: every point is binned by the
+                                      bit-exact restatement (results are identical either way; for A/B timing) */
 #define SCGPU_FLAG_FRESH_TREE 1u /* search keys [0, size - exclude_recent) on EVERY detect instead of emulating the
                                     reference's periodically rebuilt KD-tree snapshot (SC.cpp:264-276) */
 
@@ -184,6 +186,11 @@ int scgpu_probe_bins(scgpu_handle* h, const float* xyz, size_t n, int32_t* bin, 
 /* Device time (CUDA events on the handle's stream) of the last scgpu_replay_batched / scgpu_append_scans_batched /
  * scgpu_query_batched call: whole call, its k_build launches only, and everything after them. */
 int scgpu_get_timing(scgpu_handle* h, double* ms_total, double* ms_build, double* ms_query);
+/* On-device self check of the binning front end: n pseudo-random points (mode 0: uniform over the ROI square;
+ * mode 1: on / next to ring and sector boundaries), fast-path+fallback bin vs the exact restatement.
+ * first_bad (optional, 5 floats): x, y, z, fast bin, exact bin of the first mismatch. */
+int scgpu_probe_selfcheck(scgpu_handle* h, uint64_t n, uint64_t seed, int mode, uint64_t* mismatches,
+                          uint64_t* fallbacks, float* first_bad);
 /* Number of kernels launched by this handle so far (bench.py's gpu_launches). */
 int scgpu_launch_count(scgpu_handle* h, uint64_t* out);
 

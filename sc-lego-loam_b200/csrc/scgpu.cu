@@ -189,10 +189,7 @@ int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_
   else ppb = 2048;
   if (pts_per_scan == 0) ppb = 256;
   p.pts_per_block = ppb;
-  p.bc.R = h->L.R;
-  p.bc.S = h->L.S;
-  p.bc.lidar_height = h->cfg.lidar_height;
-  p.bc.max_radius = h->cfg.max_radius;
+  p.bc = make_bin_const(h->L.R, h->L.S, h->cfg.lidar_height, h->cfg.max_radius, !(h->cfg.flags & SCGPU_FLAG_EXACT_BINNING));
   p.L = h->L;
   p.gbins = h->gbins.as<int>();
   p.tickets = h->btickets.as<unsigned>();
@@ -207,9 +204,23 @@ int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_
     q.gbins = p.gbins;  // per-launch scan index restarts at 0: workspace rows [0, ns)
     dim3 grid(tiles, (unsigned)ns);
     const bool al16 = (((uintptr_t)q.pts & 15) == 0);
-    if (stride == 16 && al16) k_build<16><<<grid, 256, smem, st>>>(q);
-    else if (stride == 32 && al16) k_build<32><<<grid, 256, smem, st>>>(q);
-    else k_build<0><<<grid, 256, smem, st>>>(q);
+    const int sk = (stride == 16 && al16) ? 16 : ((stride == 32 && al16) ? 32 : 0);
+    const int variant = sk * 4 + (q.bc.fast ? 2 : 0) + (q.bc.lh_is_float ? 1 : 0);
+#define SCGPU_BUILD_CASE(SK, F, L) \
+  case (SK) * 4 + ((F) ? 2 : 0) + ((L) ? 1 : 0): k_build<SK, F, L><<<grid, 256, smem, st>>>(q); break;
+    switch (variant) {
+      SCGPU_BUILD_CASE(16, true, true)
+      SCGPU_BUILD_CASE(16, true, false)
+      SCGPU_BUILD_CASE(32, true, true)
+      SCGPU_BUILD_CASE(32, true, false)
+      SCGPU_BUILD_CASE(0, true, true)
+      SCGPU_BUILD_CASE(0, true, false)
+      default:  // exact binning: one instantiation per stride kind
+        if (sk == 16) k_build<16, false, false><<<grid, 256, smem, st>>>(q);
+        else if (sk == 32) k_build<32, false, false><<<grid, 256, smem, st>>>(q);
+        else k_build<0, false, false><<<grid, 256, smem, st>>>(q);
+    }
+#undef SCGPU_BUILD_CASE
     h->launches++;
     CK(cudaGetLastError());
   }
@@ -1000,11 +1011,7 @@ int scgpu_probe_bins(scgpu_handle* h, const float* xyz, size_t n, int32_t* bin, 
   CK(cudaMalloc(&dt, n * 4));
   CK(cudaMalloc(&db, n * 4));
   CK(cudaMemcpy(dx, xyz, n * 12, cudaMemcpyHostToDevice));
-  BinConst bc;
-  bc.R = h->L.R;
-  bc.S = h->L.S;
-  bc.lidar_height = h->cfg.lidar_height;
-  bc.max_radius = h->cfg.max_radius;
+  const BinConst bc = make_bin_const(h->L.R, h->L.S, h->cfg.lidar_height, h->cfg.max_radius, !(h->cfg.flags & SCGPU_FLAG_EXACT_BINNING));
   k_probe_bins<<<(unsigned)((n + 255) / 256), 256>>>(dx, n, bc, db, dh, dt);
   h->launches++;
   cudaError_t e = cudaGetLastError();
@@ -1016,6 +1023,37 @@ int scgpu_probe_bins(scgpu_handle* h, const float* xyz, size_t n, int32_t* bin, 
   cudaFree(dt);
   cudaFree(db);
   if (e != cudaSuccess) return fail(SCGPU_E_CUDA, "probe_bins: %s", cudaGetErrorString(e));
+  return SCGPU_OK;
+}
+
+int scgpu_probe_selfcheck(scgpu_handle* h, uint64_t n, uint64_t seed, int mode, uint64_t* mismatches, uint64_t* fallbacks, float* first_bad) {
+  if (!h || !mismatches || !fallbacks) return fail(SCGPU_E_INVALID, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  unsigned long long* d = nullptr;
+  float* db = nullptr;
+  CK(cudaMalloc(&d, 16));
+  CK(cudaMalloc(&db, 5 * sizeof(float)));
+  CK(cudaMemset(d, 0, 16));
+  CK(cudaMemset(db, 0, 5 * sizeof(float)));
+  const BinConst bc = make_bin_const(h->L.R, h->L.S, h->cfg.lidar_height, h->cfg.max_radius, 1);
+  cudaError_t e = cudaSuccess;
+  const uint64_t slab = 1ull << 28;
+  for (uint64_t s0 = 0; s0 < n && e == cudaSuccess; s0 += slab) {
+    const uint64_t m = n - s0 < slab ? n - s0 : slab;
+    k_selfcheck<<<(unsigned)((m + 255) / 256), 256>>>(m, seed + s0, mode, bc, d, d + 1, db);
+    h->launches++;
+    e = cudaGetLastError();
+  }
+  unsigned long long out[2] = {0, 0};
+  float bad[5] = {0, 0, 0, 0, 0};
+  if (e == cudaSuccess) e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(bad, db, sizeof bad, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  cudaFree(db);
+  if (e != cudaSuccess) return fail(SCGPU_E_CUDA, "selfcheck: %s", cudaGetErrorString(e));
+  *mismatches = out[0];
+  *fallbacks = out[1];
+  if (first_bad) memcpy(first_bad, bad, sizeof bad);
   return SCGPU_OK;
 }
 
@@ -1033,7 +1071,7 @@ int scgpu_xy2theta(float x, float y, float* out_deg) {
   CK(cudaMalloc(&dt, 4));
   CK(cudaMalloc(&db, 4));
   CK(cudaMemcpy(dx, xyz, 12, cudaMemcpyHostToDevice));
-  BinConst bc{20, 60, 2.0, 80.0};
+  const BinConst bc = make_bin_const(20, 60, 2.0, 80.0, 0);
   k_probe_bins<<<1, 32>>>(dx, 1, bc, db, dh, dt);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpy(out_deg, dt, 4, cudaMemcpyDeviceToHost);

@@ -125,7 +125,33 @@ __device__ __forceinline__ float xy2theta_exact(float x, float y) {
 struct BinConst {
   int R, S;
   double lidar_height, max_radius;
+  // fast-path gating (never the source of a result, only of the decision WHICH path computes it)
+  float lh_f;         // (float)lidar_height
+  int lh_is_float;    // lidar_height is exactly a float: float(double(z)+H) == fadd(z, H)  (53 >= 2*24+2)
+  int fast;           // 0: every point takes the exact path
+  float ring_scale;   // R / max_radius
+  float sec_scale;    // S / (2 pi)
+  float eps_r, eps_s; // distance to the nearest ring / sector boundary below which the exact path decides
 };
+
+__host__ inline BinConst make_bin_const(int R, int S, double lidar_height, double max_radius, int fast) {
+  BinConst c;
+  c.R = R;
+  c.S = S;
+  c.lidar_height = lidar_height;
+  c.max_radius = max_radius;
+  c.lh_f = (float)lidar_height;
+  c.lh_is_float = ((double)c.lh_f == lidar_height);
+  c.fast = fast;
+  c.ring_scale = (float)((double)R / max_radius);
+  c.sec_scale = (float)((double)S / 6.283185307179586476925);
+  // error budget (DESIGN.md "binning fast path"): fast ring coordinate |err| <= 3.2e-5 at 64 rings, reference's own
+  // deviation from the true value <= 4e-6; fast sector coordinate |err| <= 2.5e-7 S, reference's <= 1e-7 S.
+  c.eps_r = 1.0e-4f * (R > 64 ? (float)R / 64.f : 1.f);
+  c.eps_s = 3.4e-6f * (float)S;
+  if (c.eps_s < 2.0e-4f) c.eps_s = 2.0e-4f;
+  return c;
+}
 
 // SC.cpp:166-183 for one point.  Returns the 0-based bin (sector*R + ring) or -1 when the point does not
 // contribute (outside the ROI, NaN coordinate, or a height that can never win the max).
@@ -142,6 +168,66 @@ __device__ __forceinline__ int bin_point_exact(const BinConst& c, float x, float
   const int ring = max(min(c.R, __double2int_rz(qr)), 1);
   const int sector = max(min(c.S, __double2int_rz(qs)), 1);
   return (sector - 1) * c.R + (ring - 1);
+}
+
+// The same function with a cheap FP32 front end.  The approximate polar coordinates (one MUFU.RSQ, one MUFU.RCP,
+// a degree-7 odd atan polynomial, |error| <= 1.3e-7 rad) decide the bin ONLY when the point is farther from every
+// ring and sector boundary than the sum of the approximation error and the reference's own rounding error (see
+// make_bin_const); everything else -- boundary neighbourhoods, points on an axis (where the reference's quadrant
+// tests on -0.0 matter), the ROI edge, zero / subnormal / non-finite inputs (which the .ftz approximations turn into
+// inf or NaN and thereby into "not safe") -- is decided by bin_point_exact.  Either way the result is the
+// reference's.  Branch-free up to the (rare) hand-over.  tests: scgpu_probe_selfcheck compares the two paths over
+// billions of device-generated points.
+__device__ __forceinline__ float mufu_rsq(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <bool FAST, bool LH_FLOAT>
+__device__ __forceinline__ int bin_point(const BinConst& c, float x, float y, float z, float& height, bool* fell_back = nullptr) {
+  if (!FAST) return bin_point_exact(c, x, y, z, height);
+  const float fR = (float)c.R, fS = (float)c.S;
+  const float r2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+  const float qr = __fmul_rn(__fmul_rn(r2, mufu_rsq(r2)), c.ring_scale);  // ~ range * R / max_radius
+  const float h = LH_FLOAT ? __fadd_rn(z, c.lh_f) : __double2float_rn(__dadd_rn((double)z, c.lidar_height));
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float a = __fmul_rn(mn, mufu_rcp(mx));
+  const float s = __fmul_rn(a, a);
+  float p = __uint_as_float(0xbb84dc15u);
+  p = __fmaf_rn(p, s, __uint_as_float(0x3cb319dcu));
+  p = __fmaf_rn(p, s, __uint_as_float(0xbd650442u));
+  p = __fmaf_rn(p, s, __uint_as_float(0x3dc578dcu));
+  p = __fmaf_rn(p, s, __uint_as_float(0xbe0e6ca2u));
+  p = __fmaf_rn(p, s, __uint_as_float(0x3e4c40b9u));
+  p = __fmaf_rn(p, s, __uint_as_float(0xbeaaa61du));
+  p = __fmaf_rn(p, s, __uint_as_float(0x3f7ffff5u));
+  float t = __fmul_rn(__fmul_rn(a, p), c.sec_scale);  // octant angle in sector units, [0, S/8]
+  t = (ay > ax) ? __fsub_rn(0.25f * fS, t) : t;
+  t = (x < 0.f) ? __fsub_rn(0.5f * fS, t) : t;
+  t = (y < 0.f) ? __fsub_rn(fS, t) : t;
+  // nearest integers and the signed distances to them on the FP32 add pipe: v + 2^23 rounds v (< 2^22) to an
+  // integer held in the low mantissa bits
+  const float MAGIC = 8388608.0f;
+  const float qr_m = __fadd_rn(qr, MAGIC), t_m = __fadd_rn(t, MAGIC);
+  const float dr = __fsub_rn(qr, __fsub_rn(qr_m, MAGIC)), ds = __fsub_rn(t, __fsub_rn(t_m, MAGIC));
+  const int kr = (__float_as_int(qr_m) & 0x7fffff) - (dr < 0.f);  // floor(qr)
+  const int ks = (__float_as_int(t_m) & 0x7fffff) - (ds < 0.f);   // floor(t)
+  // beyond the ROI by more than the error (finite qr only: inf / NaN come from 0, subnormal or overflowing r2)
+  const bool outside = (qr > fR + c.eps_r) & (qr <= 3.0e38f);
+  // |dr| > eps also excludes qr in [R, R+eps] and NaN; |ds| > eps excludes t near 0 and S and NaN / inf
+  const bool safe = (fabsf(dr) > c.eps_r) & (fabsf(ds) > c.eps_s) & (mn > 0.f) & (h == h);
+  height = h;
+  if (outside) return -1;
+  if (safe) return ks * c.R + kr;
+  if (fell_back) *fell_back = true;
+  return bin_point_exact(c, x, y, z, height);
 }
 
 // order-preserving float <-> int map so that atomicMax on ints is max on floats (SC.cpp:182-183)
@@ -273,21 +359,16 @@ __device__ __forceinline__ void load_point(const unsigned char* p, float& x, flo
   }
 }
 
-// One atomicMax per distinct bin per warp: consecutive points of a scan share a beam and neighbouring
-// azimuths, so a warp usually touches one or two bins.
+// One atomicMax per distinct bin per warp: consecutive points of a scan share a beam and neighbouring azimuths,
+// so a warp touches a handful of bins.  match.any groups the lanes by bin, redux.sync takes each group's maximum,
+// the lowest lane of each group issues the shared-memory atomic.
 __device__ __forceinline__ void warp_bin_max(int* s_bins, int bin, int enc) {
-  unsigned todo = __ballot_sync(FULL, bin >= 0);
-  while (todo) {
-    const int leader = __ffs(todo) - 1;
-    const int b = __shfl_sync(FULL, bin, leader);
-    const bool mine = (bin == b);
-    const int m = __reduce_max_sync(FULL, mine ? enc : INT_MIN);
-    if ((threadIdx.x & 31) == leader) atomicMax(&s_bins[b], m);
-    todo &= ~__ballot_sync(FULL, mine);
-  }
+  const unsigned peers = __match_any_sync(FULL, bin);
+  const int m = __reduce_max_sync(peers, enc);
+  if (bin >= 0 && (threadIdx.x & 31) == (__ffs(peers) - 1)) atomicMax(&s_bins[bin], m);
 }
 
-template <int STRIDE>
+template <int STRIDE, bool FAST, bool LH_FLOAT>
 __global__ void __launch_bounds__(256) k_build(const BuildParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* s_bins = reinterpret_cast<int*>(smem_raw);
@@ -300,17 +381,26 @@ __global__ void __launch_bounds__(256) k_build(const BuildParams p) {
   const unsigned start = blockIdx.x * p.pts_per_block;
   const unsigned end = min(start + p.pts_per_block, p.n_pts);
   const unsigned char* base = p.pts + (unsigned long long)scan * p.scan_pitch;
-  // whole warps iterate together (the aggregation uses full-mask warp primitives)
-  for (unsigned i0 = start + (threadIdx.x & ~31u); i0 < end; i0 += blockDim.x) {
-    const unsigned i = i0 + (threadIdx.x & 31u);
-    int bin = -1, enc = INT_MIN;
-    if (i < end) {
-      float x, y, z, h;
-      load_point<STRIDE>(base + (unsigned long long)i * p.stride, x, y, z);
-      bin = bin_point_exact(p.bc, x, y, z, h);
-      enc = enc_float(h);
+  // whole warps iterate together (the aggregation uses full-mask warp primitives); UNROLL independent loads are
+  // issued before the first point is processed so that enough bytes are in flight per SM to cover HBM latency
+  constexpr int UNROLL = 4;
+  const unsigned lane_base = start + threadIdx.x;
+  for (unsigned i0 = start + (threadIdx.x & ~31u); i0 < end; i0 += UNROLL * blockDim.x) {
+    float px[UNROLL], py[UNROLL], pz[UNROLL];
+    const unsigned i = lane_base + (i0 - (start + (threadIdx.x & ~31u)));
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const unsigned iu = i + u * blockDim.x;
+      px[u] = py[u] = pz[u] = __int_as_float(0x7fc00000);  // NaN: dropped
+      if (iu < end) load_point<STRIDE>(base + (unsigned long long)iu * p.stride, px[u], py[u], pz[u]);
     }
-    warp_bin_max(s_bins, bin, enc);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (i0 + u * blockDim.x >= end) break;  // warp-uniform
+      float h;
+      const int bin = bin_point<FAST, LH_FLOAT>(p.bc, px[u], py[u], pz[u], h);
+      warp_bin_max(s_bins, bin, bin >= 0 ? enc_float(h) : INT_MIN);
+    }
   }
   __syncthreads();
 
@@ -936,9 +1026,68 @@ __global__ void k_probe_bins(const float* xyz, size_t n, BinConst bc, int* bin, 
   if (i >= n) return;
   float h;
   const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
-  bin[i] = bin_point_exact(bc, x, y, z, h);
+  const int b = bc.fast ? (bc.lh_is_float ? bin_point<true, true>(bc, x, y, z, h) : bin_point<true, false>(bc, x, y, z, h))
+                        : bin_point_exact(bc, x, y, z, h);   // the function k_build uses
+  bin[i] = b;
+  if (b < 0) h = __double2float_rn(__dadd_rn((double)z, bc.lidar_height));
   height[i] = h;
   theta[i] = xy2theta_exact(x, y);
+}
+
+// On-device self check of the binning front end: n pseudo-random points per launch, bin_point vs bin_point_exact.
+//   mode 0: uniform in the square [-1.15, 1.15] * max_radius;
+//   mode 1: adversarial -- on a sector boundary angle or a ring boundary radius, displaced by 2^-e (e = 6..45) of
+//           a sector / ring width to either side, so that the hand-over between the two paths is swept densely.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__global__ void k_selfcheck(unsigned long long n, unsigned long long seed, int mode, BinConst bc, unsigned long long* mismatches,
+                            unsigned long long* fallbacks, float* first_bad) {
+  const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long h0 = mix64(seed ^ (i * 0x100000001b3ull)), h1 = mix64(h0), h2 = mix64(h1), h3 = mix64(h2);
+  const double u0 = (double)(h0 >> 11) * (1.0 / 9007199254740992.0), u1 = (double)(h1 >> 11) * (1.0 / 9007199254740992.0);
+  float x, y;
+  const float z = (float)(16.0 * ((double)(h2 >> 11) * (1.0 / 9007199254740992.0)) - 4.0);
+  if (mode == 0) {
+    x = (float)((2.0 * u0 - 1.0) * 1.15 * bc.max_radius);
+    y = (float)((2.0 * u1 - 1.0) * 1.15 * bc.max_radius);
+  } else {
+    const int e = 6 + (int)(h3 % 40);
+    const double off = ((h3 >> 8) & 1 ? 1.0 : -1.0) * exp2(-(double)e) * (((h3 >> 9) & 1) ? 1.0 : 0.0);
+    double ang, rad;
+    if ((h3 >> 10) & 1) {  // sector boundary
+      const int k = (int)(h0 % (unsigned long long)(bc.S + 1));
+      ang = ((double)k + off) * (6.283185307179586476925 / (double)bc.S);
+      rad = u1 * 1.05 * bc.max_radius;
+    } else {               // ring boundary
+      const int k = 1 + (int)(h0 % (unsigned long long)bc.R);
+      rad = ((double)k + off) * (bc.max_radius / (double)bc.R);
+      ang = u1 * 6.283185307179586476925;
+    }
+    x = (float)(rad * cos(ang));
+    y = (float)(rad * sin(ang));
+    if (((h3 >> 11) & 7) == 0) x = __uint_as_float(__float_as_uint(x) + (unsigned)((h3 >> 14) & 3) - 1u);  // +-1 ulp nudges
+    if (((h3 >> 16) & 7) == 0) y = __uint_as_float(__float_as_uint(y) + (unsigned)((h3 >> 19) & 3) - 1u);
+  }
+  float ha, hb;
+  bool fb = false;
+  const int a = bc.lh_is_float ? bin_point<true, true>(bc, x, y, z, ha, &fb) : bin_point<true, false>(bc, x, y, z, ha, &fb);
+  const int b = bin_point_exact(bc, x, y, z, hb);
+  const bool bad = (a != b) || (a >= 0 && __float_as_uint(ha) != __float_as_uint(hb));
+  if (fb) atomicAdd(fallbacks, 1ull);
+  if (bad) {
+    if (atomicAdd(mismatches, 1ull) == 0) {
+      first_bad[0] = x;
+      first_bad[1] = y;
+      first_bad[2] = z;
+      first_bad[3] = (float)a;
+      first_bad[4] = (float)b;
+    }
+  }
 }
 
 }  // namespace scgpu

@@ -13,6 +13,7 @@ from . import build as _build
 
 OK = 0
 FLAG_FRESH_TREE = 1
+FLAG_EXACT_BINNING = 2
 
 
 class ScgpuError(RuntimeError):
@@ -70,6 +71,7 @@ _SIGNATURES = {
     "scgpu_xy2theta": [C.c_float, C.c_float, _pf],
     "scgpu_probe_atanf": [_vp, _sz, _vp],
     "scgpu_probe_bins": [_vp, _vp, _sz, _vp, _vp, _vp],
+    "scgpu_probe_selfcheck": [_vp, _u64, _u64, _i, C.POINTER(_u64), C.POINTER(_u64), _vp],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["scgpu_last_error", "scgpu_version"])
 
@@ -306,6 +308,13 @@ class SCManager:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _check(self.lib.scgpu_get_timing(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def selfcheck_binning(self, n, seed=1, mode=0):
+        """(mismatches, fallbacks, first_bad) of the binning front end vs the exact path over n device-generated points."""
+        mm, fb = _u64(), _u64()
+        bad = np.zeros(5, np.float32)
+        _check(self.lib.scgpu_probe_selfcheck(self.h, n, seed, mode, C.byref(mm), C.byref(fb), bad.ctypes.data))
+        return mm.value, fb.value, bad
 
     def record_bytes(self):
         n = _sz()

@@ -104,6 +104,32 @@ def test_device_bins_match_oracle(variant):
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
+def test_binning_front_end_never_disagrees_with_exact_path(variant):
+    """k_build bins through an FP32 front end that hands every point near a ring/sector boundary, on an axis or
+    at the ROI edge to the bit-exact path.  On-device self check over 2^31 uniform points and 2^30 adversarial
+    points (on / within 2^-6..2^-45 of a boundary, +-1 ulp nudges): zero mismatches, and the hand-over is used."""
+    p = params_from_golden(golden(variant))
+    m = mgr(p)
+    n = 1 << 31 if variant == "default" else 1 << 28
+    mm, fb, bad = m.selfcheck_binning(n, seed=7, mode=0)
+    assert mm == 0, f"{mm} mismatches, first at x,y,z={bad[:3]} fast={bad[3]} exact={bad[4]}"
+    assert 0 < fb < 0.02 * n, fb           # the fallback exists but is rare on real-looking data
+    mm, fb2, bad = m.selfcheck_binning(n >> 1, seed=11, mode=1)
+    assert mm == 0, f"{mm} mismatches, first at x,y,z={bad[:3]} fast={bad[3]} exact={bad[4]}"
+    assert fb2 > 0.3 * (n >> 1), fb2       # adversarial points are mostly decided by the exact path
+
+
+def test_exact_binning_flag_gives_identical_descriptors():
+    from sc_lego_loam_b200 import scgpu
+    from sc_lego_loam_b200.synth import ScanGen
+    gen = ScanGen("hdl64", seed=8, n_places=9)
+    a, b = mgr(orc.Params()), mgr(orc.Params(), flags=scgpu.FLAG_EXACT_BINNING)
+    for i in range(4):
+        s = gen.scan(i, 4)
+        assert np.array_equal(a.makeScancontext(s), b.makeScancontext(s))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_make_sc_and_keys_match_golden(variant):
     g = golden(variant)
     m = mgr(params_from_golden(g))
