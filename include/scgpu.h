@@ -42,6 +42,8 @@ extern "C" {
 /* flags */
 #define SCGPU_FLAG_EXACT_BINNING 2u /* disable the FP32 front end of the binning kernel: every point is binned by the
                                       bit-exact restatement (results are identical either way; for A/B timing) */
+#define SCGPU_FLAG_NO_SCREENING 4u /* exhaustive search scores every entry with the FP64 pair kernel (no FP32 screening
+                                      pass, no second copy of the database); results are identical, for A/B timing */
 #define SCGPU_FLAG_FRESH_TREE 1u /* search keys [0, size - exclude_recent) on EVERY detect instead of emulating the
                                     reference's periodically rebuilt KD-tree snapshot (SC.cpp:264-276) */
 
@@ -138,6 +140,9 @@ int scgpu_truncate(scgpu_handle* h, uint64_t n);
  * its columns reversed (forward first).  Outputs are for the global winner. */
 int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped, double* best_dist,
                      int* best_shift, int64_t* best_idx, int* best_flip);
+/* How many entries the last scgpu_exhaustive had to rescore with the exact FP64 kernel (the rest was ruled out
+ * by the FP32 screening pass with a proven margin). */
+int scgpu_exhaustive_stats(scgpu_handle* h, uint64_t* rescored);
 /* Flat binary save / load of the descriptor database. */
 int scgpu_save(scgpu_handle* h, const char* path);
 int scgpu_load(scgpu_handle* h, const char* path);
@@ -170,6 +175,10 @@ int scgpu_stage_merge(scgpu_handle* h, const uint64_t* d_keys_parts, int parts, 
  * {double dist; int32 rank_in_list; int32 shift; int64 global_idx} (24 bytes), dist = +inf when none. */
 int scgpu_stage_score(scgpu_handle* h, const void* d_query_records, size_t n_queries, const uint64_t* d_keys,
                       const uint64_t* d_n_search, void* d_best_out, void* stream);
+/* Exhaustive search of this shard for one query record: {double dist; int32 n_rescored; int32 shift; int64 global_idx}
+ * of the shard's strict-min winner (dist = 1e7 when none).  The global winner is the minimum over shards by
+ * (dist, global_idx). */
+int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_query_record, uint64_t n_search, void* d_best_out, void* stream);
 /* Reduce `parts` per-shard bests (layout [parts][n_queries]) to the reference's result per query
  * (d_n_search[q] == 0 marks a query that took the early return of SC.cpp:257-261). */
 int scgpu_stage_finalize(scgpu_handle* h, const void* d_best_parts, int parts, size_t n_queries,

@@ -12,6 +12,7 @@
 
 #include <vector>
 
+#include "scgpu_exhaustive.cuh"
 #include "scgpu_kernels.cuh"
 
 using namespace scgpu;
@@ -95,6 +96,14 @@ struct scgpu_handle {
   // database shard
   Db db{};
   uint64_t n_global = 0;
+  // screening copy for the exhaustive search (only for configurations k_exh_screen is instantiated for)
+  bool exh = false;
+  float* x_sc_hat = nullptr;
+  float* x_vkey32 = nullptr;
+  ExhAux* x_aux = nullptr;
+  DevBuf x_query, x_d32, x_keys, x_pd, x_ps, x_small, x_best;
+  int sm_count = 148;
+  unsigned last_exh_rescored = 0;
   // build workspace
   DevBuf gbins, btickets;
   size_t build_cap = 0;
@@ -135,7 +144,20 @@ int db_reserve(scgpu_handle* h, uint64_t want_local) {
   CK(cudaMalloc(&nd.ringT, cap * L.R * sizeof(float)));
   CK(cudaMalloc(&nd.sector, cap * L.S * sizeof(double)));
   CK(cudaMalloc(&nd.colnorm, cap * L.S * sizeof(double)));
+  float* n_hat = nullptr;
+  float* n_vk = nullptr;
+  ExhAux* n_aux = nullptr;
+  if (h->exh) {
+    CK(cudaMalloc(&n_hat, cap * L.RS * sizeof(float)));
+    CK(cudaMalloc(&n_vk, cap * L.S * sizeof(float)));
+    CK(cudaMalloc(&n_aux, (cap + 8) * sizeof(ExhAux)));
+  }
   const uint64_t n = local_count(h, h->n_global);
+  if (h->exh && h->db.cap && n) {
+    CK(cudaMemcpyAsync(n_hat, h->x_sc_hat, n * L.RS * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(n_vk, h->x_vkey32, n * L.S * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(n_aux, h->x_aux, n * sizeof(ExhAux), cudaMemcpyDeviceToDevice, h->stream));
+  }
   if (h->db.cap && n) {
     CK(cudaMemcpyAsync(nd.sc, h->db.sc, n * L.RS * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpy2DAsync(nd.ringT, cap * sizeof(float), h->db.ringT, h->db.cap * sizeof(float), n * sizeof(float), L.R,
@@ -149,8 +171,16 @@ int db_reserve(scgpu_handle* h, uint64_t want_local) {
     cudaFree(h->db.ringT);
     cudaFree(h->db.sector);
     cudaFree(h->db.colnorm);
+    if (h->exh) {
+      cudaFree(h->x_sc_hat);
+      cudaFree(h->x_vkey32);
+      cudaFree(h->x_aux);
+    }
   }
   h->db = nd;
+  h->x_sc_hat = n_hat;
+  h->x_vkey32 = n_vk;
+  h->x_aux = n_aux;
   return SCGPU_OK;
 }
 
@@ -236,6 +266,12 @@ int launch_append(scgpu_handle* h, const void* d_records, uint64_t first_global,
   k_append<<<(unsigned)n, 128, 0, st>>>(static_cast<const unsigned char*>(d_records), h->L, h->db, first_global, step);
   h->launches++;
   CK(cudaGetLastError());
+  if (h->exh) {
+    k_exh_append<<<(unsigned)n, 128, 0, st>>>(static_cast<const unsigned char*>(d_records), h->L, h->db, h->x_sc_hat, h->x_vkey32, h->x_aux,
+                                              first_global, step);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
   if (new_size > h->n_global) h->n_global = new_size;
   return SCGPU_OK;
 }
@@ -333,6 +369,7 @@ int launch_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t*
   p.pair_dist = d_pair_dist;
   p.pair_shift = d_pair_shift;
   p.flip = flip;
+  p.active = nullptr;
   const size_t smem = pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float));
   dim3 grid((unsigned)K_eff, (unsigned)nq);
   k_score<<<grid, 128, smem, st>>>(p);
@@ -499,6 +536,66 @@ int pair_api(scgpu_handle* h, const double* a, size_t na, const double* b, size_
   return SCGPU_OK;
 }
 
+constexpr unsigned EXH_CAND_CAP = 16384;
+
+// Screen + rescore for ONE query record on the device; the result (Best: dist, rank = #rescored, shift, global idx)
+// is written to d_best_out.  Everything is enqueued on st; no host synchronisation.
+int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrec, uint64_t n_search, Best* d_best_out, cudaStream_t st,
+                           cudaEvent_t ev_screen0, cudaEvent_t ev_screen1) {
+  const uint64_t n_local = local_count(h, n_search);
+  RET(h->x_query.reserve(sizeof(ExhQuery)));
+  RET(h->x_d32.reserve((n_local + 8) * sizeof(float)));
+  RET(h->x_keys.reserve(EXH_CAND_CAP * sizeof(uint64_t)));
+  RET(h->x_pd.reserve(EXH_CAND_CAP * sizeof(double)));
+  RET(h->x_ps.reserve(EXH_CAND_CAP * sizeof(int)));
+  RET(h->x_small.reserve(64));
+  unsigned* d_min = h->x_small.as<unsigned>();
+  unsigned* d_count = d_min + 1;
+  unsigned long long* d_one = reinterpret_cast<unsigned long long*>(d_min + 2);  // "n_search" != 0 for k_score
+  k_exh_prep<<<1, 128, 0, st>>>(d_qrec, h->L, h->x_query.as<ExhQuery>());
+  k_exh_init<<<1, 1, 0, st>>>(d_min, d_count);
+  CK(cudaMemsetAsync(d_one, 0xff, 8, st));
+  h->launches += 2;
+  if (n_local) {
+    ExhScreenParams sp;
+    sp.db.sc_hat = h->x_sc_hat;
+    sp.db.vkey32 = h->x_vkey32;
+    sp.db.aux = h->x_aux;
+    sp.q = h->x_query.as<ExhQuery>();
+    sp.n_local = n_local;
+    sp.d32 = h->x_d32.as<float>();
+    const uint64_t groups = (n_local + EXH_WARPS - 1) / EXH_WARPS;
+    const unsigned grid = (unsigned)(groups < (uint64_t)h->sm_count ? groups : (uint64_t)h->sm_count);
+    const size_t smem = exh_smem_bytes<20, 60, 3>();
+    if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
+    k_exh_screen<20, 60, 3><<<grid, (EXH_WARPS + 1) * 32, smem, st>>>(sp);
+    if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
+    CK(cudaGetLastError());
+    const unsigned rb = (unsigned)((n_local + 1023) / 1024 < 592 ? (n_local + 1023) / 1024 : 592);
+    k_exh_min<<<rb, 256, 0, st>>>(sp.d32, n_local, d_min);
+    k_exh_compact<<<rb, 256, 0, st>>>(sp.d32, n_local, d_min, h->db.rank, h->db.G, h->x_keys.as<unsigned long long>(), d_count, EXH_CAND_CAP);
+    ScoreParams p;
+    p.qrecords = d_qrec;
+    p.L = h->L;
+    p.db = h->db;
+    p.keys = h->x_keys.as<unsigned long long>();
+    p.n_search = d_one;
+    p.K = (int)EXH_CAND_CAP;
+    p.radius = h->radius;
+    p.pair_dist = h->x_pd.as<double>();
+    p.pair_shift = h->x_ps.as<int>();
+    p.flip = 0;
+    p.active = d_count;
+    k_score<<<dim3(EXH_CAND_CAP, 1), 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p);
+    h->launches += 4;
+    CK(cudaGetLastError());
+  }
+  k_exh_final<<<1, 256, 0, st>>>(h->x_pd.as<double>(), h->x_ps.as<int>(), h->x_keys.as<unsigned long long>(), d_count, EXH_CAND_CAP, d_best_out);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -551,6 +648,8 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   h->W = 2 * h->radius + 1;
   h->db.rank = cfg->shard_rank;
   h->db.G = cfg->shard_count;
+  h->exh = (h->L.R == 20 && h->L.S == 60 && h->radius == 3) && !(cfg->flags & SCGPU_FLAG_NO_SCREENING);
+  cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   const size_t smem_f = pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float));
   const size_t smem_d = pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(double));
   if (smem_d > 220 * 1024) {
@@ -567,6 +666,9 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t1);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t2);
+  if (e == cudaSuccess && h->exh)
+    e = cudaFuncSetAttribute(k_exh_screen<20, 60, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)exh_smem_bytes<20, 60, 3>());
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e == cudaSuccess && smem_d > 48 * 1024) e = cudaFuncSetAttribute(k_pair_api, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
   if (e != cudaSuccess) {
@@ -603,7 +705,14 @@ int scgpu_destroy(scgpu_handle* h) {
     cudaFree(h->db.ringT);
     cudaFree(h->db.sector);
     cudaFree(h->db.colnorm);
+    if (h->exh) {
+      cudaFree(h->x_sc_hat);
+      cudaFree(h->x_vkey32);
+      cudaFree(h->x_aux);
+    }
   }
+  DevBuf* xb[] = {&h->x_query, &h->x_d32, &h->x_keys, &h->x_pd, &h->x_ps, &h->x_small, &h->x_best};
+  for (DevBuf* b : xb) b->release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
@@ -887,6 +996,25 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
   if (n_search == 0) return SCGPU_OK;
   k_gather<<<1, 128, 0, st>>>(h->rec_single.as<unsigned char>(), h->L, h->db, q);
   h->launches++;
+  if (h->exh && !flipped) {
+    RET(h->x_best.reserve(sizeof(Best)));
+    CK(cudaEventRecord(h->ev_t0, st));
+    RET(launch_exhaustive_fast(h, h->rec_single.as<unsigned char>(), n_search, h->x_best.as<Best>(), st, h->ev_t0, h->ev_t1));
+    CK(cudaEventRecord(h->ev_t2, st));
+    h->timing_valid = true;
+    Best b;
+    CK(cudaMemcpyAsync(&b, h->x_best.p, sizeof b, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if ((unsigned)b.rank <= EXH_CAND_CAP) {
+      *best_dist = b.dist;
+      *best_shift = b.shift;
+      *best_idx = b.idx;
+      h->last_exh_rescored = (unsigned)b.rank;
+      return SCGPU_OK;
+    }
+    // more near-ties than the rescoring list holds (e.g. a database of duplicates): score everything exactly
+  }
+  h->last_exh_rescored = (unsigned)n_search;
   const size_t n = (size_t)n_search;
   DevBuf keys, pd, ps, ns;
   RET(keys.reserve(n * 8));
@@ -915,6 +1043,7 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
       p.pair_dist = pd.as<double>() + f * n + s0;
       p.pair_shift = ps.as<int>() + f * n + s0;
       p.flip = f;
+      p.active = nullptr;
       k_score<<<dim3((unsigned)m, 1), 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p);
       h->launches++;
       if (cudaGetLastError() != cudaSuccess) rc = fail(SCGPU_E_CUDA, "k_score launch failed");
@@ -940,6 +1069,12 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
         if (best_flip) *best_flip = f;
       }
     }
+  return SCGPU_OK;
+}
+
+int scgpu_exhaustive_stats(scgpu_handle* h, uint64_t* rescored) {
+  if (!h || !rescored) return fail(SCGPU_E_INVALID, "null argument");
+  *rescored = h->last_exh_rescored;
   return SCGPU_OK;
 }
 
@@ -1128,6 +1263,14 @@ int scgpu_stage_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint
   RET(query_reserve(h, nq, 1, st));
   RET(launch_score(h, d_qrec, nq, d_keys, d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
   return launch_best(h, nq, d_keys, static_cast<Best*>(d_best_out), st);
+}
+
+int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_qrecord, uint64_t n_search, void* d_best_out, void* stream) {
+  if (!h || !d_qrecord || !d_best_out) return fail(SCGPU_E_INVALID, "null argument");
+  if (!h->exh) return fail(SCGPU_E_INVALID, "screening kernel is instantiated for 20x60, search radius 3 only");
+  CK(cudaSetDevice(h->cfg.device));
+  return launch_exhaustive_fast(h, static_cast<const unsigned char*>(d_qrecord), n_search, static_cast<Best*>(d_best_out), ST(stream), nullptr,
+                                nullptr);
 }
 
 int scgpu_stage_finalize(scgpu_handle* h, const void* d_best_parts, int parts, size_t nq, const uint64_t* d_ns, int32_t* d_loop_id,

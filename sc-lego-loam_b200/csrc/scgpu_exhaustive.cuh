@@ -1,0 +1,440 @@
+// scgpu_exhaustive.cuh -- exhaustive loop search: EVERY database entry scored against the query
+// (BASELINE config 4: 100k keyframes, 20x60) at HBM speed, with the reference's exact result.
+//
+// Two phases.
+//   screen  (k_exh_screen, this file): an FP32 pass that streams the database once from HBM through a TMA-fed
+//           shared-memory ring and produces, per entry, an approximation d32 of distanceBtnScanContext
+//           (SC.cpp:116-148) with |d32 - d| <= EXH_EPS -- or a flag saying "cannot tell" (-1).
+//   rescore (k_exh_min / k_exh_compact / k_score / k_exh_final): the entries that can still be the argmin
+//           (d32 <= min d32 + 2*EXH_EPS, plus every flagged entry) go through the bit-exact FP64 pair kernel; the
+//           winner is the strict minimum in index order, exactly the loop of SC.cpp:296-311 over all entries.
+//
+// Screening math (the "query-column x candidate-column contraction" of SURVEY.md 8a): with unit-normalised
+// columns A^ (query) and B^ (candidate; zero columns stay zero), distDirectSC at shift s is
+//       1 - (1/n_s) * sum_j sum_r A^[r][j] * B^[r][(j - s) mod S],     n_s = #{ j : both columns non-zero }
+// so a lane that owns ROW r loads B^[r][0..S) of the candidate into registers (the screening copy of the database is
+// row-major: 15 conflict-free LDS.128), streams A^[r][*] of the query from a DOUBLED row table in shared memory
+// (position p + shift never wraps, so the loads use immediate offsets -- no index arithmetic) through a
+// (2*RAD+1)-deep register window and accumulates all 2*RAD+1 shifts of the reference's search window at once:
+// one LDS per 2*RAD+1 FMAs.
+// The sector-key alignment (SC.cpp:93-113) is argmax_s sum_p v2[p] * v1[(p + s) mod S]; it has exactly the same
+// shape, so the lanes of the warp that own no row compute it -- for the NEXT entry, while the row lanes work on
+// the current one (software pipeline across entries inside a warp; nothing but warp shuffles in between).
+//
+// Exactness: the alignment is accepted only when the best correlation beats the runner-up by more than the
+// FP32 error bound (otherwise -> flag); d32 NaN -> flag.  Error budget in DESIGN.md ("exhaustive screening").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "scgpu_kernels.cuh"
+
+namespace scgpu {
+
+constexpr float EXH_EPS = 1.0e-5f;         // |d32 - d| bound used for candidate selection (observed: < 2e-6)
+constexpr float EXH_ALIGN_MARGIN = 1.6e-5f;  // relative (to |v1||v2|) gap below which the alignment is ambiguous
+constexpr int EXH_STAGES = 4;               // window(k-1) | alignment(k) | in flight(k+1, k+2)
+constexpr int EXH_WARPS = 10;              // consumer warps per block = entries per stage
+
+// ---- hand-written PTX wrappers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP) -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// per-entry auxiliary record kept next to the normalised descriptor
+struct ExhAux {
+  unsigned long long vmask;  // bit c: column c has a non-zero norm
+  float vnorm;               // |sector key| (float)
+  unsigned flags;            // bit 0: a column norm is not representable / not finite in FP32 -> always rescore
+};
+
+struct ExhDb {
+  const float* sc_hat;   // [cap][R][S] unit-normalised columns, ROW-major per entry
+  const float* vkey32;   // [cap][S]
+  const ExhAux* aux;     // [cap]
+};
+
+__global__ void k_exh_init(unsigned* min_bits, unsigned* count) {
+  *min_bits = 0x7f800000u;
+  *count = 0;
+}
+
+// query pack built by k_exh_prep: normalised query, float sector key, valid-column mask, |v1|
+struct ExhQuery {
+  float qhat[64 * 64];   // row-major like the database copy; only R*S used (instantiations keep R*S <= 4096)
+  float v1[64];
+  unsigned long long qmask;
+  float v1norm;
+  unsigned flags;
+};
+
+// Screening side data of one record (descriptor, keys): used by k_append for the database and by k_exh_prep for
+// the query.  One block; every thread may call.
+__device__ __forceinline__ void exh_normalise(const unsigned char* rec, const Layout& L, float* sc_hat, float* vkey32,
+                                              unsigned long long* vmask, float* vnorm, unsigned* flags) {
+  const float* sc = reinterpret_cast<const float*>(rec);
+  const double* sector = reinterpret_cast<const double*>(rec + L.off_sector);
+  const double* norm = reinterpret_cast<const double*>(rec + L.off_norm);
+  __shared__ unsigned long long s_mask;
+  __shared__ unsigned s_flags;
+  __shared__ float s_v2;
+  if (threadIdx.x == 0) {
+    s_mask = 0;
+    s_flags = 0;
+    s_v2 = 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L.RS; i += blockDim.x) {  // ROW-major output: element (r, c) at r*S + c
+    const int c = i / L.R, r = i - c * L.R;
+    const double n = norm[c];
+    sc_hat[r * L.S + c] = (n == 0.0) ? 0.f : (float)((double)sc[i] / n);
+  }
+  for (int c = threadIdx.x; c < L.S; c += blockDim.x) {
+    const double n = norm[c];
+    const float nf = (float)n, v = (float)sector[c];
+    vkey32[c] = v;
+    if (n != 0.0 && c < 64) atomicOr(&s_mask, 1ull << c);
+    if (n != 0.0 && !(nf > 1e-30f && nf < 1e30f)) atomicOr(&s_flags, 1u);  // subnormal-ish, inf or NaN norm
+    if (!(fabsf(v) < 1e30f)) atomicOr(&s_flags, 1u);
+    atomicAdd(&s_v2, v * v);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *vmask = s_mask;
+    *vnorm = sqrtf(s_v2);
+    *flags = s_flags;
+  }
+  __syncthreads();
+}
+
+// database side of the screening data: entries first_global + i*step owned by this shard
+__global__ void __launch_bounds__(128) k_exh_append(const unsigned char* records, Layout L, Db db, float* sc_hat, float* vkey32, ExhAux* aux,
+                                                    unsigned long long first_global, unsigned long long step) {
+  const unsigned long long g = first_global + blockIdx.x * step;
+  if ((int)(g % (unsigned long long)db.G) != db.rank) return;
+  const unsigned long long l = g / (unsigned long long)db.G;
+  exh_normalise(records + (size_t)blockIdx.x * L.rec_bytes, L, sc_hat + l * L.RS, vkey32 + l * L.S, &aux[l].vmask, &aux[l].vnorm, &aux[l].flags);
+}
+
+__global__ void __launch_bounds__(128) k_exh_prep(const unsigned char* qrec, Layout L, ExhQuery* q) {
+  exh_normalise(qrec, L, q->qhat, q->v1, &q->qmask, &q->v1norm, &q->flags);
+}
+
+struct ExhScreenParams {
+  ExhDb db;
+  const ExhQuery* q;
+  unsigned long long n_local;  // local entries to score: [0, n_local)
+  float* d32;                  // [n_local] out: approx distance; -1 = must be rescored; +inf = can never win
+};
+
+// shared memory ring: per stage, EXH_WARPS entries
+template <int R, int S>
+struct ExhStage {
+  float sc_hat[EXH_WARPS][R * S];
+  float vkey[EXH_WARPS][S];
+  ExhAux aux[EXH_WARPS];
+};
+
+template <int R, int S, int RAD>
+constexpr size_t exh_smem_bytes() {
+  return sizeof(ExhStage<R, S>) * EXH_STAGES + 2 * EXH_STAGES * sizeof(uint64_t) + (size_t)(R + 1) * (((2 * S + 2 * RAD + 1) | 1)) * sizeof(float);
+}
+
+template <int R, int S, int RAD>
+__global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const ExhScreenParams p) {
+  constexpr int W = 2 * RAD + 1;
+  constexpr int ALIGN_LANES = (S + W - 1) / W;
+  constexpr int PITCH = (2 * S + W) | 1;  // odd pitch: lanes (rows) hit distinct banks
+  static_assert(R + ALIGN_LANES <= 32, "rows + alignment lanes must fit one warp");
+  static_assert(S <= 64 && S % 4 == 0, "valid-column masks are 64 bits; rows are read with 16-byte loads");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using Stage = ExhStage<R, S>;
+  Stage* stages = reinterpret_cast<Stage*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage) * EXH_STAGES);
+  uint64_t* empty = full + EXH_STAGES;
+  float* qtable = reinterpret_cast<float*>(empty + EXH_STAGES);  // [(R+1)][PITCH]: rows 0..R-1 = A^ rows, row R = v1, each doubled
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned long long n_groups = (p.n_local + EXH_WARPS - 1) / EXH_WARPS;  // groups of EXH_WARPS entries
+  const unsigned long long my_groups = n_groups > blockIdx.x ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < EXH_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], EXH_WARPS);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < (R + 1) * PITCH; i += blockDim.x) {
+    const int r = i / PITCH, c = (i - r * PITCH) % S;
+    qtable[i] = r < R ? p.q->qhat[r * S + c] : p.q->v1[c];
+  }
+  __syncthreads();
+
+  if (warp == EXH_WARPS) {
+    // ===== producer: one lane feeds the ring with TMA bulk copies =====
+    if (lane == 0) {
+      for (unsigned long long k = 0; k < my_groups; ++k) {
+        const int slot = (int)(k % EXH_STAGES);
+        if (k >= EXH_STAGES) mbar_wait(&empty[slot], (uint32_t)(((k / EXH_STAGES) - 1) & 1));
+        const unsigned long long e0 = (blockIdx.x + k * gridDim.x) * EXH_WARPS;
+        const unsigned n = (unsigned)(p.n_local - e0 < EXH_WARPS ? p.n_local - e0 : EXH_WARPS);
+        const unsigned b_sc = n * R * S * 4u, b_vk = n * S * 4u, b_aux = n * (unsigned)sizeof(ExhAux);
+        mbar_arrive_expect_tx(&full[slot], b_sc + b_vk + b_aux);
+        tma_bulk_g2s(&stages[slot].sc_hat[0][0], p.db.sc_hat + e0 * R * S, b_sc, &full[slot]);
+        tma_bulk_g2s(&stages[slot].vkey[0][0], p.db.vkey32 + e0 * S, b_vk, &full[slot]);
+        tma_bulk_g2s(&stages[slot].aux[0], p.db.aux + e0, b_aux, &full[slot]);
+      }
+    }
+    return;
+  }
+
+  // ===== consumers: warp w scores entry w of every group =====
+  // lane roles: [0, R) own a descriptor row; [R, R+ALIGN_LANES) own W consecutive alignment shifts
+  const bool row_lane = lane < R, align_lane = lane >= R && lane < R + ALIGN_LANES;
+  const unsigned long long qmask = p.q->qmask;
+  const float v1norm = p.q->v1norm;
+  const bool q_flag = (p.q->flags & 1u) != 0;
+  const float* qrow = qtable + (row_lane ? lane : R) * PITCH;
+
+  int a_cur = 0;          // alignment of the entry whose window is scored in this iteration
+  bool amb_cur = false;
+  for (unsigned long long k = 0; k <= my_groups; ++k) {
+    // iteration k: window of group k-1 (row lanes) + alignment of group k (alignment lanes)
+    const bool has_win = k >= 1, has_al = k < my_groups;
+    const int slot_w = (int)((k + EXH_STAGES - 1) % EXH_STAGES), slot_a = (int)(k % EXH_STAGES);
+    bool ent_w = false, ent_a = false;
+    unsigned long long e_w = 0;
+    if (has_win) {
+      e_w = (blockIdx.x + (k - 1) * gridDim.x) * EXH_WARPS + warp;
+      ent_w = e_w < p.n_local;
+    }
+    if (has_al) {
+      mbar_wait(&full[slot_a], (uint32_t)((k / EXH_STAGES) & 1));
+      ent_a = (blockIdx.x + k * gridDim.x) * EXH_WARPS + warp < p.n_local;
+    }
+    // held[p]: the candidate's row (row lanes) / sector key (alignment lanes); base: first shift of this lane
+    const float4* held4 = nullptr;
+    int base = 0;
+    if (row_lane && ent_w) {
+      held4 = reinterpret_cast<const float4*>(&stages[slot_w].sc_hat[warp][lane * S]);
+      base = ((a_cur - RAD) % S + S) % S;
+    } else if (align_lane && ent_a) {
+      held4 = reinterpret_cast<const float4*>(&stages[slot_a].vkey[warp][0]);
+      base = (lane - R) * W;
+    }
+    float acc[W];
+#pragma unroll
+    for (int d = 0; d < W; ++d) acc[d] = 0.f;
+    if (held4) {
+      // acc[d] = sum_p held[p] * q[(p + base + d) mod S]; the doubled table makes (p + base + d) a plain offset
+      float held[S];
+#pragma unroll
+      for (int i = 0; i < S / 4; ++i) {
+        const float4 v = held4[i];
+        held[4 * i] = v.x;
+        held[4 * i + 1] = v.y;
+        held[4 * i + 2] = v.z;
+        held[4 * i + 3] = v.w;
+      }
+      const float* qs = qrow + base;
+      float win[W];
+#pragma unroll
+      for (int d = 0; d < W - 1; ++d) win[d] = qs[d];
+#pragma unroll
+      for (int pp = 0; pp < S; ++pp) {
+        win[W - 1] = qs[pp + W - 1];
+#pragma unroll
+        for (int d = 0; d < W; ++d) acc[d] = __fmaf_rn(held[pp], win[d], acc[d]);
+#pragma unroll
+        for (int d = 0; d < W - 1; ++d) win[d] = win[d + 1];
+      }
+    }
+    // ---- window result of group k-1: acc[d] belongs to shift a_cur - RAD + d ----------------------
+    if (has_win) {
+      // transpose-reduce over the row lanes: 8 -> 4 -> 2 -> 1 values per lane while summing across xor 16, 8, 4,
+      // then xor 2, 1; lane l ends with the total of shift index d = 4*bit4(l) + 2*bit3(l) + bit2(l)
+      static_assert(W <= 8, "the transpose-reduce handles up to 8 shifts");
+      float r8[8];
+#pragma unroll
+      for (int d = 0; d < 8; ++d) r8[d] = (row_lane && d < W) ? acc[d] : 0.f;
+      float r4[4], r2[2], r1;
+      {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r4[i] = (hi ? r8[4 + i] : r8[i]) + __shfl_xor_sync(FULL, hi ? r8[i] : r8[4 + i], 16);
+      }
+      {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) r2[i] = (hi ? r4[2 + i] : r4[i]) + __shfl_xor_sync(FULL, hi ? r4[i] : r4[2 + i], 8);
+      }
+      {
+        const bool hi = lane & 4;
+        r1 = (hi ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, hi ? r2[0] : r2[1], 4);
+      }
+      r1 += __shfl_xor_sync(FULL, r1, 2);
+      r1 += __shfl_xor_sync(FULL, r1, 1);
+      const int d_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+      // every lane: distance of "its" shift; acc index d belongs to shift a_cur - RAD + d
+      const ExhAux ax = stages[slot_w].aux[ent_w ? warp : 0];
+      float dist = __int_as_float(0x7f800000);  // +inf: no valid column pair at this shift -> the reference yields NaN there
+      bool nan_here = false;
+      if (d_mine < W) {
+        int sft = (a_cur + d_mine - RAD) % S;  // query column j pairs with candidate column (j - sft) mod S
+        if (sft < 0) sft += S;
+        const unsigned long long m = ax.vmask;
+        const unsigned long long rot = sft == 0 ? m : (((m << sft) | (m >> (S - sft))) & ((S == 64) ? ~0ull : ((1ull << S) - 1)));
+        const int n = __popcll(qmask & rot);
+        if (n > 0) {
+          dist = 1.0f - r1 / (float)n;
+          nan_here = !(dist == dist);
+        }
+      }
+      const bool any_nan = __any_sync(FULL, nan_here);
+      float best = nan_here ? __int_as_float(0x7f800000) : dist;
+      best = fminf(best, __shfl_xor_sync(FULL, best, 16));
+      best = fminf(best, __shfl_xor_sync(FULL, best, 8));
+      best = fminf(best, __shfl_xor_sync(FULL, best, 4));
+      if (lane == 0 && ent_w) {
+        float out = best;
+        if (amb_cur || any_nan || (ax.flags & 1u) || q_flag) out = -1.0f;
+        else if (out < 0.f) out = 0.f;  // tiny negative from rounding: keep it a valid "certain" value
+        p.d32[e_w] = out;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot_w]);  // this warp is done with group k-1's slot
+    }
+    // ---- alignment result of group k (becomes a_cur of the next iteration): acc[d] = corr(base + d) ----
+    if (has_al) {
+      float b1 = -__int_as_float(0x7f800000), b2 = b1;  // best / runner-up correlation
+      int s1 = 0x7fffffff;
+      if (align_lane && ent_a) {
+#pragma unroll
+        for (int d = 0; d < W; ++d) {
+          const int s = base + d;
+          if (s < S) {
+            const float c = acc[d];
+            if (c > b1 || (c == b1 && s < s1)) {
+              b2 = b1;
+              b1 = c;
+              s1 = s;
+            } else if (c > b2) {
+              b2 = c;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob1 = __shfl_xor_sync(FULL, b1, o), ob2 = __shfl_xor_sync(FULL, b2, o);
+        const int os1 = __shfl_xor_sync(FULL, s1, o);
+        if (ob1 > b1 || (ob1 == b1 && os1 < s1)) {
+          b2 = fmaxf(b1, ob2);
+          b1 = ob1;
+          s1 = os1;
+        } else {
+          b2 = fmaxf(b2, ob1);
+        }
+      }
+      const float vn = ent_a ? stages[slot_a].aux[warp].vnorm : 0.f;
+      a_cur = (s1 == 0x7fffffff) ? 0 : s1;
+      // ambiguous: runner-up within the FP32 error bound of the best, or anything non-finite
+      amb_cur = !((b1 - b2) > EXH_ALIGN_MARGIN * v1norm * vn) || !(b1 == b1);
+    }
+  }
+}
+
+// ---- rescoring side -----------------------------------------------------------------------------------
+// smallest certain d32 (non-negative floats order like their bit patterns)
+__global__ void k_exh_min(const float* d32, unsigned long long n, unsigned* min_bits) {
+  unsigned m = 0x7f800000u;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float v = d32[i];
+    if (v >= 0.f) m = min(m, __float_as_uint(v));
+  }
+  m = __reduce_min_sync(FULL, m);
+  if ((threadIdx.x & 31) == 0 && m != 0x7f800000u) atomicMin(min_bits, m);
+}
+
+// candidates = flagged entries + entries within 2*EXH_EPS of the smallest certain value -> key list (global index)
+__global__ void k_exh_compact(const float* d32, unsigned long long n, const unsigned* min_bits, int rank, int G,
+                              unsigned long long* keys, unsigned* count, unsigned cap) {
+  const float thr = __uint_as_float(*min_bits) + 2.0f * EXH_EPS;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float v = d32[i];
+    if (v < 0.f || (v <= thr && v < __int_as_float(0x7f800000))) {
+      const unsigned slot = atomicAdd(count, 1u);
+      if (slot < cap) keys[slot] = i * (unsigned long long)G + rank;
+    }
+  }
+}
+
+// strict minimum in index order over the rescored candidates (SC.cpp:296-311 over every entry)
+__global__ void __launch_bounds__(256) k_exh_final(const double* pair_dist, const int* pair_shift, const unsigned long long* keys,
+                                                   const unsigned* count, unsigned cap, Best* out) {
+  __shared__ Best s_best[256];
+  Best b;
+  b.dist = 10000000.0;
+  b.rank = 0;
+  b.shift = 0;
+  b.idx = -1;
+  const unsigned n = min(*count, cap);
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = pair_dist[i];
+    const long long idx = (long long)keys[i];
+    if (pair_shift[i] >= 0 && d < 10000000.0 && (d < b.dist || (d == b.dist && (b.idx < 0 || idx < b.idx)))) {
+      b.dist = d;
+      b.shift = pair_shift[i];
+      b.idx = idx;
+    }
+  }
+  s_best[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const Best x = s_best[threadIdx.x + o];
+      Best& y = s_best[threadIdx.x];
+      if (x.idx >= 0 && (y.idx < 0 || x.dist < y.dist || (x.dist == y.dist && x.idx < y.idx))) y = x;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    Best r = s_best[0];
+    r.rank = (int)min(*count, 0x7fffffffu);  // number of rescored candidates (overflow check on the host)
+    if (r.idx < 0) {
+      r.idx = 0;
+      r.shift = 0;
+      r.dist = 10000000.0;
+    }
+    *out = r;
+  }
+}
+
+}  // namespace scgpu

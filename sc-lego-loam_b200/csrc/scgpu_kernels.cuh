@@ -838,6 +838,7 @@ struct ScoreParams {
   double* pair_dist;  // [nq][K]
   int* pair_shift;    // [nq][K]; -1 = candidate not owned by this shard
   int flip;           // score the candidate with its columns reversed (composed "reverse loop" search)
+  const unsigned* active;  // optional: only slots k < *active are scored (fixed-size grid over a device-side count)
 };
 
 __global__ void __launch_bounds__(128) k_score(const ScoreParams p) {
@@ -845,6 +846,7 @@ __global__ void __launch_bounds__(128) k_score(const ScoreParams p) {
   const int k = blockIdx.x, q = blockIdx.y;
   const int R = p.L.R, S = p.L.S, W = 2 * p.radius + 1;
   const size_t o = (size_t)q * p.K + k;
+  if (p.active && (unsigned)k >= *p.active) return;
   if (p.n_search[q] == 0) {
     if (threadIdx.x == 0) {
       p.pair_dist[o] = 10000000.0;

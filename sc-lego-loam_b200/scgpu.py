@@ -14,6 +14,7 @@ from . import build as _build
 OK = 0
 FLAG_FRESH_TREE = 1
 FLAG_EXACT_BINNING = 2
+FLAG_NO_SCREENING = 4
 
 
 class ScgpuError(RuntimeError):
@@ -55,6 +56,8 @@ _SIGNATURES = {
     "scgpu_get_entry": [_vp, _u64, _vp, _vp, _vp],
     "scgpu_truncate": [_vp, _u64],
     "scgpu_exhaustive": [_vp, _u64, _u64, _i, _pd, _pi, C.POINTER(C.c_int64), _pi],
+    "scgpu_exhaustive_stats": [_vp, C.POINTER(_u64)],
+    "scgpu_stage_exhaustive": [_vp, _vp, _u64, _vp, _vp],
     "scgpu_save": [_vp, C.c_char_p],
     "scgpu_load": [_vp, C.c_char_p],
     "scgpu_record_bytes": [_vp, C.POINTER(_sz)],
@@ -283,6 +286,11 @@ class SCManager:
         _check(self.lib.scgpu_exhaustive(self.h, q, n_search, int(flipped), C.byref(d), C.byref(s), C.byref(i),
                                          C.byref(f)))
         return d.value, s.value, i.value, f.value
+
+    def exhaustive_rescored(self):
+        n = _u64()
+        _check(self.lib.scgpu_exhaustive_stats(self.h, C.byref(n)))
+        return n.value
 
     def save(self, path):
         _check(self.lib.scgpu_save(self.h, os.fsencode(path)))

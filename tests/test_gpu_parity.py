@@ -316,6 +316,44 @@ def test_exhaustive_matches_port(variant, flipped):
         assert m.exhaustive(300, 200, True)[2:] == (7, 1)
 
 
+def test_exhaustive_screening_equals_exact_and_port_at_scale():
+    """20x60 exhaustive search goes through the TMA-fed FP32 screening kernel + FP64 rescoring of the survivors.
+    20,000 entries with planted traps: exact duplicates of the winner (index tie-break), a rotated copy, entries
+    with all-zero and partially zero columns, near-duplicates within 1e-6 of the winner.  The winner must equal
+    (a) the same library with screening disabled (every entry scored in FP64) and (b) the oracle port."""
+    from sc_lego_loam_b200 import scgpu
+    from sc_lego_loam_b200.synth import ScanGen
+    p = orc.Params()
+    gen = ScanGen("hdl64", seed=77, n_places=6000)
+    n = 20000
+    descs = gen.descs(0, n)
+    S, R = p.S, p.R
+    q = n - 1
+    base = descs[q].reshape(S, R)
+    descs[4321] = np.roll(base, 11, axis=0).ravel()                       # rotated copy of the query
+    descs[9000] = descs[4321]                                             # exact duplicate: lower index must win
+    near = np.roll(base, 5, axis=0).copy(); near[3, 4] += np.float32(1e-3); descs[150] = near.ravel()
+    descs[17] = 0                                                          # all-zero entry (NaN distance)
+    z = descs[18].reshape(S, R).copy(); z[::2] = 0; descs[18] = z.ravel()  # half the columns empty
+    fast, exact, port = mgr(p, capacity_hint=n), mgr(p, capacity_hint=n, flags=scgpu.FLAG_NO_SCREENING), orc.Port(p)
+    fast.append_descs(descs)
+    exact.append_descs(descs)
+    for ns in (n - 50, 9000, 4321, 150, 19):
+        f, e = fast.exhaustive(q, ns), exact.exhaustive(q, ns)
+        assert f[1:] == e[1:], (ns, f, e)
+        assert f[0] == e[0]
+        assert fast.exhaustive_rescored() < 200 and exact.exhaustive_rescored() == ns
+    for d in descs[:9100]:
+        port.append_desc(d.astype(np.float64))
+    want = port.exhaustive(descs[q].astype(np.float64), 9100)
+    got = fast.exhaustive(q, 9100)
+    assert got[1:3] == want[1:3] and close(got[0], want[0]) and got[2] == 4321
+    # other queries, including the all-zero one
+    for qq in (17, 18, 150, 12345):
+        f, e = fast.exhaustive(qq, n - 50), exact.exhaustive(qq, n - 50)
+        assert f == e, (qq, f, e)
+
+
 def test_save_load_roundtrip(tmp_path):
     from sc_lego_loam_b200.synth import ScanGen
     p = orc.Params()
