@@ -33,8 +33,9 @@ namespace scgpu {
 
 constexpr float EXH_EPS = 1.0e-5f;         // |d32 - d| bound used for candidate selection (observed: < 2e-6)
 constexpr float EXH_ALIGN_MARGIN = 1.6e-5f;  // relative (to |v1||v2|) gap below which the alignment is ambiguous
-constexpr int EXH_STAGES = 4;               // window(k-1) | alignment(k) | in flight(k+1, k+2)
-constexpr int EXH_WARPS = 10;              // consumer warps per block = entries per stage
+constexpr int EXH_SC_STAGES = 3;            // descriptor ring: window(k-1) | landed/loading(k) | loading(k+1)
+constexpr int EXH_VK_STAGES = 4;            // sector-key/aux ring: window(k-1) | alignment(k) | loading(k+1, k+2)
+constexpr int EXH_WARPS = 14;              // consumer warps per block = entries per group
 
 // ---- hand-written PTX wrappers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP) -------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -153,17 +154,22 @@ struct ExhScreenParams {
   float* d32;                  // [n_local] out: approx distance; -1 = must be rescored; +inf = can never win
 };
 
-// shared memory ring: per stage, EXH_WARPS entries
+// shared memory rings: one slot holds a group of EXH_WARPS entries.  The descriptor of group g is needed one
+// iteration later than its sector key, so the two live in rings of different depth (more warps fit).
 template <int R, int S>
-struct ExhStage {
+struct ExhScSlot {
   float sc_hat[EXH_WARPS][R * S];
+};
+template <int S>
+struct ExhVkSlot {
   float vkey[EXH_WARPS][S];
   ExhAux aux[EXH_WARPS];
 };
 
 template <int R, int S, int RAD>
 constexpr size_t exh_smem_bytes() {
-  return sizeof(ExhStage<R, S>) * EXH_STAGES + 2 * EXH_STAGES * sizeof(uint64_t) + (size_t)(R + 1) * (((2 * S + 2 * RAD + 1) | 1)) * sizeof(float);
+  return sizeof(ExhScSlot<R, S>) * EXH_SC_STAGES + sizeof(ExhVkSlot<S>) * EXH_VK_STAGES +
+         2 * (EXH_SC_STAGES + EXH_VK_STAGES) * sizeof(uint64_t) + (size_t)(R + 1) * (((2 * S + 2 * RAD + 1) | 1)) * sizeof(float);
 }
 
 template <int R, int S, int RAD>
@@ -174,20 +180,26 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
   static_assert(R + ALIGN_LANES <= 32, "rows + alignment lanes must fit one warp");
   static_assert(S <= 64 && S % 4 == 0, "valid-column masks are 64 bits; rows are read with 16-byte loads");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using Stage = ExhStage<R, S>;
-  Stage* stages = reinterpret_cast<Stage*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + sizeof(Stage) * EXH_STAGES);
-  uint64_t* empty = full + EXH_STAGES;
-  float* qtable = reinterpret_cast<float*>(empty + EXH_STAGES);  // [(R+1)][PITCH]: rows 0..R-1 = A^ rows, row R = v1, each doubled
+  ExhScSlot<R, S>* sc_ring = reinterpret_cast<ExhScSlot<R, S>*>(smem_raw);
+  ExhVkSlot<S>* vk_ring = reinterpret_cast<ExhVkSlot<S>*>(smem_raw + sizeof(ExhScSlot<R, S>) * EXH_SC_STAGES);
+  uint64_t* full_sc = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(vk_ring) + sizeof(ExhVkSlot<S>) * EXH_VK_STAGES);
+  uint64_t* empty_sc = full_sc + EXH_SC_STAGES;
+  uint64_t* full_vk = empty_sc + EXH_SC_STAGES;
+  uint64_t* empty_vk = full_vk + EXH_VK_STAGES;
+  float* qtable = reinterpret_cast<float*>(empty_vk + EXH_VK_STAGES);  // [(R+1)][PITCH]: rows 0..R-1 = A^ rows, row R = v1, each doubled
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const unsigned long long n_groups = (p.n_local + EXH_WARPS - 1) / EXH_WARPS;  // groups of EXH_WARPS entries
   const unsigned long long my_groups = n_groups > blockIdx.x ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < EXH_STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], EXH_WARPS);
+    for (int s = 0; s < EXH_SC_STAGES; ++s) {
+      mbar_init(&full_sc[s], 1);
+      mbar_init(&empty_sc[s], EXH_WARPS);
+    }
+    for (int s = 0; s < EXH_VK_STAGES; ++s) {
+      mbar_init(&full_vk[s], 1);
+      mbar_init(&empty_vk[s], EXH_WARPS);
     }
     fence_barrier_init();
   }
@@ -198,18 +210,20 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
   __syncthreads();
 
   if (warp == EXH_WARPS) {
-    // ===== producer: one lane feeds the ring with TMA bulk copies =====
+    // ===== producer: one lane feeds both rings with TMA bulk copies =====
     if (lane == 0) {
       for (unsigned long long k = 0; k < my_groups; ++k) {
-        const int slot = (int)(k % EXH_STAGES);
-        if (k >= EXH_STAGES) mbar_wait(&empty[slot], (uint32_t)(((k / EXH_STAGES) - 1) & 1));
         const unsigned long long e0 = (blockIdx.x + k * gridDim.x) * EXH_WARPS;
         const unsigned n = (unsigned)(p.n_local - e0 < EXH_WARPS ? p.n_local - e0 : EXH_WARPS);
         const unsigned b_sc = n * R * S * 4u, b_vk = n * S * 4u, b_aux = n * (unsigned)sizeof(ExhAux);
-        mbar_arrive_expect_tx(&full[slot], b_sc + b_vk + b_aux);
-        tma_bulk_g2s(&stages[slot].sc_hat[0][0], p.db.sc_hat + e0 * R * S, b_sc, &full[slot]);
-        tma_bulk_g2s(&stages[slot].vkey[0][0], p.db.vkey32 + e0 * S, b_vk, &full[slot]);
-        tma_bulk_g2s(&stages[slot].aux[0], p.db.aux + e0, b_aux, &full[slot]);
+        const int sv = (int)(k % EXH_VK_STAGES), ss = (int)(k % EXH_SC_STAGES);
+        if (k >= EXH_VK_STAGES) mbar_wait(&empty_vk[sv], (uint32_t)(((k / EXH_VK_STAGES) - 1) & 1));
+        mbar_arrive_expect_tx(&full_vk[sv], b_vk + b_aux);
+        tma_bulk_g2s(&vk_ring[sv].vkey[0][0], p.db.vkey32 + e0 * S, b_vk, &full_vk[sv]);
+        tma_bulk_g2s(&vk_ring[sv].aux[0], p.db.aux + e0, b_aux, &full_vk[sv]);
+        if (k >= EXH_SC_STAGES) mbar_wait(&empty_sc[ss], (uint32_t)(((k / EXH_SC_STAGES) - 1) & 1));
+        mbar_arrive_expect_tx(&full_sc[ss], b_sc);
+        tma_bulk_g2s(&sc_ring[ss].sc_hat[0][0], p.db.sc_hat + e0 * R * S, b_sc, &full_sc[ss]);
       }
     }
     return;
@@ -228,25 +242,27 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
   for (unsigned long long k = 0; k <= my_groups; ++k) {
     // iteration k: window of group k-1 (row lanes) + alignment of group k (alignment lanes)
     const bool has_win = k >= 1, has_al = k < my_groups;
-    const int slot_w = (int)((k + EXH_STAGES - 1) % EXH_STAGES), slot_a = (int)(k % EXH_STAGES);
+    const int vk_w = (int)((k + EXH_VK_STAGES - 1) % EXH_VK_STAGES), vk_a = (int)(k % EXH_VK_STAGES);
+    const int sc_w = (int)((k + EXH_SC_STAGES - 1) % EXH_SC_STAGES);
     bool ent_w = false, ent_a = false;
     unsigned long long e_w = 0;
     if (has_win) {
       e_w = (blockIdx.x + (k - 1) * gridDim.x) * EXH_WARPS + warp;
       ent_w = e_w < p.n_local;
+      mbar_wait(&full_sc[sc_w], (uint32_t)(((k - 1) / EXH_SC_STAGES) & 1));
     }
     if (has_al) {
-      mbar_wait(&full[slot_a], (uint32_t)((k / EXH_STAGES) & 1));
+      mbar_wait(&full_vk[vk_a], (uint32_t)((k / EXH_VK_STAGES) & 1));
       ent_a = (blockIdx.x + k * gridDim.x) * EXH_WARPS + warp < p.n_local;
     }
     // held[p]: the candidate's row (row lanes) / sector key (alignment lanes); base: first shift of this lane
     const float4* held4 = nullptr;
     int base = 0;
     if (row_lane && ent_w) {
-      held4 = reinterpret_cast<const float4*>(&stages[slot_w].sc_hat[warp][lane * S]);
+      held4 = reinterpret_cast<const float4*>(&sc_ring[sc_w].sc_hat[warp][lane * S]);
       base = ((a_cur - RAD) % S + S) % S;
     } else if (align_lane && ent_a) {
-      held4 = reinterpret_cast<const float4*>(&stages[slot_a].vkey[warp][0]);
+      held4 = reinterpret_cast<const float4*>(&vk_ring[vk_a].vkey[warp][0]);
       base = (lane - R) * W;
     }
     float acc[W];
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
       r1 += __shfl_xor_sync(FULL, r1, 1);
       const int d_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
       // every lane: distance of "its" shift; acc index d belongs to shift a_cur - RAD + d
-      const ExhAux ax = stages[slot_w].aux[ent_w ? warp : 0];
+      const ExhAux ax = vk_ring[vk_w].aux[ent_w ? warp : 0];
       float dist = __int_as_float(0x7f800000);  // +inf: no valid column pair at this shift -> the reference yields NaN there
       bool nan_here = false;
       if (d_mine < W) {
@@ -329,7 +345,10 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
         p.d32[e_w] = out;
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[slot_w]);  // this warp is done with group k-1's slot
+      if (lane == 0) {  // this warp is done with group k-1's slots
+        mbar_arrive(&empty_sc[sc_w]);
+        mbar_arrive(&empty_vk[vk_w]);
+      }
     }
     // ---- alignment result of group k (becomes a_cur of the next iteration): acc[d] = corr(base + d) ----
     if (has_al) {
@@ -363,7 +382,7 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
           b2 = fmaxf(b2, ob1);
         }
       }
-      const float vn = ent_a ? stages[slot_a].aux[warp].vnorm : 0.f;
+      const float vn = ent_a ? vk_ring[vk_a].aux[warp].vnorm : 0.f;
       a_cur = (s1 == 0x7fffffff) ? 0 : s1;
       // ambiguous: runner-up within the FP32 error bound of the best, or anything non-finite
       amb_cur = !((b1 - b2) > EXH_ALIGN_MARGIN * v1norm * vn) || !(b1 == b1);
