@@ -140,6 +140,10 @@ int scgpu_truncate(scgpu_handle* h, uint64_t n);
  * its columns reversed (forward first).  Outputs are for the global winner. */
 int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped, double* best_dist,
                      int* best_shift, int64_t* best_idx, int* best_flip);
+/* nq exhaustive searches (query entry q[i] against entries [0, n_search[i])) enqueued back to back on the device
+ * with one host synchronisation at the end; results as scgpu_exhaustive (forward search). */
+int scgpu_exhaustive_batched(scgpu_handle* h, const uint64_t* q, const uint64_t* n_search, size_t nq, double* best_dist,
+                             int* best_shift, int64_t* best_idx);
 /* How many entries the last scgpu_exhaustive had to rescore with the exact FP64 kernel (the rest was ruled out
  * by the FP32 screening pass with a proven margin). */
 int scgpu_exhaustive_stats(scgpu_handle* h, uint64_t* rescored);

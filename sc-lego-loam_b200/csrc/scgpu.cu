@@ -548,14 +548,15 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrec, uint64_
   RET(h->x_keys.reserve(EXH_CAND_CAP * sizeof(uint64_t)));
   RET(h->x_pd.reserve(EXH_CAND_CAP * sizeof(double)));
   RET(h->x_ps.reserve(EXH_CAND_CAP * sizeof(int)));
-  RET(h->x_small.reserve(64));
+  if (!h->x_small.p) {
+    RET(h->x_small.reserve(64));
+    CK(cudaMemsetAsync(h->x_small.p, 0xff, 64, st));  // includes the constant non-zero "n_search" cell k_score reads
+  }
   unsigned* d_min = h->x_small.as<unsigned>();
   unsigned* d_count = d_min + 1;
   unsigned long long* d_one = reinterpret_cast<unsigned long long*>(d_min + 2);  // "n_search" != 0 for k_score
-  k_exh_prep<<<1, 128, 0, st>>>(d_qrec, h->L, h->x_query.as<ExhQuery>());
-  k_exh_init<<<1, 1, 0, st>>>(d_min, d_count);
-  CK(cudaMemsetAsync(d_one, 0xff, 8, st));
-  h->launches += 2;
+  k_exh_prep<<<1, 256, 0, st>>>(d_qrec, h->L, h->x_query.as<ExhQuery>(), d_min, d_count);
+  h->launches += 1;
   if (n_local) {
     ExhScreenParams sp;
     sp.db.sc_hat = h->x_sc_hat;
@@ -564,6 +565,7 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrec, uint64_
     sp.q = h->x_query.as<ExhQuery>();
     sp.n_local = n_local;
     sp.d32 = h->x_d32.as<float>();
+    sp.min_bits = d_min;
     const uint64_t groups = (n_local + EXH_WARPS - 1) / EXH_WARPS;
     const unsigned grid = (unsigned)(groups < (uint64_t)h->sm_count ? groups : (uint64_t)h->sm_count);
     const size_t smem = exh_smem_bytes<20, 60, 3>();
@@ -572,7 +574,6 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrec, uint64_
     if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
     CK(cudaGetLastError());
     const unsigned rb = (unsigned)((n_local + 1023) / 1024 < 592 ? (n_local + 1023) / 1024 : 592);
-    k_exh_min<<<rb, 256, 0, st>>>(sp.d32, n_local, d_min);
     k_exh_compact<<<rb, 256, 0, st>>>(sp.d32, n_local, d_min, h->db.rank, h->db.G, h->x_keys.as<unsigned long long>(), d_count, EXH_CAND_CAP);
     ScoreParams p;
     p.qrecords = d_qrec;
@@ -586,8 +587,8 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrec, uint64_
     p.pair_shift = h->x_ps.as<int>();
     p.flip = 0;
     p.active = d_count;
-    k_score<<<dim3(EXH_CAND_CAP, 1), 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p);
-    h->launches += 4;
+    k_score<<<dim3((unsigned)h->sm_count * 4, 1), 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p);
+    h->launches += 3;
     CK(cudaGetLastError());
   }
   k_exh_final<<<1, 256, 0, st>>>(h->x_pd.as<double>(), h->x_ps.as<int>(), h->x_keys.as<unsigned long long>(), d_count, EXH_CAND_CAP, d_best_out);
@@ -1069,6 +1070,47 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
         if (best_flip) *best_flip = f;
       }
     }
+  return SCGPU_OK;
+}
+
+int scgpu_exhaustive_batched(scgpu_handle* h, const uint64_t* q, const uint64_t* n_search, size_t nq, double* best_dist, int* best_shift,
+                             int64_t* best_idx) {
+  if (!h || ((!q || !n_search || !best_dist || !best_shift || !best_idx) && nq)) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "scgpu_exhaustive_batched is single-shard; use the staged API for shards");
+  for (size_t i = 0; i < nq; ++i)
+    if (q[i] >= h->n_global || n_search[i] > h->n_global) return fail(SCGPU_E_INVALID, "range outside the database");
+  if (nq == 0) return SCGPU_OK;
+  if (!h->exh) {
+    for (size_t i = 0; i < nq; ++i) RET(scgpu_exhaustive(h, q[i], n_search[i], 0, best_dist + i, best_shift + i, best_idx + i, nullptr));
+    return SCGPU_OK;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  RET(h->records.reserve(nq * h->L.rec_bytes));
+  RET(h->x_best.reserve(nq * sizeof(Best)));
+  CK(cudaEventRecord(h->ev_t0, st));
+  CK(cudaEventRecord(h->ev_t1, st));
+  for (size_t i = 0; i < nq; ++i) {
+    unsigned char* rec = h->records.as<unsigned char>() + i * h->L.rec_bytes;
+    k_gather<<<1, 128, 0, st>>>(rec, h->L, h->db, q[i]);
+    h->launches++;
+    RET(launch_exhaustive_fast(h, rec, n_search[i], h->x_best.as<Best>() + i, st, nullptr, nullptr));
+  }
+  CK(cudaEventRecord(h->ev_t2, st));
+  h->timing_valid = true;
+  std::vector<Best> b(nq);
+  CK(cudaMemcpyAsync(b.data(), h->x_best.p, nq * sizeof(Best), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < nq; ++i) {
+    if (n_search[i] == 0 || (unsigned)b[i].rank > EXH_CAND_CAP) {
+      RET(scgpu_exhaustive(h, q[i], n_search[i], 0, best_dist + i, best_shift + i, best_idx + i, nullptr));
+      continue;
+    }
+    best_dist[i] = b[i].dist;
+    best_shift[i] = b[i].shift;
+    best_idx[i] = b[i].idx;
+    h->last_exh_rescored = (unsigned)b[i].rank;
+  }
   return SCGPU_OK;
 }
 

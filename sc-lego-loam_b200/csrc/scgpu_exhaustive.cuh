@@ -5,7 +5,7 @@
 //   screen  (k_exh_screen, this file): an FP32 pass that streams the database once from HBM through a TMA-fed
 //           shared-memory ring and produces, per entry, an approximation d32 of distanceBtnScanContext
 //           (SC.cpp:116-148) with |d32 - d| <= EXH_EPS -- or a flag saying "cannot tell" (-1).
-//   rescore (k_exh_min / k_exh_compact / k_score / k_exh_final): the entries that can still be the argmin
+//   rescore (k_exh_compact / k_score / k_exh_final): the entries that can still be the argmin
 //           (d32 <= min d32 + 2*EXH_EPS, plus every flagged entry) go through the bit-exact FP64 pair kernel; the
 //           winner is the strict minimum in index order, exactly the loop of SC.cpp:296-311 over all entries.
 //
@@ -53,14 +53,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!done);
+  // try_wait with a suspend-time hint: the warp sleeps in hardware instead of burning issue slots in a poll loop
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "SCGPU_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra SCGPU_DONE;\n\t"
+      "bra SCGPU_WAIT;\n\t"
+      "SCGPU_DONE:\n\t"
+      "}"
+      :
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -80,11 +85,6 @@ struct ExhDb {
   const float* vkey32;   // [cap][S]
   const ExhAux* aux;     // [cap]
 };
-
-__global__ void k_exh_init(unsigned* min_bits, unsigned* count) {
-  *min_bits = 0x7f800000u;
-  *count = 0;
-}
 
 // query pack built by k_exh_prep: normalised query, float sector key, valid-column mask, |v1|
 struct ExhQuery {
@@ -111,10 +111,15 @@ __device__ __forceinline__ void exh_normalise(const unsigned char* rec, const La
     s_v2 = 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < L.RS; i += blockDim.x) {  // ROW-major output: element (r, c) at r*S + c
-    const int c = i / L.R, r = i - c * L.R;
+  __shared__ float s_inv[1024];
+  for (int c = threadIdx.x; c < L.S; c += blockDim.x) {
     const double n = norm[c];
-    sc_hat[r * L.S + c] = (n == 0.0) ? 0.f : (float)((double)sc[i] / n);
+    s_inv[c] = (n == 0.0) ? 0.f : (float)(1.0 / n);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < L.RS; i += blockDim.x) {  // ROW-major output: element (r, c) at r*S + c
+    const int r = i / L.S, c = i - r * L.S;
+    sc_hat[i] = sc[c * L.R + r] * s_inv[c];
   }
   for (int c = threadIdx.x; c < L.S; c += blockDim.x) {
     const double n = norm[c];
@@ -143,7 +148,12 @@ __global__ void __launch_bounds__(128) k_exh_append(const unsigned char* records
   exh_normalise(records + (size_t)blockIdx.x * L.rec_bytes, L, sc_hat + l * L.RS, vkey32 + l * L.S, &aux[l].vmask, &aux[l].vnorm, &aux[l].flags);
 }
 
-__global__ void __launch_bounds__(128) k_exh_prep(const unsigned char* qrec, Layout L, ExhQuery* q) {
+// query pack + reset of the per-query reduction cells (one launch instead of three)
+__global__ void __launch_bounds__(256) k_exh_prep(const unsigned char* qrec, Layout L, ExhQuery* q, unsigned* min_bits, unsigned* count) {
+  if (threadIdx.x == 0) {
+    *min_bits = 0x7f800000u;
+    *count = 0;
+  }
   exh_normalise(qrec, L, q->qhat, q->v1, &q->qmask, &q->v1norm, &q->flags);
 }
 
@@ -152,6 +162,7 @@ struct ExhScreenParams {
   const ExhQuery* q;
   unsigned long long n_local;  // local entries to score: [0, n_local)
   float* d32;                  // [n_local] out: approx distance; -1 = must be rescored; +inf = can never win
+  unsigned* min_bits;          // out: bit pattern of the smallest certain d32 (atomicMin; pre-set to +inf)
 };
 
 // shared memory rings: one slot holds a group of EXH_WARPS entries.  The descriptor of group g is needed one
@@ -239,6 +250,7 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
 
   int a_cur = 0;          // alignment of the entry whose window is scored in this iteration
   bool amb_cur = false;
+  unsigned my_min = 0x7f800000u;  // lane 0: smallest certain distance this warp has seen
   for (unsigned long long k = 0; k <= my_groups; ++k) {
     // iteration k: window of group k-1 (row lanes) + alignment of group k (alignment lanes)
     const bool has_win = k >= 1, has_al = k < my_groups;
@@ -343,6 +355,7 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
         if (amb_cur || any_nan || (ax.flags & 1u) || q_flag) out = -1.0f;
         else if (out < 0.f) out = 0.f;  // tiny negative from rounding: keep it a valid "certain" value
         p.d32[e_w] = out;
+        if (out >= 0.f) my_min = min(my_min, __float_as_uint(out));
       }
       __syncwarp();
       if (lane == 0) {  // this warp is done with group k-1's slots
@@ -388,20 +401,10 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
       amb_cur = !((b1 - b2) > EXH_ALIGN_MARGIN * v1norm * vn) || !(b1 == b1);
     }
   }
+  if (lane == 0 && my_min != 0x7f800000u) atomicMin(p.min_bits, my_min);
 }
 
 // ---- rescoring side -----------------------------------------------------------------------------------
-// smallest certain d32 (non-negative floats order like their bit patterns)
-__global__ void k_exh_min(const float* d32, unsigned long long n, unsigned* min_bits) {
-  unsigned m = 0x7f800000u;
-  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-    const float v = d32[i];
-    if (v >= 0.f) m = min(m, __float_as_uint(v));
-  }
-  m = __reduce_min_sync(FULL, m);
-  if ((threadIdx.x & 31) == 0 && m != 0x7f800000u) atomicMin(min_bits, m);
-}
-
 // candidates = flagged entries + entries within 2*EXH_EPS of the smallest certain value -> key list (global index)
 __global__ void k_exh_compact(const float* d32, unsigned long long n, const unsigned* min_bits, int rank, int G,
                               unsigned long long* keys, unsigned* count, unsigned cap) {

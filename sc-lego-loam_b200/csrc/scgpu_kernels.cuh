@@ -841,12 +841,9 @@ struct ScoreParams {
   const unsigned* active;  // optional: only slots k < *active are scored (fixed-size grid over a device-side count)
 };
 
-__global__ void __launch_bounds__(128) k_score(const ScoreParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int k = blockIdx.x, q = blockIdx.y;
+__device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, const int q, unsigned char* smem_raw) {
   const int R = p.L.R, S = p.L.S, W = 2 * p.radius + 1;
   const size_t o = (size_t)q * p.K + k;
-  if (p.active && (unsigned)k >= *p.active) return;
   if (p.n_search[q] == 0) {
     if (threadIdx.x == 0) {
       p.pair_dist[o] = 10000000.0;
@@ -895,6 +892,21 @@ __global__ void __launch_bounds__(128) k_score(const ScoreParams p) {
     p.pair_dist[o] = d;
     p.pair_shift[o] = s;
   }
+}
+
+// grid (K, nq): block (k, q) scores candidate slot k of query q.  With p.active set (exhaustive rescoring: one query,
+// a device-side candidate count) the grid is persistent and the blocks stride over the list.
+__global__ void __launch_bounds__(128) k_score(const ScoreParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (p.active) {
+    const unsigned n = min(*p.active, (unsigned)p.K);
+    for (unsigned k = blockIdx.x; k < n; k += gridDim.x) {
+      score_pair(p, (int)k, 0, smem_raw);
+      __syncthreads();
+    }
+    return;
+  }
+  score_pair(p, blockIdx.x, blockIdx.y, smem_raw);
 }
 
 // The public pairwise functions on caller-provided double matrices (SC.h:64-69).

@@ -56,6 +56,7 @@ _SIGNATURES = {
     "scgpu_get_entry": [_vp, _u64, _vp, _vp, _vp],
     "scgpu_truncate": [_vp, _u64],
     "scgpu_exhaustive": [_vp, _u64, _u64, _i, _pd, _pi, C.POINTER(C.c_int64), _pi],
+    "scgpu_exhaustive_batched": [_vp, _vp, _vp, _sz, _vp, _vp, _vp],
     "scgpu_exhaustive_stats": [_vp, C.POINTER(_u64)],
     "scgpu_stage_exhaustive": [_vp, _vp, _u64, _vp, _vp],
     "scgpu_save": [_vp, C.c_char_p],
@@ -286,6 +287,14 @@ class SCManager:
         _check(self.lib.scgpu_exhaustive(self.h, q, n_search, int(flipped), C.byref(d), C.byref(s), C.byref(i),
                                          C.byref(f)))
         return d.value, s.value, i.value, f.value
+
+    def exhaustive_batched(self, queries, n_search):
+        q = np.ascontiguousarray(queries, np.uint64)
+        ns = np.ascontiguousarray(np.broadcast_to(np.asarray(n_search, np.uint64), q.shape))
+        d, s, i = np.empty(q.size, np.float64), np.empty(q.size, np.int32), np.empty(q.size, np.int64)
+        _check(self.lib.scgpu_exhaustive_batched(self.h, q.ctypes.data, ns.ctypes.data, q.size, d.ctypes.data, s.ctypes.data,
+                                                 i.ctypes.data))
+        return d, s, i
 
     def exhaustive_rescored(self):
         n = _u64()

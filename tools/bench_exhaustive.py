@@ -25,6 +25,11 @@ def main():
     R, S = 20, 60
     gen = ScanGen("hdl64", seed=20181004, n_places=70000)
     descs = gen.descs(0, a.n, R, S)
+    peak = 6523.3
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
     m = SCManager(capacity_hint=a.n + 8)
     m.append_descs(descs)
     qs = [a.n - 1 - 37 * i for i in range(a.queries)]
@@ -39,15 +44,19 @@ def main():
         t_scr.append(scr)
         resc.append(m.exhaustive_rescored())
     wall = time.perf_counter() - t0
-    peak = 6523.3
-    try:
-        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-    except Exception:
-        pass
+    # throughput: all queries enqueued back to back, one synchronisation
+    m.exhaustive_batched(qs, a.n - 50)
+    t0 = time.perf_counter()
+    bd, bs, bi = m.exhaustive_batched(qs, a.n - 50)
+    wall_b = time.perf_counter() - t0
+    ms_batched = m.timing()[0] / len(qs)
+    same = all(res[i][1] == bs[i] and res[i][2] == bi[i] and res[i][0] == bd[i] for i in range(len(qs)))
     ms_scr, ms_tot = float(np.median(t_scr)), float(np.median(t_tot))
     algo = 4 * R * S * (a.n - 50)
     out = {"config": f"exhaustive_{a.n}_20x60", "queries": len(qs), "queries_per_sec_device": 1e3 / ms_tot,
-           "queries_per_sec_wall": len(qs) / wall, "ms_per_query_device": ms_tot, "ms_screen_kernel": ms_scr,
+           "queries_per_sec_wall": len(qs) / wall,
+           "batched": {"queries_per_sec_device": 1e3 / ms_batched, "queries_per_sec_wall": len(qs) / wall_b, "ms_per_query_device": ms_batched,
+                       "frac_of_hbm_roofline_whole_query": 4 * R * S * (a.n - 50) / (ms_batched * 1e-3) / 1e9 / peak, "equal_to_single": bool(same)}, "ms_per_query_device": ms_tot, "ms_screen_kernel": ms_scr,
            "roofline": {"kernel": "k_exh_screen", "bound": "hbm", "achieved": algo / (ms_scr * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": algo / (ms_scr * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": algo,
                         "frac_whole_query": algo / (ms_tot * 1e-3) / 1e9 / peak},
