@@ -179,6 +179,8 @@ int scgpu_stage_merge(scgpu_handle* h, const uint64_t* d_keys_parts, int parts, 
  * {double dist; int32 rank_in_list; int32 shift; int64 global_idx} (24 bytes), dist = +inf when none. */
 int scgpu_stage_score(scgpu_handle* h, const void* d_query_records, size_t n_queries, const uint64_t* d_keys,
                       const uint64_t* d_n_search, void* d_best_out, void* stream);
+/* The packed record of stored entry global_idx (which must live on this shard) -> d_record. */
+int scgpu_stage_gather(scgpu_handle* h, uint64_t global_idx, void* d_record, void* stream);
 /* Exhaustive search of this shard for one query record: {double dist; int32 n_rescored; int32 shift; int64 global_idx}
  * of the shard's strict-min winner (dist = 1e7 when none).  The global winner is the minimum over shards by
  * (dist, global_idx). */

@@ -1307,6 +1307,17 @@ int scgpu_stage_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint
   return launch_best(h, nq, d_keys, static_cast<Best*>(d_best_out), st);
 }
 
+int scgpu_stage_gather(scgpu_handle* h, uint64_t global_idx, void* d_record, void* stream) {
+  if (!h || !d_record) return fail(SCGPU_E_INVALID, "null argument");
+  if (global_idx >= h->n_global) return fail(SCGPU_E_INVALID, "entry out of range");
+  if ((int)(global_idx % (uint64_t)h->cfg.shard_count) != h->cfg.shard_rank) return fail(SCGPU_E_INVALID, "entry lives on another shard");
+  CK(cudaSetDevice(h->cfg.device));
+  k_gather<<<1, 128, 0, ST(stream)>>>(static_cast<unsigned char*>(d_record), h->L, h->db, global_idx / (uint64_t)h->cfg.shard_count);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
+
 int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_qrecord, uint64_t n_search, void* d_best_out, void* stream) {
   if (!h || !d_qrecord || !d_best_out) return fail(SCGPU_E_INVALID, "null argument");
   if (!h->exh) return fail(SCGPU_E_INVALID, "screening kernel is instantiated for 20x60, search radius 3 only");

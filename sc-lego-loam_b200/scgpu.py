@@ -59,6 +59,7 @@ _SIGNATURES = {
     "scgpu_exhaustive_batched": [_vp, _vp, _vp, _sz, _vp, _vp, _vp],
     "scgpu_exhaustive_stats": [_vp, C.POINTER(_u64)],
     "scgpu_stage_exhaustive": [_vp, _vp, _u64, _vp, _vp],
+    "scgpu_stage_gather": [_vp, _u64, _vp, _vp],
     "scgpu_save": [_vp, C.c_char_p],
     "scgpu_load": [_vp, C.c_char_p],
     "scgpu_record_bytes": [_vp, C.POINTER(_sz)],

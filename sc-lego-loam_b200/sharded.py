@@ -45,6 +45,15 @@ class ShardedSearch:
         self.st.prefill(descs)          # ownership (i % G == rank) is applied by the backend
         self.size = self.st.size()
 
+    def exhaustive(self, global_idx, n_search):
+        """Every entry [0, n_search) of every shard scored against stored entry global_idx (BASELINE config 4):
+        the owner broadcasts the query record, each shard searches its part, one all_gather of 24 bytes per rank."""
+        owner = global_idx % self.world
+        rec = self.st.gather(global_idx) if self.rank == owner else torch.empty(self.st.rec_bytes, dtype=torch.uint8, device=self.st.device)
+        if self.world > 1:
+            dist.broadcast(rec, src=owner, group=self.group)
+        return reduce_exhaustive(self._all_gather(self.st.exhaustive(rec, n_search).unsqueeze(0)).reshape(self.world, 3))
+
     def step(self, scans_local):
         """scans_local: this rank's B scans ([B, P, k] float32 on the stage device).  Scan j of rank r becomes
         global entry size + j*G + r.  Returns the detect results of all G*B new entries in global order
@@ -62,6 +71,21 @@ class ShardedSearch:
         keys = self.st.merge(self._all_gather(keys_local))                       # exchange 2
         best_local = self.st.score(rec_global, keys, n_search)                   # [GB, 3] int64
         return self.st.finalize(self._all_gather(best_local), n_search)          # exchange 3
+
+
+def reduce_exhaustive(parts):
+    """parts: [G, 3] int64 views of {f64 dist, (i32 n_rescored, i32 shift), i64 global idx} -> (dist, shift, idx) of the
+    global winner: minimum by (dist, idx) over shards with dist < 1e7 (the strict-min in index order of
+    Scancontext.cpp:296-311 over every entry); (1e7, 0, 0) when no shard has a finite distance."""
+    p = parts.cpu().numpy()
+    best = (1e7, 0, 0)
+    found = False
+    for g in range(p.shape[0]):
+        d = float(p[g, 0:1].view(np.float64)[0])
+        shift, idx = int(p[g, 1] >> 32), int(p[g, 2])
+        if d < 1e7 and (not found or d < best[0] or (d == best[0] and idx < best[2])):
+            best, found = (d, shift, idx), True
+    return best
 
 
 class GpuStages:
@@ -125,6 +149,17 @@ class GpuStages:
         best = torch.empty((nq, 3), dtype=torch.int64, device=self.device)   # {f64 dist, i32 rank, i32 shift, i64 idx}
         self._check(self.lib.scgpu_stage_score(self.h, qrec.data_ptr(), nq, keys.data_ptr(), n_search.data_ptr(),
                                                best.data_ptr(), self._stream()))
+        return best
+
+    def gather(self, global_idx):
+        rec = torch.empty(self.rec_bytes, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.scgpu_stage_gather(self.h, global_idx, rec.data_ptr(), self._stream()))
+        return rec
+
+    def exhaustive(self, qrec, n_search):
+        """This shard's exhaustive winner for one query record: [3] int64 (see reduce_exhaustive)."""
+        best = torch.empty(3, dtype=torch.int64, device=self.device)
+        self._check(self.lib.scgpu_stage_exhaustive(self.h, qrec.data_ptr(), int(n_search), best.data_ptr(), self._stream()))
         return best
 
     def finalize(self, parts, n_search):

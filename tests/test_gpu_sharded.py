@@ -80,6 +80,32 @@ def test_emulated_shards_equal_single_device(G, K):
                     m.get_entry(i)
 
 
+def test_emulated_sharded_exhaustive_equals_single_device():
+    """BASELINE config 4 sharded: each shard screens + rescans its own entries (scgpu_stage_exhaustive), the global
+    winner is the minimum by (distance, index) -- identical to the single-device exhaustive search."""
+    import torch
+    from sc_lego_loam_b200.scgpu import SCManager
+    from sc_lego_loam_b200.sharded import GpuStages, reduce_exhaustive
+    from sc_lego_loam_b200.synth import ScanGen
+    G, n = 4, 6000
+    descs = ScanGen("hdl64", seed=5, n_places=2500).descs(0, n)
+    descs[5000] = np.roll(descs[77].reshape(60, 20), 9, axis=0).ravel()
+    descs[123] = descs[77]                    # duplicate on another shard: the lower index must win
+    single = SCManager(capacity_hint=n)
+    single.append_descs(descs)
+    st = [GpuStages(SCManager(shard_rank=r, shard_count=G, capacity_hint=n), "cuda:0") for r in range(G)]
+    for s_ in st:
+        s_.prefill(descs)
+    for q, ns in ((5000, 4000), (5999, 5949), (300, 250), (5000, 100)):
+        rec = st[q % G].gather(q)
+        parts = torch.stack([s_.exhaustive(rec, ns) for s_ in st])
+        got = reduce_exhaustive(parts)
+        want = single.exhaustive(q, ns)
+        assert got == want[:3], (q, ns, got, want)
+    assert reduce_exhaustive(torch.stack([s_.exhaustive(st[0].gather(5000 - 5000 % G), 4000) for s_ in st]))[2] >= 0
+    assert single.exhaustive(5000, 4000)[2] == 77
+
+
 _WORKER = r'''
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["SCGPU_ROOT"])
@@ -101,10 +127,12 @@ for s in range(steps):
     scans = torch.from_numpy(np.stack([gen.scan(first + j * world + rank, 4) for j in range(B)])).cuda()
     r = search.step(scans)
     outs.append({k: v.cpu().numpy() for k, v in r.items()})
+ex = search.exhaustive(61 + 5, 61)          # sharded exhaustive search, query = a stored keyframe
 if rank == 0:
     single = SCManager(device=0)
     single.append_descs(pre)
     want = single.replay(gen.scans(0, steps * B * world, 4))
+    assert ex == single.exhaustive(61 + 5, 61)[:3], ex
     for k in want:
         got = np.concatenate([o[k] for o in outs])
         assert np.array_equal(got.view(np.uint8), want[k].view(np.uint8)), k
