@@ -2,7 +2,7 @@
 """bench.py -- Scan Context loop-closure hot path on B200: loop queries/s (each = one keyframe through
 makeAndSaveScancontextAndKeys + detectLoopClosureID), next to the reference CPU SCManager.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl scgpu|reference] [--sweep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl scgpu|reference] [--no-sweep]
 
 Workload (BASELINE.json configs[1]): KITTI-00-shaped synthetic run -- 4,541 keyframes, HDL-64 scans (64 x 1875 =
 120,000 points, float4 records), 20x60 descriptor, 10 candidates, exclude-recent 50.  One "step" replays the
@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="scgpu", choices=["scgpu", "reference"])
     ap.add_argument("--batch", type=int, default=DB_SIZE, help="keyframes replayed per step (per GPU); default = the whole run")
-    ap.add_argument("--sweep", action="store_true", help="also time query-only throughput vs database size")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the query-only database-size sweep / exhaustive 100k extras")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -292,20 +292,27 @@ def run_single_gpu(args):
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single(m, scans, res_dev, n0)
-    if args.sweep:
-        line["sweep"] = db_size_sweep(m, torch)
+    if not args.no_sweep:
+        del d_scans, m
+        torch.cuda.empty_cache()
+        line["db_size_sweep"] = db_size_sweep(torch)
     print(json.dumps(line))
 
 
-def db_size_sweep(m, torch):
-    """Query-only throughput (k_topk + k_score + argmin for 256 stored keyframes) vs database size."""
+def db_size_sweep(torch):
+    """BASELINE's "queries/sec vs DB size": (a) the reference's top-10 search (k_topk + k_score + argmin) for 256 stored
+    keyframes against databases of 1k..100k keyframes, and (b) the exhaustive every-entry search at 100k (config 4)."""
+    from sc_lego_loam_b200.scgpu import SCManager
     from sc_lego_loam_b200.synth import ScanGen
     gen = ScanGen("hdl64", seed=SEED + 1, n_places=80000)
-    out = []
-    m.truncate(0)
+    sizes = (1000, 10000, 100000)
+    descs = gen.descs(0, sizes[-1], R, S, threads=min(16, os.cpu_count() or 1))
+    m = SCManager(device=0, capacity_hint=sizes[-1] + 8)
+    peak, _ = measured_peak()
+    out = {"top10": []}
     have = 0
-    for n in (1000, 2000, 5000, 10000, 20000, 50000, 100000):
-        m.append_descs(gen.descs(have, n - have, R, S))
+    for n in sizes:
+        m.append_descs(descs[have:n])
         have = n
         nq = 256
         for _ in range(3):
@@ -315,8 +322,22 @@ def db_size_sweep(m, torch):
             m.query_batched(n - nq, nq)
             ts.append(m.timing()[2])
         ms = float(np.median(ts))
-        out.append({"db": n, "queries_per_sec": nq / (ms * 1e-3), "ms_per_256_queries": ms,
-                    "ringkey_stream_gbs": nq * n * 4 * R / (ms * 1e-3) / 1e9})
+        out["top10"].append({"db": n, "queries_per_sec": nq / (ms * 1e-3), "ms_per_256_queries": ms})
+    n = sizes[-1]
+    qs = [n - 1 - 37 * i for i in range(32)]
+    m.exhaustive_batched(qs, n - 50)
+    m.exhaustive_batched(qs, n - 50)
+    ms = m.timing()[0] / len(qs)
+    single = []
+    for q in qs[:8]:
+        m.exhaustive(q, n - 50)
+        single.append(m.timing()[1])
+    ms_screen = float(np.median(single))
+    algo = 4 * R * S * (n - 50)
+    out["exhaustive_100k"] = {"queries_per_sec": 1e3 / ms, "ms_per_query": ms, "rescored_last": m.exhaustive_rescored(),
+                              "roofline": {"kernel": "k_exh_screen", "bound": "hbm", "achieved": algo / (ms_screen * 1e-3) / 1e9, "peak": peak,
+                                           "unit": "GB/s", "frac": algo / (ms_screen * 1e-3) / 1e9 / peak, "ms_per_launch": ms_screen,
+                                           "algorithmic_bytes_per_launch": algo}}
     return out
 
 

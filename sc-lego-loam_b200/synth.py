@@ -77,8 +77,20 @@ class ScanGen:
         _L().scangen_desc(C.byref(self.cfg), i, R, S, out.ctypes.data)
         return out
 
-    def descs(self, start, count, R=20, S=60):
+    def descs(self, start, count, R=20, S=60, threads=0):
+        """count descriptors; threads > 0 generates in parallel (the C generator releases the GIL)."""
         out = np.empty((count, R * S), np.float32)
-        for j in range(count):
-            _L().scangen_desc(C.byref(self.cfg), start + j, R, S, out[j].ctypes.data)
+        lib, cfg = _L(), C.byref(self.cfg)
+
+        def run(lo, hi):
+            for j in range(lo, hi):
+                lib.scangen_desc(cfg, start + j, R, S, out[j].ctypes.data)
+
+        if threads and count >= 4 * threads:
+            from concurrent.futures import ThreadPoolExecutor
+            edges = np.linspace(0, count, threads + 1).astype(int)
+            with ThreadPoolExecutor(threads) as ex:
+                list(ex.map(lambda k: run(int(edges[k]), int(edges[k + 1])), range(threads)))
+        else:
+            run(0, count)
         return out
