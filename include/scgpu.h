@@ -44,6 +44,7 @@ extern "C" {
                                       bit-exact restatement (results are identical either way; for A/B timing) */
 #define SCGPU_FLAG_NO_SCREENING 4u /* exhaustive search scores every entry with the FP64 pair kernel (no FP32 screening
                                       pass, no second copy of the database); results are identical, for A/B timing */
+#define SCGPU_FLAG_NO_TMA_BUILD 8u /* bin with the register-staged k_build instead of the TMA-staged k_build_tma (A/B) */
 #define SCGPU_FLAG_FRESH_TREE 1u /* search keys [0, size - exclude_recent) on EVERY detect instead of emulating the
                                     reference's periodically rebuilt KD-tree snapshot (SC.cpp:264-276) */
 

@@ -235,6 +235,17 @@ int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_
     dim3 grid(tiles, (unsigned)ns);
     const bool al16 = (((uintptr_t)q.pts & 15) == 0);
     const int sk = (stride == 16 && al16) ? 16 : ((stride == 32 && al16) ? 32 : 0);
+    if (sk && q.bc.fast && !(h->cfg.flags & SCGPU_FLAG_NO_TMA_BUILD)) {
+      // TMA-staged variant (tile start offsets are multiples of 16 bytes because pts_per_block * stride is)
+      const size_t sm = sk == 16 ? build_tma_smem<16>(h->L.RS) : build_tma_smem<32>(h->L.RS);
+      if (sk == 16 && q.bc.lh_is_float) k_build_tma<16, true, true><<<grid, 256, sm, st>>>(q);
+      else if (sk == 16) k_build_tma<16, true, false><<<grid, 256, sm, st>>>(q);
+      else if (q.bc.lh_is_float) k_build_tma<32, true, true><<<grid, 256, sm, st>>>(q);
+      else k_build_tma<32, true, false><<<grid, 256, sm, st>>>(q);
+      h->launches++;
+      CK(cudaGetLastError());
+      continue;
+    }
     const int variant = sk * 4 + (q.bc.fast ? 2 : 0) + (q.bc.lh_is_float ? 1 : 0);
 #define SCGPU_BUILD_CASE(SK, F, L) \
   case (SK) * 4 + ((F) ? 2 : 0) + ((L) ? 1 : 0): k_build<SK, F, L><<<grid, 256, smem, st>>>(q); break;
@@ -587,7 +598,7 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrec, uint64_
     p.pair_shift = h->x_ps.as<int>();
     p.flip = 0;
     p.active = d_count;
-    k_score<<<dim3((unsigned)h->sm_count * 4, 1), 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p);
+    k_score_list<<<dim3((unsigned)h->sm_count * 4, 1), 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p);
     h->launches += 3;
     CK(cudaGetLastError());
   }
@@ -667,10 +678,15 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t1);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t2);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<16>(h->L.RS));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<16>(h->L.RS));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
   if (e == cudaSuccess && h->exh)
     e = cudaFuncSetAttribute(k_exh_screen<20, 60, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)exh_smem_bytes<20, 60, 3>());
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+  if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e == cudaSuccess && smem_d > 48 * 1024) e = cudaFuncSetAttribute(k_pair_api, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
   if (e != cudaSuccess) {
     delete h;

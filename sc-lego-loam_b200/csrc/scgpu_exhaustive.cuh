@@ -459,4 +459,112 @@ __global__ void __launch_bounds__(256) k_exh_final(const double* pair_dist, cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// k_build_tma: k_build with the point stream staged through shared memory by TMA bulk copies (UBLKCP).
+// An elected thread keeps BUILD_STAGES chunks of BUILD_CHUNK points in flight per block, so HBM latency is covered by
+// bytes in flight in the async proxy instead of by registers / resident warps; every thread then picks its points
+// from shared memory with conflict-free 16-byte loads.  Binning, aggregation and the record epilogue are k_build's.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BUILD_STAGES = 3;
+constexpr int BUILD_UNROLL = 4;
+constexpr int BUILD_CHUNK = 256 * BUILD_UNROLL;  // points per chunk
+
+template <int STRIDE, bool FAST, bool LH_FLOAT>  // STRIDE = 16 or 32 (bytes per point, 16-byte aligned base)
+__global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* ring = smem_raw;                                             // [BUILD_STAGES][BUILD_CHUNK * STRIDE]
+  int* s_bins = reinterpret_cast<int*>(smem_raw + (size_t)BUILD_STAGES * BUILD_CHUNK * STRIDE);
+  __shared__ __align__(8) uint64_t full[BUILD_STAGES];
+  __shared__ bool s_last;
+  const int RS = p.L.RS;
+  const unsigned scan = blockIdx.y;
+  const unsigned start = blockIdx.x * p.pts_per_block;
+  const unsigned end = min(start + p.pts_per_block, p.n_pts);
+  const unsigned n_chunks = end > start ? (end - start + BUILD_CHUNK - 1) / BUILD_CHUNK : 0;
+  const unsigned char* base = p.pts + (unsigned long long)scan * p.scan_pitch + (unsigned long long)start * STRIDE;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < BUILD_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < RS; i += blockDim.x) s_bins[i] = SCGPU_ENC_NOPOINT;
+  __syncthreads();
+  auto issue = [&](unsigned c) {
+    const unsigned pts = min((unsigned)BUILD_CHUNK, end - start - c * BUILD_CHUNK);
+    const int slot = (int)(c % BUILD_STAGES);
+    mbar_arrive_expect_tx(&full[slot], pts * STRIDE);
+    tma_bulk_g2s(ring + (size_t)slot * BUILD_CHUNK * STRIDE, base + (unsigned long long)c * BUILD_CHUNK * STRIDE, pts * STRIDE, &full[slot]);
+  };
+  if (threadIdx.x == 0)
+    for (unsigned c = 0; c < BUILD_STAGES - 1 && c < n_chunks; ++c) issue(c);
+
+  for (unsigned c = 0; c < n_chunks; ++c) {
+    // the slot chunk c+STAGES-1 goes to was read in iteration c-1; every thread has passed that iteration's barrier
+    if (threadIdx.x == 0 && c + BUILD_STAGES - 1 < n_chunks) issue(c + BUILD_STAGES - 1);
+    const int slot = (int)(c % BUILD_STAGES);
+    mbar_wait(&full[slot], (c / BUILD_STAGES) & 1);
+    const unsigned pts = min((unsigned)BUILD_CHUNK, end - start - c * BUILD_CHUNK);
+    const unsigned char* sp = ring + (size_t)slot * BUILD_CHUNK * STRIDE;
+    float px[BUILD_UNROLL], py[BUILD_UNROLL], pz[BUILD_UNROLL];
+#pragma unroll
+    for (int u = 0; u < BUILD_UNROLL; ++u) {
+      const unsigned i = u * 256 + threadIdx.x;
+      px[u] = py[u] = pz[u] = __int_as_float(0x7fc00000);  // NaN: dropped
+      if (i < pts) {
+        const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)i * STRIDE);
+        px[u] = v.x;
+        py[u] = v.y;
+        pz[u] = v.z;
+      }
+    }
+    __syncthreads();  // slot may be refilled from the next iteration on
+#pragma unroll
+    for (int u = 0; u < BUILD_UNROLL; ++u) {
+      if (u * 256 + (threadIdx.x & ~31u) >= pts) break;  // warp-uniform
+      float h;
+      const int bin = bin_point<FAST, LH_FLOAT>(p.bc, px[u], py[u], pz[u], h);
+      warp_bin_max(s_bins, bin, bin >= 0 ? enc_float(h) : INT_MIN);
+    }
+  }
+  __syncthreads();
+
+  if (gridDim.x > 1) {
+    int* g = p.gbins + (unsigned long long)scan * RS;
+    for (int i = threadIdx.x; i < RS; i += blockDim.x) {
+      const int v = s_bins[i];
+      if (v != SCGPU_ENC_NOPOINT) atomicMax(&g[i], v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&p.tickets[scan], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < RS; i += blockDim.x) {
+      s_bins[i] = __ldcg(&g[i]);
+      g[i] = SCGPU_ENC_NOPOINT;
+    }
+    if (threadIdx.x == 0) p.tickets[scan] = 0;
+    __syncthreads();
+  }
+  unsigned char* rec = p.records + (unsigned long long)scan * p.L.rec_bytes;
+  float* s_sc = reinterpret_cast<float*>(s_bins);
+  float* rec_sc = reinterpret_cast<float*>(rec);
+  for (int i = threadIdx.x; i < RS; i += blockDim.x) {
+    float f = dec_float(s_bins[i]);
+    if (f == -1000.0f) f = 0.0f;
+    s_sc[i] = f;
+    rec_sc[i] = f;
+  }
+  __syncthreads();
+  keys_from_sc<float>(s_sc, p.L.R, p.L.S, p.L.R, nullptr, reinterpret_cast<float*>(rec + p.L.off_ring),
+                      reinterpret_cast<double*>(rec + p.L.off_sector), reinterpret_cast<double*>(rec + p.L.off_norm));
+}
+
+template <int STRIDE>
+constexpr size_t build_tma_smem(int RS) {
+  return (size_t)BUILD_STAGES * BUILD_CHUNK * STRIDE + (size_t)RS * sizeof(int);
+}
+
 }  // namespace scgpu

@@ -308,16 +308,16 @@ struct CoeffShiftDiffSq {
 // Keys of one descriptor held in shared memory (T = float from binning, or double from the public API):
 // ring key (SC.cpp:198-211), sector key (SC.cpp:214-227), column norms (SC.cpp:78).  Whole block cooperates.
 template <class T>
-__device__ __forceinline__ void keys_from_sc(const T* s_sc, int R, int S, double* ring_d, float* ring_f, double* sector,
-                                             double* colnorm) {
+__device__ __forceinline__ void keys_from_sc(const T* s_sc, int R, int S, int ld, double* ring_d, float* ring_f, double* sector,
+                                             double* colnorm) {  // ld: elements between consecutive columns (>= R)
   for (int t = threadIdx.x; t < R + S; t += blockDim.x) {
     if (t < R) {
-      const double m = __ddiv_rn(redux_eigen(S, CoeffStrided<T>{s_sc + t, R}), (double)S);
+      const double m = __ddiv_rn(redux_eigen(S, CoeffStrided<T>{s_sc + t, ld}), (double)S);
       if (ring_d) ring_d[t] = m;
       if (ring_f) ring_f[t] = __double2float_rn(m);  // eig2stdvec, SC.cpp:62-66
     } else {
       const int c = t - R;
-      const T* col = s_sc + c * R;
+      const T* col = s_sc + c * ld;
       if (sector) sector[c] = __ddiv_rn(redux_eigen(R, CoeffStrided<T>{col, 1}), (double)R);
       if (colnorm) colnorm[c] = __dsqrt_rn(redux_eigen(R, CoeffSquare<T>{col}));
     }
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(256) k_build(const BuildParams p) {
     rec_sc[i] = f;
   }
   __syncthreads();
-  keys_from_sc<float>(s_sc, p.L.R, p.L.S, nullptr, reinterpret_cast<float*>(rec + p.L.off_ring),
+  keys_from_sc<float>(s_sc, p.L.R, p.L.S, p.L.R, nullptr, reinterpret_cast<float*>(rec + p.L.off_ring),
                       reinterpret_cast<double*>(rec + p.L.off_sector), reinterpret_cast<double*>(rec + p.L.off_norm));
 }
 
@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(128) k_records_from_sc(const float* sc, Layout
     reinterpret_cast<float*>(rec)[i] = f;
   }
   __syncthreads();
-  keys_from_sc<float>(s_sc, L.R, L.S, nullptr, reinterpret_cast<float*>(rec + L.off_ring),
+  keys_from_sc<float>(s_sc, L.R, L.S, L.R, nullptr, reinterpret_cast<float*>(rec + L.off_ring),
                       reinterpret_cast<double*>(rec + L.off_sector), reinterpret_cast<double*>(rec + L.off_norm));
 }
 
@@ -702,8 +702,11 @@ struct PairSmem {
 
 constexpr int SCORE_WB = 16;  // shifts evaluated per pass (bounds the shared-memory footprint)
 
+// descriptors sit in shared memory with an ODD column pitch: threads that work on consecutive columns hit distinct banks
+__host__ __device__ inline int pair_pitch(int R) { return R | 1; }
+
 __host__ __device__ inline size_t pair_smem_bytes(int R, int S, int W, size_t elem) {
-  size_t b = 2 * (size_t)R * S * elem;         // the two descriptors
+  size_t b = 2 * (size_t)pair_pitch(R) * S * elem;  // the two descriptors
   b = (b + 7) & ~(size_t)7;
   b += 4 * (size_t)S * 8;                      // vk1 vk2 n1 n2
   const int wb = W < SCORE_WB ? W : SCORE_WB;
@@ -716,8 +719,8 @@ __host__ __device__ inline size_t pair_smem_bytes(int R, int S, int W, size_t el
 template <class T>
 __device__ __forceinline__ PairSmem carve_pair_smem(unsigned char* raw, int R, int S, int W, T*& a, T*& b) {
   a = reinterpret_cast<T*>(raw);
-  b = a + (size_t)R * S;
-  size_t off = 2 * (size_t)R * S * sizeof(T);
+  b = a + (size_t)pair_pitch(R) * S;
+  size_t off = 2 * (size_t)pair_pitch(R) * S * sizeof(T);
   off = (off + 7) & ~(size_t)7;
   PairSmem m;
   m.vk1 = reinterpret_cast<double*>(raw + off);
@@ -777,7 +780,7 @@ __device__ __forceinline__ void dist_direct_block(const PairSmem& m, const T* a,
       const double na = m.n1[j], nb = m.n2[jb];
       double sim = 0.0;
       if (!((na == 0.0) | (nb == 0.0))) {
-        const double dot = redux_eigen(R, CoeffProduct<T>{a + (size_t)j * R, b + (size_t)jb * R});
+        const double dot = redux_eigen(R, CoeffProduct<T>{a + (size_t)j * pair_pitch(R), b + (size_t)jb * pair_pitch(R)});
         sim = __ddiv_rn(dot, __dmul_rn(na, nb));
       }
       m.work[t] = sim;
@@ -866,11 +869,11 @@ __device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, co
   const unsigned char* qrec = p.qrecords + (size_t)q * p.L.rec_bytes;
   const float* qsc = reinterpret_cast<const float*>(qrec);
   const float* csc = p.db.sc + l * p.L.RS;
+  const int RP = pair_pitch(R);
   for (int i = threadIdx.x; i < p.L.RS; i += blockDim.x) {
-    a[i] = qsc[i];
-    int src = i;
-    if (p.flip) src = (S - 1 - i / R) * R + (i % R);
-    b[i] = csc[src];
+    const int c = i / R, r = i - c * R;
+    a[c * RP + r] = qsc[i];
+    b[c * RP + r] = csc[p.flip ? (S - 1 - c) * R + r : i];
   }
   const double* qv = reinterpret_cast<const double*>(qrec + p.L.off_sector);
   const double* qn = reinterpret_cast<const double*>(qrec + p.L.off_norm);
@@ -894,19 +897,20 @@ __device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, co
   }
 }
 
-// grid (K, nq): block (k, q) scores candidate slot k of query q.  With p.active set (exhaustive rescoring: one query,
-// a device-side candidate count) the grid is persistent and the blocks stride over the list.
+// grid (K, nq): block (k, q) scores candidate slot k of query q.
 __global__ void __launch_bounds__(128) k_score(const ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  if (p.active) {
-    const unsigned n = min(*p.active, (unsigned)p.K);
-    for (unsigned k = blockIdx.x; k < n; k += gridDim.x) {
-      score_pair(p, (int)k, 0, smem_raw);
-      __syncthreads();
-    }
-    return;
-  }
   score_pair(p, blockIdx.x, blockIdx.y, smem_raw);
+}
+
+// Exhaustive rescoring: one query, a device-side candidate count (p.active); a persistent grid strides over the list.
+__global__ void __launch_bounds__(128) k_score_list(const ScoreParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned n = min(*p.active, (unsigned)p.K);
+  for (unsigned k = blockIdx.x; k < n; k += gridDim.x) {
+    score_pair(p, (int)k, 0, smem_raw);
+    __syncthreads();
+  }
 }
 
 // The public pairwise functions on caller-provided double matrices (SC.h:64-69).
@@ -930,17 +934,19 @@ __global__ void __launch_bounds__(128) k_pair_api(const double* sc1, const doubl
     if (threadIdx.x == 0) out_i[0] = al;
     return;
   }
+  const int RP = pair_pitch(R);
   for (int i = threadIdx.x; i < R * S; i += blockDim.x) {
-    a[i] = sc1[i];
-    if (mode != 3) b[i] = sc2[i];
+    const int c = i / R, r = i - c * R;
+    a[c * RP + r] = sc1[i];
+    if (mode != 3) b[c * RP + r] = sc2[i];
   }
   __syncthreads();
   if (mode == 3) {
-    keys_from_sc<double>(a, R, S, out_d, nullptr, out_d + R, nullptr);
+    keys_from_sc<double>(a, R, S, RP, out_d, nullptr, out_d + R, nullptr);
     return;
   }
-  keys_from_sc<double>(a, R, S, nullptr, nullptr, m.vk1, m.n1);
-  keys_from_sc<double>(b, R, S, nullptr, nullptr, m.vk2, m.n2);
+  keys_from_sc<double>(a, R, S, RP, nullptr, nullptr, m.vk1, m.n1);
+  keys_from_sc<double>(b, R, S, RP, nullptr, nullptr, m.vk2, m.n2);
   __syncthreads();
   if (mode == 1) {
     if (threadIdx.x == 0) m.shifts[0] = 0;

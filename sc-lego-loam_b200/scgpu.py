@@ -15,6 +15,7 @@ OK = 0
 FLAG_FRESH_TREE = 1
 FLAG_EXACT_BINNING = 2
 FLAG_NO_SCREENING = 4
+FLAG_NO_TMA_BUILD = 8
 
 
 class ScgpuError(RuntimeError):

@@ -129,6 +129,30 @@ def test_exact_binning_flag_gives_identical_descriptors():
         assert np.array_equal(a.makeScancontext(s), b.makeScancontext(s))
 
 
+@pytest.mark.parametrize("floats", [4, 8])
+def test_tma_staged_build_equals_register_staged_and_port(floats):
+    """k_build_tma (TMA bulk copies into a shared-memory ring; strides 16 and 32) against the register-staged kernel
+    and the oracle, for point counts around every chunk / tile edge (0, 1, 1023..1025, 2047, odd tails, full size)
+    and for batches (several scans per launch)."""
+    from sc_lego_loam_b200 import scgpu
+    from sc_lego_loam_b200.synth import ScanGen
+    p = orc.Params()
+    port = orc.Port(p)
+    tma, reg = mgr(p), mgr(p, flags=scgpu.FLAG_NO_TMA_BUILD)
+    full = ScanGen("hdl64", seed=12, n_places=4).scan(2, floats)
+    for n in (0, 1, 31, 1023, 1024, 1025, 2047, 4097, 16383, 16385, 50001, 120000):
+        s = np.ascontiguousarray(full[:n])
+        a, b = tma.makeScancontext(s), reg.makeScancontext(s)
+        assert np.array_equal(a, b), n
+        assert np.array_equal(a, port.make_sc(s)), n
+    batch = np.stack([ScanGen("hdl64", seed=12, n_places=4, n_azim=333).scan(i, floats) for i in range(40)])
+    tma.append_scans(batch)
+    reg.append_scans(batch)
+    for i in (0, 17, 39):
+        for x, y in zip(tma.get_entry(i), reg.get_entry(i)):
+            assert np.array_equal(x, y)
+
+
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_make_sc_and_keys_match_golden(variant):
     g = golden(variant)
