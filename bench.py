@@ -349,6 +349,8 @@ def run_multi_gpu(args):
     from sc_lego_loam_b200.scgpu import SCManager
     from sc_lego_loam_b200.sharded import GpuStages, ShardedSearch
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("SCGPU_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's banner goes to stdout; rank 0 must print exactly one JSON line
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     G = world
@@ -363,6 +365,18 @@ def run_multi_gpu(args):
         search.prefill_descs(gen.descs(0, n0, R, S))
     d_scans = h_scans.cuda()
     d_stage = torch.empty_like(d_scans)
+
+    ns_cache = {}
+    plan_uncached = search.st.plan_n_search
+
+    def plan_cached(first_size, n):
+        """Every step restarts from the same database size (truncate resets the snapshot state), so the n_search
+        plan is the same device tensor each time: computing it once keeps the step free of host synchronisation."""
+        if (first_size, n) not in ns_cache:
+            ns_cache[(first_size, n)] = plan_uncached(first_size, n)
+        return ns_cache[(first_size, n)]
+
+    search.st.plan_n_search = plan_cached
 
     def step(e2e):
         m.truncate(n0)
