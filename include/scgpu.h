@@ -182,10 +182,12 @@ int scgpu_stage_score(scgpu_handle* h, const void* d_query_records, size_t n_que
                       const uint64_t* d_n_search, void* d_best_out, void* stream);
 /* The packed record of stored entry global_idx (which must live on this shard) -> d_record. */
 int scgpu_stage_gather(scgpu_handle* h, uint64_t global_idx, void* d_record, void* stream);
-/* Exhaustive search of this shard for one query record: {double dist; int32 n_rescored; int32 shift; int64 global_idx}
- * of the shard's strict-min winner (dist = 1e7 when none).  The global winner is the minimum over shards by
- * (dist, global_idx). */
-int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_query_record, uint64_t n_search, void* d_best_out, void* stream);
+/* Exhaustive search of this shard for nq query records (host array n_search[nq]): per query
+ * {double dist; int32 n_rescored; int32 shift; int64 global_idx} of the shard's strict-min winner (dist = 1e7 when
+ * none) -> d_best_out[nq].  The global winner is the minimum over shards by (dist, global_idx).  Queries are screened
+ * in batches of up to 64 per launch so the small per-query kernels are shared. */
+int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_query_records, size_t nq, const uint64_t* n_search, void* d_best_out,
+                           void* stream);
 /* Reduce `parts` per-shard bests (layout [parts][n_queries]) to the reference's result per query
  * (d_n_search[q] == 0 marks a query that took the early return of SC.cpp:257-261). */
 int scgpu_stage_finalize(scgpu_handle* h, const void* d_best_parts, int parts, size_t n_queries,

@@ -92,6 +92,7 @@ struct scgpu_handle {
   cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr}, ev_pin[2] = {nullptr, nullptr};
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;  // call start / builds done / call end
+  cudaEvent_t ev_nl = nullptr;
   bool timing_valid = false;
   // database shard
   Db db{};
@@ -547,47 +548,65 @@ int pair_api(scgpu_handle* h, const double* a, size_t na, const double* b, size_
   return SCGPU_OK;
 }
 
-constexpr unsigned EXH_CAND_CAP = 16384;
+constexpr unsigned EXH_CAND_CAP = 65536;   // rescoring list of one batch
+constexpr size_t EXH_MAX_BATCH = 64;       // queries per screening launch
 
-// Screen + rescore for ONE query record on the device; the result (Best: dist, rank = #rescored, shift, global idx)
-// is written to d_best_out.  Everything is enqueued on st; no host synchronisation.
-int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrec, uint64_t n_search, Best* d_best_out, cudaStream_t st,
-                           cudaEvent_t ev_screen0, cudaEvent_t ev_screen1) {
-  const uint64_t n_local = local_count(h, n_search);
-  RET(h->x_query.reserve(sizeof(ExhQuery)));
-  RET(h->x_d32.reserve((n_local + 8) * sizeof(float)));
+// Screen + rescore for nq (<= EXH_MAX_BATCH) query records on the device; result q (Best: dist, rank = #rescored in the
+// batch, shift, global idx) goes to d_best_out[q].  Everything is enqueued on st; no host synchronisation.
+int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t nq, const uint64_t* h_n_search, Best* d_best_out,
+                           cudaStream_t st, cudaEvent_t ev_screen0, cudaEvent_t ev_screen1) {
+  if (nq == 0) return SCGPU_OK;
+  if (nq > EXH_MAX_BATCH) return fail(SCGPU_E_INVALID, "at most %zu queries per exhaustive batch", EXH_MAX_BATCH);
+  uint64_t n_max = 0;
+  std::vector<unsigned long long> nl(nq);
+  for (size_t i = 0; i < nq; ++i) {
+    nl[i] = local_count(h, h_n_search[i]);
+    if (nl[i] > n_max) n_max = nl[i];
+  }
+  const uint64_t pitch = (n_max + 15) & ~15ull;
+  RET(h->x_query.reserve(EXH_MAX_BATCH * sizeof(ExhQuery)));
+  RET(h->x_d32.reserve((nq * pitch + 16) * sizeof(float)));
   RET(h->x_keys.reserve(EXH_CAND_CAP * sizeof(uint64_t)));
   RET(h->x_pd.reserve(EXH_CAND_CAP * sizeof(double)));
   RET(h->x_ps.reserve(EXH_CAND_CAP * sizeof(int)));
   if (!h->x_small.p) {
-    RET(h->x_small.reserve(64));
-    CK(cudaMemsetAsync(h->x_small.p, 0xff, 64, st));  // includes the constant non-zero "n_search" cell k_score reads
+    RET(h->x_small.reserve(4096));
+    CK(cudaMemsetAsync(h->x_small.p, 0xff, 4096, st));  // includes the constant non-zero "n_search" cell k_score_list reads
   }
-  unsigned* d_min = h->x_small.as<unsigned>();
-  unsigned* d_count = d_min + 1;
-  unsigned long long* d_one = reinterpret_cast<unsigned long long*>(d_min + 2);  // "n_search" != 0 for k_score
-  k_exh_prep<<<1, 256, 0, st>>>(d_qrec, h->L, h->x_query.as<ExhQuery>(), d_min, d_count);
+  // x_small: [0] count | [2..3] non-zero u64 | [16 .. 16+64) min_bits | [256 ..] n_local (u64 x 64)
+  unsigned* d_count = h->x_small.as<unsigned>();
+  unsigned long long* d_one = reinterpret_cast<unsigned long long*>(d_count + 2);
+  unsigned* d_min = d_count + 16;
+  unsigned long long* d_nl = reinterpret_cast<unsigned long long*>(h->x_small.as<unsigned char>() + 1024);
+  RET(h->h_ns.reserve(EXH_MAX_BATCH * 8 * 2));
+  CK(cudaEventSynchronize(h->ev_nl));  // the pinned staging cell of the previous batch has been consumed
+  memcpy(h->h_ns.p, nl.data(), nq * 8);
+  CK(cudaMemcpyAsync(d_nl, h->h_ns.p, nq * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(h->ev_nl, st));
+  k_exh_prep<<<(unsigned)nq, 256, 0, st>>>(d_qrecs, h->L, h->x_query.as<ExhQuery>(), d_min, d_count);
   h->launches += 1;
-  if (n_local) {
+  if (n_max) {
     ExhScreenParams sp;
     sp.db.sc_hat = h->x_sc_hat;
     sp.db.vkey32 = h->x_vkey32;
     sp.db.aux = h->x_aux;
     sp.q = h->x_query.as<ExhQuery>();
-    sp.n_local = n_local;
+    sp.n_local = d_nl;
+    sp.d32_pitch = pitch;
     sp.d32 = h->x_d32.as<float>();
     sp.min_bits = d_min;
-    const uint64_t groups = (n_local + EXH_WARPS - 1) / EXH_WARPS;
+    const uint64_t groups = (n_max + EXH_WARPS - 1) / EXH_WARPS;
     const unsigned grid = (unsigned)(groups < (uint64_t)h->sm_count ? groups : (uint64_t)h->sm_count);
     const size_t smem = exh_smem_bytes<20, 60, 3>();
     if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
-    k_exh_screen<20, 60, 3><<<grid, (EXH_WARPS + 1) * 32, smem, st>>>(sp);
+    k_exh_screen<20, 60, 3><<<dim3(grid, (unsigned)nq), (EXH_WARPS + 1) * 32, smem, st>>>(sp);
     if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
     CK(cudaGetLastError());
-    const unsigned rb = (unsigned)((n_local + 1023) / 1024 < 592 ? (n_local + 1023) / 1024 : 592);
-    k_exh_compact<<<rb, 256, 0, st>>>(sp.d32, n_local, d_min, h->db.rank, h->db.G, h->x_keys.as<unsigned long long>(), d_count, EXH_CAND_CAP);
+    const unsigned rb = (unsigned)((n_max + 1023) / 1024 < 296 ? (n_max + 1023) / 1024 : 296);
+    k_exh_compact<<<dim3(rb, (unsigned)nq), 256, 0, st>>>(sp.d32, pitch, d_nl, d_min, h->db.rank, h->db.G, h->x_keys.as<unsigned long long>(),
+                                                         d_count, EXH_CAND_CAP);
     ScoreParams p;
-    p.qrecords = d_qrec;
+    p.qrecords = d_qrecs;
     p.L = h->L;
     p.db = h->db;
     p.keys = h->x_keys.as<unsigned long long>();
@@ -602,7 +621,7 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrec, uint64_
     h->launches += 3;
     CK(cudaGetLastError());
   }
-  k_exh_final<<<1, 256, 0, st>>>(h->x_pd.as<double>(), h->x_ps.as<int>(), h->x_keys.as<unsigned long long>(), d_count, EXH_CAND_CAP, d_best_out);
+  k_exh_final<<<(unsigned)nq, 256, 0, st>>>(h->x_pd.as<double>(), h->x_ps.as<int>(), h->x_keys.as<unsigned long long>(), d_count, EXH_CAND_CAP, d_best_out);
   h->launches++;
   CK(cudaGetLastError());
   return SCGPU_OK;
@@ -678,6 +697,7 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t0);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t1);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t2);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_nl, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<16>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<16>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
@@ -738,6 +758,7 @@ int scgpu_destroy(scgpu_handle* h) {
   if (h->ev_t0) cudaEventDestroy(h->ev_t0);
   if (h->ev_t1) cudaEventDestroy(h->ev_t1);
   if (h->ev_t2) cudaEventDestroy(h->ev_t2);
+  if (h->ev_nl) cudaEventDestroy(h->ev_nl);
   if (h->stream) cudaStreamDestroy(h->stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   delete h;
@@ -1016,7 +1037,7 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
   if (h->exh && !flipped) {
     RET(h->x_best.reserve(sizeof(Best)));
     CK(cudaEventRecord(h->ev_t0, st));
-    RET(launch_exhaustive_fast(h, h->rec_single.as<unsigned char>(), n_search, h->x_best.as<Best>(), st, h->ev_t0, h->ev_t1));
+    RET(launch_exhaustive_fast(h, h->rec_single.as<unsigned char>(), 1, &n_search, h->x_best.as<Best>(), st, h->ev_t0, h->ev_t1));
     CK(cudaEventRecord(h->ev_t2, st));
     h->timing_valid = true;
     Best b;
@@ -1110,7 +1131,11 @@ int scgpu_exhaustive_batched(scgpu_handle* h, const uint64_t* q, const uint64_t*
     unsigned char* rec = h->records.as<unsigned char>() + i * h->L.rec_bytes;
     k_gather<<<1, 128, 0, st>>>(rec, h->L, h->db, q[i]);
     h->launches++;
-    RET(launch_exhaustive_fast(h, rec, n_search[i], h->x_best.as<Best>() + i, st, nullptr, nullptr));
+  }
+  for (size_t i0 = 0; i0 < nq; i0 += EXH_MAX_BATCH) {
+    const size_t m = nq - i0 < EXH_MAX_BATCH ? nq - i0 : EXH_MAX_BATCH;
+    RET(launch_exhaustive_fast(h, h->records.as<unsigned char>() + i0 * h->L.rec_bytes, m, n_search + i0, h->x_best.as<Best>() + i0, st, nullptr,
+                               nullptr));
   }
   CK(cudaEventRecord(h->ev_t2, st));
   h->timing_valid = true;
@@ -1334,12 +1359,16 @@ int scgpu_stage_gather(scgpu_handle* h, uint64_t global_idx, void* d_record, voi
   return SCGPU_OK;
 }
 
-int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_qrecord, uint64_t n_search, void* d_best_out, void* stream) {
-  if (!h || !d_qrecord || !d_best_out) return fail(SCGPU_E_INVALID, "null argument");
+int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_qrecords, size_t nq, const uint64_t* n_search, void* d_best_out, void* stream) {
+  if (!h || !d_qrecords || !d_best_out || (!n_search && nq)) return fail(SCGPU_E_INVALID, "null argument");
   if (!h->exh) return fail(SCGPU_E_INVALID, "screening kernel is instantiated for 20x60, search radius 3 only");
   CK(cudaSetDevice(h->cfg.device));
-  return launch_exhaustive_fast(h, static_cast<const unsigned char*>(d_qrecord), n_search, static_cast<Best*>(d_best_out), ST(stream), nullptr,
-                                nullptr);
+  for (size_t i0 = 0; i0 < nq; i0 += EXH_MAX_BATCH) {
+    const size_t m = nq - i0 < EXH_MAX_BATCH ? nq - i0 : EXH_MAX_BATCH;
+    RET(launch_exhaustive_fast(h, static_cast<const unsigned char*>(d_qrecords) + i0 * h->L.rec_bytes, m, n_search + i0,
+                               static_cast<Best*>(d_best_out) + i0, ST(stream), nullptr, nullptr));
+  }
+  return SCGPU_OK;
 }
 
 int scgpu_stage_finalize(scgpu_handle* h, const void* d_best_parts, int parts, size_t nq, const uint64_t* d_ns, int32_t* d_loop_id,

@@ -149,20 +149,23 @@ __global__ void __launch_bounds__(128) k_exh_append(const unsigned char* records
 }
 
 // query pack + reset of the per-query reduction cells (one launch instead of three)
-__global__ void __launch_bounds__(256) k_exh_prep(const unsigned char* qrec, Layout L, ExhQuery* q, unsigned* min_bits, unsigned* count) {
+__global__ void __launch_bounds__(256) k_exh_prep(const unsigned char* qrecs, Layout L, ExhQuery* qs, unsigned* min_bits, unsigned* count) {
+  const unsigned q = blockIdx.x;  // one block per query of the batch
   if (threadIdx.x == 0) {
-    *min_bits = 0x7f800000u;
-    *count = 0;
+    min_bits[q] = 0x7f800000u;
+    if (q == 0) *count = 0;
   }
-  exh_normalise(qrec, L, q->qhat, q->v1, &q->qmask, &q->v1norm, &q->flags);
+  ExhQuery* dst = qs + q;
+  exh_normalise(qrecs + (size_t)q * L.rec_bytes, L, dst->qhat, dst->v1, &dst->qmask, &dst->v1norm, &dst->flags);
 }
 
-struct ExhScreenParams {
+struct ExhScreenParams {     // grid (blocks, queries): blockIdx.y selects the query of the batch
   ExhDb db;
-  const ExhQuery* q;
-  unsigned long long n_local;  // local entries to score: [0, n_local)
-  float* d32;                  // [n_local] out: approx distance; -1 = must be rescored; +inf = can never win
-  unsigned* min_bits;          // out: bit pattern of the smallest certain d32 (atomicMin; pre-set to +inf)
+  const ExhQuery* q;                   // [nq]
+  const unsigned long long* n_local;   // [nq] local entries to score per query: [0, n_local[q])
+  unsigned long long d32_pitch;        // elements between the d32 rows of consecutive queries
+  float* d32;                          // [nq][d32_pitch] out: approx distance; -1 = must be rescored; +inf = can never win
+  unsigned* min_bits;                  // [nq] out: bit pattern of the smallest certain d32 (atomicMin; pre-set to +inf)
 };
 
 // shared memory rings: one slot holds a group of EXH_WARPS entries.  The descriptor of group g is needed one
@@ -184,7 +187,20 @@ constexpr size_t exh_smem_bytes() {
 }
 
 template <int R, int S, int RAD>
-__global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const ExhScreenParams p) {
+__global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const ExhScreenParams pp) {
+  // this block's query
+  struct {
+    ExhDb db;
+    const ExhQuery* q;
+    unsigned long long n_local;
+    float* d32;
+    unsigned* min_bits;
+  } p;
+  p.db = pp.db;
+  p.q = pp.q + blockIdx.y;
+  p.n_local = pp.n_local[blockIdx.y];
+  p.d32 = pp.d32 + blockIdx.y * pp.d32_pitch;
+  p.min_bits = pp.min_bits + blockIdx.y;
   constexpr int W = 2 * RAD + 1;
   constexpr int ALIGN_LANES = (S + W - 1) / W;
   constexpr int PITCH = (2 * S + W) | 1;  // odd pitch: lanes (rows) hit distinct banks
@@ -405,23 +421,29 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
 }
 
 // ---- rescoring side -----------------------------------------------------------------------------------
-// candidates = flagged entries + entries within 2*EXH_EPS of the smallest certain value -> key list (global index)
-__global__ void k_exh_compact(const float* d32, unsigned long long n, const unsigned* min_bits, int rank, int G,
-                              unsigned long long* keys, unsigned* count, unsigned cap) {
-  const float thr = __uint_as_float(*min_bits) + 2.0f * EXH_EPS;
+// candidates = flagged entries + entries within 2*EXH_EPS of the query's smallest certain value -> one flat key list
+// (query index << 32 | global entry index); grid (blocks, queries)
+__global__ void k_exh_compact(const float* d32, unsigned long long d32_pitch, const unsigned long long* n_local, const unsigned* min_bits,
+                              int rank, int G, unsigned long long* keys, unsigned* count, unsigned cap) {
+  const unsigned q = blockIdx.y;
+  const float* row = d32 + q * d32_pitch;
+  const unsigned long long n = n_local[q];
+  const float thr = __uint_as_float(min_bits[q]) + 2.0f * EXH_EPS;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-    const float v = d32[i];
+    const float v = row[i];
     if (v < 0.f || (v <= thr && v < __int_as_float(0x7f800000))) {
       const unsigned slot = atomicAdd(count, 1u);
-      if (slot < cap) keys[slot] = i * (unsigned long long)G + rank;
+      if (slot < cap) keys[slot] = ((unsigned long long)q << 32) | (i * (unsigned long long)G + rank);
     }
   }
 }
 
-// strict minimum in index order over the rescored candidates (SC.cpp:296-311 over every entry)
+// per query (one block each): strict minimum in index order over its rescored candidates (SC.cpp:296-311 over every
+// entry); rank = total number of rescored candidates of the batch (overflow check on the host)
 __global__ void __launch_bounds__(256) k_exh_final(const double* pair_dist, const int* pair_shift, const unsigned long long* keys,
                                                    const unsigned* count, unsigned cap, Best* out) {
   __shared__ Best s_best[256];
+  const unsigned q = blockIdx.x;
   Best b;
   b.dist = 10000000.0;
   b.rank = 0;
@@ -429,8 +451,10 @@ __global__ void __launch_bounds__(256) k_exh_final(const double* pair_dist, cons
   b.idx = -1;
   const unsigned n = min(*count, cap);
   for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned long long key = keys[i];
+    if ((unsigned)(key >> 32) != q) continue;
     const double d = pair_dist[i];
-    const long long idx = (long long)keys[i];
+    const long long idx = (long long)(key & 0xffffffffull);
     if (pair_shift[i] >= 0 && d < 10000000.0 && (d < b.dist || (d == b.dist && (b.idx < 0 || idx < b.idx)))) {
       b.dist = d;
       b.shift = pair_shift[i];
@@ -449,16 +473,15 @@ __global__ void __launch_bounds__(256) k_exh_final(const double* pair_dist, cons
   }
   if (threadIdx.x == 0) {
     Best r = s_best[0];
-    r.rank = (int)min(*count, 0x7fffffffu);  // number of rescored candidates (overflow check on the host)
+    r.rank = (int)min(*count, 0x7fffffffu);
     if (r.idx < 0) {
       r.idx = 0;
       r.shift = 0;
       r.dist = 10000000.0;
     }
-    *out = r;
+    out[q] = r;
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------------------
 // k_build_tma: k_build with the point stream staged through shared memory by TMA bulk copies (UBLKCP).

@@ -844,10 +844,12 @@ struct ScoreParams {
   const unsigned* active;  // optional: only slots k < *active are scored (fixed-size grid over a device-side count)
 };
 
-__device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, const int q, unsigned char* smem_raw) {
+template <bool LIST>  // LIST: slot k of one flat list whose keys are (query index << 32 | global entry index)
+__device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, int q, unsigned char* smem_raw) {
   const int R = p.L.R, S = p.L.S, W = 2 * p.radius + 1;
-  const size_t o = (size_t)q * p.K + k;
-  if (p.n_search[q] == 0) {
+  const size_t o = LIST ? (size_t)k : (size_t)q * p.K + k;
+  if (LIST) q = (int)(p.keys[o] >> 32);
+  if (!LIST && p.n_search[q] == 0) {
     if (threadIdx.x == 0) {
       p.pair_dist[o] = 10000000.0;
       p.pair_shift[o] = -1;
@@ -855,7 +857,7 @@ __device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, co
     return;
   }
   const unsigned long long key = p.keys[o];
-  const unsigned long long g = (key == KEY_NONE) ? 0ull : (key & 0xffffffffull);
+  const unsigned long long g = (!LIST && key == KEY_NONE) ? 0ull : (key & 0xffffffffull);
   if ((int)(g % (unsigned long long)p.db.G) != p.db.rank) {
     if (threadIdx.x == 0) {
       p.pair_dist[o] = 10000000.0;
@@ -900,15 +902,16 @@ __device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, co
 // grid (K, nq): block (k, q) scores candidate slot k of query q.
 __global__ void __launch_bounds__(128) k_score(const ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  score_pair(p, blockIdx.x, blockIdx.y, smem_raw);
+  score_pair<false>(p, blockIdx.x, blockIdx.y, smem_raw);
 }
 
-// Exhaustive rescoring: one query, a device-side candidate count (p.active); a persistent grid strides over the list.
+// Exhaustive rescoring: a flat candidate list (keys = query << 32 | entry) with a device-side count (p.active); a
+// persistent grid strides over it.
 __global__ void __launch_bounds__(128) k_score_list(const ScoreParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const unsigned n = min(*p.active, (unsigned)p.K);
   for (unsigned k = blockIdx.x; k < n; k += gridDim.x) {
-    score_pair(p, (int)k, 0, smem_raw);
+    score_pair<true>(p, (int)k, 0, smem_raw);
     __syncthreads();
   }
 }

@@ -59,7 +59,7 @@ _SIGNATURES = {
     "scgpu_exhaustive": [_vp, _u64, _u64, _i, _pd, _pi, C.POINTER(C.c_int64), _pi],
     "scgpu_exhaustive_batched": [_vp, _vp, _vp, _sz, _vp, _vp, _vp],
     "scgpu_exhaustive_stats": [_vp, C.POINTER(_u64)],
-    "scgpu_stage_exhaustive": [_vp, _vp, _u64, _vp, _vp],
+    "scgpu_stage_exhaustive": [_vp, _vp, _sz, _vp, _vp, _vp],
     "scgpu_stage_gather": [_vp, _u64, _vp, _vp],
     "scgpu_save": [_vp, C.c_char_p],
     "scgpu_load": [_vp, C.c_char_p],

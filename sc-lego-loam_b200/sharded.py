@@ -54,6 +54,20 @@ class ShardedSearch:
             dist.broadcast(rec, src=owner, group=self.group)
         return reduce_exhaustive(self._all_gather(self.st.exhaustive(rec, n_search).unsqueeze(0)).reshape(self.world, 3))
 
+    def exhaustive_stored(self, first_idx, nq, n_search):
+        """Exhaustive search for the stored entries first_idx .. first_idx+nq-1 as queries (first_idx and nq multiples
+        of the world size): every rank gathers the records of the queries it owns, one all_gather makes them global."""
+        G = self.world
+        assert first_idx % G == 0 and nq % G == 0
+        mine = torch.stack([self.st.gather(first_idx + j * G + self.rank) for j in range(nq // G)])     # [nq/G, rec]
+        recs = self._all_gather(mine).transpose(0, 1).reshape(nq, -1).contiguous()                      # query i = j*G + r
+        return self.exhaustive_records(recs, n_search)
+
+    def exhaustive_records(self, qrecs, n_search):
+        """The same for a batch of query records present on every rank ([nq, rec]); returns device tensors
+        (dist, shift, idx) per query.  One all_gather of 24 bytes per query per rank."""
+        return reduce_exhaustive_batch(self._all_gather(self.st.exhaustive(qrecs, n_search)))
+
     def step(self, scans_local):
         """scans_local: this rank's B scans ([B, P, k] float32 on the stage device).  Scan j of rank r becomes
         global entry size + j*G + r.  Returns the detect results of all G*B new entries in global order
@@ -71,6 +85,25 @@ class ShardedSearch:
         keys = self.st.merge(self._all_gather(keys_local))                       # exchange 2
         best_local = self.st.score(rec_global, keys, n_search)                   # [GB, 3] int64
         return self.st.finalize(self._all_gather(best_local), n_search)          # exchange 3
+
+
+def reduce_exhaustive_batch(parts):
+    """parts: [G, nq, 3] int64 -> (dist [nq] f64, shift [nq] i32, idx [nq] i64) of the global winners, on the device:
+    per query the minimum by (dist, idx) over the shards with dist < 1e7; (1e7, 0, 0) when none."""
+    d = parts[..., 0].contiguous().view(torch.float64)                      # [G, nq]
+    idx = parts[..., 2]
+    shift = parts[..., 1] >> 32
+    big = torch.iinfo(torch.int64).max
+    dmin = d.min(dim=0).values                                              # [nq]
+    cand = (d == dmin) & (d < 1e7)
+    idx_masked = torch.where(cand, idx, torch.full_like(idx, big))
+    g = idx_masked.argmin(dim=0)                                            # shard of the winner
+    none = ~cand.any(dim=0)
+    take = lambda t: t.gather(0, g.unsqueeze(0)).squeeze(0)                 # noqa: E731
+    out_d = torch.where(none, torch.full_like(dmin, 1e7), take(d))
+    out_s = torch.where(none, torch.zeros_like(g), take(shift)).to(torch.int32)
+    out_i = torch.where(none, torch.zeros_like(g), take(idx))
+    return out_d, out_s, out_i
 
 
 def reduce_exhaustive(parts):
@@ -157,10 +190,13 @@ class GpuStages:
         return rec
 
     def exhaustive(self, qrec, n_search):
-        """This shard's exhaustive winner for one query record: [3] int64 (see reduce_exhaustive)."""
-        best = torch.empty(3, dtype=torch.int64, device=self.device)
-        self._check(self.lib.scgpu_stage_exhaustive(self.h, qrec.data_ptr(), int(n_search), best.data_ptr(), self._stream()))
-        return best
+        """This shard's exhaustive winners for the query record(s) qrec ([rec] or [nq, rec]): [3] / [nq, 3] int64."""
+        single = qrec.dim() == 1
+        nq = 1 if single else qrec.shape[0]
+        ns = np.ascontiguousarray(np.broadcast_to(np.asarray(n_search, np.uint64), (nq,)))
+        best = torch.empty((nq, 3), dtype=torch.int64, device=self.device)
+        self._check(self.lib.scgpu_stage_exhaustive(self.h, qrec.data_ptr(), nq, ns.ctypes.data, best.data_ptr(), self._stream()))
+        return best[0] if single else best
 
     def finalize(self, parts, n_search):
         G, nq, _ = parts.shape

@@ -14,12 +14,61 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def main_sharded(a):
+    """torchrun: the N-entry database sharded i % G over the ranks; batches of 64 stored entries as queries."""
+    import torch
+    import torch.distributed as dist
+    from sc_lego_loam_b200.scgpu import SCManager
+    from sc_lego_loam_b200.sharded import GpuStages, ShardedSearch
+    from sc_lego_loam_b200.synth import ScanGen
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    R, S = 20, 60
+    descs = ScanGen("hdl64", seed=20181004, n_places=70000).descs(0, a.n, R, S, threads=max(2, (os.cpu_count() or 8) // world))
+    m = SCManager(device=local, shard_rank=rank, shard_count=world, capacity_hint=a.n + 8)
+    search = ShardedSearch(GpuStages(m, f"cuda:{local}"), rank, world)
+    search.prefill_descs(descs)
+    nq = 64
+    first = (a.n - 64 - 8 * world) // world * world
+    ns = first - 50
+    for _ in range(3):
+        out = search.exhaustive_stored(first, nq, ns)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(1, a.queries // nq)
+    e0.record()
+    for _ in range(reps):
+        out = search.exhaustive_stored(first, nq, ns)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        peak = 6523.3
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        per_q = ms.item() / (reps * nq)
+        print(json.dumps({"config": f"exhaustive_{a.n}_20x60_sharded", "n_gpus": world, "queries": reps * nq, "ms_per_query": per_q,
+                          "queries_per_sec": 1e3 / per_q, "aggregate_db_stream_gbs": 4 * R * S * ns / (per_q * 1e-3) / 1e9,
+                          "frac_of_aggregate_hbm_roofline": 4 * R * S * ns / (per_q * 1e-3) / 1e9 / (peak * world),
+                          "winner_idx_sample": [int(x) for x in out[2][:4].cpu()]}))
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=100000)
     ap.add_argument("--queries", type=int, default=32)
     ap.add_argument("--cpu", type=int, default=0, help="time the CPU reference on this many entries (0 = skip)")
     a = ap.parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return main_sharded(a)
     from sc_lego_loam_b200.scgpu import SCManager
     from sc_lego_loam_b200.synth import ScanGen
     R, S = 20, 60
