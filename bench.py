@@ -349,8 +349,6 @@ def run_multi_gpu(args):
     from sc_lego_loam_b200.scgpu import SCManager
     from sc_lego_loam_b200.sharded import GpuStages, ShardedSearch
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("SCGPU_KEEP_NCCL_DEBUG"):
-        os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's banner goes to stdout; rank 0 must print exactly one JSON line
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     G = world
@@ -437,6 +435,11 @@ def run_multi_gpu(args):
 
 def main():
     args = parse()
+    # Libraries (NCCL's version banner, ...) write to stdout; the contract is ONE JSON line from rank 0.  Everything
+    # written to fd 1 during the run goes to stderr; print() is pointed at the real stdout.
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) == 0:

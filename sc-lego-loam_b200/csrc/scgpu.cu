@@ -105,6 +105,7 @@ struct scgpu_handle {
   DevBuf x_query, x_d32, x_keys, x_pd, x_ps, x_small, x_best;
   int sm_count = 148;
   unsigned last_exh_rescored = 0;
+  uint64_t x_upto = 0;  // local entries [0, x_upto) have an up-to-date screening copy
   // build workspace
   DevBuf gbins, btickets;
   size_t build_cap = 0;
@@ -154,7 +155,9 @@ int db_reserve(scgpu_handle* h, uint64_t want_local) {
     CK(cudaMalloc(&n_aux, (cap + 8) * sizeof(ExhAux)));
   }
   const uint64_t n = local_count(h, h->n_global);
-  if (h->exh && h->db.cap && n) {
+  if (h->x_upto > n) h->x_upto = n;
+  if (h->exh && h->db.cap && h->x_upto) {
+    const uint64_t n = h->x_upto;
     CK(cudaMemcpyAsync(n_hat, h->x_sc_hat, n * L.RS * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(n_vk, h->x_vkey32, n * L.S * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(n_aux, h->x_aux, n * sizeof(ExhAux), cudaMemcpyDeviceToDevice, h->stream));
@@ -278,12 +281,6 @@ int launch_append(scgpu_handle* h, const void* d_records, uint64_t first_global,
   k_append<<<(unsigned)n, 128, 0, st>>>(static_cast<const unsigned char*>(d_records), h->L, h->db, first_global, step);
   h->launches++;
   CK(cudaGetLastError());
-  if (h->exh) {
-    k_exh_append<<<(unsigned)n, 128, 0, st>>>(static_cast<const unsigned char*>(d_records), h->L, h->db, h->x_sc_hat, h->x_vkey32, h->x_aux,
-                                              first_global, step);
-    h->launches++;
-    CK(cudaGetLastError());
-  }
   if (new_size > h->n_global) h->n_global = new_size;
   return SCGPU_OK;
 }
@@ -564,6 +561,13 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
     if (nl[i] > n_max) n_max = nl[i];
   }
   const uint64_t pitch = (n_max + 15) & ~15ull;
+  if (n_max > h->x_upto) {  // bring the screening copy up to date with the entries appended since the last search
+    const uint64_t have = local_count(h, h->n_global);
+    k_exh_append<<<(unsigned)(have - h->x_upto), 128, 0, st>>>(h->L, h->db, h->x_sc_hat, h->x_vkey32, h->x_aux, h->x_upto);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->x_upto = have;
+  }
   RET(h->x_query.reserve(EXH_MAX_BATCH * sizeof(ExhQuery)));
   RET(h->x_d32.reserve((nq * pitch + 16) * sizeof(float)));
   RET(h->x_keys.reserve(EXH_CAND_CAP * sizeof(uint64_t)));
@@ -1007,6 +1011,7 @@ int scgpu_get_entry(scgpu_handle* h, uint64_t i, float* sc, float* ring, double*
 int scgpu_truncate(scgpu_handle* h, uint64_t n) {
   if (!h) return fail(SCGPU_E_INVALID, "null argument");
   if (n < h->n_global) h->n_global = n;
+  if (h->x_upto > local_count(h, h->n_global)) h->x_upto = local_count(h, h->n_global);
   // the snapshot may reference forgotten entries: the next detect takes a fresh one (counter % period == 0)
   h->counter = 0;
   h->n_tree = 0;

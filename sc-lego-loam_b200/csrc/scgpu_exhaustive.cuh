@@ -97,11 +97,8 @@ struct ExhQuery {
 
 // Screening side data of one record (descriptor, keys): used by k_append for the database and by k_exh_prep for
 // the query.  One block; every thread may call.
-__device__ __forceinline__ void exh_normalise(const unsigned char* rec, const Layout& L, float* sc_hat, float* vkey32,
-                                              unsigned long long* vmask, float* vnorm, unsigned* flags) {
-  const float* sc = reinterpret_cast<const float*>(rec);
-  const double* sector = reinterpret_cast<const double*>(rec + L.off_sector);
-  const double* norm = reinterpret_cast<const double*>(rec + L.off_norm);
+__device__ __forceinline__ void exh_normalise(const float* sc, const double* sector, const double* norm, const Layout& L, float* sc_hat,
+                                              float* vkey32, unsigned long long* vmask, float* vnorm, unsigned* flags) {
   __shared__ unsigned long long s_mask;
   __shared__ unsigned s_flags;
   __shared__ float s_v2;
@@ -139,13 +136,12 @@ __device__ __forceinline__ void exh_normalise(const unsigned char* rec, const La
   __syncthreads();
 }
 
-// database side of the screening data: entries first_global + i*step owned by this shard
-__global__ void __launch_bounds__(128) k_exh_append(const unsigned char* records, Layout L, Db db, float* sc_hat, float* vkey32, ExhAux* aux,
-                                                    unsigned long long first_global, unsigned long long step) {
-  const unsigned long long g = first_global + blockIdx.x * step;
-  if ((int)(g % (unsigned long long)db.G) != db.rank) return;
-  const unsigned long long l = g / (unsigned long long)db.G;
-  exh_normalise(records + (size_t)blockIdx.x * L.rec_bytes, L, sc_hat + l * L.RS, vkey32 + l * L.S, &aux[l].vmask, &aux[l].vnorm, &aux[l].flags);
+// database side of the screening data: local entries [first_local, first_local + gridDim.x), derived from the stored
+// descriptor / sector key / column norms (built lazily, right before the first exhaustive search that needs them)
+__global__ void __launch_bounds__(128) k_exh_append(Layout L, Db db, float* sc_hat, float* vkey32, ExhAux* aux, unsigned long long first_local) {
+  const unsigned long long l = first_local + blockIdx.x;
+  exh_normalise(db.sc + l * L.RS, db.sector + l * L.S, db.colnorm + l * L.S, L, sc_hat + l * L.RS, vkey32 + l * L.S, &aux[l].vmask,
+                &aux[l].vnorm, &aux[l].flags);
 }
 
 // query pack + reset of the per-query reduction cells (one launch instead of three)
@@ -156,7 +152,9 @@ __global__ void __launch_bounds__(256) k_exh_prep(const unsigned char* qrecs, La
     if (q == 0) *count = 0;
   }
   ExhQuery* dst = qs + q;
-  exh_normalise(qrecs + (size_t)q * L.rec_bytes, L, dst->qhat, dst->v1, &dst->qmask, &dst->v1norm, &dst->flags);
+  const unsigned char* rec = qrecs + (size_t)q * L.rec_bytes;
+  exh_normalise(reinterpret_cast<const float*>(rec), reinterpret_cast<const double*>(rec + L.off_sector),
+                reinterpret_cast<const double*>(rec + L.off_norm), L, dst->qhat, dst->v1, &dst->qmask, &dst->v1norm, &dst->flags);
 }
 
 struct ExhScreenParams {     // grid (blocks, queries): blockIdx.y selects the query of the batch

@@ -22,8 +22,7 @@ def main_sharded(a):
     from sc_lego_loam_b200.sharded import GpuStages, ShardedSearch
     from sc_lego_loam_b200.synth import ScanGen
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", f"/tmp/scgpu_nccl_{os.getpid()}_%h_%p.log")  # keep stdout to the JSON line
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     R, S = 20, 60
@@ -63,7 +62,7 @@ def main_sharded(a):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--entries", dest="n", type=int, default=100000)
     ap.add_argument("--queries", type=int, default=32)
     ap.add_argument("--cpu", type=int, default=0, help="time the CPU reference on this many entries (0 = skip)")
     a = ap.parse_args()
