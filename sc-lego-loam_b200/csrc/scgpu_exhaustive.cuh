@@ -526,26 +526,51 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
     const int slot = (int)(c % BUILD_STAGES);
     mbar_wait(&full[slot], (c / BUILD_STAGES) & 1);
     const unsigned pts = min((unsigned)BUILD_CHUNK, end - start - c * BUILD_CHUNK);
-    const unsigned char* sp = ring + (size_t)slot * BUILD_CHUNK * STRIDE;
+    const unsigned char* sp = ring + (size_t)slot * BUILD_CHUNK * STRIDE + (size_t)threadIdx.x * STRIDE;
     float px[BUILD_UNROLL], py[BUILD_UNROLL], pz[BUILD_UNROLL];
+    if (pts == BUILD_CHUNK) {  // full chunk: no bounds checks
 #pragma unroll
-    for (int u = 0; u < BUILD_UNROLL; ++u) {
-      const unsigned i = u * 256 + threadIdx.x;
-      px[u] = py[u] = pz[u] = __int_as_float(0x7fc00000);  // NaN: dropped
-      if (i < pts) {
-        const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)i * STRIDE);
+      for (int u = 0; u < BUILD_UNROLL; ++u) {
+        const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)u * 256 * STRIDE);
         px[u] = v.x;
         py[u] = v.y;
         pz[u] = v.z;
       }
+    } else {
+#pragma unroll
+      for (int u = 0; u < BUILD_UNROLL; ++u) {
+        px[u] = py[u] = pz[u] = __int_as_float(0x7fc00000);  // NaN: dropped
+        if (u * 256 + threadIdx.x < pts) {
+          const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)u * 256 * STRIDE);
+          px[u] = v.x;
+          py[u] = v.y;
+          pz[u] = v.z;
+        }
+      }
     }
     __syncthreads();  // slot may be refilled from the next iteration on
+    // front end for all points of the thread first; the (rare) undecided ones go through ONE divergent region
+    int bin[BUILD_UNROLL];
+    float hh[BUILD_UNROLL];
+    bool undecided = false;
 #pragma unroll
     for (int u = 0; u < BUILD_UNROLL; ++u) {
-      if (u * 256 + (threadIdx.x & ~31u) >= pts) break;  // warp-uniform
-      float h;
-      const int bin = bin_point<FAST, LH_FLOAT>(p.bc, px[u], py[u], pz[u], h);
-      warp_bin_max(s_bins, bin, bin >= 0 ? enc_float(h) : INT_MIN);
+      bin[u] = bin_point_fast<LH_FLOAT>(p.bc, px[u], py[u], pz[u], hh[u]);
+      undecided |= (bin[u] == BIN_UNDECIDED);
+    }
+    if (undecided) {
+#pragma unroll
+      for (int u = 0; u < BUILD_UNROLL; ++u)
+        if (bin[u] == BIN_UNDECIDED) bin[u] = bin_point_exact_noinline(p.bc, px[u], py[u], pz[u], hh[u]);
+    }
+    // max into the block's grid.  A bin's value only ever grows, so a plain read is a valid filter: a point that does
+    // not beat the value read cannot beat the current one; after the first few points of a bin almost none does.
+#pragma unroll
+    for (int u = 0; u < BUILD_UNROLL; ++u) {
+      if (bin[u] >= 0) {
+        const int e = enc_float(hh[u]);
+        if (e > s_bins[bin[u]]) atomicMax(&s_bins[bin[u]], e);
+      }
     }
   }
   __syncthreads();

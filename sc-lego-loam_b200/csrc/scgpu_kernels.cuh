@@ -189,9 +189,28 @@ __device__ __forceinline__ float mufu_rcp(float x) {
   return r;
 }
 
+// out-of-line copy of the exact path for the kernels that defer it (keeps their hot loop small)
+__device__ __noinline__ int bin_point_exact_noinline(const BinConst& c, float x, float y, float z, float& height) {
+  return bin_point_exact(c, x, y, z, height);
+}
+
+constexpr int BIN_UNDECIDED = -2;  // bin_point_fast: the exact path has to decide this point
+
+// The front end alone: returns the bin, -1 (outside the ROI by more than the error), or BIN_UNDECIDED.  Branch-free.
+template <bool LH_FLOAT>
+__device__ __forceinline__ int bin_point_fast(const BinConst& c, float x, float y, float z, float& height);
+
 template <bool FAST, bool LH_FLOAT>
 __device__ __forceinline__ int bin_point(const BinConst& c, float x, float y, float z, float& height, bool* fell_back = nullptr) {
   if (!FAST) return bin_point_exact(c, x, y, z, height);
+  const int b = bin_point_fast<LH_FLOAT>(c, x, y, z, height);
+  if (b != BIN_UNDECIDED) return b;
+  if (fell_back) *fell_back = true;
+  return bin_point_exact(c, x, y, z, height);
+}
+
+template <bool LH_FLOAT>
+__device__ __forceinline__ int bin_point_fast(const BinConst& c, float x, float y, float z, float& height) {
   const float fR = (float)c.R, fS = (float)c.S;
   const float r2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
   const float qr = __fmul_rn(__fmul_rn(r2, mufu_rsq(r2)), c.ring_scale);  // ~ range * R / max_radius
@@ -224,10 +243,7 @@ __device__ __forceinline__ int bin_point(const BinConst& c, float x, float y, fl
   // |dr| > eps also excludes qr in [R, R+eps] and NaN; |ds| > eps excludes t near 0 and S and NaN / inf
   const bool safe = (fabsf(dr) > c.eps_r) & (fabsf(ds) > c.eps_s) & (mn > 0.f) & (h == h);
   height = h;
-  if (outside) return -1;
-  if (safe) return ks * c.R + kr;
-  if (fell_back) *fell_back = true;
-  return bin_point_exact(c, x, y, z, height);
+  return outside ? -1 : (safe ? ks * c.R + kr : BIN_UNDECIDED);
 }
 
 // order-preserving float <-> int map so that atomicMax on ints is max on floats (SC.cpp:182-183)
