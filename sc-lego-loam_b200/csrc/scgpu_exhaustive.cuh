@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
   unsigned char* ring = smem_raw;                                             // [BUILD_STAGES][BUILD_CHUNK * STRIDE]
   int* s_bins = reinterpret_cast<int*>(smem_raw + (size_t)BUILD_STAGES * BUILD_CHUNK * STRIDE);
   __shared__ __align__(8) uint64_t full[BUILD_STAGES];
+  __shared__ __align__(8) uint64_t empty[BUILD_STAGES];  // one arrival per warp once it has copied its points out
   __shared__ bool s_last;
   const int RS = p.L.RS;
   const unsigned scan = blockIdx.y;
@@ -506,7 +507,10 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
   const unsigned char* base = p.pts + (unsigned long long)scan * p.scan_pitch + (unsigned long long)start * STRIDE;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < BUILD_STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < BUILD_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 256 / 32);
+    }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < RS; i += blockDim.x) s_bins[i] = SCGPU_ENC_NOPOINT;
@@ -514,6 +518,7 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
   auto issue = [&](unsigned c) {
     const unsigned pts = min((unsigned)BUILD_CHUNK, end - start - c * BUILD_CHUNK);
     const int slot = (int)(c % BUILD_STAGES);
+    if (c >= BUILD_STAGES) mbar_wait(&empty[slot], ((c / BUILD_STAGES) - 1) & 1);  // every warp has copied chunk c-STAGES out
     mbar_arrive_expect_tx(&full[slot], pts * STRIDE);
     tma_bulk_g2s(ring + (size_t)slot * BUILD_CHUNK * STRIDE, base + (unsigned long long)c * BUILD_CHUNK * STRIDE, pts * STRIDE, &full[slot]);
   };
@@ -521,7 +526,7 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
     for (unsigned c = 0; c < BUILD_STAGES - 1 && c < n_chunks; ++c) issue(c);
 
   for (unsigned c = 0; c < n_chunks; ++c) {
-    // the slot chunk c+STAGES-1 goes to was read in iteration c-1; every thread has passed that iteration's barrier
+    // refill the slot that chunk c-1 occupied (no block-wide barrier: warps only report "copied out" per slot)
     if (threadIdx.x == 0 && c + BUILD_STAGES - 1 < n_chunks) issue(c + BUILD_STAGES - 1);
     const int slot = (int)(c % BUILD_STAGES);
     mbar_wait(&full[slot], (c / BUILD_STAGES) & 1);
@@ -548,7 +553,8 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
         }
       }
     }
-    __syncthreads();  // slot may be refilled from the next iteration on
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[slot]);  // this warp's points are in registers
     // front end for all points of the thread first; the (rare) undecided ones go through ONE divergent region
     int bin[BUILD_UNROLL];
     float hh[BUILD_UNROLL];
