@@ -106,6 +106,9 @@ struct scgpu_handle {
   int sm_count = 148;
   unsigned last_exh_rescored = 0;
   uint64_t x_upto = 0;  // local entries [0, x_upto) have an up-to-date screening copy
+  DevBuf c_d32, c_list, c_count;
+  bool last_screened = false;  // the last pipeline scored only the candidates that could win exactly
+  const void* last_qrec = nullptr;
   // build workspace
   DevBuf gbins, btickets;
   size_t build_cap = 0;
@@ -387,6 +390,59 @@ int launch_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t*
   return SCGPU_OK;
 }
 
+// bring the screening copy of the shard up to date (entries appended since the last search that used it)
+int exh_sync(scgpu_handle* h, cudaStream_t st) {
+  const uint64_t have = local_count(h, h->n_global);
+  if (have > h->x_upto) {
+    k_exh_append<<<(unsigned)(have - h->x_upto), 128, 0, st>>>(h->L, h->db, h->x_sc_hat, h->x_vkey32, h->x_aux, h->x_upto);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->x_upto = have;
+  }
+  return SCGPU_OK;
+}
+
+// Stage 4 for the top-K path: FP32 screening of all K candidates, exact FP64 scoring of those that can be the minimum.
+int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* d_keys, const uint64_t* d_ns, cudaStream_t st) {
+  if (nq == 0) return SCGPU_OK;
+  RET(exh_sync(h, st));
+  RET(h->c_d32.reserve(nq * h->K * sizeof(float)));
+  RET(h->c_list.reserve(nq * h->K * sizeof(uint64_t)));
+  RET(h->c_count.reserve(16));
+  CK(cudaMemsetAsync(h->c_count.p, 0, 4, st));
+  CandScreenParams cp;
+  cp.qrecords = static_cast<const unsigned char*>(d_qrec);
+  cp.L = h->L;
+  cp.db = h->db;
+  cp.xdb.sc_hat = h->x_sc_hat;
+  cp.xdb.vkey32 = h->x_vkey32;
+  cp.xdb.aux = h->x_aux;
+  cp.keys = reinterpret_cast<const unsigned long long*>(d_keys);
+  cp.n_search = reinterpret_cast<const unsigned long long*>(d_ns);
+  cp.K = h->K;
+  cp.d32 = h->c_d32.as<float>();
+  k_cand_screen<20, 60, 3><<<(unsigned)nq, CAND_WARPS * 32, 0, st>>>(cp);
+  k_cand_select<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(h->c_d32.as<float>(), (unsigned)nq, h->K, h->c_list.as<unsigned long long>(),
+                                                             h->c_count.as<unsigned>(), h->pair_dist.as<double>(), h->pair_shift.as<int>());
+  ScoreParams p;
+  p.qrecords = static_cast<const unsigned char*>(d_qrec);
+  p.L = h->L;
+  p.db = h->db;
+  p.keys = reinterpret_cast<const unsigned long long*>(d_keys);
+  p.n_search = reinterpret_cast<const unsigned long long*>(d_ns);
+  p.K = h->K;
+  p.radius = h->radius;
+  p.pair_dist = h->pair_dist.as<double>();
+  p.pair_shift = h->pair_shift.as<int>();
+  p.flip = 0;
+  p.active = nullptr;
+  k_score_pairs<<<(unsigned)h->sm_count * 8, 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p, h->c_list.as<unsigned long long>(),
+                                                                                                            h->c_count.as<unsigned>());
+  h->launches += 3;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
+
 int launch_best(scgpu_handle* h, size_t nq, const uint64_t* d_keys, Best* d_best, cudaStream_t st) {
   if (nq == 0) return SCGPU_OK;
   k_best<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(h->pair_dist.as<double>(), h->pair_shift.as<int>(),
@@ -434,7 +490,10 @@ int run_pipeline(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t*
   RET(query_reserve(h, nq, chunks, st));
   const uint64_t* d_ns = h->nsearch.as<uint64_t>();
   RET(launch_topk(h, d_qrec, nq, d_ns, h->keys.as<uint64_t>(), st));
-  RET(launch_score(h, d_qrec, nq, h->keys.as<uint64_t>(), d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
+  h->last_screened = h->exh && !(h->cfg.flags & SCGPU_FLAG_NO_SCREENING);
+  h->last_qrec = d_qrec;
+  if (h->last_screened) RET(launch_score_screened(h, d_qrec, nq, h->keys.as<uint64_t>(), d_ns, st));
+  else RET(launch_score(h, d_qrec, nq, h->keys.as<uint64_t>(), d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
   RET(launch_best(h, nq, h->keys.as<uint64_t>(), h->best.as<Best>(), st));
   RET(launch_finalize(h, h->best.as<Best>(), 1, nq, d_ns, h->o_loop.as<int>(), h->o_yaw.as<float>(), h->o_dist.as<double>(),
                       h->o_idx.as<int>(), h->o_shift.as<int>(), st));
@@ -561,13 +620,7 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
     if (nl[i] > n_max) n_max = nl[i];
   }
   const uint64_t pitch = (n_max + 15) & ~15ull;
-  if (n_max > h->x_upto) {  // bring the screening copy up to date with the entries appended since the last search
-    const uint64_t have = local_count(h, h->n_global);
-    k_exh_append<<<(unsigned)(have - h->x_upto), 128, 0, st>>>(h->L, h->db, h->x_sc_hat, h->x_vkey32, h->x_aux, h->x_upto);
-    h->launches++;
-    CK(cudaGetLastError());
-    h->x_upto = have;
-  }
+  RET(exh_sync(h, st));
   RET(h->x_query.reserve(EXH_MAX_BATCH * sizeof(ExhQuery)));
   RET(h->x_d32.reserve((nq * pitch + 16) * sizeof(float)));
   RET(h->x_keys.reserve(EXH_CAND_CAP * sizeof(uint64_t)));
@@ -752,7 +805,7 @@ int scgpu_destroy(scgpu_handle* h) {
       cudaFree(h->x_aux);
     }
   }
-  DevBuf* xb[] = {&h->x_query, &h->x_d32, &h->x_keys, &h->x_pd, &h->x_ps, &h->x_small, &h->x_best};
+  DevBuf* xb[] = {&h->x_query, &h->x_d32, &h->x_keys, &h->x_pd, &h->x_ps, &h->x_small, &h->x_best, &h->c_d32, &h->c_list, &h->c_count};
   for (DevBuf* b : xb) b->release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
@@ -967,6 +1020,13 @@ int scgpu_get_batch_candidates(scgpu_handle* h, size_t q, uint64_t* cand_idx, fl
   if (!h) return fail(SCGPU_E_INVALID, "null argument");
   if (q >= h->last_nq) return fail(SCGPU_E_INVALID, "no such query in the last call");
   CK(cudaSetDevice(h->cfg.device));
+  if (h->last_screened) {
+    // the pipeline scored exactly only the candidates that could win; complete the table for the dump
+    RET(launch_score(h, h->last_qrec, h->last_nq, h->keys.as<uint64_t>(), h->nsearch.as<uint64_t>(), h->K, h->pair_dist.as<double>(),
+                     h->pair_shift.as<int>(), 0, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->last_screened = false;
+  }
   const int K = h->K;
   std::vector<uint64_t> keys(K);
   std::vector<double> pd(K);
@@ -1349,7 +1409,8 @@ int scgpu_stage_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = ST(stream);
   RET(query_reserve(h, nq, 1, st));
-  RET(launch_score(h, d_qrec, nq, d_keys, d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
+  if (h->exh && !(h->cfg.flags & SCGPU_FLAG_NO_SCREENING)) RET(launch_score_screened(h, d_qrec, nq, d_keys, d_ns, st));
+  else RET(launch_score(h, d_qrec, nq, d_keys, d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
   return launch_best(h, nq, d_keys, static_cast<Best*>(d_best_out), st);
 }
 

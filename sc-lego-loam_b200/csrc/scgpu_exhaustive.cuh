@@ -482,6 +482,235 @@ __global__ void __launch_bounds__(256) k_exh_final(const double* pair_dist, cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Top-K path: the same FP32 screening applied to the K retrieved candidates of each query (SC.cpp:296-311).
+//   k_cand_screen : one block per query (query table built from its record), one warp per candidate slot; the
+//                   candidate's screening copy is read straight from global memory (L2-resident) into registers.
+//   k_cand_select : per query, candidates whose screened distance is within 2*EXH_EPS of the smallest certain one
+//                   (plus every flagged one) go on a list; the others cannot be the minimum and are marked skipped.
+//   k_score_pairs : the exact FP64 pair kernel over that list (typically 1-2 of the K candidates per query).
+// The strict-min in candidate order (k_best) then runs over exactly-scored candidates only, so the result is the
+// reference's.  scgpu_get_candidates rescoring everything exactly on demand keeps the parity dumps complete.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int CAND_WARPS = 10;
+
+struct CandScreenParams {
+  const unsigned char* qrecords;
+  Layout L;
+  Db db;                                // ownership (rank, G)
+  ExhDb xdb;                            // screening copy
+  const unsigned long long* keys;       // [nq][K]
+  const unsigned long long* n_search;   // [nq]
+  int K;
+  float* d32;                           // [nq][K] out: approx distance; -1 = rescore; +inf = cannot win / not mine
+};
+
+template <int S, int W>
+__device__ __forceinline__ void window_fma(const float4* held4, const float* qs, float (&acc)[W]) {
+  // acc[d] = sum_p held[p] * qs[p + d]
+  float held[S];
+#pragma unroll
+  for (int i = 0; i < S / 4; ++i) {
+    const float4 v = held4[i];
+    held[4 * i] = v.x;
+    held[4 * i + 1] = v.y;
+    held[4 * i + 2] = v.z;
+    held[4 * i + 3] = v.w;
+  }
+  float win[W];
+#pragma unroll
+  for (int d = 0; d < W - 1; ++d) win[d] = qs[d];
+#pragma unroll
+  for (int pp = 0; pp < S; ++pp) {
+    win[W - 1] = qs[pp + W - 1];
+#pragma unroll
+    for (int d = 0; d < W; ++d) acc[d] = __fmaf_rn(held[pp], win[d], acc[d]);
+#pragma unroll
+    for (int d = 0; d < W - 1; ++d) win[d] = win[d + 1];
+  }
+}
+
+template <int R, int S, int RAD>
+__global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScreenParams p) {
+  constexpr int W = 2 * RAD + 1;
+  constexpr int ALIGN_LANES = (S + W - 1) / W;
+  constexpr int PITCH = (2 * S + W) | 1;
+  static_assert(R + ALIGN_LANES <= 32 && S <= 64 && S % 4 == 0 && W <= 8, "see k_exh_screen");
+  __shared__ float qtable[(R + 1) * PITCH];
+  __shared__ float s_inv[S];
+  __shared__ unsigned long long s_mask;
+  __shared__ unsigned s_flags;
+  __shared__ float s_v2;
+  const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool early = p.n_search[q] == 0;
+  const unsigned char* qrec = p.qrecords + (size_t)q * p.L.rec_bytes;
+  const float* qsc = reinterpret_cast<const float*>(qrec);
+  const double* qsector = reinterpret_cast<const double*>(qrec + p.L.off_sector);
+  const double* qnorm = reinterpret_cast<const double*>(qrec + p.L.off_norm);
+  if (threadIdx.x == 0) {
+    s_mask = 0;
+    s_flags = 0;
+    s_v2 = 0.f;
+  }
+  __syncthreads();
+  if (!early) {
+    for (int c = threadIdx.x; c < S; c += blockDim.x) {
+      const double n = qnorm[c];
+      const float nf = (float)n, v = (float)qsector[c];
+      s_inv[c] = (n == 0.0) ? 0.f : (float)(1.0 / n);
+      if (n != 0.0) atomicOr(&s_mask, 1ull << c);
+      if ((n != 0.0 && !(nf > 1e-30f && nf < 1e30f)) || !(fabsf(v) < 1e30f)) atomicOr(&s_flags, 1u);
+      atomicAdd(&s_v2, v * v);
+    }
+  }
+  __syncthreads();
+  if (!early) {
+    for (int i = threadIdx.x; i < (R + 1) * PITCH; i += blockDim.x) {
+      const int r = i / PITCH, c = (i - r * PITCH) % S;
+      qtable[i] = r < R ? qsc[c * R + r] * s_inv[c] : (float)qsector[c];
+    }
+  }
+  __syncthreads();
+  const unsigned long long qmask = s_mask;
+  const float v1norm = sqrtf(s_v2);
+  const bool q_flag = s_flags != 0;
+  const bool row_lane = lane < R, align_lane = lane >= R && lane < R + ALIGN_LANES;
+  const float* qrow = qtable + (row_lane ? lane : R) * PITCH;
+
+  for (int k = warp; k < p.K; k += CAND_WARPS) {
+    const size_t o = (size_t)q * p.K + k;
+    const unsigned long long key = p.keys[o];
+    const unsigned long long g = (key == KEY_NONE) ? 0ull : (key & 0xffffffffull);
+    if (early || (int)(g % (unsigned long long)p.db.G) != p.db.rank) {
+      if (lane == 0) p.d32[o] = __int_as_float(0x7f800000);
+      continue;
+    }
+    const unsigned long long l = g / (unsigned long long)p.db.G;
+    const ExhAux ax = p.xdb.aux[l];
+    // ---- alignment: acc[d] = corr(base + d) on the alignment lanes
+    float acc[W];
+#pragma unroll
+    for (int d = 0; d < W; ++d) acc[d] = 0.f;
+    int base = (lane - R) * W;
+    if (align_lane) window_fma<S, W>(reinterpret_cast<const float4*>(p.xdb.vkey32 + l * S), qrow + base, acc);
+    float b1 = -__int_as_float(0x7f800000), b2 = b1;
+    int s1 = 0x7fffffff;
+    if (align_lane) {
+#pragma unroll
+      for (int d = 0; d < W; ++d) {
+        const int s = base + d;
+        if (s < S) {
+          const float c = acc[d];
+          if (c > b1 || (c == b1 && s < s1)) {
+            b2 = b1;
+            b1 = c;
+            s1 = s;
+          } else if (c > b2) {
+            b2 = c;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob1 = __shfl_xor_sync(FULL, b1, off), ob2 = __shfl_xor_sync(FULL, b2, off);
+      const int os1 = __shfl_xor_sync(FULL, s1, off);
+      if (ob1 > b1 || (ob1 == b1 && os1 < s1)) {
+        b2 = fmaxf(b1, ob2);
+        b1 = ob1;
+        s1 = os1;
+      } else {
+        b2 = fmaxf(b2, ob1);
+      }
+    }
+    const int a_cur = (s1 == 0x7fffffff) ? 0 : s1;
+    const bool amb = !((b1 - b2) > EXH_ALIGN_MARGIN * v1norm * ax.vnorm) || !(b1 == b1);
+    // ---- window: acc[d] belongs to shift a_cur - RAD + d, on the row lanes
+#pragma unroll
+    for (int d = 0; d < W; ++d) acc[d] = 0.f;
+    base = ((a_cur - RAD) % S + S) % S;
+    if (row_lane) window_fma<S, W>(reinterpret_cast<const float4*>(p.xdb.sc_hat + l * (R * S) + lane * S), qrow + base, acc);
+    float r8[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) r8[d] = (row_lane && d < W) ? acc[d] : 0.f;
+    float r4[4], r2[2], r1;
+    {
+      const bool hi = lane & 16;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) r4[i] = (hi ? r8[4 + i] : r8[i]) + __shfl_xor_sync(FULL, hi ? r8[i] : r8[4 + i], 16);
+    }
+    {
+      const bool hi = lane & 8;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) r2[i] = (hi ? r4[2 + i] : r4[i]) + __shfl_xor_sync(FULL, hi ? r4[i] : r4[2 + i], 8);
+    }
+    {
+      const bool hi = lane & 4;
+      r1 = (hi ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, hi ? r2[0] : r2[1], 4);
+    }
+    r1 += __shfl_xor_sync(FULL, r1, 2);
+    r1 += __shfl_xor_sync(FULL, r1, 1);
+    const int d_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    float dist = __int_as_float(0x7f800000);
+    bool nan_here = false;
+    if (d_mine < W) {
+      int sft = (a_cur + d_mine - RAD) % S;
+      if (sft < 0) sft += S;
+      const unsigned long long m = ax.vmask;
+      const unsigned long long rot = sft == 0 ? m : (((m << sft) | (m >> (S - sft))) & ((S == 64) ? ~0ull : ((1ull << S) - 1)));
+      const int n = __popcll(qmask & rot);
+      if (n > 0) {
+        dist = 1.0f - r1 / (float)n;
+        nan_here = !(dist == dist);
+      }
+    }
+    const bool any_nan = __any_sync(FULL, nan_here);
+    float best = nan_here ? __int_as_float(0x7f800000) : dist;
+    best = fminf(best, __shfl_xor_sync(FULL, best, 16));
+    best = fminf(best, __shfl_xor_sync(FULL, best, 8));
+    best = fminf(best, __shfl_xor_sync(FULL, best, 4));
+    if (lane == 0) {
+      float out = best;
+      if (amb || any_nan || (ax.flags & 1u) || q_flag) out = -1.0f;
+      else if (out < 0.f) out = 0.f;
+      p.d32[o] = out;
+    }
+  }
+}
+
+// per query: which candidate slots need the exact kernel
+__global__ void k_cand_select(const float* d32, unsigned nq, int K, unsigned long long* list, unsigned* count, double* pair_dist, int* pair_shift) {
+  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  float mn = __int_as_float(0x7f800000);
+  for (int k = 0; k < K; ++k) {
+    const float v = d32[(size_t)q * K + k];
+    if (v >= 0.f) mn = fminf(mn, v);
+  }
+  const float thr = mn + 2.0f * EXH_EPS;
+  for (int k = 0; k < K; ++k) {
+    const size_t o = (size_t)q * K + k;
+    const float v = d32[o];
+    if (v < 0.f || (v <= thr && v < __int_as_float(0x7f800000))) {
+      list[atomicAdd(count, 1u)] = ((unsigned long long)q << 32) | (unsigned)k;
+    } else {  // cannot be the minimum (or not this shard's): skipped by k_best
+      pair_dist[o] = 10000000.0;
+      pair_shift[o] = -1;
+    }
+  }
+}
+
+// the exact pair kernel over a (query, slot) list; persistent grid
+__global__ void __launch_bounds__(128) k_score_pairs(const ScoreParams p, const unsigned long long* list, const unsigned* count) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const unsigned n = *count;
+  for (unsigned i = blockIdx.x; i < n; i += gridDim.x) {
+    const unsigned long long e = list[i];
+    score_pair<false>(p, (int)(e & 0xffffffffull), (int)(e >> 32), smem_raw);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // k_build_tma: k_build with the point stream staged through shared memory by TMA bulk copies (UBLKCP).
 // An elected thread keeps BUILD_STAGES chunks of BUILD_CHUNK points in flight per block, so HBM latency is covered by
 // bytes in flight in the async proxy instead of by registers / resident warps; every thread then picks its points
