@@ -38,6 +38,9 @@ DB_SIZE = 4541
 PTS = 120000
 R, S, K_CAND = 20, 60, 10
 ALGO_BYTES_PER_SCAN = 16 * PTS + 4 * R * S + 4 * R + 8 * S   # 1,925,360 B
+# dram__bytes_read.sum + dram__bytes_write.sum of the bench's own k_build_tma launch (4,541 scans), one `ncu --set full`
+# capture, profiles/r1_k_build_tma_final_ncu_summary.txt: 8.782 GB + 1.194 GB
+NCU_TRAFFIC_BYTES_PER_SCAN = (8.782069e9 + 1.193974e9) / 4541
 SEED = 20181002
 WORKLOAD = "kitti00_shaped_4541kf_hdl64_120kpts_sc20x60_k10_excl50"
 
@@ -283,8 +286,9 @@ def run_single_gpu(args):
                 "d2h_bytes_per_step": B * 24, "ms_per_step": 1e3 * dt_e2e / args.steps, "results_equal_device_leg": bool(same),
                 "h2d_gbs": (B * PTS * 16) / (dt_e2e / args.steps) / 1e9},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_build", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SCAN * B,
+        "roofline": {"kernel": "k_build_tma", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_TRAFFIC_BYTES_PER_SCAN * B, "traffic_source": "ncu --set full capture of this launch (profiles/r1_k_build_tma_final_ncu_summary.txt)",
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SCAN * B,
                      "ms_per_launch": ms_build},
         "stages": {"build_ms_per_step": ms_build, "query_ms_per_step": ms_query, "builds_per_sec": B / (ms_build * 1e-3),
                    "queries_only_per_sec": B / (ms_query * 1e-3), "loops_found": int((res_dev["loop_id"] >= 0).sum())},
