@@ -21,6 +21,54 @@ from sc_lego_loam_b200.scgpu import SCManager  # noqa: E402
 from sc_lego_loam_b200.synth import ScanGen  # noqa: E402
 
 
+def config1(n=2000):
+    """BASELINE config 1: the reference's own CPU-runnable case -- 2,000 synthetic HDL-64 scans (120,000 points,
+    32-byte pcl::PointXYZI records), 20x60, 10 candidates, exclude-recent 50 -- run through the reference (one thread)
+    and through the GPU path (sequential API semantics via one batched replay), EVERYTHING compared: loop id, yaw bits,
+    nearest distance, and for a sample of queries the candidate lists with their squared distances, shifts, distances."""
+    gen = ScanGen("hdl64", seed=20181001, n_places=(n * 10) // 13)
+    kind = "reference" if orc.ref_available("default") else "port"
+    ref = orc.Ref("default") if kind == "reference" else orc.Port()
+    m = SCManager(capacity_hint=n + 8)
+    chunk = 250
+    ids, yaws, dists, cands = [], [], [], {}
+    t_ref = t_gpu = 0.0
+    sample = set(range(60, n, 97))
+    for c0 in range(0, n, chunk):
+        scans = gen.scans(c0, chunk, 8)
+        t0 = time.perf_counter()
+        out = m.replay(scans)
+        t_gpu += time.perf_counter() - t0
+        for q in range(chunk):
+            if c0 + q in sample:
+                cands[c0 + q] = m.candidates(q)
+        t0 = time.perf_counter()
+        for j, s in enumerate(scans):
+            ref.append_scan(s)
+            d = ref.detect(details=(c0 + j) in sample) if kind == "reference" else ref.detect()
+            ids.append(d["loop_id"]); yaws.append(d["yaw"]); dists.append(d.get("min_dist", np.nan))
+            if (c0 + j) in sample and d["k"]:
+                g = cands[c0 + j]
+                assert np.array_equal(g["cand_idx"], d["cand_idx"]) and np.array_equal(g["cand_shift"], d["cand_shift"]), c0 + j
+                assert np.array_equal(g["cand_d2"].view(np.uint32), d["cand_d2"].view(np.uint32)), c0 + j
+                assert np.allclose(g["cand_dist"], d["cand_dist"], rtol=1e-5, atol=1e-9, equal_nan=True), c0 + j
+                assert g["n_tree"] == d["n_tree"]
+        t_ref += time.perf_counter() - t0
+        if c0 == 0:
+            got = {k: [v.copy()] for k, v in out.items()}
+        else:
+            for k, v in out.items():
+                got[k].append(v.copy())
+    got = {k: np.concatenate(v) for k, v in got.items()}
+    ids, yaws = np.array(ids), np.array(yaws, np.float32)
+    res = {"config": "1: 2,000 HDL-64 scans (120k pts, PointXYZI stride), 20x60, K=10, exclude 50: reference vs GPU", "keyframes": n,
+           "loop_ids_equal": bool(np.array_equal(ids, got["loop_id"])), "yaw_bits_equal": bool(np.array_equal(yaws.view(np.uint32), got["yaw"].view(np.uint32))),
+           "loops_found": int((ids >= 0).sum()), "candidate_lists_checked": len(cands), "reference_kind": kind,
+           "reference_seconds_1_core": t_ref, "reference_queries_per_sec": n / t_ref, "gpu_seconds_incl_pageable_h2d": t_gpu,
+           "gpu_queries_per_sec_from_pageable_host": n / t_gpu}
+    print(json.dumps(res))
+
+
 def config3(n_db=40000, batch=512, check=48):
     gen = ScanGen("os1", seed=20181003, n_places=30000)
     descs = gen.descs(0, n_db, 20, 60, threads=16)
@@ -90,7 +138,9 @@ def config5(n_db=20000, n_check=1500):
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["3", "5"]
+    which = sys.argv[1:] or ["1", "3", "5"]
+    if "1" in which:
+        config1()
     if "3" in which:
         config3()
     if "5" in which:
