@@ -719,6 +719,7 @@ __global__ void __launch_bounds__(128) k_score_pairs(const ScoreParams p, const 
 constexpr int BUILD_STAGES = 3;
 constexpr int BUILD_UNROLL = 4;
 constexpr int BUILD_CHUNK = 256 * BUILD_UNROLL;  // points per chunk
+constexpr int BUILD_QCAP = 128;                  // undecided points parked per block (overflow: decided on the spot)
 
 template <int STRIDE, bool FAST, bool LH_FLOAT>  // STRIDE = 16 or 32 (bytes per point, 16-byte aligned base)
 __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
@@ -727,6 +728,8 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
   int* s_bins = reinterpret_cast<int*>(smem_raw + (size_t)BUILD_STAGES * BUILD_CHUNK * STRIDE);
   __shared__ __align__(8) uint64_t full[BUILD_STAGES];
   __shared__ __align__(8) uint64_t empty[BUILD_STAGES];  // one arrival per warp once it has copied its points out
+  __shared__ float s_queue[BUILD_QCAP * 3];               // points the front end could not decide: exact path, converged, at the end
+  __shared__ unsigned s_qcount;
   __shared__ bool s_last;
   const int RS = p.L.RS;
   const unsigned scan = blockIdx.y;
@@ -743,6 +746,7 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < RS; i += blockDim.x) s_bins[i] = SCGPU_ENC_NOPOINT;
+  if (threadIdx.x == 0) s_qcount = 0;
   __syncthreads();
   auto issue = [&](unsigned c) {
     const unsigned pts = min((unsigned)BUILD_CHUNK, end - start - c * BUILD_CHUNK);
@@ -793,10 +797,20 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
       bin[u] = bin_point_fast<LH_FLOAT>(p.bc, px[u], py[u], pz[u], hh[u]);
       undecided |= (bin[u] == BIN_UNDECIDED);
     }
-    if (undecided) {
+    if (undecided) {  // rare (~3e-4 of the points): park the point; only if the queue is full decide it here
 #pragma unroll
       for (int u = 0; u < BUILD_UNROLL; ++u)
-        if (bin[u] == BIN_UNDECIDED) bin[u] = bin_point_exact_noinline(p.bc, px[u], py[u], pz[u], hh[u]);
+        if (bin[u] == BIN_UNDECIDED) {
+          const unsigned slot = atomicAdd(&s_qcount, 1u);
+          if (slot < (unsigned)BUILD_QCAP) {
+            s_queue[3 * slot] = px[u];
+            s_queue[3 * slot + 1] = py[u];
+            s_queue[3 * slot + 2] = pz[u];
+            bin[u] = -1;
+          } else {
+            bin[u] = bin_point_exact_noinline(p.bc, px[u], py[u], pz[u], hh[u]);
+          }
+        }
     }
     // max into the block's grid.  A bin's value only ever grows, so a plain read is a valid filter: a point that does
     // not beat the value read cannot beat the current one; after the first few points of a bin almost none does.
@@ -806,6 +820,15 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
         const int e = enc_float(hh[u]);
         if (e > s_bins[bin[u]]) atomicMax(&s_bins[bin[u]], e);
       }
+    }
+  }
+  __syncthreads();
+  {  // the parked points: exact path, all lanes busy
+    const unsigned nq = min(s_qcount, (unsigned)BUILD_QCAP);
+    for (unsigned i = threadIdx.x; i < nq; i += blockDim.x) {
+      float h;
+      const int b = bin_point_exact(p.bc, s_queue[3 * i], s_queue[3 * i + 1], s_queue[3 * i + 2], h);
+      if (b >= 0) atomicMax(&s_bins[b], enc_float(h));
     }
   }
   __syncthreads();
