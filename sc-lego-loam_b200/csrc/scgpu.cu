@@ -99,6 +99,7 @@ struct scgpu_handle {
   uint64_t n_global = 0;
   // screening copy for the exhaustive search (only for configurations k_exh_screen is instantiated for)
   bool exh = false;
+  int exh_cfg = 0;  // 1: 20x60 radius 3, 2: 40x120 radius 6
   float* x_sc_hat = nullptr;
   float* x_vkey32 = nullptr;
   ExhAux* x_aux = nullptr;
@@ -421,7 +422,8 @@ int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const 
   cp.n_search = reinterpret_cast<const unsigned long long*>(d_ns);
   cp.K = h->K;
   cp.d32 = h->c_d32.as<float>();
-  k_cand_screen<20, 60, 3><<<(unsigned)nq, CAND_WARPS * 32, 0, st>>>(cp);
+  if (h->exh_cfg == 1) k_cand_screen<20, 60, 3, 1><<<(unsigned)nq, CAND_WARPS * 32, cand_smem_bytes<20, 60, 3>(), st>>>(cp);
+  else k_cand_screen<40, 120, 6, 2><<<(unsigned)nq, CAND_WARPS * 32, cand_smem_bytes<40, 120, 6>(), st>>>(cp);
   k_cand_select<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(h->c_d32.as<float>(), (unsigned)nq, h->K, h->c_list.as<unsigned long long>(),
                                                              h->c_count.as<unsigned>(), h->pair_dist.as<double>(), h->pair_shift.as<int>());
   ScoreParams p;
@@ -652,11 +654,14 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
     sp.d32_pitch = pitch;
     sp.d32 = h->x_d32.as<float>();
     sp.min_bits = d_min;
-    const uint64_t groups = (n_max + EXH_WARPS - 1) / EXH_WARPS;
+    const uint64_t ew = h->exh_cfg == 1 ? 14 : 3;  // consumer warps = entries per ring slot of the instantiation
+    const uint64_t groups = (n_max + ew - 1) / ew;
     const unsigned grid = (unsigned)(groups < (uint64_t)h->sm_count ? groups : (uint64_t)h->sm_count);
-    const size_t smem = exh_smem_bytes<20, 60, 3>();
     if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
-    k_exh_screen<20, 60, 3><<<dim3(grid, (unsigned)nq), (EXH_WARPS + 1) * 32, smem, st>>>(sp);
+    if (h->exh_cfg == 1)
+      k_exh_screen<20, 60, 3, 1, 14><<<dim3(grid, (unsigned)nq), (14 + 1) * 32, exh_smem_bytes<20, 60, 3, 14>(), st>>>(sp);
+    else
+      k_exh_screen<40, 120, 6, 2, 3><<<dim3(grid, (unsigned)nq), (3 + 1) * 32, exh_smem_bytes<40, 120, 6, 3>(), st>>>(sp);
     if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
     CK(cudaGetLastError());
     const unsigned rb = (unsigned)((n_max + 1023) / 1024 < 296 ? (n_max + 1023) / 1024 : 296);
@@ -736,7 +741,9 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   h->W = 2 * h->radius + 1;
   h->db.rank = cfg->shard_rank;
   h->db.G = cfg->shard_count;
-  h->exh = (h->L.R == 20 && h->L.S == 60 && h->radius == 3) && !(cfg->flags & SCGPU_FLAG_NO_SCREENING);
+  // FP32 screening kernels are instantiated for the reference's 20x60 (radius 3) and BASELINE's 40x120 (radius 6)
+  h->exh_cfg = (h->L.R == 20 && h->L.S == 60 && h->radius == 3) ? 1 : ((h->L.R == 40 && h->L.S == 120 && h->radius == 6) ? 2 : 0);
+  h->exh = h->exh_cfg != 0 && !(cfg->flags & SCGPU_FLAG_NO_SCREENING);
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   const size_t smem_f = pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float));
   const size_t smem_d = pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(double));
@@ -760,10 +767,13 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
   if (e == cudaSuccess && h->exh)
-    e = cudaFuncSetAttribute(k_exh_screen<20, 60, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)exh_smem_bytes<20, 60, 3>());
+    e = h->exh_cfg == 1 ? cudaFuncSetAttribute(k_exh_screen<20, 60, 3, 1, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)exh_smem_bytes<20, 60, 3, 14>())
+                        : cudaFuncSetAttribute(k_exh_screen<40, 120, 6, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)exh_smem_bytes<40, 120, 6, 3>());
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
+  if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e == cudaSuccess && smem_d > 48 * 1024) e = cudaFuncSetAttribute(k_pair_api, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
   if (e != cudaSuccess) {
     delete h;
@@ -1427,7 +1437,7 @@ int scgpu_stage_gather(scgpu_handle* h, uint64_t global_idx, void* d_record, voi
 
 int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_qrecords, size_t nq, const uint64_t* n_search, void* d_best_out, void* stream) {
   if (!h || !d_qrecords || !d_best_out || (!n_search && nq)) return fail(SCGPU_E_INVALID, "null argument");
-  if (!h->exh) return fail(SCGPU_E_INVALID, "screening kernel is instantiated for 20x60, search radius 3 only");
+  if (!h->exh) return fail(SCGPU_E_INVALID, "screening kernels are instantiated for 20x60 (radius 3) and 40x120 (radius 6) only");
   CK(cudaSetDevice(h->cfg.device));
   for (size_t i0 = 0; i0 < nq; i0 += EXH_MAX_BATCH) {
     const size_t m = nq - i0 < EXH_MAX_BATCH ? nq - i0 : EXH_MAX_BATCH;

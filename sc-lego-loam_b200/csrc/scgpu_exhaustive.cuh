@@ -73,11 +73,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                : "memory");
 }
 
-// per-entry auxiliary record kept next to the normalised descriptor
+// per-entry auxiliary record kept next to the normalised descriptor (32 bytes: TMA copies need multiples of 16)
 struct ExhAux {
-  unsigned long long vmask;  // bit c: column c has a non-zero norm
-  float vnorm;               // |sector key| (float)
-  unsigned flags;            // bit 0: a column norm is not representable / not finite in FP32 -> always rescore
+  unsigned long long vmask[2];  // bit c: column c has a non-zero norm (up to 128 sectors)
+  float vnorm;                  // |sector key| (float)
+  unsigned flags;               // bit 0: a column norm is not representable / not finite in FP32 -> always rescore
+  unsigned long long pad;
 };
 
 struct ExhDb {
@@ -88,48 +89,44 @@ struct ExhDb {
 
 // query pack built by k_exh_prep: normalised query, float sector key, valid-column mask, |v1|
 struct ExhQuery {
-  float qhat[64 * 64];   // row-major like the database copy; only R*S used (instantiations keep R*S <= 4096)
-  float v1[64];
-  unsigned long long qmask;
+  float qhat[40 * 128];  // row-major like the database copy; only R*S used
+  float v1[128];
+  unsigned long long qmask[2];
   float v1norm;
   unsigned flags;
 };
 
-// Screening side data of one record (descriptor, keys): used by k_append for the database and by k_exh_prep for
-// the query.  One block; every thread may call.
+// Screening side data of one descriptor (stored entry or query record).  One block; every thread calls.
 __device__ __forceinline__ void exh_normalise(const float* sc, const double* sector, const double* norm, const Layout& L, float* sc_hat,
                                               float* vkey32, unsigned long long* vmask, float* vnorm, unsigned* flags) {
-  __shared__ unsigned long long s_mask;
+  __shared__ unsigned long long s_mask[2];
   __shared__ unsigned s_flags;
   __shared__ float s_v2;
+  __shared__ float s_inv[128];
   if (threadIdx.x == 0) {
-    s_mask = 0;
+    s_mask[0] = s_mask[1] = 0;
     s_flags = 0;
     s_v2 = 0.f;
   }
   __syncthreads();
-  __shared__ float s_inv[1024];
   for (int c = threadIdx.x; c < L.S; c += blockDim.x) {
     const double n = norm[c];
+    const float nf = (float)n, v = (float)sector[c];
     s_inv[c] = (n == 0.0) ? 0.f : (float)(1.0 / n);
+    vkey32[c] = v;
+    if (n != 0.0) atomicOr(&s_mask[c >> 6], 1ull << (c & 63));
+    if (n != 0.0 && !(nf > 1e-30f && nf < 1e30f)) atomicOr(&s_flags, 1u);  // subnormal-ish, inf or NaN norm
+    if (!(fabsf(v) < 1e30f)) atomicOr(&s_flags, 1u);
+    atomicAdd(&s_v2, v * v);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < L.RS; i += blockDim.x) {  // ROW-major output: element (r, c) at r*S + c
     const int r = i / L.S, c = i - r * L.S;
     sc_hat[i] = sc[c * L.R + r] * s_inv[c];
   }
-  for (int c = threadIdx.x; c < L.S; c += blockDim.x) {
-    const double n = norm[c];
-    const float nf = (float)n, v = (float)sector[c];
-    vkey32[c] = v;
-    if (n != 0.0 && c < 64) atomicOr(&s_mask, 1ull << c);
-    if (n != 0.0 && !(nf > 1e-30f && nf < 1e30f)) atomicOr(&s_flags, 1u);  // subnormal-ish, inf or NaN norm
-    if (!(fabsf(v) < 1e30f)) atomicOr(&s_flags, 1u);
-    atomicAdd(&s_v2, v * v);
-  }
-  __syncthreads();
   if (threadIdx.x == 0) {
-    *vmask = s_mask;
+    vmask[0] = s_mask[0];
+    vmask[1] = s_mask[1];
     *vnorm = sqrtf(s_v2);
     *flags = s_flags;
   }
@@ -137,10 +134,10 @@ __device__ __forceinline__ void exh_normalise(const float* sc, const double* sec
 }
 
 // database side of the screening data: local entries [first_local, first_local + gridDim.x), derived from the stored
-// descriptor / sector key / column norms (built lazily, right before the first exhaustive search that needs them)
+// descriptor / sector key / column norms (built lazily, right before the first search that needs them)
 __global__ void __launch_bounds__(128) k_exh_append(Layout L, Db db, float* sc_hat, float* vkey32, ExhAux* aux, unsigned long long first_local) {
   const unsigned long long l = first_local + blockIdx.x;
-  exh_normalise(db.sc + l * L.RS, db.sector + l * L.S, db.colnorm + l * L.S, L, sc_hat + l * L.RS, vkey32 + l * L.S, &aux[l].vmask,
+  exh_normalise(db.sc + l * L.RS, db.sector + l * L.S, db.colnorm + l * L.S, L, sc_hat + l * L.RS, vkey32 + l * L.S, aux[l].vmask,
                 &aux[l].vnorm, &aux[l].flags);
 }
 
@@ -154,7 +151,7 @@ __global__ void __launch_bounds__(256) k_exh_prep(const unsigned char* qrecs, La
   ExhQuery* dst = qs + q;
   const unsigned char* rec = qrecs + (size_t)q * L.rec_bytes;
   exh_normalise(reinterpret_cast<const float*>(rec), reinterpret_cast<const double*>(rec + L.off_sector),
-                reinterpret_cast<const double*>(rec + L.off_norm), L, dst->qhat, dst->v1, &dst->qmask, &dst->v1norm, &dst->flags);
+                reinterpret_cast<const double*>(rec + L.off_norm), L, dst->qhat, dst->v1, dst->qmask, &dst->v1norm, &dst->flags);
 }
 
 struct ExhScreenParams {     // grid (blocks, queries): blockIdx.y selects the query of the batch
@@ -166,26 +163,171 @@ struct ExhScreenParams {     // grid (blocks, queries): blockIdx.y selects the q
   unsigned* min_bits;                  // [nq] out: bit pattern of the smallest certain d32 (atomicMin; pre-set to +inf)
 };
 
-// shared memory rings: one slot holds a group of EXH_WARPS entries.  The descriptor of group g is needed one
-// iteration later than its sector key, so the two live in rings of different depth (more warps fit).
-template <int R, int S>
-struct ExhScSlot {
-  float sc_hat[EXH_WARPS][R * S];
-};
+// ---- pieces shared by k_exh_screen and k_cand_screen -------------------------------------------------------------
+// acc[d] += sum_p held[p] * qs[p + d]   (held: S floats read with 16-byte loads; qs: doubled query row)
+template <int S, int W>
+__device__ __forceinline__ void window_fma(const float4* held4, const float* qs, float (&acc)[W]) {
+  float held[S];
+#pragma unroll
+  for (int i = 0; i < S / 4; ++i) {
+    const float4 v = held4[i];
+    held[4 * i] = v.x;
+    held[4 * i + 1] = v.y;
+    held[4 * i + 2] = v.z;
+    held[4 * i + 3] = v.w;
+  }
+  float win[W];
+#pragma unroll
+  for (int d = 0; d < W - 1; ++d) win[d] = qs[d];
+#pragma unroll
+  for (int pp = 0; pp < S; ++pp) {
+    win[W - 1] = qs[pp + W - 1];
+#pragma unroll
+    for (int d = 0; d < W; ++d) acc[d] = __fmaf_rn(held[pp], win[d], acc[d]);
+#pragma unroll
+    for (int d = 0; d < W - 1; ++d) win[d] = win[d + 1];
+  }
+}
+
+// Sum acc[0..W) over the lanes flagged `contributes` with a transpose-reduce (NV -> NV/2 -> ... -> 1 values per lane
+// while summing across xor 16, 8, ...); returns the total that belongs to this lane's shift index *d_mine.
+template <int W>
+__device__ __forceinline__ float transpose_reduce(const float (&acc)[W], bool contributes, int lane, int* d_mine) {
+  static_assert(W <= 16, "at most 16 shifts per window");
+  if (W <= 8) {
+    float r8[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) r8[d] = (contributes && d < W) ? acc[d < W ? d : 0] : 0.f;
+    float r4[4], r2[2], r1;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r4[i] = (h16 ? r8[4 + i] : r8[i]) + __shfl_xor_sync(FULL, h16 ? r8[i] : r8[4 + i], 16);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) r2[i] = (h8 ? r4[2 + i] : r4[i]) + __shfl_xor_sync(FULL, h8 ? r4[i] : r4[2 + i], 8);
+    r1 = (h4 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, h4 ? r2[0] : r2[1], 4);
+    r1 += __shfl_xor_sync(FULL, r1, 2);
+    r1 += __shfl_xor_sync(FULL, r1, 1);
+    *d_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    return r1;
+  } else {
+    float r16[16];
+#pragma unroll
+    for (int d = 0; d < 16; ++d) r16[d] = (contributes && d < W) ? acc[d < W ? d : 0] : 0.f;
+    float r8[8], r4[4], r2[2], r1;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r8[i] = (h16 ? r16[8 + i] : r16[i]) + __shfl_xor_sync(FULL, h16 ? r16[i] : r16[8 + i], 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r4[i] = (h8 ? r8[4 + i] : r8[i]) + __shfl_xor_sync(FULL, h8 ? r8[i] : r8[4 + i], 8);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) r2[i] = (h4 ? r4[2 + i] : r4[i]) + __shfl_xor_sync(FULL, h4 ? r4[i] : r4[2 + i], 4);
+    r1 = (h2 ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, h2 ? r2[0] : r2[1], 2);
+    r1 += __shfl_xor_sync(FULL, r1, 1);
+    *d_mine = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    return r1;
+  }
+}
+
+// number of column pairs (query column j, candidate column (j - sft) mod S) with both columns non-zero
 template <int S>
+__device__ __forceinline__ int valid_pairs(const unsigned long long (&qmask)[2], const unsigned long long (&vmask)[2], int sft) {
+  if (S <= 64) {
+    const unsigned long long m = vmask[0];
+    const unsigned long long rot = sft == 0 ? m : (((m << sft) | (m >> (S - sft))) & ((S == 64) ? ~0ull : ((1ull << (S & 63)) - 1)));
+    return __popcll(qmask[0] & rot);
+  } else {
+    typedef unsigned __int128 u128;
+    const u128 m = ((u128)vmask[1] << 64) | vmask[0];
+    const u128 full = (S == 128) ? ~(u128)0 : ((((u128)1) << (S & 127)) - 1);
+    const u128 rot = sft == 0 ? m : (((m << sft) | (m >> (S - sft))) & full);
+    return __popcll(qmask[0] & (unsigned long long)rot) + __popcll(qmask[1] & (unsigned long long)(rot >> 64));
+  }
+}
+
+// The screened distance of one entry from the per-shift totals: every lane evaluates "its" shift (acc index d belongs
+// to shift a_cur - RAD + d), then a warp minimum.  Returns the value to store (-1 = rescore, +inf = cannot win).
+template <int S, int RAD>
+__device__ __forceinline__ float screened_distance(float total, int d_mine, int a_cur, const unsigned long long (&qmask)[2], const ExhAux& ax,
+                                                   bool ambiguous, bool q_flag) {
+  constexpr int W = 2 * RAD + 1;
+  float dist = __int_as_float(0x7f800000);  // +inf: no valid column pair at this shift -> the reference yields NaN there
+  bool nan_here = false;
+  if (d_mine < W) {
+    int sft = (a_cur + d_mine - RAD) % S;
+    if (sft < 0) sft += S;
+    const int n = valid_pairs<S>(qmask, ax.vmask, sft);
+    if (n > 0) {
+      dist = 1.0f - total / (float)n;
+      nan_here = !(dist == dist);
+    }
+  }
+  const bool any_nan = __any_sync(FULL, nan_here);
+  float best = nan_here ? __int_as_float(0x7f800000) : dist;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(FULL, best, o));
+  if (ambiguous || any_nan || (ax.flags & 1u) || q_flag) return -1.0f;
+  return best < 0.f ? 0.f : best;  // tiny negative from rounding stays a valid "certain" value
+}
+
+// argmax over the alignment lanes' correlations acc[d] = corr(base + d): best shift and whether the runner-up is
+// within the FP32 error bound (ambiguous -> the exact path must decide)
+template <int S, int W>
+__device__ __forceinline__ void align_argmax(const float (&acc)[W], bool has, int base, float margin_scale, int* a_out, bool* amb_out) {
+  float b1 = -__int_as_float(0x7f800000), b2 = b1;
+  int s1 = 0x7fffffff;
+  if (has) {
+#pragma unroll
+    for (int d = 0; d < W; ++d) {
+      const int s = base + d;
+      if (s < S) {
+        const float c = acc[d];
+        if (c > b1 || (c == b1 && s < s1)) {
+          b2 = b1;
+          b1 = c;
+          s1 = s;
+        } else if (c > b2) {
+          b2 = c;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob1 = __shfl_xor_sync(FULL, b1, o), ob2 = __shfl_xor_sync(FULL, b2, o);
+    const int os1 = __shfl_xor_sync(FULL, s1, o);
+    if (ob1 > b1 || (ob1 == b1 && os1 < s1)) {
+      b2 = fmaxf(b1, ob2);
+      b1 = ob1;
+      s1 = os1;
+    } else {
+      b2 = fmaxf(b2, ob1);
+    }
+  }
+  *a_out = (s1 == 0x7fffffff) ? 0 : s1;
+  *amb_out = !((b1 - b2) > EXH_ALIGN_MARGIN * margin_scale) || !(b1 == b1);
+}
+
+// shared memory rings: one slot holds a group of EW entries.  The descriptor of group g is needed one iteration later
+// than its sector key, so the two live in rings of different depth (more warps fit).
+template <int R, int S, int EW>
+struct ExhScSlot {
+  float sc_hat[EW][R * S];
+};
+template <int S, int EW>
 struct ExhVkSlot {
-  float vkey[EXH_WARPS][S];
-  ExhAux aux[EXH_WARPS];
+  float vkey[EW][S];
+  ExhAux aux[EW];
 };
 
-template <int R, int S, int RAD>
+template <int R, int S, int RAD, int EW>
 constexpr size_t exh_smem_bytes() {
-  return sizeof(ExhScSlot<R, S>) * EXH_SC_STAGES + sizeof(ExhVkSlot<S>) * EXH_VK_STAGES +
+  return sizeof(ExhScSlot<R, S, EW>) * EXH_SC_STAGES + sizeof(ExhVkSlot<S, EW>) * EXH_VK_STAGES +
          2 * (EXH_SC_STAGES + EXH_VK_STAGES) * sizeof(uint64_t) + (size_t)(R + 1) * (((2 * S + 2 * RAD + 1) | 1)) * sizeof(float);
 }
 
-template <int R, int S, int RAD>
-__global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const ExhScreenParams pp) {
+// R x S descriptor, search radius RAD, RPL descriptor rows per lane, EW consumer warps (= entries per ring slot)
+template <int R, int S, int RAD, int RPL, int EW>
+__global__ void __launch_bounds__((EW + 1) * 32, 1) k_exh_screen(const ExhScreenParams pp) {
   // this block's query
   struct {
     ExhDb db;
@@ -200,31 +342,32 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
   p.d32 = pp.d32 + blockIdx.y * pp.d32_pitch;
   p.min_bits = pp.min_bits + blockIdx.y;
   constexpr int W = 2 * RAD + 1;
+  constexpr int ROW_LANES = R / RPL;
   constexpr int ALIGN_LANES = (S + W - 1) / W;
   constexpr int PITCH = (2 * S + W) | 1;  // odd pitch: lanes (rows) hit distinct banks
-  static_assert(R + ALIGN_LANES <= 32, "rows + alignment lanes must fit one warp");
-  static_assert(S <= 64 && S % 4 == 0, "valid-column masks are 64 bits; rows are read with 16-byte loads");
+  static_assert(R % RPL == 0 && ROW_LANES + ALIGN_LANES <= 32, "rows + alignment lanes must fit one warp");
+  static_assert(S <= 128 && S % 4 == 0, "valid-column masks are 128 bits; rows are read with 16-byte loads");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ExhScSlot<R, S>* sc_ring = reinterpret_cast<ExhScSlot<R, S>*>(smem_raw);
-  ExhVkSlot<S>* vk_ring = reinterpret_cast<ExhVkSlot<S>*>(smem_raw + sizeof(ExhScSlot<R, S>) * EXH_SC_STAGES);
-  uint64_t* full_sc = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(vk_ring) + sizeof(ExhVkSlot<S>) * EXH_VK_STAGES);
+  ExhScSlot<R, S, EW>* sc_ring = reinterpret_cast<ExhScSlot<R, S, EW>*>(smem_raw);
+  ExhVkSlot<S, EW>* vk_ring = reinterpret_cast<ExhVkSlot<S, EW>*>(smem_raw + sizeof(ExhScSlot<R, S, EW>) * EXH_SC_STAGES);
+  uint64_t* full_sc = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(vk_ring) + sizeof(ExhVkSlot<S, EW>) * EXH_VK_STAGES);
   uint64_t* empty_sc = full_sc + EXH_SC_STAGES;
   uint64_t* full_vk = empty_sc + EXH_SC_STAGES;
   uint64_t* empty_vk = full_vk + EXH_VK_STAGES;
   float* qtable = reinterpret_cast<float*>(empty_vk + EXH_VK_STAGES);  // [(R+1)][PITCH]: rows 0..R-1 = A^ rows, row R = v1, each doubled
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned long long n_groups = (p.n_local + EXH_WARPS - 1) / EXH_WARPS;  // groups of EXH_WARPS entries
+  const unsigned long long n_groups = (p.n_local + EW - 1) / EW;  // groups of EW entries
   const unsigned long long my_groups = n_groups > blockIdx.x ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < EXH_SC_STAGES; ++s) {
       mbar_init(&full_sc[s], 1);
-      mbar_init(&empty_sc[s], EXH_WARPS);
+      mbar_init(&empty_sc[s], EW);
     }
     for (int s = 0; s < EXH_VK_STAGES; ++s) {
       mbar_init(&full_vk[s], 1);
-      mbar_init(&empty_vk[s], EXH_WARPS);
+      mbar_init(&empty_vk[s], EW);
     }
     fence_barrier_init();
   }
@@ -234,12 +377,12 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
   }
   __syncthreads();
 
-  if (warp == EXH_WARPS) {
+  if (warp == EW) {
     // ===== producer: one lane feeds both rings with TMA bulk copies =====
     if (lane == 0) {
       for (unsigned long long k = 0; k < my_groups; ++k) {
-        const unsigned long long e0 = (blockIdx.x + k * gridDim.x) * EXH_WARPS;
-        const unsigned n = (unsigned)(p.n_local - e0 < EXH_WARPS ? p.n_local - e0 : EXH_WARPS);
+        const unsigned long long e0 = (blockIdx.x + k * gridDim.x) * EW;
+        const unsigned n = (unsigned)(p.n_local - e0 < EW ? p.n_local - e0 : EW);
         const unsigned b_sc = n * R * S * 4u, b_vk = n * S * 4u, b_aux = n * (unsigned)sizeof(ExhAux);
         const int sv = (int)(k % EXH_VK_STAGES), ss = (int)(k % EXH_SC_STAGES);
         if (k >= EXH_VK_STAGES) mbar_wait(&empty_vk[sv], (uint32_t)(((k / EXH_VK_STAGES) - 1) & 1));
@@ -255,12 +398,11 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
   }
 
   // ===== consumers: warp w scores entry w of every group =====
-  // lane roles: [0, R) own a descriptor row; [R, R+ALIGN_LANES) own W consecutive alignment shifts
-  const bool row_lane = lane < R, align_lane = lane >= R && lane < R + ALIGN_LANES;
-  const unsigned long long qmask = p.q->qmask;
+  // lane roles: [0, ROW_LANES) own RPL descriptor rows each; [ROW_LANES, ROW_LANES+ALIGN_LANES) own W alignment shifts
+  const bool row_lane = lane < ROW_LANES, align_lane = lane >= ROW_LANES && lane < ROW_LANES + ALIGN_LANES;
+  const unsigned long long qmask[2] = {p.q->qmask[0], p.q->qmask[1]};
   const float v1norm = p.q->v1norm;
   const bool q_flag = (p.q->flags & 1u) != 0;
-  const float* qrow = qtable + (row_lane ? lane : R) * PITCH;
 
   int a_cur = 0;          // alignment of the entry whose window is scored in this iteration
   bool amb_cur = false;
@@ -273,101 +415,44 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
     bool ent_w = false, ent_a = false;
     unsigned long long e_w = 0;
     if (has_win) {
-      e_w = (blockIdx.x + (k - 1) * gridDim.x) * EXH_WARPS + warp;
+      e_w = (blockIdx.x + (k - 1) * gridDim.x) * EW + warp;
       ent_w = e_w < p.n_local;
       mbar_wait(&full_sc[sc_w], (uint32_t)(((k - 1) / EXH_SC_STAGES) & 1));
     }
     if (has_al) {
       mbar_wait(&full_vk[vk_a], (uint32_t)((k / EXH_VK_STAGES) & 1));
-      ent_a = (blockIdx.x + k * gridDim.x) * EXH_WARPS + warp < p.n_local;
-    }
-    // held[p]: the candidate's row (row lanes) / sector key (alignment lanes); base: first shift of this lane
-    const float4* held4 = nullptr;
-    int base = 0;
-    if (row_lane && ent_w) {
-      held4 = reinterpret_cast<const float4*>(&sc_ring[sc_w].sc_hat[warp][lane * S]);
-      base = ((a_cur - RAD) % S + S) % S;
-    } else if (align_lane && ent_a) {
-      held4 = reinterpret_cast<const float4*>(&vk_ring[vk_a].vkey[warp][0]);
-      base = (lane - R) * W;
+      ent_a = (blockIdx.x + k * gridDim.x) * EW + warp < p.n_local;
     }
     float acc[W];
 #pragma unroll
     for (int d = 0; d < W; ++d) acc[d] = 0.f;
-    if (held4) {
-      // acc[d] = sum_p held[p] * q[(p + base + d) mod S]; the doubled table makes (p + base + d) a plain offset
-      float held[S];
+    // One instruction stream for both lane roles (row lanes: window of group k-1; alignment lanes: correlation of
+    // group k): each lane only differs in WHERE its held values and its query row come from.
+    //   acc[d] = sum over my rows r, columns p of held_r[p] * q_r[(p + base + d) mod S]  (doubled table: plain index)
+    int base = 0;
+    if (row_lane && ent_w) base = ((a_cur - RAD) % S + S) % S;
+    else if (align_lane && ent_a) base = (lane - ROW_LANES) * W;
 #pragma unroll
-      for (int i = 0; i < S / 4; ++i) {
-        const float4 v = held4[i];
-        held[4 * i] = v.x;
-        held[4 * i + 1] = v.y;
-        held[4 * i + 2] = v.z;
-        held[4 * i + 3] = v.w;
+    for (int i = 0; i < RPL; ++i) {
+      const float4* held4 = nullptr;
+      const float* qs = nullptr;
+      if (row_lane && ent_w) {
+        const int r = lane + i * ROW_LANES;
+        held4 = reinterpret_cast<const float4*>(&sc_ring[sc_w].sc_hat[warp][r * S]);
+        qs = qtable + r * PITCH + base;
+      } else if (i == 0 && align_lane && ent_a) {
+        held4 = reinterpret_cast<const float4*>(&vk_ring[vk_a].vkey[warp][0]);
+        qs = qtable + R * PITCH + base;
       }
-      const float* qs = qrow + base;
-      float win[W];
-#pragma unroll
-      for (int d = 0; d < W - 1; ++d) win[d] = qs[d];
-#pragma unroll
-      for (int pp = 0; pp < S; ++pp) {
-        win[W - 1] = qs[pp + W - 1];
-#pragma unroll
-        for (int d = 0; d < W; ++d) acc[d] = __fmaf_rn(held[pp], win[d], acc[d]);
-#pragma unroll
-        for (int d = 0; d < W - 1; ++d) win[d] = win[d + 1];
-      }
+      if (held4) window_fma<S, W>(held4, qs, acc);
     }
-    // ---- window result of group k-1: acc[d] belongs to shift a_cur - RAD + d ----------------------
+    // ---- window result of group k-1 ------------------------------------------------------------------
     if (has_win) {
-      // transpose-reduce over the row lanes: 8 -> 4 -> 2 -> 1 values per lane while summing across xor 16, 8, 4,
-      // then xor 2, 1; lane l ends with the total of shift index d = 4*bit4(l) + 2*bit3(l) + bit2(l)
-      static_assert(W <= 8, "the transpose-reduce handles up to 8 shifts");
-      float r8[8];
-#pragma unroll
-      for (int d = 0; d < 8; ++d) r8[d] = (row_lane && d < W) ? acc[d] : 0.f;
-      float r4[4], r2[2], r1;
-      {
-        const bool hi = lane & 16;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) r4[i] = (hi ? r8[4 + i] : r8[i]) + __shfl_xor_sync(FULL, hi ? r8[i] : r8[4 + i], 16);
-      }
-      {
-        const bool hi = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) r2[i] = (hi ? r4[2 + i] : r4[i]) + __shfl_xor_sync(FULL, hi ? r4[i] : r4[2 + i], 8);
-      }
-      {
-        const bool hi = lane & 4;
-        r1 = (hi ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, hi ? r2[0] : r2[1], 4);
-      }
-      r1 += __shfl_xor_sync(FULL, r1, 2);
-      r1 += __shfl_xor_sync(FULL, r1, 1);
-      const int d_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-      // every lane: distance of "its" shift; acc index d belongs to shift a_cur - RAD + d
+      int d_mine;
+      const float total = transpose_reduce<W>(acc, row_lane, lane, &d_mine);
       const ExhAux ax = vk_ring[vk_w].aux[ent_w ? warp : 0];
-      float dist = __int_as_float(0x7f800000);  // +inf: no valid column pair at this shift -> the reference yields NaN there
-      bool nan_here = false;
-      if (d_mine < W) {
-        int sft = (a_cur + d_mine - RAD) % S;  // query column j pairs with candidate column (j - sft) mod S
-        if (sft < 0) sft += S;
-        const unsigned long long m = ax.vmask;
-        const unsigned long long rot = sft == 0 ? m : (((m << sft) | (m >> (S - sft))) & ((S == 64) ? ~0ull : ((1ull << S) - 1)));
-        const int n = __popcll(qmask & rot);
-        if (n > 0) {
-          dist = 1.0f - r1 / (float)n;
-          nan_here = !(dist == dist);
-        }
-      }
-      const bool any_nan = __any_sync(FULL, nan_here);
-      float best = nan_here ? __int_as_float(0x7f800000) : dist;
-      best = fminf(best, __shfl_xor_sync(FULL, best, 16));
-      best = fminf(best, __shfl_xor_sync(FULL, best, 8));
-      best = fminf(best, __shfl_xor_sync(FULL, best, 4));
+      const float out = screened_distance<S, RAD>(total, d_mine, a_cur, qmask, ax, amb_cur, q_flag);
       if (lane == 0 && ent_w) {
-        float out = best;
-        if (amb_cur || any_nan || (ax.flags & 1u) || q_flag) out = -1.0f;
-        else if (out < 0.f) out = 0.f;  // tiny negative from rounding: keep it a valid "certain" value
         p.d32[e_w] = out;
         if (out >= 0.f) my_min = min(my_min, __float_as_uint(out));
       }
@@ -377,42 +462,10 @@ __global__ void __launch_bounds__((EXH_WARPS + 1) * 32, 1) k_exh_screen(const Ex
         mbar_arrive(&empty_vk[vk_w]);
       }
     }
-    // ---- alignment result of group k (becomes a_cur of the next iteration): acc[d] = corr(base + d) ----
+    // ---- alignment result of group k (becomes a_cur of the next iteration) -------------------------------
     if (has_al) {
-      float b1 = -__int_as_float(0x7f800000), b2 = b1;  // best / runner-up correlation
-      int s1 = 0x7fffffff;
-      if (align_lane && ent_a) {
-#pragma unroll
-        for (int d = 0; d < W; ++d) {
-          const int s = base + d;
-          if (s < S) {
-            const float c = acc[d];
-            if (c > b1 || (c == b1 && s < s1)) {
-              b2 = b1;
-              b1 = c;
-              s1 = s;
-            } else if (c > b2) {
-              b2 = c;
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob1 = __shfl_xor_sync(FULL, b1, o), ob2 = __shfl_xor_sync(FULL, b2, o);
-        const int os1 = __shfl_xor_sync(FULL, s1, o);
-        if (ob1 > b1 || (ob1 == b1 && os1 < s1)) {
-          b2 = fmaxf(b1, ob2);
-          b1 = ob1;
-          s1 = os1;
-        } else {
-          b2 = fmaxf(b2, ob1);
-        }
-      }
       const float vn = ent_a ? vk_ring[vk_a].aux[warp].vnorm : 0.f;
-      a_cur = (s1 == 0x7fffffff) ? 0 : s1;
-      // ambiguous: runner-up within the FP32 error bound of the best, or anything non-finite
-      amb_cur = !((b1 - b2) > EXH_ALIGN_MARGIN * v1norm * vn) || !(b1 == b1);
+      align_argmax<S, W>(acc, align_lane && ent_a, base, v1norm * vn, &a_cur, &amb_cur);
     }
   }
   if (lane == 0 && my_min != 0x7f800000u) atomicMin(p.min_bits, my_min);
@@ -504,40 +557,16 @@ struct CandScreenParams {
   float* d32;                           // [nq][K] out: approx distance; -1 = rescore; +inf = cannot win / not mine
 };
 
-template <int S, int W>
-__device__ __forceinline__ void window_fma(const float4* held4, const float* qs, float (&acc)[W]) {
-  // acc[d] = sum_p held[p] * qs[p + d]
-  float held[S];
-#pragma unroll
-  for (int i = 0; i < S / 4; ++i) {
-    const float4 v = held4[i];
-    held[4 * i] = v.x;
-    held[4 * i + 1] = v.y;
-    held[4 * i + 2] = v.z;
-    held[4 * i + 3] = v.w;
-  }
-  float win[W];
-#pragma unroll
-  for (int d = 0; d < W - 1; ++d) win[d] = qs[d];
-#pragma unroll
-  for (int pp = 0; pp < S; ++pp) {
-    win[W - 1] = qs[pp + W - 1];
-#pragma unroll
-    for (int d = 0; d < W; ++d) acc[d] = __fmaf_rn(held[pp], win[d], acc[d]);
-#pragma unroll
-    for (int d = 0; d < W - 1; ++d) win[d] = win[d + 1];
-  }
-}
-
-template <int R, int S, int RAD>
+template <int R, int S, int RAD, int RPL>
 __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScreenParams p) {
   constexpr int W = 2 * RAD + 1;
+  constexpr int ROW_LANES = R / RPL;
   constexpr int ALIGN_LANES = (S + W - 1) / W;
   constexpr int PITCH = (2 * S + W) | 1;
-  static_assert(R + ALIGN_LANES <= 32 && S <= 64 && S % 4 == 0 && W <= 8, "see k_exh_screen");
-  __shared__ float qtable[(R + 1) * PITCH];
+  static_assert(R % RPL == 0 && ROW_LANES + ALIGN_LANES <= 32 && S <= 128 && S % 4 == 0, "see k_exh_screen");
+  extern __shared__ __align__(16) float qtable[];  // [(R + 1)][PITCH]
   __shared__ float s_inv[S];
-  __shared__ unsigned long long s_mask;
+  __shared__ unsigned long long s_mask[2];
   __shared__ unsigned s_flags;
   __shared__ float s_v2;
   const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -547,7 +576,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
   const double* qsector = reinterpret_cast<const double*>(qrec + p.L.off_sector);
   const double* qnorm = reinterpret_cast<const double*>(qrec + p.L.off_norm);
   if (threadIdx.x == 0) {
-    s_mask = 0;
+    s_mask[0] = s_mask[1] = 0;
     s_flags = 0;
     s_v2 = 0.f;
   }
@@ -557,7 +586,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
       const double n = qnorm[c];
       const float nf = (float)n, v = (float)qsector[c];
       s_inv[c] = (n == 0.0) ? 0.f : (float)(1.0 / n);
-      if (n != 0.0) atomicOr(&s_mask, 1ull << c);
+      if (n != 0.0) atomicOr(&s_mask[c >> 6], 1ull << (c & 63));
       if ((n != 0.0 && !(nf > 1e-30f && nf < 1e30f)) || !(fabsf(v) < 1e30f)) atomicOr(&s_flags, 1u);
       atomicAdd(&s_v2, v * v);
     }
@@ -570,11 +599,10 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
     }
   }
   __syncthreads();
-  const unsigned long long qmask = s_mask;
+  const unsigned long long qmask[2] = {s_mask[0], s_mask[1]};
   const float v1norm = sqrtf(s_v2);
   const bool q_flag = s_flags != 0;
-  const bool row_lane = lane < R, align_lane = lane >= R && lane < R + ALIGN_LANES;
-  const float* qrow = qtable + (row_lane ? lane : R) * PITCH;
+  const bool row_lane = lane < ROW_LANES, align_lane = lane >= ROW_LANES && lane < ROW_LANES + ALIGN_LANES;
 
   for (int k = warp; k < p.K; k += CAND_WARPS) {
     const size_t o = (size_t)q * p.K + k;
@@ -586,95 +614,36 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
     }
     const unsigned long long l = g / (unsigned long long)p.db.G;
     const ExhAux ax = p.xdb.aux[l];
-    // ---- alignment: acc[d] = corr(base + d) on the alignment lanes
+    // ---- alignment on the alignment lanes
     float acc[W];
 #pragma unroll
     for (int d = 0; d < W; ++d) acc[d] = 0.f;
-    int base = (lane - R) * W;
-    if (align_lane) window_fma<S, W>(reinterpret_cast<const float4*>(p.xdb.vkey32 + l * S), qrow + base, acc);
-    float b1 = -__int_as_float(0x7f800000), b2 = b1;
-    int s1 = 0x7fffffff;
-    if (align_lane) {
-#pragma unroll
-      for (int d = 0; d < W; ++d) {
-        const int s = base + d;
-        if (s < S) {
-          const float c = acc[d];
-          if (c > b1 || (c == b1 && s < s1)) {
-            b2 = b1;
-            b1 = c;
-            s1 = s;
-          } else if (c > b2) {
-            b2 = c;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float ob1 = __shfl_xor_sync(FULL, b1, off), ob2 = __shfl_xor_sync(FULL, b2, off);
-      const int os1 = __shfl_xor_sync(FULL, s1, off);
-      if (ob1 > b1 || (ob1 == b1 && os1 < s1)) {
-        b2 = fmaxf(b1, ob2);
-        b1 = ob1;
-        s1 = os1;
-      } else {
-        b2 = fmaxf(b2, ob1);
-      }
-    }
-    const int a_cur = (s1 == 0x7fffffff) ? 0 : s1;
-    const bool amb = !((b1 - b2) > EXH_ALIGN_MARGIN * v1norm * ax.vnorm) || !(b1 == b1);
-    // ---- window: acc[d] belongs to shift a_cur - RAD + d, on the row lanes
+    int base = (lane - ROW_LANES) * W;
+    if (align_lane) window_fma<S, W>(reinterpret_cast<const float4*>(p.xdb.vkey32 + l * S), qtable + R * PITCH + base, acc);
+    int a_cur;
+    bool amb;
+    align_argmax<S, W>(acc, align_lane, base, v1norm * ax.vnorm, &a_cur, &amb);
+    // ---- window on the row lanes: acc[d] belongs to shift a_cur - RAD + d
 #pragma unroll
     for (int d = 0; d < W; ++d) acc[d] = 0.f;
     base = ((a_cur - RAD) % S + S) % S;
-    if (row_lane) window_fma<S, W>(reinterpret_cast<const float4*>(p.xdb.sc_hat + l * (R * S) + lane * S), qrow + base, acc);
-    float r8[8];
+    if (row_lane) {
 #pragma unroll
-    for (int d = 0; d < 8; ++d) r8[d] = (row_lane && d < W) ? acc[d] : 0.f;
-    float r4[4], r2[2], r1;
-    {
-      const bool hi = lane & 16;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) r4[i] = (hi ? r8[4 + i] : r8[i]) + __shfl_xor_sync(FULL, hi ? r8[i] : r8[4 + i], 16);
-    }
-    {
-      const bool hi = lane & 8;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) r2[i] = (hi ? r4[2 + i] : r4[i]) + __shfl_xor_sync(FULL, hi ? r4[i] : r4[2 + i], 8);
-    }
-    {
-      const bool hi = lane & 4;
-      r1 = (hi ? r2[1] : r2[0]) + __shfl_xor_sync(FULL, hi ? r2[0] : r2[1], 4);
-    }
-    r1 += __shfl_xor_sync(FULL, r1, 2);
-    r1 += __shfl_xor_sync(FULL, r1, 1);
-    const int d_mine = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-    float dist = __int_as_float(0x7f800000);
-    bool nan_here = false;
-    if (d_mine < W) {
-      int sft = (a_cur + d_mine - RAD) % S;
-      if (sft < 0) sft += S;
-      const unsigned long long m = ax.vmask;
-      const unsigned long long rot = sft == 0 ? m : (((m << sft) | (m >> (S - sft))) & ((S == 64) ? ~0ull : ((1ull << S) - 1)));
-      const int n = __popcll(qmask & rot);
-      if (n > 0) {
-        dist = 1.0f - r1 / (float)n;
-        nan_here = !(dist == dist);
+      for (int i = 0; i < RPL; ++i) {
+        const int r = lane + i * ROW_LANES;
+        window_fma<S, W>(reinterpret_cast<const float4*>(p.xdb.sc_hat + l * (R * S) + r * S), qtable + r * PITCH + base, acc);
       }
     }
-    const bool any_nan = __any_sync(FULL, nan_here);
-    float best = nan_here ? __int_as_float(0x7f800000) : dist;
-    best = fminf(best, __shfl_xor_sync(FULL, best, 16));
-    best = fminf(best, __shfl_xor_sync(FULL, best, 8));
-    best = fminf(best, __shfl_xor_sync(FULL, best, 4));
-    if (lane == 0) {
-      float out = best;
-      if (amb || any_nan || (ax.flags & 1u) || q_flag) out = -1.0f;
-      else if (out < 0.f) out = 0.f;
-      p.d32[o] = out;
-    }
+    int d_mine;
+    const float total = transpose_reduce<W>(acc, row_lane, lane, &d_mine);
+    const float out = screened_distance<S, RAD>(total, d_mine, a_cur, qmask, ax, amb, q_flag);
+    if (lane == 0) p.d32[o] = out;
   }
+}
+
+template <int R, int S, int RAD>
+constexpr size_t cand_smem_bytes() {
+  return (size_t)(R + 1) * (((2 * S + 2 * RAD + 1) | 1)) * sizeof(float);
 }
 
 // per query: which candidate slots need the exact kernel

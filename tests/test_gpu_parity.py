@@ -316,7 +316,7 @@ def test_retrieval_matches_port_on_large_key_set():
             assert out["nn_idx"][q] == best[1] and out["nn_shift"][q] == best[0][1] and close(out["min_dist"][q], best[0][0])
 
 
-@pytest.mark.parametrize("variant,flipped", [("default", False), ("default", True), ("40x120", True), ("full", False)])
+@pytest.mark.parametrize("variant,flipped", [("default", False), ("default", True), ("40x120", False), ("40x120", True), ("full", False)])
 def test_exhaustive_matches_port(variant, flipped):
     """Every entry scored (BASELINE configs 4/5): winner (index, shift, flip) equal, distance within tolerance.
     The flipped pass is the composed oracle: reference distance on the column-reversed candidate, forward first."""
