@@ -654,14 +654,14 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
     sp.d32_pitch = pitch;
     sp.d32 = h->x_d32.as<float>();
     sp.min_bits = d_min;
-    const uint64_t ew = h->exh_cfg == 1 ? 14 : 3;  // consumer warps = entries per ring slot of the instantiation
+    const uint64_t ew = h->exh_cfg == 1 ? 20 : 4;  // consumer warps = entries per ring slot of the instantiation
     const uint64_t groups = (n_max + ew - 1) / ew;
     const unsigned grid = (unsigned)(groups < (uint64_t)h->sm_count ? groups : (uint64_t)h->sm_count);
     if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
     if (h->exh_cfg == 1)
-      k_exh_screen<20, 60, 3, 1, 14><<<dim3(grid, (unsigned)nq), (14 + 1) * 32, exh_smem_bytes<20, 60, 3, 14>(), st>>>(sp);
+      k_exh_screen<20, 60, 3, 1, 20><<<dim3(grid, (unsigned)nq), (20 + 1) * 32, exh_smem_bytes<20, 60, 3, 20>(), st>>>(sp);
     else
-      k_exh_screen<40, 120, 6, 2, 3><<<dim3(grid, (unsigned)nq), (3 + 1) * 32, exh_smem_bytes<40, 120, 6, 3>(), st>>>(sp);
+      k_exh_screen<40, 120, 6, 2, 4><<<dim3(grid, (unsigned)nq), (4 + 1) * 32, exh_smem_bytes<40, 120, 6, 4>(), st>>>(sp);
     if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
     CK(cudaGetLastError());
     const unsigned rb = (unsigned)((n_max + 1023) / 1024 < 296 ? (n_max + 1023) / 1024 : 296);
@@ -767,10 +767,10 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
   if (e == cudaSuccess && h->exh)
-    e = h->exh_cfg == 1 ? cudaFuncSetAttribute(k_exh_screen<20, 60, 3, 1, 14>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)exh_smem_bytes<20, 60, 3, 14>())
-                        : cudaFuncSetAttribute(k_exh_screen<40, 120, 6, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)exh_smem_bytes<40, 120, 6, 3>());
+    e = h->exh_cfg == 1 ? cudaFuncSetAttribute(k_exh_screen<20, 60, 3, 1, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)exh_smem_bytes<20, 60, 3, 20>())
+                        : cudaFuncSetAttribute(k_exh_screen<40, 120, 6, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)exh_smem_bytes<40, 120, 6, 4>());
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);

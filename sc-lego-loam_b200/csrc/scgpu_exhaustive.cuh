@@ -33,9 +33,8 @@ namespace scgpu {
 
 constexpr float EXH_EPS = 1.0e-5f;         // |d32 - d| bound used for candidate selection (observed: < 2e-6)
 constexpr float EXH_ALIGN_MARGIN = 1.6e-5f;  // relative (to |v1||v2|) gap below which the alignment is ambiguous
-constexpr int EXH_SC_STAGES = 3;            // descriptor ring: window(k-1) | landed/loading(k) | loading(k+1)
-constexpr int EXH_VK_STAGES = 4;            // sector-key/aux ring: window(k-1) | alignment(k) | loading(k+1, k+2)
-constexpr int EXH_WARPS = 14;              // consumer warps per block = entries per group
+constexpr int EXH_SC_STAGES = 2;            // descriptor ring: window(k-1) | loading(k) (needed at iteration k+1)
+constexpr int EXH_VK_STAGES = 3;            // sector-key/aux ring: window(k-1) | alignment(k) | loading(k+1)
 
 // ---- hand-written PTX wrappers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP) -------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
