@@ -612,9 +612,10 @@ constexpr size_t EXH_MAX_BATCH = 64;       // queries per screening launch
 // Screen + rescore for nq (<= EXH_MAX_BATCH) query records on the device; result q (Best: dist, rank = #rescored in the
 // batch, shift, global idx) goes to d_best_out[q].  Everything is enqueued on st; no host synchronisation.
 int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t nq, const uint64_t* h_n_search, Best* d_best_out,
-                           cudaStream_t st, cudaEvent_t ev_screen0, cudaEvent_t ev_screen1) {
+                           cudaStream_t st, cudaEvent_t ev_screen0, cudaEvent_t ev_screen1, int flipped = 0) {
   if (nq == 0) return SCGPU_OK;
-  if (nq > EXH_MAX_BATCH) return fail(SCGPU_E_INVALID, "at most %zu queries per exhaustive batch", EXH_MAX_BATCH);
+  const size_t rows = nq * (flipped ? 2 : 1);  // screening rows: forward (+ column-reversed) pass per query
+  if (rows > EXH_MAX_BATCH) return fail(SCGPU_E_INVALID, "at most %zu screening rows per exhaustive batch", EXH_MAX_BATCH);
   uint64_t n_max = 0;
   std::vector<unsigned long long> nl(nq);
   for (size_t i = 0; i < nq; ++i) {
@@ -624,7 +625,7 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
   const uint64_t pitch = (n_max + 15) & ~15ull;
   RET(exh_sync(h, st));
   RET(h->x_query.reserve(EXH_MAX_BATCH * sizeof(ExhQuery)));
-  RET(h->x_d32.reserve((nq * pitch + 16) * sizeof(float)));
+  RET(h->x_d32.reserve((rows * pitch + 16) * sizeof(float)));
   RET(h->x_keys.reserve(EXH_CAND_CAP * sizeof(uint64_t)));
   RET(h->x_pd.reserve(EXH_CAND_CAP * sizeof(double)));
   RET(h->x_ps.reserve(EXH_CAND_CAP * sizeof(int)));
@@ -654,19 +655,20 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
     sp.d32_pitch = pitch;
     sp.d32 = h->x_d32.as<float>();
     sp.min_bits = d_min;
+    sp.flip_mode = flipped ? 1 : 0;
     const uint64_t ew = h->exh_cfg == 1 ? 20 : 4;  // consumer warps = entries per ring slot of the instantiation
     const uint64_t groups = (n_max + ew - 1) / ew;
     const unsigned grid = (unsigned)(groups < (uint64_t)h->sm_count ? groups : (uint64_t)h->sm_count);
     if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
     if (h->exh_cfg == 1)
-      k_exh_screen<20, 60, 3, 1, 20><<<dim3(grid, (unsigned)nq), (20 + 1) * 32, exh_smem_bytes<20, 60, 3, 20>(), st>>>(sp);
+      k_exh_screen<20, 60, 3, 1, 20><<<dim3(grid, (unsigned)rows), (20 + 1) * 32, exh_smem_bytes<20, 60, 3, 20>(), st>>>(sp);
     else
-      k_exh_screen<40, 120, 6, 2, 4><<<dim3(grid, (unsigned)nq), (4 + 1) * 32, exh_smem_bytes<40, 120, 6, 4>(), st>>>(sp);
+      k_exh_screen<40, 120, 6, 2, 4><<<dim3(grid, (unsigned)rows), (4 + 1) * 32, exh_smem_bytes<40, 120, 6, 4>(), st>>>(sp);
     if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
     CK(cudaGetLastError());
     const unsigned rb = (unsigned)((n_max + 1023) / 1024 < 296 ? (n_max + 1023) / 1024 : 296);
-    k_exh_compact<<<dim3(rb, (unsigned)nq), 256, 0, st>>>(sp.d32, pitch, d_nl, d_min, h->db.rank, h->db.G, h->x_keys.as<unsigned long long>(),
-                                                         d_count, EXH_CAND_CAP);
+    k_exh_compact<<<dim3(rb, (unsigned)rows), 256, 0, st>>>(sp.d32, pitch, d_nl, d_min, h->db.rank, h->db.G, sp.flip_mode,
+                                                           h->x_keys.as<unsigned long long>(), d_count, EXH_CAND_CAP);
     ScoreParams p;
     p.qrecords = d_qrecs;
     p.L = h->L;
@@ -1109,10 +1111,10 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
   if (n_search == 0) return SCGPU_OK;
   k_gather<<<1, 128, 0, st>>>(h->rec_single.as<unsigned char>(), h->L, h->db, q);
   h->launches++;
-  if (h->exh && !flipped) {
+  if (h->exh) {
     RET(h->x_best.reserve(sizeof(Best)));
     CK(cudaEventRecord(h->ev_t0, st));
-    RET(launch_exhaustive_fast(h, h->rec_single.as<unsigned char>(), 1, &n_search, h->x_best.as<Best>(), st, h->ev_t0, h->ev_t1));
+    RET(launch_exhaustive_fast(h, h->rec_single.as<unsigned char>(), 1, &n_search, h->x_best.as<Best>(), st, h->ev_t0, h->ev_t1, flipped));
     CK(cudaEventRecord(h->ev_t2, st));
     h->timing_valid = true;
     Best b;
@@ -1120,8 +1122,9 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
     CK(cudaStreamSynchronize(st));
     if ((unsigned)b.rank <= EXH_CAND_CAP) {
       *best_dist = b.dist;
-      *best_shift = b.shift;
+      *best_shift = b.shift & 0x3fffffff;
       *best_idx = b.idx;
+      if (best_flip) *best_flip = (b.shift >> 30) & 1;
       h->last_exh_rescored = (unsigned)b.rank;
       return SCGPU_OK;
     }
@@ -1223,7 +1226,7 @@ int scgpu_exhaustive_batched(scgpu_handle* h, const uint64_t* q, const uint64_t*
       continue;
     }
     best_dist[i] = b[i].dist;
-    best_shift[i] = b[i].shift;
+    best_shift[i] = b[i].shift & 0x3fffffff;
     best_idx[i] = b[i].idx;
     h->last_exh_rescored = (unsigned)b[i].rank;
   }

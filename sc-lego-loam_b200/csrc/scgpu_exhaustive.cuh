@@ -158,13 +158,15 @@ struct ExhScreenParams {     // grid (blocks, queries): blockIdx.y selects the q
   const ExhQuery* q;                   // [nq]
   const unsigned long long* n_local;   // [nq] local entries to score per query: [0, n_local[q])
   unsigned long long d32_pitch;        // elements between the d32 rows of consecutive queries
-  float* d32;                          // [nq][d32_pitch] out: approx distance; -1 = must be rescored; +inf = can never win
+  float* d32;                          // [rows][d32_pitch] out: approx distance; -1 = must be rescored; +inf = can never win
   unsigned* min_bits;                  // [nq] out: bit pattern of the smallest certain d32 (atomicMin; pre-set to +inf)
+  int flip_mode;                       // 0: row = query, forward.  1: row = 2*query + f, f = 1 scores column-reversed candidates
 };
 
 // ---- pieces shared by k_exh_screen and k_cand_screen -------------------------------------------------------------
 // acc[d] += sum_p held[p] * qs[p + d]   (held: S floats read with 16-byte loads; qs: doubled query row)
-template <int S, int W>
+// REV: the held sequence is read back to front (a candidate with its columns reversed -- the "flipped" search)
+template <int S, int W, bool REV = false>
 __device__ __forceinline__ void window_fma(const float4* held4, const float* qs, float (&acc)[W]) {
   float held[S];
 #pragma unroll
@@ -182,7 +184,7 @@ __device__ __forceinline__ void window_fma(const float4* held4, const float* qs,
   for (int pp = 0; pp < S; ++pp) {
     win[W - 1] = qs[pp + W - 1];
 #pragma unroll
-    for (int d = 0; d < W; ++d) acc[d] = __fmaf_rn(held[pp], win[d], acc[d]);
+    for (int d = 0; d < W; ++d) acc[d] = __fmaf_rn(held[REV ? S - 1 - pp : pp], win[d], acc[d]);
 #pragma unroll
     for (int d = 0; d < W - 1; ++d) win[d] = win[d + 1];
   }
@@ -224,6 +226,20 @@ __device__ __forceinline__ float transpose_reduce(const float (&acc)[W], bool co
     r1 += __shfl_xor_sync(FULL, r1, 1);
     *d_mine = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
     return r1;
+  }
+}
+
+// valid-column mask of a candidate with its columns reversed: bit c <-> bit S-1-c
+template <int S>
+__device__ __forceinline__ void reverse_mask(unsigned long long (&m)[2]) {
+  if (S <= 64) {
+    m[0] = __brevll(m[0]) >> (64 - S);
+  } else {
+    typedef unsigned __int128 u128;
+    const u128 r = (((u128)__brevll(m[0])) << 64) | (u128)__brevll(m[1]);  // 128-bit reversal
+    const u128 v = r >> (128 - S);
+    m[0] = (unsigned long long)v;
+    m[1] = (unsigned long long)(v >> 64);
   }
 }
 
@@ -335,11 +351,13 @@ __global__ void __launch_bounds__((EW + 1) * 32, 1) k_exh_screen(const ExhScreen
     float* d32;
     unsigned* min_bits;
   } p;
+  const unsigned qi = pp.flip_mode ? blockIdx.y >> 1 : blockIdx.y;
+  const bool rev = pp.flip_mode && (blockIdx.y & 1);
   p.db = pp.db;
-  p.q = pp.q + blockIdx.y;
-  p.n_local = pp.n_local[blockIdx.y];
+  p.q = pp.q + qi;
+  p.n_local = pp.n_local[qi];
   p.d32 = pp.d32 + blockIdx.y * pp.d32_pitch;
-  p.min_bits = pp.min_bits + blockIdx.y;
+  p.min_bits = pp.min_bits + qi;
   constexpr int W = 2 * RAD + 1;
   constexpr int ROW_LANES = R / RPL;
   constexpr int ALIGN_LANES = (S + W - 1) / W;
@@ -443,13 +461,17 @@ __global__ void __launch_bounds__((EW + 1) * 32, 1) k_exh_screen(const ExhScreen
         held4 = reinterpret_cast<const float4*>(&vk_ring[vk_a].vkey[warp][0]);
         qs = qtable + R * PITCH + base;
       }
-      if (held4) window_fma<S, W>(held4, qs, acc);
+      if (held4) {
+        if (rev) window_fma<S, W, true>(held4, qs, acc);
+        else window_fma<S, W, false>(held4, qs, acc);
+      }
     }
     // ---- window result of group k-1 ------------------------------------------------------------------
     if (has_win) {
       int d_mine;
       const float total = transpose_reduce<W>(acc, row_lane, lane, &d_mine);
-      const ExhAux ax = vk_ring[vk_w].aux[ent_w ? warp : 0];
+      ExhAux ax = vk_ring[vk_w].aux[ent_w ? warp : 0];
+      if (rev) reverse_mask<S>(ax.vmask);
       const float out = screened_distance<S, RAD>(total, d_mine, a_cur, qmask, ax, amb_cur, q_flag);
       if (lane == 0 && ent_w) {
         p.d32[e_w] = out;
@@ -472,18 +494,19 @@ __global__ void __launch_bounds__((EW + 1) * 32, 1) k_exh_screen(const ExhScreen
 
 // ---- rescoring side -----------------------------------------------------------------------------------
 // candidates = flagged entries + entries within 2*EXH_EPS of the query's smallest certain value -> one flat key list
-// (query index << 32 | global entry index); grid (blocks, queries)
+// (flip << 63 | query index << 32 | global entry index); grid (blocks, rows)
 __global__ void k_exh_compact(const float* d32, unsigned long long d32_pitch, const unsigned long long* n_local, const unsigned* min_bits,
-                              int rank, int G, unsigned long long* keys, unsigned* count, unsigned cap) {
-  const unsigned q = blockIdx.y;
-  const float* row = d32 + q * d32_pitch;
+                              int rank, int G, int flip_mode, unsigned long long* keys, unsigned* count, unsigned cap) {
+  const unsigned row = blockIdx.y, q = flip_mode ? row >> 1 : row;
+  const unsigned long long fbit = (flip_mode && (row & 1)) ? (1ull << 63) : 0ull;
+  const float* rowp = d32 + row * d32_pitch;
   const unsigned long long n = n_local[q];
   const float thr = __uint_as_float(min_bits[q]) + 2.0f * EXH_EPS;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
-    const float v = row[i];
+    const float v = rowp[i];
     if (v < 0.f || (v <= thr && v < __int_as_float(0x7f800000))) {
       const unsigned slot = atomicAdd(count, 1u);
-      if (slot < cap) keys[slot] = ((unsigned long long)q << 32) | (i * (unsigned long long)G + rank);
+      if (slot < cap) keys[slot] = fbit | ((unsigned long long)q << 32) | (i * (unsigned long long)G + rank);
     }
   }
 }
@@ -502,13 +525,14 @@ __global__ void __launch_bounds__(256) k_exh_final(const double* pair_dist, cons
   const unsigned n = min(*count, cap);
   for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned long long key = keys[i];
-    if ((unsigned)(key >> 32) != q) continue;
+    if ((unsigned)((key >> 32) & 0x7fffffffull) != q) continue;
     const double d = pair_dist[i];
-    const long long idx = (long long)(key & 0xffffffffull);
-    if (pair_shift[i] >= 0 && d < 10000000.0 && (d < b.dist || (d == b.dist && (b.idx < 0 || idx < b.idx)))) {
+    // order: distance, then entry index, then forward before flipped -> sort key idx2 = idx * 2 + flip
+    const long long idx2 = (long long)((key & 0xffffffffull) * 2 + (key >> 63));
+    if (pair_shift[i] >= 0 && d < 10000000.0 && (d < b.dist || (d == b.dist && (b.idx < 0 || idx2 < b.idx)))) {
       b.dist = d;
       b.shift = pair_shift[i];
-      b.idx = idx;
+      b.idx = idx2;
     }
   }
   s_best[threadIdx.x] = b;
@@ -528,6 +552,9 @@ __global__ void __launch_bounds__(256) k_exh_final(const double* pair_dist, cons
       r.idx = 0;
       r.shift = 0;
       r.dist = 10000000.0;
+    } else {
+      r.shift |= (int)(r.idx & 1) << 30;  // flipped winner flagged in bit 30 of the shift
+      r.idx >>= 1;
     }
     out[q] = r;
   }

@@ -864,7 +864,7 @@ template <bool LIST>  // LIST: slot k of one flat list whose keys are (query ind
 __device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, int q, unsigned char* smem_raw) {
   const int R = p.L.R, S = p.L.S, W = 2 * p.radius + 1;
   const size_t o = LIST ? (size_t)k : (size_t)q * p.K + k;
-  if (LIST) q = (int)(p.keys[o] >> 32);
+  if (LIST) q = (int)((p.keys[o] >> 32) & 0x7fffffffull);
   if (!LIST && p.n_search[q] == 0) {
     if (threadIdx.x == 0) {
       p.pair_dist[o] = 10000000.0;
@@ -888,15 +888,16 @@ __device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, in
   const float* qsc = reinterpret_cast<const float*>(qrec);
   const float* csc = p.db.sc + l * p.L.RS;
   const int RP = pair_pitch(R);
+  const bool flip = LIST ? (key >> 63) != 0 : p.flip != 0;
   for (int i = threadIdx.x; i < p.L.RS; i += blockDim.x) {
     const int c = i / R, r = i - c * R;
     a[c * RP + r] = qsc[i];
-    b[c * RP + r] = csc[p.flip ? (S - 1 - c) * R + r : i];
+    b[c * RP + r] = csc[flip ? (S - 1 - c) * R + r : i];
   }
   const double* qv = reinterpret_cast<const double*>(qrec + p.L.off_sector);
   const double* qn = reinterpret_cast<const double*>(qrec + p.L.off_norm);
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
-    const int ci = p.flip ? (S - 1 - i) : i;
+    const int ci = flip ? (S - 1 - i) : i;
     m.vk1[i] = qv[i];
     m.n1[i] = qn[i];
     m.vk2[i] = p.db.sector[l * S + ci];

@@ -124,8 +124,8 @@ def config5(n_db=20000, n_check=1500):
     fwd_rescored = m.exhaustive_rescored()
     both = m.exhaustive(q, n_db - 50, True)
     t2 = time.perf_counter()
-    res = {"config": "5: 40x120, 20k keyframes, exhaustive search on 1 B200: forward = FP32 screening (k_exh_screen<40,120,6>) + exact "
-                     "rescoring; forward + column-reversed = exact FP64 pair kernel for every entry",
+    res = {"config": "5: 40x120, 20k keyframes, exhaustive search on 1 B200: FP32 screening (k_exh_screen<40,120,6>; the column-reversed "
+                     "pass reads the candidate rows back to front) + exact FP64 rescoring of the survivors",
            "ms_per_query_forward": 1e3 * (t1 - t0), "ms_per_query_forward_device": ms_fwd_dev, "ms_forward_screen_kernel": ms_fwd_screen,
            "forward_rescored": fwd_rescored, "ms_per_query_forward_plus_flipped": 1e3 * (t2 - t1),
            "winner_forward": fwd, "winner_flipped_search": both, "finds_reversed_revisit": bool(both[2] == 4242 and both[3] == 1)}
