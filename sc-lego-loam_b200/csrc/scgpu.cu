@@ -346,9 +346,17 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
   p.tickets = h->ttickets.as<unsigned>();
   p.keys_out = reinterpret_cast<unsigned long long*>(d_keys_out);
   dim3 grid(chunks, (unsigned)nq);
-  if (h->slots == 1) k_topk<1><<<grid, TOPK_THREADS, 0, st>>>(p);
-  else if (h->slots == 2) k_topk<2><<<grid, TOPK_THREADS, 0, st>>>(p);
-  else k_topk<4><<<grid, TOPK_THREADS, 0, st>>>(p);
+  const bool many = (uint64_t)chunks * nq >= 4096;  // enough blocks to fill the GPU with 2-warp blocks
+  if (h->slots == 1) {
+    if (many) k_topk<1, 2><<<grid, 64, 0, st>>>(p);
+    else k_topk<1, 8><<<grid, 256, 0, st>>>(p);
+  } else if (h->slots == 2) {
+    if (many) k_topk<2, 2><<<grid, 64, 0, st>>>(p);
+    else k_topk<2, 8><<<grid, 256, 0, st>>>(p);
+  } else {
+    if (many) k_topk<4, 2><<<grid, 64, 0, st>>>(p);
+    else k_topk<4, 8><<<grid, 256, 0, st>>>(p);
+  }
   h->launches++;
   CK(cudaGetLastError());
   return SCGPU_OK;

@@ -640,15 +640,20 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
     }
     const unsigned long long l = g / (unsigned long long)p.db.G;
     const ExhAux ax = p.xdb.aux[l];
-    // ---- alignment on the alignment lanes
-    float acc[W];
-#pragma unroll
-    for (int d = 0; d < W; ++d) acc[d] = 0.f;
-    int base = (lane - ROW_LANES) * W;
-    if (align_lane) window_fma<S, W>(reinterpret_cast<const float4*>(p.xdb.vkey32 + l * S), qtable + R * PITCH + base, acc);
+    // ---- alignment with ALL lanes (nothing else to do in this phase): lane l takes the WA shifts l*WA .. l*WA+WA-1
+    constexpr int WA = (S + 31) / 32;
     int a_cur;
     bool amb;
-    align_argmax<S, W>(acc, align_lane, base, v1norm * ax.vnorm, &a_cur, &amb);
+    {
+      float ca[WA];
+#pragma unroll
+      for (int d = 0; d < WA; ++d) ca[d] = 0.f;
+      const int ab = lane * WA;
+      if (ab < S) window_fma<S, WA>(reinterpret_cast<const float4*>(p.xdb.vkey32 + l * S), qtable + R * PITCH + ab, ca);
+      align_argmax<S, WA>(ca, ab < S, ab, v1norm * ax.vnorm, &a_cur, &amb);
+    }
+    float acc[W];
+    int base;
     // ---- window on the row lanes: acc[d] belongs to shift a_cur - RAD + d
 #pragma unroll
     for (int d = 0; d < W; ++d) acc[d] = 0.f;

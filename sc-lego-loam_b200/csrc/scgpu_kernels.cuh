@@ -595,9 +595,31 @@ struct WarpList {
 };
 
 // nf.hpp:383-408: four squared differences added left to right, then added to the running sum; FP32, no FMA.
-template <int RMAX>
-__device__ __forceinline__ float ringkey_dist2(const float* q, const float* ringT, unsigned long long cap, unsigned long long l, int R) {
+// RC > 0: compile-time dimension -- the loop unrolls and all RC loads are in flight together (with a run-time bound
+// every group of four loads was a separate round trip to L2); RC = 0: any dimension.
+template <int RC>
+__device__ __forceinline__ float ringkey_dist2(const float* q, const float* ringT, unsigned long long cap, unsigned long long l, int R_rt) {
+  const int R = RC > 0 ? RC : R_rt;
   float result = 0.f;
+  if (RC > 0) {
+    float kv[RC > 0 ? RC : 1];
+#pragma unroll
+    for (int d = 0; d < RC; ++d) kv[d] = __ldg(ringT + (size_t)d * cap + l);
+    int d = 0;
+#pragma unroll
+    for (; d + 3 < RC; d += 4) {
+      const float d0 = __fsub_rn(q[d], kv[d]), d1 = __fsub_rn(q[d + 1], kv[d + 1]);
+      const float d2 = __fsub_rn(q[d + 2], kv[d + 2]), d3 = __fsub_rn(q[d + 3], kv[d + 3]);
+      const float t = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
+      result = __fadd_rn(result, t);
+    }
+#pragma unroll
+    for (; d < RC; ++d) {
+      const float d0 = __fsub_rn(q[d], kv[d]);
+      result = __fadd_rn(result, __fmul_rn(d0, d0));
+    }
+    return result;
+  }
   int d = 0;
   for (; d + 3 < R; d += 4) {
     const float d0 = __fsub_rn(q[d], __ldg(ringT + (size_t)d * cap + l));
@@ -627,11 +649,11 @@ struct TopkParams {
   unsigned long long* keys_out;        // [nq][K]
 };
 
-constexpr int TOPK_THREADS = 256;
-constexpr int TOPK_WARPS = TOPK_THREADS / 32;
-
-template <int SLOTS>
-__global__ void __launch_bounds__(TOPK_THREADS) k_topk(const TopkParams p) {
+// TOPK_WARPS warps share one (query, chunk).  Every warp's list has a warm-up phase of ~K(1 + ln(n_warp / K)) insertions,
+// so many queries per launch use few warps per query (long streams per warp), few queries use many (latency).
+template <int SLOTS, int TOPK_WARPS>
+__global__ void __launch_bounds__(TOPK_WARPS * 32) k_topk(const TopkParams p) {
+  constexpr int TOPK_THREADS = TOPK_WARPS * 32;
   __shared__ float s_q[64];
   __shared__ unsigned long long s_lists[TOPK_WARPS * 32 * SLOTS];
   __shared__ bool s_last;
@@ -655,7 +677,8 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk(const TopkParams p) {
     const unsigned long long l = base + lane;
     unsigned long long key = KEY_NONE;
     if (l < end) {
-      const float d2 = ringkey_dist2<64>(s_q, p.db.ringT, p.db.cap, l, R);
+      const float d2 = R == 20 ? ringkey_dist2<20>(s_q, p.db.ringT, p.db.cap, l, R)
+                               : (R == 40 ? ringkey_dist2<40>(s_q, p.db.ringT, p.db.cap, l, R) : ringkey_dist2<0>(s_q, p.db.ringT, p.db.cap, l, R));
       key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(l * p.db.G + p.db.rank);
     }
     list.offer(key, K);
