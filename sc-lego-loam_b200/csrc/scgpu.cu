@@ -101,8 +101,7 @@ struct scgpu_handle {
   bool exh = false;
   int exh_cfg = 0;  // 1: 20x60 radius 3, 2: 40x120 radius 6
   float* x_sc_hat = nullptr;
-  float* x_vkey32 = nullptr;
-  ExhAux* x_aux = nullptr;
+  unsigned char* x_vk = nullptr;  // [cap] ExhVkRec: float sector key + aux
   DevBuf x_query, x_d32, x_keys, x_pd, x_ps, x_small, x_best;
   int sm_count = 148;
   unsigned last_exh_rescored = 0;
@@ -151,20 +150,17 @@ int db_reserve(scgpu_handle* h, uint64_t want_local) {
   CK(cudaMalloc(&nd.sector, cap * L.S * sizeof(double)));
   CK(cudaMalloc(&nd.colnorm, cap * L.S * sizeof(double)));
   float* n_hat = nullptr;
-  float* n_vk = nullptr;
-  ExhAux* n_aux = nullptr;
+  unsigned char* n_vk = nullptr;
   if (h->exh) {
     CK(cudaMalloc(&n_hat, cap * L.RS * sizeof(float)));
-    CK(cudaMalloc(&n_vk, cap * L.S * sizeof(float)));
-    CK(cudaMalloc(&n_aux, (cap + 8) * sizeof(ExhAux)));
+    CK(cudaMalloc(&n_vk, (cap + 8) * exh_vk_bytes(L.S)));
   }
   const uint64_t n = local_count(h, h->n_global);
   if (h->x_upto > n) h->x_upto = n;
   if (h->exh && h->db.cap && h->x_upto) {
     const uint64_t n = h->x_upto;
     CK(cudaMemcpyAsync(n_hat, h->x_sc_hat, n * L.RS * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(n_vk, h->x_vkey32, n * L.S * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpyAsync(n_aux, h->x_aux, n * sizeof(ExhAux), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaMemcpyAsync(n_vk, h->x_vk, n * exh_vk_bytes(L.S), cudaMemcpyDeviceToDevice, h->stream));
   }
   if (h->db.cap && n) {
     CK(cudaMemcpyAsync(nd.sc, h->db.sc, n * L.RS * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
@@ -181,14 +177,12 @@ int db_reserve(scgpu_handle* h, uint64_t want_local) {
     cudaFree(h->db.colnorm);
     if (h->exh) {
       cudaFree(h->x_sc_hat);
-      cudaFree(h->x_vkey32);
-      cudaFree(h->x_aux);
+      cudaFree(h->x_vk);
     }
   }
   h->db = nd;
   h->x_sc_hat = n_hat;
-  h->x_vkey32 = n_vk;
-  h->x_aux = n_aux;
+  h->x_vk = n_vk;
   return SCGPU_OK;
 }
 
@@ -403,7 +397,7 @@ int launch_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t*
 int exh_sync(scgpu_handle* h, cudaStream_t st) {
   const uint64_t have = local_count(h, h->n_global);
   if (have > h->x_upto) {
-    k_exh_append<<<(unsigned)(have - h->x_upto), 128, 0, st>>>(h->L, h->db, h->x_sc_hat, h->x_vkey32, h->x_aux, h->x_upto);
+    k_exh_append<<<(unsigned)(have - h->x_upto), 128, 0, st>>>(h->L, h->db, h->x_sc_hat, h->x_vk, h->x_upto);
     h->launches++;
     CK(cudaGetLastError());
     h->x_upto = have;
@@ -424,8 +418,7 @@ int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const 
   cp.L = h->L;
   cp.db = h->db;
   cp.xdb.sc_hat = h->x_sc_hat;
-  cp.xdb.vkey32 = h->x_vkey32;
-  cp.xdb.aux = h->x_aux;
+  cp.xdb.vk = h->x_vk;
   cp.keys = reinterpret_cast<const unsigned long long*>(d_keys);
   cp.n_search = reinterpret_cast<const unsigned long long*>(d_ns);
   cp.K = h->K;
@@ -656,22 +649,21 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
   if (n_max) {
     ExhScreenParams sp;
     sp.db.sc_hat = h->x_sc_hat;
-    sp.db.vkey32 = h->x_vkey32;
-    sp.db.aux = h->x_aux;
+    sp.db.vk = h->x_vk;
     sp.q = h->x_query.as<ExhQuery>();
     sp.n_local = d_nl;
     sp.d32_pitch = pitch;
     sp.d32 = h->x_d32.as<float>();
     sp.min_bits = d_min;
     sp.flip_mode = flipped ? 1 : 0;
-    const uint64_t ew = h->exh_cfg == 1 ? 20 : 4;  // consumer warps = entries per ring slot of the instantiation
+    const uint64_t ew = h->exh_cfg == 1 ? 20 : 4;  // consumer warps per block of the instantiation
     const uint64_t groups = (n_max + ew - 1) / ew;
     const unsigned grid = (unsigned)(groups < (uint64_t)h->sm_count ? groups : (uint64_t)h->sm_count);
     if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
     if (h->exh_cfg == 1)
-      k_exh_screen<20, 60, 3, 1, 20><<<dim3(grid, (unsigned)rows), (20 + 1) * 32, exh_smem_bytes<20, 60, 3, 20>(), st>>>(sp);
+      k_exh_screen<20, 60, 3, 1, 20><<<dim3(grid, (unsigned)rows), 20 * 32, exh_smem_bytes<20, 60, 3, 20>(), st>>>(sp);
     else
-      k_exh_screen<40, 120, 6, 2, 4><<<dim3(grid, (unsigned)rows), (4 + 1) * 32, exh_smem_bytes<40, 120, 6, 4>(), st>>>(sp);
+      k_exh_screen<40, 120, 6, 2, 4><<<dim3(grid, (unsigned)rows), 4 * 32, exh_smem_bytes<40, 120, 6, 4>(), st>>>(sp);
     if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
     CK(cudaGetLastError());
     const unsigned rb = (unsigned)((n_max + 1023) / 1024 < 296 ? (n_max + 1023) / 1024 : 296);
@@ -781,6 +773,8 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
                                                (int)exh_smem_bytes<20, 60, 3, 20>())
                         : cudaFuncSetAttribute(k_exh_screen<40, 120, 6, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)exh_smem_bytes<40, 120, 6, 4>());
+  if (e == cudaSuccess && h->exh && h->exh_cfg == 2)
+    e = cudaFuncSetAttribute(k_cand_screen<40, 120, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem_bytes<40, 120, 6>());
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
@@ -821,8 +815,7 @@ int scgpu_destroy(scgpu_handle* h) {
     cudaFree(h->db.colnorm);
     if (h->exh) {
       cudaFree(h->x_sc_hat);
-      cudaFree(h->x_vkey32);
-      cudaFree(h->x_aux);
+      cudaFree(h->x_vk);
     }
   }
   DevBuf* xb[] = {&h->x_query, &h->x_d32, &h->x_keys, &h->x_pd, &h->x_ps, &h->x_small, &h->x_best, &h->c_d32, &h->c_list, &h->c_count};

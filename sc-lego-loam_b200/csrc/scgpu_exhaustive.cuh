@@ -33,8 +33,6 @@ namespace scgpu {
 
 constexpr float EXH_EPS = 1.0e-5f;         // |d32 - d| bound used for candidate selection (observed: < 2e-6)
 constexpr float EXH_ALIGN_MARGIN = 1.6e-5f;  // relative (to |v1||v2|) gap below which the alignment is ambiguous
-constexpr int EXH_SC_STAGES = 2;            // descriptor ring: window(k-1) | loading(k) (needed at iteration k+1)
-constexpr int EXH_VK_STAGES = 3;            // sector-key/aux ring: window(k-1) | alignment(k) | loading(k+1)
 
 // ---- hand-written PTX wrappers: mbarrier + TMA 1-D bulk copy (cp.async.bulk, SASS: UBLKCP) -------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,10 +78,17 @@ struct ExhAux {
   unsigned long long pad;
 };
 
+// float sector key + aux of one entry, adjacent in memory so that ONE bulk copy fetches both
+template <int S>
+struct ExhVkRec {
+  float vkey[S];
+  ExhAux aux;
+};
+__host__ __device__ __forceinline__ size_t exh_vk_bytes(int S) { return (size_t)S * sizeof(float) + sizeof(ExhAux); }
+
 struct ExhDb {
-  const float* sc_hat;   // [cap][R][S] unit-normalised columns, ROW-major per entry
-  const float* vkey32;   // [cap][S]
-  const ExhAux* aux;     // [cap]
+  const float* sc_hat;       // [cap][R][S] unit-normalised columns, ROW-major per entry, pair-interleaved (window_fma)
+  const unsigned char* vk;   // [cap] ExhVkRec<S>
 };
 
 // query pack built by k_exh_prep: normalised query, float sector key, valid-column mask, |v1|
@@ -95,7 +100,11 @@ struct ExhQuery {
   unsigned flags;
 };
 
+// storage position of column c in the pair-interleaved screening copy (see window_fma)
+__host__ __device__ __forceinline__ int pair_pos(int c, int S) { return c < S / 2 ? 2 * c : 2 * (c - S / 2) + 1; }
+
 // Screening side data of one descriptor (stored entry or query record).  One block; every thread calls.
+template <bool PAIRED>  // PAIRED: pair-interleaved column order (the database side of window_fma)
 __device__ __forceinline__ void exh_normalise(const float* sc, const double* sector, const double* norm, const Layout& L, float* sc_hat,
                                               float* vkey32, unsigned long long* vmask, float* vnorm, unsigned* flags) {
   __shared__ unsigned long long s_mask[2];
@@ -112,7 +121,7 @@ __device__ __forceinline__ void exh_normalise(const float* sc, const double* sec
     const double n = norm[c];
     const float nf = (float)n, v = (float)sector[c];
     s_inv[c] = (n == 0.0) ? 0.f : (float)(1.0 / n);
-    vkey32[c] = v;
+    vkey32[PAIRED ? pair_pos(c, L.S) : c] = v;
     if (n != 0.0) atomicOr(&s_mask[c >> 6], 1ull << (c & 63));
     if (n != 0.0 && !(nf > 1e-30f && nf < 1e30f)) atomicOr(&s_flags, 1u);  // subnormal-ish, inf or NaN norm
     if (!(fabsf(v) < 1e30f)) atomicOr(&s_flags, 1u);
@@ -121,7 +130,7 @@ __device__ __forceinline__ void exh_normalise(const float* sc, const double* sec
   __syncthreads();
   for (int i = threadIdx.x; i < L.RS; i += blockDim.x) {  // ROW-major output: element (r, c) at r*S + c
     const int r = i / L.S, c = i - r * L.S;
-    sc_hat[i] = sc[c * L.R + r] * s_inv[c];
+    sc_hat[PAIRED ? r * L.S + pair_pos(c, L.S) : i] = sc[c * L.R + r] * s_inv[c];
   }
   if (threadIdx.x == 0) {
     vmask[0] = s_mask[0];
@@ -134,10 +143,12 @@ __device__ __forceinline__ void exh_normalise(const float* sc, const double* sec
 
 // database side of the screening data: local entries [first_local, first_local + gridDim.x), derived from the stored
 // descriptor / sector key / column norms (built lazily, right before the first search that needs them)
-__global__ void __launch_bounds__(128) k_exh_append(Layout L, Db db, float* sc_hat, float* vkey32, ExhAux* aux, unsigned long long first_local) {
+__global__ void __launch_bounds__(128) k_exh_append(Layout L, Db db, float* sc_hat, unsigned char* vk, unsigned long long first_local) {
   const unsigned long long l = first_local + blockIdx.x;
-  exh_normalise(db.sc + l * L.RS, db.sector + l * L.S, db.colnorm + l * L.S, L, sc_hat + l * L.RS, vkey32 + l * L.S, aux[l].vmask,
-                &aux[l].vnorm, &aux[l].flags);
+  float* vkey32 = reinterpret_cast<float*>(vk + l * exh_vk_bytes(L.S));
+  ExhAux* aux = reinterpret_cast<ExhAux*>(vkey32 + L.S);
+  exh_normalise<true>(db.sc + l * L.RS, db.sector + l * L.S, db.colnorm + l * L.S, L, sc_hat + l * L.RS, vkey32, aux->vmask, &aux->vnorm,
+                      &aux->flags);
 }
 
 // query pack + reset of the per-query reduction cells (one launch instead of three)
@@ -149,7 +160,7 @@ __global__ void __launch_bounds__(256) k_exh_prep(const unsigned char* qrecs, La
   }
   ExhQuery* dst = qs + q;
   const unsigned char* rec = qrecs + (size_t)q * L.rec_bytes;
-  exh_normalise(reinterpret_cast<const float*>(rec), reinterpret_cast<const double*>(rec + L.off_sector),
+  exh_normalise<false>(reinterpret_cast<const float*>(rec), reinterpret_cast<const double*>(rec + L.off_sector),
                 reinterpret_cast<const double*>(rec + L.off_norm), L, dst->qhat, dst->v1, dst->qmask, &dst->v1norm, &dst->flags);
 }
 
@@ -164,30 +175,86 @@ struct ExhScreenParams {     // grid (blocks, queries): blockIdx.y selects the q
 };
 
 // ---- pieces shared by k_exh_screen and k_cand_screen -------------------------------------------------------------
-// acc[d] += sum_p held[p] * qs[p + d]   (held: S floats read with 16-byte loads; qs: doubled query row)
-// REV: the held sequence is read back to front (a candidate with its columns reversed -- the "flipped" search)
+// Packed FP32 (sm_100: FFMA2 -- two independent FMAs per issued instruction on an aligned register pair).
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ float sum2(unsigned long long v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// Pairing.  A lane's sum over the S columns is split into the halves p and p + S/2 (H = S/2):
+//     acc[d] = sum_{p<H}  held[p] * q[base+p+d]  +  held[p+H] * q[base+p+H+d]
+// so with the screening copy of the database stored PAIR-INTERLEAVED (position 2p = column p, 2p+1 = column p+H) and a
+// query table of pairs  T[i] = (q[i mod S], q[(i+H) mod S])  every operand is an aligned 8-byte register pair / 8-byte
+// shared-memory load for any base and shift: W FFMA2 + one LDS.64 per two columns (scalar form: 2W FFMA + two LDS.32).
+// Rows 0..R-1 of the table are the unit-normalised query rows, row R the float sector key; NP pairs per row with NP odd,
+// so the 8-byte loads of 16 consecutive rows fall into 16 distinct bank pairs.
+__host__ __device__ constexpr int qtab_pairs(int S, int W) { return (3 * S / 2 + W) | 1; }
+template <int R, int S, int W>
+constexpr size_t qtab_bytes() {
+  return (size_t)(R + 1) * qtab_pairs(S, W) * 2 * sizeof(float);
+}
+// fill by the whole block; value(r, c) = element c of table row r.  Source-driven: each of the (R+1)*S values is
+// produced once (consecutive threads take consecutive r: the query record is column-major) and stored to the <= 4
+// table positions that hold it.
+template <int R, int S, int W, class F>
+__device__ __forceinline__ void qtab_fill(float* qtable, F value) {
+  constexpr int NP = qtab_pairs(S, W), H = S / 2;
+  static_assert(NP <= 2 * S, "a value appears at most twice per half");
+  for (int t = threadIdx.x; t < (R + 1) * S; t += blockDim.x) {
+    const int c = t / (R + 1), r = t - c * (R + 1);
+    const float v = value(r, c);
+    float* row = qtable + r * 2 * NP;
+    const int i1 = c < H ? c + H : c - H;  // pairs whose second half is column c
+    row[2 * c] = v;
+    if (c + S < NP) row[2 * (c + S)] = v;
+    row[2 * i1 + 1] = v;
+    if (i1 + S < NP) row[2 * (i1 + S) + 1] = v;
+  }
+}
+
+// acc[d] += sum_p held[p] * q[base + p + d]   (held4: a pair-interleaved row of S floats, read with 16-byte loads;
+// qrow: the lane's row of the pair table).  REV: the held sequence is read back to front (a candidate with its columns
+// reversed -- the "flipped" search): the pair (held[H-1-p], held[S-1-p]) meets (q[base+p+H+d], q[base+p+d]) =
+// T[base+H+p+d], i.e. the same table entered H later with the held pairs walked downwards.
 template <int S, int W, bool REV = false>
-__device__ __forceinline__ void window_fma(const float4* held4, const float* qs, float (&acc)[W]) {
-  float held[S];
+__device__ __forceinline__ void window_fma(const float4* held4, const float* qrow, int base, float (&acc)[W]) {
+  static_assert(S % 4 == 0, "rows are read with 16-byte loads");
+  constexpr int H = S / 2;
+  unsigned long long held[H];
 #pragma unroll
   for (int i = 0; i < S / 4; ++i) {
-    const float4 v = held4[i];
-    held[4 * i] = v.x;
-    held[4 * i + 1] = v.y;
-    held[4 * i + 2] = v.z;
-    held[4 * i + 3] = v.w;
+    const ulonglong2 v = reinterpret_cast<const ulonglong2*>(held4)[i];
+    held[2 * i] = v.x;
+    held[2 * i + 1] = v.y;
   }
-  float win[W];
+  if (REV) base = base + H >= S ? base + H - S : base + H;
+  const unsigned long long* qp = reinterpret_cast<const unsigned long long*>(qrow) + base;
+  unsigned long long acc2[W], win[W];
 #pragma unroll
-  for (int d = 0; d < W - 1; ++d) win[d] = qs[d];
+  for (int d = 0; d < W; ++d) acc2[d] = 0ull;
 #pragma unroll
-  for (int pp = 0; pp < S; ++pp) {
-    win[W - 1] = qs[pp + W - 1];
+  for (int d = 0; d < W - 1; ++d) win[d] = qp[d];
 #pragma unroll
-    for (int d = 0; d < W; ++d) acc[d] = __fmaf_rn(held[REV ? S - 1 - pp : pp], win[d], acc[d]);
+  for (int pp = 0; pp < H; ++pp) {
+    win[W - 1] = qp[pp + W - 1];
+#pragma unroll
+    for (int d = 0; d < W; ++d) acc2[d] = fma2(held[REV ? H - 1 - pp : pp], win[d], acc2[d]);
 #pragma unroll
     for (int d = 0; d < W - 1; ++d) win[d] = win[d + 1];
   }
+#pragma unroll
+  for (int d = 0; d < W; ++d) acc[d] += sum2(acc2[d]);
 }
 
 // Sum acc[0..W) over the lanes flagged `contributes` with a transpose-reduce (NV -> NV/2 -> ... -> 1 values per lane
@@ -228,6 +295,13 @@ __device__ __forceinline__ float transpose_reduce(const float (&acc)[W], bool co
     return r1;
   }
 }
+
+// warp-wide max / min of order-encoded floats: one CREDUX instead of a five-round shuffle butterfly
+__device__ __forceinline__ int enc_ord(float f) {  // order-preserving float -> int (enc_float without the branch)
+  const int i = __float_as_int(f);
+  return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float dec_ord(int e) { return __int_as_float(e ^ ((e >> 31) & 0x7fffffff)); }
 
 // valid-column mask of a candidate with its columns reversed: bit c <-> bit S-1-c
 template <int S>
@@ -272,77 +346,63 @@ __device__ __forceinline__ float screened_distance(float total, int d_mine, int 
     if (sft < 0) sft += S;
     const int n = valid_pairs<S>(qmask, ax.vmask, sft);
     if (n > 0) {
-      dist = 1.0f - total / (float)n;
+      dist = 1.0f - __fdividef(total, (float)n);  // n <= 128: the approximate reciprocal costs < 2.4e-7 absolute
       nan_here = !(dist == dist);
     }
   }
   const bool any_nan = __any_sync(FULL, nan_here);
-  float best = nan_here ? __int_as_float(0x7f800000) : dist;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) best = fminf(best, __shfl_xor_sync(FULL, best, o));
+  const float best = dec_ord(__reduce_min_sync(FULL, enc_ord(nan_here ? __int_as_float(0x7f800000) : dist)));
   if (ambiguous || any_nan || (ax.flags & 1u) || q_flag) return -1.0f;
   return best < 0.f ? 0.f : best;  // tiny negative from rounding stays a valid "certain" value
 }
 
-// argmax over the alignment lanes' correlations acc[d] = corr(base + d): best shift and whether the runner-up is
-// within the FP32 error bound (ambiguous -> the exact path must decide)
+// argmax over the alignment lanes' correlations acc[d] = corr(base + d): best shift (smallest on ties) and whether the
+// runner-up is within the FP32 error bound (ambiguous -> the exact path must decide).  `base` must grow with the lane
+// index (ties across lanes go to the lowest lane).  Branch-free top-2 per lane, then two CREDUX, a ballot and a shuffle.
 template <int S, int W>
 __device__ __forceinline__ void align_argmax(const float (&acc)[W], bool has, int base, float margin_scale, int* a_out, bool* amb_out) {
-  float b1 = -__int_as_float(0x7f800000), b2 = b1;
-  int s1 = 0x7fffffff;
-  if (has) {
+  constexpr int NONE = (int)0x807fffff;  // enc_ord(-inf)
+  int e1 = NONE, e2 = NONE, s1 = 0x7fffffff;
 #pragma unroll
-    for (int d = 0; d < W; ++d) {
-      const int s = base + d;
-      if (s < S) {
-        const float c = acc[d];
-        if (c > b1 || (c == b1 && s < s1)) {
-          b2 = b1;
-          b1 = c;
-          s1 = s;
-        } else if (c > b2) {
-          b2 = c;
-        }
-      }
-    }
+  for (int d = 0; d < W; ++d) {
+    const int s = base + d;
+    const int e = (has && s < S) ? enc_ord(acc[d]) : NONE;
+    const bool gt = e > e1;  // strict: the earlier (smaller) shift keeps a tie
+    e2 = max(e2, gt ? e1 : e);
+    s1 = gt ? s : s1;
+    e1 = max(e1, e);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ob1 = __shfl_xor_sync(FULL, b1, o), ob2 = __shfl_xor_sync(FULL, b2, o);
-    const int os1 = __shfl_xor_sync(FULL, s1, o);
-    if (ob1 > b1 || (ob1 == b1 && os1 < s1)) {
-      b2 = fmaxf(b1, ob2);
-      b1 = ob1;
-      s1 = os1;
-    } else {
-      b2 = fmaxf(b2, ob1);
-    }
-  }
-  *a_out = (s1 == 0x7fffffff) ? 0 : s1;
+  const int E1 = __reduce_max_sync(FULL, e1);
+  const unsigned winners = __ballot_sync(FULL, e1 == E1);
+  const int wl = __ffs(winners) - 1;
+  const int S1 = __shfl_sync(FULL, s1, wl);
+  const int E2 = __reduce_max_sync(FULL, (int)(threadIdx.x & 31) == wl ? e2 : e1);
+  const float b1 = dec_ord(E1), b2 = dec_ord(E2);
+  *a_out = (S1 == 0x7fffffff) ? 0 : S1;
   *amb_out = !((b1 - b2) > EXH_ALIGN_MARGIN * margin_scale) || !(b1 == b1);
 }
 
-// shared memory rings: one slot holds a group of EW entries.  The descriptor of group g is needed one iteration later
-// than its sector key, so the two live in rings of different depth (more warps fit).
-template <int R, int S, int EW>
-struct ExhScSlot {
-  float sc_hat[EW][R * S];
-};
-template <int S, int EW>
-struct ExhVkSlot {
-  float vkey[EW][S];
-  ExhAux aux[EW];
+// Shared memory: every consumer warp owns a private ring -- two descriptors, two (sector key + aux) records -- and the
+// four mbarriers that guard it.  A warp feeds its own ring: lane 0 issues the TMA bulk copies for the entries the warp
+// will need next as soon as the warp has finished reading a slot, so there is no producer warp, no "slot empty"
+// barrier and no block-wide convoy (the first version staged groups of EW entries per slot: every warp waited for the
+// whole 96 KB group and the next group could not be requested before the slowest warp had released the slot).
+template <int R, int S>
+struct ExhWarpRing {
+  float sc_hat[2][R * S];
+  ExhVkRec<S> vk[2];
 };
 
 template <int R, int S, int RAD, int EW>
 constexpr size_t exh_smem_bytes() {
-  return sizeof(ExhScSlot<R, S, EW>) * EXH_SC_STAGES + sizeof(ExhVkSlot<S, EW>) * EXH_VK_STAGES +
-         2 * (EXH_SC_STAGES + EXH_VK_STAGES) * sizeof(uint64_t) + (size_t)(R + 1) * (((2 * S + 2 * RAD + 1) | 1)) * sizeof(float);
+  return sizeof(ExhWarpRing<R, S>) * EW + (size_t)EW * 4 * sizeof(uint64_t) + qtab_bytes<R, S, 2 * RAD + 1>();
 }
 
-// R x S descriptor, search radius RAD, RPL descriptor rows per lane, EW consumer warps (= entries per ring slot)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// R x S descriptor, search radius RAD, RPL descriptor rows per lane, EW consumer warps per block
 template <int R, int S, int RAD, int RPL, int EW>
-__global__ void __launch_bounds__((EW + 1) * 32, 1) k_exh_screen(const ExhScreenParams pp) {
+__global__ void __launch_bounds__(EW * 32, 1) k_exh_screen(const ExhScreenParams pp) {
   // this block's query
   struct {
     ExhDb db;
@@ -361,60 +421,45 @@ __global__ void __launch_bounds__((EW + 1) * 32, 1) k_exh_screen(const ExhScreen
   constexpr int W = 2 * RAD + 1;
   constexpr int ROW_LANES = R / RPL;
   constexpr int ALIGN_LANES = (S + W - 1) / W;
-  constexpr int PITCH = (2 * S + W) | 1;  // odd pitch: lanes (rows) hit distinct banks
+  constexpr int PITCH = 2 * qtab_pairs(S, W);  // floats per table row
   static_assert(R % RPL == 0 && ROW_LANES + ALIGN_LANES <= 32, "rows + alignment lanes must fit one warp");
   static_assert(S <= 128 && S % 4 == 0, "valid-column masks are 128 bits; rows are read with 16-byte loads");
+  static_assert(sizeof(ExhWarpRing<R, S>) % 16 == 0, "TMA destinations are 16-byte aligned");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ExhScSlot<R, S, EW>* sc_ring = reinterpret_cast<ExhScSlot<R, S, EW>*>(smem_raw);
-  ExhVkSlot<S, EW>* vk_ring = reinterpret_cast<ExhVkSlot<S, EW>*>(smem_raw + sizeof(ExhScSlot<R, S, EW>) * EXH_SC_STAGES);
-  uint64_t* full_sc = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(vk_ring) + sizeof(ExhVkSlot<S, EW>) * EXH_VK_STAGES);
-  uint64_t* empty_sc = full_sc + EXH_SC_STAGES;
-  uint64_t* full_vk = empty_sc + EXH_SC_STAGES;
-  uint64_t* empty_vk = full_vk + EXH_VK_STAGES;
-  float* qtable = reinterpret_cast<float*>(empty_vk + EXH_VK_STAGES);  // [(R+1)][PITCH]: rows 0..R-1 = A^ rows, row R = v1, each doubled
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const unsigned long long n_groups = (p.n_local + EW - 1) / EW;  // groups of EW entries
-  const unsigned long long my_groups = n_groups > blockIdx.x ? (n_groups - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  ExhWarpRing<R, S>& ring = reinterpret_cast<ExhWarpRing<R, S>*>(smem_raw)[warp];
+  uint64_t* full_sc = reinterpret_cast<uint64_t*>(smem_raw + sizeof(ExhWarpRing<R, S>) * EW) + warp * 4;  // [2]
+  uint64_t* full_vk = full_sc + 2;                                                                        // [2]
+  float* qtable = reinterpret_cast<float*>(smem_raw + sizeof(ExhWarpRing<R, S>) * EW + (size_t)EW * 4 * sizeof(uint64_t));  // pair table
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < EXH_SC_STAGES; ++s) {
-      mbar_init(&full_sc[s], 1);
-      mbar_init(&empty_sc[s], EW);
-    }
-    for (int s = 0; s < EXH_VK_STAGES; ++s) {
-      mbar_init(&full_vk[s], 1);
-      mbar_init(&empty_vk[s], EW);
-    }
+  // consecutive warps of the grid take consecutive entries: warp gw scores gw, gw + TW, gw + 2 TW, ...
+  const unsigned long long TW = (unsigned long long)gridDim.x * EW, gw = (unsigned long long)blockIdx.x * EW + warp;
+  const unsigned long long my_n = p.n_local > gw ? (p.n_local - 1 - gw) / TW + 1 : 0;
+  auto issue_sc = [&](unsigned long long j) {  // descriptor of my j-th entry -> slot j & 1
+    const int slot = (int)(j & 1);
+    mbar_arrive_expect_tx(&full_sc[slot], R * S * 4u);
+    tma_bulk_g2s(&ring.sc_hat[slot][0], p.db.sc_hat + (gw + j * TW) * (R * S), R * S * 4u, &full_sc[slot]);
+  };
+  auto issue_vk = [&](unsigned long long j) {  // sector key + aux of my j-th entry -> slot j & 1
+    const int slot = (int)(j & 1);
+    mbar_arrive_expect_tx(&full_vk[slot], (unsigned)sizeof(ExhVkRec<S>));
+    tma_bulk_g2s(&ring.vk[slot], p.db.vk + (gw + j * TW) * sizeof(ExhVkRec<S>), (unsigned)sizeof(ExhVkRec<S>), &full_vk[slot]);
+  };
+  if (lane == 0) {
+    for (int s = 0; s < 4; ++s) mbar_init(&full_sc[s], 1);
     fence_barrier_init();
+    if (my_n > 0) {  // the copies do not touch the query table: start them before it is built
+      issue_vk(0);
+      issue_sc(0);
+    }
+    if (my_n > 1) issue_vk(1);
   }
-  for (int i = threadIdx.x; i < (R + 1) * PITCH; i += blockDim.x) {
-    const int r = i / PITCH, c = (i - r * PITCH) % S;
-    qtable[i] = r < R ? p.q->qhat[r * S + c] : p.q->v1[c];
+  {
+    const ExhQuery* qq = p.q;
+    qtab_fill<R, S, W>(qtable, [qq](int r, int c) { return r < R ? qq->qhat[r * S + c] : qq->v1[c]; });
   }
   __syncthreads();
 
-  if (warp == EW) {
-    // ===== producer: one lane feeds both rings with TMA bulk copies =====
-    if (lane == 0) {
-      for (unsigned long long k = 0; k < my_groups; ++k) {
-        const unsigned long long e0 = (blockIdx.x + k * gridDim.x) * EW;
-        const unsigned n = (unsigned)(p.n_local - e0 < EW ? p.n_local - e0 : EW);
-        const unsigned b_sc = n * R * S * 4u, b_vk = n * S * 4u, b_aux = n * (unsigned)sizeof(ExhAux);
-        const int sv = (int)(k % EXH_VK_STAGES), ss = (int)(k % EXH_SC_STAGES);
-        if (k >= EXH_VK_STAGES) mbar_wait(&empty_vk[sv], (uint32_t)(((k / EXH_VK_STAGES) - 1) & 1));
-        mbar_arrive_expect_tx(&full_vk[sv], b_vk + b_aux);
-        tma_bulk_g2s(&vk_ring[sv].vkey[0][0], p.db.vkey32 + e0 * S, b_vk, &full_vk[sv]);
-        tma_bulk_g2s(&vk_ring[sv].aux[0], p.db.aux + e0, b_aux, &full_vk[sv]);
-        if (k >= EXH_SC_STAGES) mbar_wait(&empty_sc[ss], (uint32_t)(((k / EXH_SC_STAGES) - 1) & 1));
-        mbar_arrive_expect_tx(&full_sc[ss], b_sc);
-        tma_bulk_g2s(&sc_ring[ss].sc_hat[0][0], p.db.sc_hat + e0 * R * S, b_sc, &full_sc[ss]);
-      }
-    }
-    return;
-  }
-
-  // ===== consumers: warp w scores entry w of every group =====
   // lane roles: [0, ROW_LANES) own RPL descriptor rows each; [ROW_LANES, ROW_LANES+ALIGN_LANES) own W alignment shifts
   const bool row_lane = lane < ROW_LANES, align_lane = lane >= ROW_LANES && lane < ROW_LANES + ALIGN_LANES;
   const unsigned long long qmask[2] = {p.q->qmask[0], p.q->qmask[1]};
@@ -423,70 +468,62 @@ __global__ void __launch_bounds__((EW + 1) * 32, 1) k_exh_screen(const ExhScreen
 
   int a_cur = 0;          // alignment of the entry whose window is scored in this iteration
   bool amb_cur = false;
+  ExhAux ax_cur;          // ... and its aux record (copied out of the ring one iteration earlier)
+  ax_cur.vmask[0] = ax_cur.vmask[1] = 0;
+  ax_cur.vnorm = 0.f;
+  ax_cur.flags = 0;
   unsigned my_min = 0x7f800000u;  // lane 0: smallest certain distance this warp has seen
-  for (unsigned long long k = 0; k <= my_groups; ++k) {
-    // iteration k: window of group k-1 (row lanes) + alignment of group k (alignment lanes)
-    const bool has_win = k >= 1, has_al = k < my_groups;
-    const int vk_w = (int)((k + EXH_VK_STAGES - 1) % EXH_VK_STAGES), vk_a = (int)(k % EXH_VK_STAGES);
-    const int sc_w = (int)((k + EXH_SC_STAGES - 1) % EXH_SC_STAGES);
-    bool ent_w = false, ent_a = false;
-    unsigned long long e_w = 0;
-    if (has_win) {
-      e_w = (blockIdx.x + (k - 1) * gridDim.x) * EW + warp;
-      ent_w = e_w < p.n_local;
-      mbar_wait(&full_sc[sc_w], (uint32_t)(((k - 1) / EXH_SC_STAGES) & 1));
-    }
-    if (has_al) {
-      mbar_wait(&full_vk[vk_a], (uint32_t)((k / EXH_VK_STAGES) & 1));
-      ent_a = (blockIdx.x + k * gridDim.x) * EW + warp < p.n_local;
-    }
+  for (unsigned long long k = 0; k <= my_n; ++k) {
+    // iteration k: window of my entry k-1 (row lanes) + alignment of my entry k (alignment lanes)
+    const bool has_win = k >= 1, has_al = k < my_n;
+    const int sc_w = (int)((k + 1) & 1), vk_a = (int)(k & 1);
+    if (has_win) mbar_wait(&full_sc[sc_w], (uint32_t)(((k - 1) >> 1) & 1));
+    if (has_al) mbar_wait(&full_vk[vk_a], (uint32_t)((k >> 1) & 1));
     float acc[W];
 #pragma unroll
     for (int d = 0; d < W; ++d) acc[d] = 0.f;
-    // One instruction stream for both lane roles (row lanes: window of group k-1; alignment lanes: correlation of
-    // group k): each lane only differs in WHERE its held values and its query row come from.
-    //   acc[d] = sum over my rows r, columns p of held_r[p] * q_r[(p + base + d) mod S]  (doubled table: plain index)
-    int base = 0;
-    if (row_lane && ent_w) base = ((a_cur - RAD) % S + S) % S;
-    else if (align_lane && ent_a) base = (lane - ROW_LANES) * W;
+    // One instruction stream for both lane roles (row lanes: window of entry k-1; alignment lanes: correlation of
+    // entry k): each lane only differs in WHERE its held values and its query row come from.
+    //   acc[d] = sum over my rows r, columns p of held_r[p] * q_r[(p + base + d) mod S]
+    // Selects, not branches: with an if / else-if here the compiler lets the two lane groups run the window code one
+    // after the other (every FFMA2 issued twice per entry).
+    const bool rw = row_lane && has_win, al = align_lane && has_al;
+    const int base = rw ? ((a_cur - RAD) % S + S) % S : (al ? (lane - ROW_LANES) * W : 0);
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
-      const float4* held4 = nullptr;
-      const float* qs = nullptr;
-      if (row_lane && ent_w) {
-        const int r = lane + i * ROW_LANES;
-        held4 = reinterpret_cast<const float4*>(&sc_ring[sc_w].sc_hat[warp][r * S]);
-        qs = qtable + r * PITCH + base;
-      } else if (i == 0 && align_lane && ent_a) {
-        held4 = reinterpret_cast<const float4*>(&vk_ring[vk_a].vkey[warp][0]);
-        qs = qtable + R * PITCH + base;
-      }
-      if (held4) {
-        if (rev) window_fma<S, W, true>(held4, qs, acc);
-        else window_fma<S, W, false>(held4, qs, acc);
+      const bool on = rw || (i == 0 && al);
+      const int r = rw ? lane + i * ROW_LANES : R;
+      const float* held = rw ? &ring.sc_hat[sc_w][r * S] : &ring.vk[vk_a].vkey[0];
+      const float* qrow = qtable + r * PITCH;
+      __syncwarp();
+      if (on) {
+        if (rev) window_fma<S, W, true>(reinterpret_cast<const float4*>(held), qrow, base, acc);
+        else window_fma<S, W, false>(reinterpret_cast<const float4*>(held), qrow, base, acc);
       }
     }
-    // ---- window result of group k-1 ------------------------------------------------------------------
+    // ---- window result of entry k-1 ------------------------------------------------------------------
     if (has_win) {
       int d_mine;
       const float total = transpose_reduce<W>(acc, row_lane, lane, &d_mine);
-      ExhAux ax = vk_ring[vk_w].aux[ent_w ? warp : 0];
+      ExhAux ax = ax_cur;
       if (rev) reverse_mask<S>(ax.vmask);
       const float out = screened_distance<S, RAD>(total, d_mine, a_cur, qmask, ax, amb_cur, q_flag);
-      if (lane == 0 && ent_w) {
-        p.d32[e_w] = out;
+      if (lane == 0) {
+        p.d32[gw + (k - 1) * TW] = out;
         if (out >= 0.f) my_min = min(my_min, __float_as_uint(out));
       }
-      __syncwarp();
-      if (lane == 0) {  // this warp is done with group k-1's slots
-        mbar_arrive(&empty_sc[sc_w]);
-        mbar_arrive(&empty_vk[vk_w]);
-      }
     }
-    // ---- alignment result of group k (becomes a_cur of the next iteration) -------------------------------
+    // ---- alignment result of entry k (becomes a_cur of the next iteration) -------------------------------
     if (has_al) {
-      const float vn = ent_a ? vk_ring[vk_a].aux[warp].vnorm : 0.f;
-      align_argmax<S, W>(acc, align_lane && ent_a, base, v1norm * vn, &a_cur, &amb_cur);
+      ax_cur = ring.vk[vk_a].aux;
+      align_argmax<S, W>(acc, align_lane, base, v1norm * ax_cur.vnorm, &a_cur, &amb_cur);
+    }
+    // ---- both slots read in this iteration are free: request what they hold next ---------------------------
+    __syncwarp();
+    if (lane == 0) {
+      fence_proxy_async();  // the warp's generic-proxy reads of the slots precede the async-proxy writes
+      if (k + 1 < my_n) issue_sc(k + 1);  // -> slot sc_w (k = 0: the still unused second slot)
+      if (k + 2 < my_n) issue_vk(k + 2);  // -> slot vk_a
     }
   }
   if (lane == 0 && my_min != 0x7f800000u) atomicMin(p.min_bits, my_min);
@@ -588,9 +625,9 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
   constexpr int W = 2 * RAD + 1;
   constexpr int ROW_LANES = R / RPL;
   constexpr int ALIGN_LANES = (S + W - 1) / W;
-  constexpr int PITCH = (2 * S + W) | 1;
+  constexpr int PITCH = 2 * qtab_pairs(S, W);
   static_assert(R % RPL == 0 && ROW_LANES + ALIGN_LANES <= 32 && S <= 128 && S % 4 == 0, "see k_exh_screen");
-  extern __shared__ __align__(16) float qtable[];  // [(R + 1)][PITCH]
+  extern __shared__ __align__(16) float qtable[];  // [(R + 1)][PITCH]: pair table
   __shared__ float s_inv[S];
   __shared__ unsigned long long s_mask[2];
   __shared__ unsigned s_flags;
@@ -619,10 +656,8 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
   }
   __syncthreads();
   if (!early) {
-    for (int i = threadIdx.x; i < (R + 1) * PITCH; i += blockDim.x) {
-      const int r = i / PITCH, c = (i - r * PITCH) % S;
-      qtable[i] = r < R ? qsc[c * R + r] * s_inv[c] : (float)qsector[c];
-    }
+    const float* inv = s_inv;
+    qtab_fill<R, S, W>(qtable, [qsc, qsector, inv](int r, int c) { return r < R ? qsc[c * R + r] * inv[c] : (float)qsector[c]; });
   }
   __syncthreads();
   const unsigned long long qmask[2] = {s_mask[0], s_mask[1]};
@@ -639,7 +674,8 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
       continue;
     }
     const unsigned long long l = g / (unsigned long long)p.db.G;
-    const ExhAux ax = p.xdb.aux[l];
+    const ExhVkRec<S>* vkr = reinterpret_cast<const ExhVkRec<S>*>(p.xdb.vk) + l;
+    const ExhAux ax = vkr->aux;
     // ---- alignment with ALL lanes (nothing else to do in this phase): lane l takes the WA shifts l*WA .. l*WA+WA-1
     constexpr int WA = (S + 31) / 32;
     int a_cur;
@@ -649,7 +685,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
 #pragma unroll
       for (int d = 0; d < WA; ++d) ca[d] = 0.f;
       const int ab = lane * WA;
-      if (ab < S) window_fma<S, WA>(reinterpret_cast<const float4*>(p.xdb.vkey32 + l * S), qtable + R * PITCH + ab, ca);
+      if (ab < S) window_fma<S, WA>(reinterpret_cast<const float4*>(vkr->vkey), qtable + R * PITCH, ab, ca);
       align_argmax<S, WA>(ca, ab < S, ab, v1norm * ax.vnorm, &a_cur, &amb);
     }
     float acc[W];
@@ -662,7 +698,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
 #pragma unroll
       for (int i = 0; i < RPL; ++i) {
         const int r = lane + i * ROW_LANES;
-        window_fma<S, W>(reinterpret_cast<const float4*>(p.xdb.sc_hat + l * (R * S) + r * S), qtable + r * PITCH + base, acc);
+        window_fma<S, W>(reinterpret_cast<const float4*>(p.xdb.sc_hat + l * (R * S) + r * S), qtable + r * PITCH, base, acc);
       }
     }
     int d_mine;
@@ -674,7 +710,7 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
 
 template <int R, int S, int RAD>
 constexpr size_t cand_smem_bytes() {
-  return (size_t)(R + 1) * (((2 * S + 2 * RAD + 1) | 1)) * sizeof(float);
+  return qtab_bytes<R, S, 2 * RAD + 1>();
 }
 
 // per query: which candidate slots need the exact kernel
