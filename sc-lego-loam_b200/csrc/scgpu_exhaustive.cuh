@@ -783,6 +783,7 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
   }
   for (int i = threadIdx.x; i < RS; i += blockDim.x) s_bins[i] = SCGPU_ENC_NOPOINT;
   if (threadIdx.x == 0) s_qcount = 0;
+  const uint32_t bins_addr = smem_u32(s_bins);
   __syncthreads();
   auto issue = [&](unsigned c) {
     const unsigned pts = min((unsigned)BUILD_CHUNK, end - start - c * BUILD_CHUNK);
@@ -794,11 +795,16 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
   if (threadIdx.x == 0)
     for (unsigned c = 0; c < BUILD_STAGES - 1 && c < n_chunks; ++c) issue(c);
 
-  for (unsigned c = 0; c < n_chunks; ++c) {
+  // chunk loop, unrolled over the ring so that slot numbers (shared-memory offsets, barrier addresses) are constants
+  for (unsigned c0 = 0; c0 < n_chunks; c0 += BUILD_STAGES) {
+    const unsigned ring_parity = (c0 / BUILD_STAGES) & 1;
+#pragma unroll
+   for (int slot = 0; slot < BUILD_STAGES; ++slot) {
+    const unsigned c = c0 + slot;
+    if (c >= n_chunks) break;
     // refill the slot that chunk c-1 occupied (no block-wide barrier: warps only report "copied out" per slot)
     if (threadIdx.x == 0 && c + BUILD_STAGES - 1 < n_chunks) issue(c + BUILD_STAGES - 1);
-    const int slot = (int)(c % BUILD_STAGES);
-    mbar_wait(&full[slot], (c / BUILD_STAGES) & 1);
+    mbar_wait(&full[slot], ring_parity);
     const unsigned pts = min((unsigned)BUILD_CHUNK, end - start - c * BUILD_CHUNK);
     const unsigned char* sp = ring + (size_t)slot * BUILD_CHUNK * STRIDE + (size_t)threadIdx.x * STRIDE;
     float px[BUILD_UNROLL], py[BUILD_UNROLL], pz[BUILD_UNROLL];
@@ -844,19 +850,36 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
             s_queue[3 * slot + 2] = pz[u];
             bin[u] = -1;
           } else {
-            bin[u] = bin_point_exact_noinline(p.bc, px[u], py[u], pz[u], hh[u]);
+            const unsigned long long r = bin_point_exact_noinline(p.bc.R, p.bc.S, p.bc.lidar_height, p.bc.max_radius, px[u], py[u], pz[u]);
+            bin[u] = (int)(unsigned)(r >> 32);
+            hh[u] = __uint_as_float((unsigned)r);
           }
         }
     }
     // max into the block's grid.  A bin's value only ever grows, so a plain read is a valid filter: a point that does
     // not beat the value read cannot beat the current one; after the first few points of a bin almost none does.
+    // Branch-free: the four reads first, then one PREDICATED shared-memory reduction per point (as C++ this compiled
+    // to a divergent branch per point that also re-derived the shared-memory window address every time).
+    int cur[BUILD_UNROLL], enc[BUILD_UNROLL];
+    uint32_t addr[BUILD_UNROLL];
 #pragma unroll
     for (int u = 0; u < BUILD_UNROLL; ++u) {
-      if (bin[u] >= 0) {
-        const int e = enc_float(hh[u]);
-        if (e > s_bins[bin[u]]) atomicMax(&s_bins[bin[u]], e);
-      }
+      addr[u] = bins_addr + 4u * (uint32_t)max(bin[u], 0);
+      enc[u] = enc_float(hh[u]);
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(cur[u]) : "r"(addr[u]));
     }
+#pragma unroll
+    for (int u = 0; u < BUILD_UNROLL; ++u)
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p, q;\n\t"
+          "setp.ge.s32 q, %3, 0;\n\t"
+          "setp.gt.and.s32 p, %1, %2, q;\n\t"
+          "@p red.shared.max.s32 [%0], %1;\n\t"
+          "}" ::"r"(addr[u]),
+          "r"(enc[u]), "r"(cur[u]), "r"(bin[u])
+          : "memory");
+   }
   }
   __syncthreads();
   {  // the parked points: exact path, all lanes busy

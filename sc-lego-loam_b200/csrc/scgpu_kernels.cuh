@@ -189,9 +189,20 @@ __device__ __forceinline__ float mufu_rcp(float x) {
   return r;
 }
 
-// out-of-line copy of the exact path for the kernels that defer it (keeps their hot loop small)
-__device__ __noinline__ int bin_point_exact_noinline(const BinConst& c, float x, float y, float z, float& height) {
-  return bin_point_exact(c, x, y, z, height);
+// out-of-line copy of the exact path for the kernels that defer it (keeps their hot loop small).  Everything by
+// value -- arguments and the (bin << 32 | height bits) result travel in registers: a version taking `const BinConst&`
+// and `float&` forced the caller's BinConst copy and its height array into local memory (160-byte stack frame, every
+// height store a local store: 1.2 GB of extra DRAM writes per 4,541-scan launch).
+__device__ __noinline__ unsigned long long bin_point_exact_noinline(int R, int S, double lidar_height, double max_radius, float x, float y,
+                                                                    float z) {
+  BinConst c;
+  c.R = R;
+  c.S = S;
+  c.lidar_height = lidar_height;
+  c.max_radius = max_radius;
+  float h;
+  const int b = bin_point_exact(c, x, y, z, h);
+  return ((unsigned long long)(unsigned)b << 32) | (unsigned long long)__float_as_uint(h);
 }
 
 constexpr int BIN_UNDECIDED = -2;  // bin_point_fast: the exact path has to decide this point
