@@ -433,8 +433,10 @@ int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const 
   cp.n_search = reinterpret_cast<const unsigned long long*>(d_ns);
   cp.K = h->K;
   cp.d32 = h->c_d32.as<float>();
-  if (h->exh_cfg == 1) k_cand_screen<20, 60, 3, 1><<<(unsigned)nq, CAND_WARPS * 32, cand_smem_bytes<20, 60, 3>(), st>>>(cp);
-  else k_cand_screen<40, 120, 6, 2><<<(unsigned)nq, CAND_WARPS * 32, cand_smem_bytes<40, 120, 6>(), st>>>(cp);
+  // warps per block, staging slots per warp.  One slot: three blocks fit an SM and cover each other's fetch latency
+  // (two slots = one block per SM measured slower at K = 50).
+  if (h->exh_cfg == 1) k_cand_screen<20, 60, 3, 1, 10, 1><<<(unsigned)nq, 10 * 32, cand_smem_bytes<20, 60, 3, 10, 1>(), st>>>(cp);
+  else k_cand_screen<40, 120, 6, 2, 5, 1><<<(unsigned)nq, 5 * 32, cand_smem_bytes<40, 120, 6, 5, 1>(), st>>>(cp);
   k_cand_select<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(h->c_d32.as<float>(), (unsigned)nq, h->K, h->c_list.as<unsigned long long>(),
                                                              h->c_count.as<unsigned>(), h->pair_dist.as<double>(), h->pair_shift.as<int>());
   ScoreParams p;
@@ -783,8 +785,10 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
                                                (int)exh_smem_bytes<20, 60, 3, 20>())
                         : cudaFuncSetAttribute(k_exh_screen<40, 120, 6, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)exh_smem_bytes<40, 120, 6, 4>());
+  if (e == cudaSuccess && h->exh && h->exh_cfg == 1)
+    e = cudaFuncSetAttribute(k_cand_screen<20, 60, 3, 1, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem_bytes<20, 60, 3, 10, 1>());
   if (e == cudaSuccess && h->exh && h->exh_cfg == 2)
-    e = cudaFuncSetAttribute(k_cand_screen<40, 120, 6, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem_bytes<40, 120, 6>());
+    e = cudaFuncSetAttribute(k_cand_screen<40, 120, 6, 2, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem_bytes<40, 120, 6, 5, 1>());
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score_list, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);

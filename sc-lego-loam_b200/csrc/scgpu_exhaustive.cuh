@@ -607,8 +607,6 @@ __global__ void __launch_bounds__(256) k_exh_final(const double* pair_dist, cons
 // The strict-min in candidate order (k_best) then runs over exactly-scored candidates only, so the result is the
 // reference's.  scgpu_get_candidates rescoring everything exactly on demand keeps the parity dumps complete.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int CAND_WARPS = 10;
-
 struct CandScreenParams {
   const unsigned char* qrecords;
   Layout L;
@@ -620,24 +618,75 @@ struct CandScreenParams {
   float* d32;                           // [nq][K] out: approx distance; -1 = rescore; +inf = cannot win / not mine
 };
 
-template <int R, int S, int RAD, int RPL>
-__global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScreenParams p) {
+// one candidate staged in shared memory: screening copy of the descriptor + its sector key / aux record
+template <int R, int S>
+struct CandSlot {
+  float sc_hat[R * S];
+  ExhVkRec<S> vk;
+};
+
+template <int R, int S, int RAD, int CW, int NS>
+constexpr size_t cand_smem_bytes() {
+  return sizeof(CandSlot<R, S>) * CW * NS + (size_t)CW * NS * sizeof(uint64_t) + qtab_bytes<R, S, 2 * RAD + 1>();
+}
+
+// CW warps per block, NS staging slots per warp.  Warp w scores candidates w, w + CW, ... of the block's query.  Each
+// warp fetches its candidates itself with TMA bulk copies (lane 0; up to NS in flight) -- the first fetch is issued
+// before the block builds the query table, so the dependent chain "key -> entry -> sector key -> descriptor rows"
+// (three L2 round trips when read with plain loads) overlaps the table build instead of following it.
+template <int R, int S, int RAD, int RPL, int CW, int NS>
+__global__ void __launch_bounds__(CW * 32) k_cand_screen(const CandScreenParams p) {
   constexpr int W = 2 * RAD + 1;
   constexpr int ROW_LANES = R / RPL;
-  constexpr int ALIGN_LANES = (S + W - 1) / W;
   constexpr int PITCH = 2 * qtab_pairs(S, W);
-  static_assert(R % RPL == 0 && ROW_LANES + ALIGN_LANES <= 32 && S <= 128 && S % 4 == 0, "see k_exh_screen");
-  extern __shared__ __align__(16) float qtable[];  // [(R + 1)][PITCH]: pair table
+  static_assert(R % RPL == 0 && ROW_LANES <= 32 && S <= 128 && S % 4 == 0, "see k_exh_screen");
+  static_assert(sizeof(CandSlot<R, S>) % 16 == 0, "TMA destinations are 16-byte aligned");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float s_inv[S];
   __shared__ unsigned long long s_mask[2];
   __shared__ unsigned s_flags;
   __shared__ float s_v2;
   const int q = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  CandSlot<R, S>* slots = reinterpret_cast<CandSlot<R, S>*>(smem_raw) + warp * NS;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + sizeof(CandSlot<R, S>) * CW * NS) + warp * NS;
+  float* qtable = reinterpret_cast<float*>(smem_raw + sizeof(CandSlot<R, S>) * CW * NS + (size_t)CW * NS * sizeof(uint64_t));
   const bool early = p.n_search[q] == 0;
   const unsigned char* qrec = p.qrecords + (size_t)q * p.L.rec_bytes;
   const float* qsc = reinterpret_cast<const float*>(qrec);
   const double* qsector = reinterpret_cast<const double*>(qrec + p.L.off_sector);
   const double* qnorm = reinterpret_cast<const double*>(qrec + p.L.off_norm);
+  const unsigned long long* qkeys = p.keys + (size_t)q * p.K;
+
+  // candidate k of this query: is it this shard's, and which local entry (warp-uniform)
+  auto owned = [&](int k, unsigned long long* l) {
+    const unsigned long long key = qkeys[k];
+    const unsigned long long g = (key == KEY_NONE) ? 0ull : (key & 0xffffffffull);
+    *l = g / (unsigned long long)p.db.G;
+    return !early && (int)(g % (unsigned long long)p.db.G) == p.db.rank;
+  };
+  int issued = 0, consumed = 0, k_issue = warp;  // fetches requested / used so far; next candidate to look at for a fetch
+  auto fetch_more = [&]() {
+    while (issued - consumed < NS && k_issue < p.K) {
+      unsigned long long l;
+      if (owned(k_issue, &l)) {
+        if (lane == 0) {
+          const int s = issued % NS;
+          mbar_arrive_expect_tx(&full[s], (unsigned)sizeof(CandSlot<R, S>));
+          tma_bulk_g2s(slots[s].sc_hat, p.xdb.sc_hat + l * (R * S), R * S * 4u, &full[s]);
+          tma_bulk_g2s(&slots[s].vk, p.xdb.vk + l * sizeof(ExhVkRec<S>), (unsigned)sizeof(ExhVkRec<S>), &full[s]);
+        }
+        ++issued;
+      }
+      k_issue += CW;
+    }
+  };
+  if (lane == 0) {
+    for (int s = 0; s < NS; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  fetch_more();
+
   if (threadIdx.x == 0) {
     s_mask[0] = s_mask[1] = 0;
     s_flags = 0;
@@ -663,19 +712,18 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
   const unsigned long long qmask[2] = {s_mask[0], s_mask[1]};
   const float v1norm = sqrtf(s_v2);
   const bool q_flag = s_flags != 0;
-  const bool row_lane = lane < ROW_LANES, align_lane = lane >= ROW_LANES && lane < ROW_LANES + ALIGN_LANES;
+  const bool row_lane = lane < ROW_LANES;
 
-  for (int k = warp; k < p.K; k += CAND_WARPS) {
+  for (int k = warp; k < p.K; k += CW) {
     const size_t o = (size_t)q * p.K + k;
-    const unsigned long long key = p.keys[o];
-    const unsigned long long g = (key == KEY_NONE) ? 0ull : (key & 0xffffffffull);
-    if (early || (int)(g % (unsigned long long)p.db.G) != p.db.rank) {
+    unsigned long long l;
+    if (!owned(k, &l)) {
       if (lane == 0) p.d32[o] = __int_as_float(0x7f800000);
       continue;
     }
-    const unsigned long long l = g / (unsigned long long)p.db.G;
-    const ExhVkRec<S>* vkr = reinterpret_cast<const ExhVkRec<S>*>(p.xdb.vk) + l;
-    const ExhAux ax = vkr->aux;
+    const CandSlot<R, S>& slot = slots[consumed % NS];
+    mbar_wait(&full[consumed % NS], (uint32_t)((consumed / NS) & 1));
+    const ExhAux ax = slot.vk.aux;
     // ---- alignment with ALL lanes (nothing else to do in this phase): lane l takes the WA shifts l*WA .. l*WA+WA-1
     constexpr int WA = (S + 31) / 32;
     int a_cur;
@@ -685,32 +733,31 @@ __global__ void __launch_bounds__(CAND_WARPS * 32) k_cand_screen(const CandScree
 #pragma unroll
       for (int d = 0; d < WA; ++d) ca[d] = 0.f;
       const int ab = lane * WA;
-      if (ab < S) window_fma<S, WA>(reinterpret_cast<const float4*>(vkr->vkey), qtable + R * PITCH, ab, ca);
+      if (ab < S) window_fma<S, WA>(reinterpret_cast<const float4*>(slot.vk.vkey), qtable + R * PITCH, ab, ca);
       align_argmax<S, WA>(ca, ab < S, ab, v1norm * ax.vnorm, &a_cur, &amb);
     }
-    float acc[W];
-    int base;
     // ---- window on the row lanes: acc[d] belongs to shift a_cur - RAD + d
+    float acc[W];
 #pragma unroll
     for (int d = 0; d < W; ++d) acc[d] = 0.f;
-    base = ((a_cur - RAD) % S + S) % S;
+    const int base = ((a_cur - RAD) % S + S) % S;
     if (row_lane) {
 #pragma unroll
       for (int i = 0; i < RPL; ++i) {
         const int r = lane + i * ROW_LANES;
-        window_fma<S, W>(reinterpret_cast<const float4*>(p.xdb.sc_hat + l * (R * S) + r * S), qtable + r * PITCH, base, acc);
+        window_fma<S, W>(reinterpret_cast<const float4*>(&slot.sc_hat[r * S]), qtable + r * PITCH, base, acc);
       }
     }
+    // ---- the slot has been read: request the next candidate, then finish this one
+    __syncwarp();
+    ++consumed;
+    if (lane == 0) fence_proxy_async();
+    fetch_more();
     int d_mine;
     const float total = transpose_reduce<W>(acc, row_lane, lane, &d_mine);
     const float out = screened_distance<S, RAD>(total, d_mine, a_cur, qmask, ax, amb, q_flag);
     if (lane == 0) p.d32[o] = out;
   }
-}
-
-template <int R, int S, int RAD>
-constexpr size_t cand_smem_bytes() {
-  return qtab_bytes<R, S, 2 * RAD + 1>();
 }
 
 // per query: which candidate slots need the exact kernel
