@@ -39,8 +39,8 @@ PTS = 120000
 R, S, K_CAND = 20, 60, 10
 ALGO_BYTES_PER_SCAN = 16 * PTS + 4 * R * S + 4 * R + 8 * S   # 1,925,360 B
 # dram__bytes_read.sum + dram__bytes_write.sum of the bench's own k_build_tma launch (4,541 scans), one `ncu --set full`
-# capture, profiles/r1_k_build_tma_final_ncu_summary.txt: 8.782 GB + 1.194 GB
-NCU_TRAFFIC_BYTES_PER_SCAN = (8.782069e9 + 1.193974e9) / 4541
+# capture, profiles/r1_k_build_tma_final_ncu_summary.txt: 8.718801 GB read + 0.029917 GB written (= 1.00 x algorithmic)
+NCU_TRAFFIC_BYTES_PER_SCAN = (8.718801e9 + 0.029917184e9) / 4541
 SEED = 20181002
 WORKLOAD = "kitti00_shaped_4541kf_hdl64_120kpts_sc20x60_k10_excl50"
 
