@@ -148,6 +148,25 @@ int scgpu_exhaustive_batched(scgpu_handle* h, const uint64_t* q, const uint64_t*
 /* How many entries the last scgpu_exhaustive had to rescore with the exact FP64 kernel (the rest was ruled out
  * by the FP32 screening pass with a proven margin). */
 int scgpu_exhaustive_stats(scgpu_handle* h, uint64_t* rescored);
+/* ---- voxel-grid downsample in front of the path ---------------------------------------
+ * The reference filters every raw scan with pcl::VoxelGrid before it reaches SCManager:
+ * downSizeFilterScancontext.setLeafSize(0.5, 0.5, 0.5) (mapOpt.cpp:264), .filter() (mapOpt.cpp:1235-1237), and the
+ * filtered cloud is what makeAndSaveScancontextAndKeys receives (mapOpt.cpp:1628-1630). */
+
+/* = downSizeFilterScancontext.setLeafSize(leaf, leaf, leaf).  leaf > 0: every scan given to scgpu_append_scan /
+ * scgpu_append_scans_batched / scgpu_replay_batched / scgpu_make_sc / scgpu_stage_build is first reduced to its voxel
+ * centroids on the device (k_build_voxel: one thread-block cluster per scan, voxel table in distributed shared
+ * memory), i.e. the caller passes the RAW scan and drops its own VoxelGrid.  leaf = 0 (default): scans are binned as
+ * given.  Leaf indices are bit-identical to PCL's; a centroid is the correctly rounded mean of its points (PCL: FP32
+ * running sum in std::sort order), so coordinates agree to a few ulp. */
+int scgpu_set_downsample_leaf(scgpu_handle* h, float leaf);
+/* = pcl::VoxelGrid<PointXYZI>::filter on one host scan: out_xyzn[i] = {centroid x, y, z, number of points} and
+ * out_idx[i] = PCL's leaf index of voxel i (order unspecified; PCL emits ascending leaf index), *out_n = number of
+ * voxels (an error if > cap).  min_b / div_b (3 ints each, optional): PCL's grid origin and extent.  *status
+ * (optional): bit 0 = PCL's "leaf size too small" refusal (the input is passed through, out_idx = point index),
+ * bits 8.. = number of key partitions the scan needed.  Intensity is not carried (the path reads x, y, z only). */
+int scgpu_voxel_downsample(scgpu_handle* h, const void* pts, size_t n, size_t stride_bytes, float leaf, float* out_xyzn,
+                           uint32_t* out_idx, size_t cap, size_t* out_n, int32_t* min_b, int32_t* div_b, int32_t* status);
 /* Flat binary save / load of the descriptor database. */
 int scgpu_save(scgpu_handle* h, const char* path);
 int scgpu_load(scgpu_handle* h, const char* path);

@@ -197,6 +197,31 @@ REF_VARIANTS = {
 }
 
 
+class Voxel:
+    """pcl::VoxelGrid restated (oracle/voxel_oracle.cpp; parity unpinned: PCL is not in this image)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_build", "libvoxoracle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        self.L = C.CDLL(path)
+        self.L.vox_downsample.restype = C.c_long
+        self.L.vox_downsample.argtypes = [_vp, _sz, _sz, _f, _vp, _vp, _vp, _sz, _vp, _vp]
+
+    def downsample(self, pts, leaf):
+        """-> dict(points (m,4) f32 in ascending leaf-index order, idx (m,) u32, count (m,) u32, min_b, div_b)."""
+        pts, ptr, n, stride = _pts_args(pts)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        idx = np.zeros(max(n, 1), np.uint32)
+        cnt = np.zeros(max(n, 1), np.uint32)
+        mb, db = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        m = self.L.vox_downsample(ptr, n, stride // 4, leaf, out.ctypes.data_as(_vp), idx.ctypes.data_as(_vp),
+                                  cnt.ctypes.data_as(_vp), out.shape[0], mb.ctypes.data_as(_vp), db.ctypes.data_as(_vp))
+        if m < 0:
+            raise ValueError("leaf size too small for the input (PCL refuses)" if m == -1 else "capacity")
+        return {"points": out[:m].copy(), "idx": idx[:m].copy(), "count": cnt[:m].copy(), "min_b": mb, "div_b": db}
+
+
 def ref_available(variant="default"):
     return os.path.exists(os.path.join(HERE, "_ref", REF_VARIANTS[variant]))
 

@@ -14,6 +14,7 @@
 
 #include "scgpu_exhaustive.cuh"
 #include "scgpu_kernels.cuh"
+#include "scgpu_voxel.cuh"
 
 using namespace scgpu;
 
@@ -94,6 +95,8 @@ struct scgpu_handle {
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_t2 = nullptr;  // call start / builds done / call end
   cudaEvent_t ev_nl = nullptr;
   bool timing_valid = false;
+  float voxel_leaf = 0.f;  // > 0: scans are voxel-grid filtered in front of the descriptor build (k_build_voxel)
+  DevBuf vox_info, vox_pts, vox_idx, vox_in;
   // database shard
   Db db{};
   uint64_t n_global = 0;
@@ -202,10 +205,50 @@ int build_reserve(scgpu_handle* h, size_t n_scans, cudaStream_t st) {
   return SCGPU_OK;
 }
 
+// Voxel-grid filter (pcl::VoxelGrid, mapOpt.cpp:264,1235-1237) fused with stage 1+2; device-resident points.
+// d_records may be null (downsample only); out_* optional device buffers [n_scans][out_cap].
+int launch_build_voxel(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_per_scan, size_t stride, float leaf, void* d_records,
+                       VoxInfo* d_info, float4* d_out_pts, unsigned* d_out_idx, unsigned out_cap, cudaStream_t st) {
+  if (n_scans == 0) return SCGPU_OK;
+  if (!(leaf > 0.f) || !(leaf < 1e30f)) return fail(SCGPU_E_INVALID, "voxel leaf size must be positive and finite");
+  if (stride < 12 || (stride & 3) || ((uintptr_t)d_pts & 3)) return fail(SCGPU_E_INVALID, "points must be 4-byte aligned, stride >= 12 and a multiple of 4");
+  if (pts_per_scan > 0xfffffff0ull) return fail(SCGPU_E_INVALID, "scan too large");
+  VoxelBuildParams p;
+  p.pts = static_cast<const unsigned char*>(d_pts);
+  p.scan_pitch = (unsigned long long)pts_per_scan * stride;
+  p.n_pts = (unsigned)pts_per_scan;
+  p.stride = (unsigned)stride;
+  p.inv_leaf = 1.0f / leaf;
+  p.bc = make_bin_const(h->L.R, h->L.S, h->cfg.lidar_height, h->cfg.max_radius, 0);
+  p.L = h->L;
+  p.out_cap = out_cap;
+  const size_t smem = vox_smem_bytes(h->L.RS);
+  const bool al16 = (((uintptr_t)d_pts & 15) == 0);
+  const int sk = (stride == 16 && al16) ? 16 : ((stride == 32 && al16) ? 32 : 0);
+  for (size_t s0 = 0; s0 < n_scans; s0 += 65535) {  // gridDim.y limit
+    const size_t ns = n_scans - s0 < 65535 ? n_scans - s0 : 65535;
+    VoxelBuildParams q = p;
+    q.pts = p.pts + s0 * p.scan_pitch;
+    q.records = d_records ? static_cast<unsigned char*>(d_records) + s0 * h->L.rec_bytes : nullptr;
+    q.info = d_info ? d_info + s0 : nullptr;
+    q.out_pts = d_out_pts ? d_out_pts + s0 * out_cap : nullptr;
+    q.out_idx = d_out_idx ? d_out_idx + s0 * out_cap : nullptr;
+    dim3 grid(VOX_CLUSTER, (unsigned)ns);
+    if (sk == 16) k_build_voxel<16><<<grid, VOX_THREADS, smem, st>>>(q);
+    else if (sk == 32) k_build_voxel<32><<<grid, VOX_THREADS, smem, st>>>(q);
+    else k_build_voxel<0><<<grid, VOX_THREADS, smem, st>>>(q);
+    h->launches++;
+    CK(cudaGetLastError());
+  }
+  return SCGPU_OK;
+}
+
 // Stage 1+2 on device-resident points.
 int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_per_scan, size_t stride, void* d_records,
                  cudaStream_t st) {
   if (n_scans == 0) return SCGPU_OK;
+  if (h->voxel_leaf > 0.f && pts_per_scan > 0)
+    return launch_build_voxel(h, d_pts, n_scans, pts_per_scan, stride, h->voxel_leaf, d_records, nullptr, nullptr, nullptr, 0, st);
   if (stride < 12 || (stride & 3) || ((uintptr_t)d_pts & 3)) return fail(SCGPU_E_INVALID, "points must be 4-byte aligned, stride >= 12 and a multiple of 4");
   if (pts_per_scan > 0xfffffff0ull || n_scans > 65535ull * 1024) return fail(SCGPU_E_INVALID, "scan too large");
   RET(build_reserve(h, n_scans, st));
@@ -780,6 +823,9 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<16>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_voxel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vox_smem_bytes(h->L.RS));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_voxel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vox_smem_bytes(h->L.RS));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_voxel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vox_smem_bytes(h->L.RS));
   if (e == cudaSuccess && h->exh)
     e = h->exh_cfg == 1 ? cudaFuncSetAttribute(k_exh_screen<20, 60, 3, 1, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)exh_smem_bytes<20, 60, 3, 20>())
@@ -816,7 +862,7 @@ int scgpu_destroy(scgpu_handle* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   DevBuf* bufs[] = {&h->gbins, &h->btickets, &h->d_pts[0], &h->d_pts[1], &h->records, &h->rec_single, &h->nsearch, &h->keys, &h->partial,
                     &h->ttickets, &h->pair_dist, &h->pair_shift, &h->best, &h->o_loop, &h->o_yaw, &h->o_dist, &h->o_idx, &h->o_shift,
-                    &h->api_in, &h->api_out};
+                    &h->api_in, &h->api_out, &h->vox_info, &h->vox_pts, &h->vox_idx, &h->vox_in};
   for (DevBuf* b : bufs) b->release();
   h->h_pts[0].release();
   h->h_pts[1].release();
@@ -1404,6 +1450,48 @@ int scgpu_stage_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t
   if (!h || !d_records) return fail(SCGPU_E_INVALID, "null argument");
   CK(cudaSetDevice(h->cfg.device));
   return launch_build(h, d_pts, n_scans, pts_per_scan, stride, d_records, ST(stream));
+}
+
+int scgpu_set_downsample_leaf(scgpu_handle* h, float leaf) {
+  if (!h) return fail(SCGPU_E_INVALID, "null handle");
+  if (!(leaf >= 0.f) || !(leaf < 1e30f)) return fail(SCGPU_E_INVALID, "leaf size must be >= 0 (0 = no downsampling) and finite");
+  if (leaf > 0.f && vox_smem_bytes(h->L.RS) > 227 * 1024) return fail(SCGPU_E_INVALID, "descriptor too large for the voxel kernel's shared memory");
+  h->voxel_leaf = leaf;
+  return SCGPU_OK;
+}
+
+int scgpu_voxel_downsample(scgpu_handle* h, const void* pts, size_t n, size_t stride_bytes, float leaf, float* out_xyzn, uint32_t* out_idx,
+                           size_t cap, size_t* out_n, int32_t* min_b, int32_t* div_b, int32_t* status) {
+  if (!h || !out_n || (n && !pts)) return fail(SCGPU_E_INVALID, "null argument");
+  if (stride_bytes < 12 || (stride_bytes & 3)) return fail(SCGPU_E_INVALID, "stride must be >= 12 and a multiple of 4");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  const unsigned ocap = (unsigned)(n ? n : 1);  // a voxel per point at most
+  RET(h->vox_in.reserve(n * stride_bytes + 16));
+  RET(h->vox_info.reserve(sizeof(VoxInfo)));
+  RET(h->vox_pts.reserve((size_t)ocap * sizeof(float4)));
+  RET(h->vox_idx.reserve((size_t)ocap * sizeof(unsigned)));
+  CK(cudaMemsetAsync(h->vox_info.p, 0, sizeof(VoxInfo), st));
+  VoxInfo vi;
+  memset(&vi, 0, sizeof vi);
+  if (n) {
+    CK(cudaMemcpyAsync(h->vox_in.p, pts, n * stride_bytes, cudaMemcpyHostToDevice, st));
+    RET(launch_build_voxel(h, h->vox_in.p, 1, n, stride_bytes, leaf, nullptr, h->vox_info.as<VoxInfo>(), h->vox_pts.as<float4>(),
+                           h->vox_idx.as<unsigned>(), ocap, st));
+    CK(cudaMemcpyAsync(&vi, h->vox_info.p, sizeof vi, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  *out_n = vi.n_out;
+  if (min_b) memcpy(min_b, vi.min_b, sizeof vi.min_b);
+  if (div_b) memcpy(div_b, vi.div_b, sizeof vi.div_b);
+  if (status) *status = vi.status | (vi.passes << 8);
+  if (vi.n_out > cap) return fail(SCGPU_E_INVALID, "output capacity %zu < %u voxels", cap, vi.n_out);
+  if (vi.n_out) {
+    if (out_xyzn) CK(cudaMemcpyAsync(out_xyzn, h->vox_pts.p, (size_t)vi.n_out * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    if (out_idx) CK(cudaMemcpyAsync(out_idx, h->vox_idx.p, (size_t)vi.n_out * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return SCGPU_OK;
 }
 
 int scgpu_stage_append(scgpu_handle* h, const void* d_records, uint64_t first_global, uint64_t global_step, size_t n, void* stream) {

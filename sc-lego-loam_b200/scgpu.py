@@ -61,6 +61,8 @@ _SIGNATURES = {
     "scgpu_exhaustive_stats": [_vp, C.POINTER(_u64)],
     "scgpu_stage_exhaustive": [_vp, _vp, _sz, _vp, _vp, _vp],
     "scgpu_stage_gather": [_vp, _u64, _vp, _vp],
+    "scgpu_set_downsample_leaf": [_vp, C.c_float],
+    "scgpu_voxel_downsample": [_vp, _vp, _sz, _sz, C.c_float, _vp, _vp, _sz, C.POINTER(_sz), _vp, _vp, _pi],
     "scgpu_save": [_vp, C.c_char_p],
     "scgpu_load": [_vp, C.c_char_p],
     "scgpu_record_bytes": [_vp, C.POINTER(_sz)],
@@ -308,6 +310,24 @@ class SCManager:
 
     def load(self, path):
         _check(self.lib.scgpu_load(self.h, os.fsencode(path)))
+
+    def set_downsample_leaf(self, leaf):
+        """downSizeFilterScancontext.setLeafSize(leaf, leaf, leaf) (mapOptmization.cpp:264); 0 = off."""
+        _check(self.lib.scgpu_set_downsample_leaf(self.h, float(leaf)))
+
+    def voxel_downsample(self, scan, leaf):
+        """pcl::VoxelGrid::filter (mapOptmization.cpp:1235-1237) on the device -> dict(points (m,4) f32 = x, y, z, count;
+        idx (m,) u32 leaf index; min_b, div_b (3,) i32; refused; passes), sorted by leaf index (PCL's output order)."""
+        pts, ptr, n, stride = _pts(scan)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        idx = np.zeros(max(n, 1), np.uint32)
+        mb, db = np.zeros(3, np.int32), np.zeros(3, np.int32)
+        m, status = _sz(), C.c_int()
+        _check(self.lib.scgpu_voxel_downsample(self.h, ptr, n, stride, float(leaf), out.ctypes.data, idx.ctypes.data, out.shape[0],
+                                               C.byref(m), mb.ctypes.data, db.ctypes.data, C.byref(status)))
+        order = np.argsort(idx[:m.value], kind="stable")
+        return {"points": out[:m.value][order], "idx": idx[:m.value][order], "min_b": mb, "div_b": db,
+                "refused": bool(status.value & 1), "passes": status.value >> 8}
 
     def plan_n_search(self, first_size, n):
         out = np.empty(n, np.uint64)
