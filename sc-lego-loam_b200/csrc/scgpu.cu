@@ -96,7 +96,7 @@ struct scgpu_handle {
   cudaEvent_t ev_nl = nullptr;
   bool timing_valid = false;
   float voxel_leaf = 0.f;  // > 0: scans are voxel-grid filtered in front of the descriptor build (k_build_voxel)
-  DevBuf vox_info, vox_pts, vox_idx, vox_in;
+  DevBuf vox_info, vox_pts, vox_idx, vox_in, vox_keys, vox_hint;
   // database shard
   Db db{};
   uint64_t n_global = 0;
@@ -219,14 +219,26 @@ int launch_build_voxel(scgpu_handle* h, const void* d_pts, size_t n_scans, size_
   p.n_pts = (unsigned)pts_per_scan;
   p.stride = (unsigned)stride;
   p.inv_leaf = 1.0f / leaf;
-  p.bc = make_bin_const(h->L.R, h->L.S, h->cfg.lidar_height, h->cfg.max_radius, 0);
+  p.bc = make_bin_const(h->L.R, h->L.S, h->cfg.lidar_height, h->cfg.max_radius, 1);
   p.L = h->L;
   p.out_cap = out_cap;
+  // scratch for the leaf indices: launches are cut so that it stays below ~512 MB
+  size_t per_launch = pts_per_scan ? (size_t)(512u << 20) / (pts_per_scan * 4) : 65535;
+  if (per_launch < 1) per_launch = 1;
+  if (per_launch > 65535) per_launch = 65535;  // gridDim.y limit
+  if (per_launch > n_scans) per_launch = n_scans;
+  RET(h->vox_keys.reserve(per_launch * pts_per_scan * 4 + 16));
+  if (!h->vox_hint.p) {
+    RET(h->vox_hint.reserve(16));
+    CK(cudaMemsetAsync(h->vox_hint.p, 0, 16, st));
+  }
+  p.keys = h->vox_keys.as<unsigned>();
+  p.passes_hint = h->vox_hint.as<int>();
   const size_t smem = vox_smem_bytes(h->L.RS);
   const bool al16 = (((uintptr_t)d_pts & 15) == 0);
   const int sk = (stride == 16 && al16) ? 16 : ((stride == 32 && al16) ? 32 : 0);
-  for (size_t s0 = 0; s0 < n_scans; s0 += 65535) {  // gridDim.y limit
-    const size_t ns = n_scans - s0 < 65535 ? n_scans - s0 : 65535;
+  for (size_t s0 = 0; s0 < n_scans; s0 += per_launch) {
+    const size_t ns = n_scans - s0 < per_launch ? n_scans - s0 : per_launch;
     VoxelBuildParams q = p;
     q.pts = p.pts + s0 * p.scan_pitch;
     q.records = d_records ? static_cast<unsigned char*>(d_records) + s0 * h->L.rec_bytes : nullptr;
@@ -862,7 +874,7 @@ int scgpu_destroy(scgpu_handle* h) {
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   DevBuf* bufs[] = {&h->gbins, &h->btickets, &h->d_pts[0], &h->d_pts[1], &h->records, &h->rec_single, &h->nsearch, &h->keys, &h->partial,
                     &h->ttickets, &h->pair_dist, &h->pair_shift, &h->best, &h->o_loop, &h->o_yaw, &h->o_dist, &h->o_idx, &h->o_shift,
-                    &h->api_in, &h->api_out, &h->vox_info, &h->vox_pts, &h->vox_idx, &h->vox_in};
+                    &h->api_in, &h->api_out, &h->vox_info, &h->vox_pts, &h->vox_idx, &h->vox_in, &h->vox_keys, &h->vox_hint};
   for (DevBuf* b : bufs) b->release();
   h->h_pts[0].release();
   h->h_pts[1].release();

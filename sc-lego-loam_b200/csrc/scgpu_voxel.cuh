@@ -15,8 +15,8 @@
 //   phase 2  per point: leaf index (bit-exact with PCL), insert / accumulate: count and the three coordinate sums.
 //            The sums are INTEGER (coordinate * 2^24 rounded to int64: exact for |x| >= 1/64 m, error < 3e-8 m below),
 //            so they do not depend on the order of the atomics: results are deterministic, and the centroid is the
-//            correctly rounded mean (PCL sums in FP32 in std::sort order: its result differs from the true mean by up
-//            to ~n ulp; tests compare within that bound).
+//            exact sum times 1/(n 2^24) in FP64, rounded to FP32 (PCL sums in FP32 in std::sort order: its result differs
+//            from the true mean by up to ~n ulp; tests compare within that bound).
 //            If a table overflows, the whole scan is redone in 2, 4, ... key partitions (max-height binning is
 //            idempotent, so bins emitted by an abandoned attempt are harmless).
 //   phase 3  every CTA walks its own slots: centroid -> exact polar bin (bin_point_exact) -> atomicMax into its own copy
@@ -63,10 +63,12 @@ struct VoxelBuildParams {
   float4* out_pts;           // [n_scans][out_cap] centroid x, y, z, w = number of points (may be null)
   unsigned* out_idx;         // [n_scans][out_cap] leaf index
   unsigned out_cap;
+  unsigned* keys;            // [scans of this launch][n_pts] scratch: leaf index of every point (VOX_EMPTY = not finite)
+  int* passes_hint;          // one int per handle: key partitions recent scans needed (performance only)
 };
 
 __host__ __device__ inline size_t vox_smem_bytes(int RS) {
-  return ((size_t)VOX_SLOTS * (4 + 4 + 3 * 8) + (size_t)RS * 4 + 256 + 15) / 16 * 16 + (size_t)(VOX_THREADS / 32) * 64 * 16;
+  return ((size_t)VOX_SLOTS * (4 + 4 + 3 * 8) + (size_t)RS * 4 + 256 + 15) / 16 * 16 + (size_t)(VOX_THREADS / 32) * 64 * 8;
 }
 
 __device__ __forceinline__ unsigned vox_hash(unsigned k) { return k * 0x9E3779B1u; }
@@ -113,8 +115,8 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
   float* s_mm = reinterpret_cast<float*>(s_bins + p.L.RS);                                   // [6] this CTA's min xyz, max xyz
   unsigned* s_flag = reinterpret_cast<unsigned*>(s_mm + 8);                                  // [0] overflow (CTA 0's is THE flag)
   const int lane = threadIdx.x & 31;
-  float4* myq = reinterpret_cast<float4*>(smem_raw + vox_smem_bytes(p.L.RS) - (size_t)(VOX_THREADS / 32) * 64 * sizeof(float4)) +
-                (threadIdx.x >> 5) * 64;                                                     // this warp's queue of owned points (x, y, z, key)
+  uint2* myq = reinterpret_cast<uint2*>(smem_raw + vox_smem_bytes(p.L.RS) - (size_t)(VOX_THREADS / 32) * 64 * sizeof(uint2)) +
+               (threadIdx.x >> 5) * 64;                                                      // this warp's queue of owned points (index, leaf index)
   const int RS = p.L.RS;
   const unsigned scan = blockIdx.y;
   const unsigned char* base = p.pts + (unsigned long long)scan * p.scan_pitch;
@@ -162,6 +164,7 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
       atomicMax(reinterpret_cast<int*>(&s_mm[3 + a]), enc_float(hi));
     }
   }
+  if (threadIdx.x == 0) reinterpret_cast<int*>(s_mm)[6] = *reinterpret_cast<volatile int*>(p.passes_hint);  // CTA 0's copy is the one used
   cluster.sync();
   float gmn[3], gmx[3];
 #pragma unroll
@@ -204,7 +207,9 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
   unsigned* out_idx = want_out ? p.out_idx + (unsigned long long)scan * p.out_cap : nullptr;
   unsigned* out_count = p.info ? &p.info[scan].n_out : nullptr;  // global counter (zeroed by the host)
 
-  int passes = 1;
+  // key partitions to start with: what recent scans needed (all CTAs of the cluster must agree: CTA 0's reading)
+  int passes = max(1, min(64, reinterpret_cast<const int*>(cluster.map_shared_rank(s_mm, 0))[6]));
+  unsigned* keys = p.keys + (unsigned long long)scan * p.n_pts;
   if (refuse) {
     // ---- PCL: "Leaf size is too small for the input dataset" -> output = input: bin the raw points ----------------
     for (unsigned i = start + threadIdx.x; i < end; i += VOX_THREADS) {
@@ -218,6 +223,27 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
       }
     }
   } else if (any_point) {
+    // ---- leaf index of every point of my chunk -> scratch (each CTA computes 1/8 of them, all CTAs read all of them)
+    for (unsigned i0 = start + threadIdx.x; i0 < end; i0 += VOX_THREADS * VOX_UNROLL) {
+      float px[VOX_UNROLL], py[VOX_UNROLL], pz[VOX_UNROLL];
+#pragma unroll
+      for (int u = 0; u < VOX_UNROLL; ++u) {
+        const unsigned i = i0 + u * VOX_THREADS;
+        px[u] = py[u] = pz[u] = __int_as_float(0x7fc00000);
+        if (i < end) vox_load<STRIDE, true>(base + (unsigned long long)i * p.stride, px[u], py[u], pz[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < VOX_UNROLL; ++u) {
+        const unsigned i = i0 + u * VOX_THREADS;
+        const float x = px[u], y = py[u], z = pz[u];
+        const int i0v = __float2int_rz(__fsub_rn(floorf(__fmul_rn(x, p.inv_leaf)), fmb0));
+        const int i1v = __float2int_rz(__fsub_rn(floorf(__fmul_rn(y, p.inv_leaf)), fmb1));
+        const int i2v = __float2int_rz(__fsub_rn(floorf(__fmul_rn(z, p.inv_leaf)), fmb2));
+        const bool fin = isfinite(x) && isfinite(y) && isfinite(z);
+        if (i < end) __stcg(&keys[i], fin ? (unsigned)(i0v + i1v * mul1 + i2v * mul2) : VOX_EMPTY);
+      }
+    }
+    cluster.sync();  // (release / acquire at cluster scope: the keys are read below with ld.global.cg)
     for (;; passes *= 2) {  // retried with twice the key partitions when a table overflows
       if (want_out && rank == 0 && threadIdx.x == 0) atomicExch(out_count, 0u);
       bool overflow = false;
@@ -238,8 +264,10 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
         // time by full warps (inserting straight away ran the probe / atomic code with ~4 active lanes per warp:
         // thread_inst_executed_per_inst 8.1 in the first ncu capture).
         int qn = 0;  // entries waiting in my warp's queue (warp-uniform)
-        auto insert = [&](const float4 e) {
-          const unsigned key = __float_as_uint(e.w);
+        auto insert = [&](const uint2 e) {  // e = (point index, leaf index)
+          float x, y, z;
+          vox_load<STRIDE, true>(base + (unsigned long long)e.x * p.stride, x, y, z);
+          const unsigned key = e.y;
           const unsigned hsh = vox_hash(key);
           unsigned slot = ((hsh >> 5) & 0xffffffu) % VOX_SLOTS;
           bool placed = false;
@@ -256,34 +284,29 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
             return;
           }
           atomicAdd(&t_cnt[slot], 1u);
-          vox_add64(t_lo, t_hi, slot, __double2ll_rn((double)e.x * 16777216.0));
-          vox_add64(t_lo + VOX_SLOTS, t_hi + VOX_SLOTS, slot, __double2ll_rn((double)e.y * 16777216.0));
-          vox_add64(t_lo + 2 * VOX_SLOTS, t_hi + 2 * VOX_SLOTS, slot, __double2ll_rn((double)e.z * 16777216.0));
+          vox_add64(t_lo, t_hi, slot, __double2ll_rn((double)x * 16777216.0));
+          vox_add64(t_lo + VOX_SLOTS, t_hi + VOX_SLOTS, slot, __double2ll_rn((double)y * 16777216.0));
+          vox_add64(t_lo + 2 * VOX_SLOTS, t_hi + 2 * VOX_SLOTS, slot, __double2ll_rn((double)z * 16777216.0));
         };
         for (unsigned i0 = threadIdx.x & ~31u; i0 < p.n_pts; i0 += VOX_THREADS * VOX_UNROLL) {  // warp-uniform trip count
-          float px[VOX_UNROLL], py[VOX_UNROLL], pz[VOX_UNROLL];
+          unsigned kk[VOX_UNROLL];
 #pragma unroll
           for (int u = 0; u < VOX_UNROLL; ++u) {
             const unsigned i = i0 + lane + u * VOX_THREADS;
-            px[u] = py[u] = pz[u] = __int_as_float(0x7fc00000);  // NaN: skipped
-            if (i < p.n_pts) vox_load<STRIDE, true>(base + (unsigned long long)i * p.stride, px[u], py[u], pz[u]);
+            kk[u] = i < p.n_pts ? __ldcg(&keys[i]) : VOX_EMPTY;
           }
 #pragma unroll
           for (int u = 0; u < VOX_UNROLL; ++u) {
-            const float x = px[u], y = py[u], z = pz[u];
-            const int i0v = __float2int_rz(__fsub_rn(floorf(__fmul_rn(x, p.inv_leaf)), fmb0));
-            const int i1v = __float2int_rz(__fsub_rn(floorf(__fmul_rn(y, p.inv_leaf)), fmb1));
-            const int i2v = __float2int_rz(__fsub_rn(floorf(__fmul_rn(z, p.inv_leaf)), fmb2));
-            const unsigned key = (unsigned)(i0v + i1v * mul1 + i2v * mul2);
-            bool own = isfinite(x) && isfinite(y) && isfinite(z) && (vox_hash(key) >> 29) == rank;  // VOX_CLUSTER == 8
+            const unsigned key = kk[u];
+            bool own = key != VOX_EMPTY && (vox_hash(key) >> 29) == rank;  // VOX_CLUSTER == 8: owner = top three hash bits
             if (passes > 1) own = own && (int)(vox_hash2(key) % (unsigned)passes) == part;
             const unsigned m = __ballot_sync(FULL, own);
-            if (own) myq[qn + __popc(m & ((1u << lane) - 1u))] = make_float4(x, y, z, __uint_as_float(key));
+            if (own) myq[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2(i0 + lane + u * VOX_THREADS, key);
             qn += __popc(m);
             if (qn >= 32) {
               __syncwarp();
               qn -= 32;
-              const float4 e = myq[qn + lane];
+              const uint2 e = myq[qn + lane];
               __syncwarp();
               insert(e);
             }
@@ -302,12 +325,12 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
         for (int i = threadIdx.x; i < VOX_SLOTS; i += VOX_THREADS) {
           const unsigned key = t_key[i];
           if (key == VOX_EMPTY) continue;
-          const double n = (double)t_cnt[i] * 16777216.0;
-          const float cx = __double2float_rn((double)vox_get64(t_lo, t_hi, i) / n);
-          const float cy = __double2float_rn((double)vox_get64(t_lo + VOX_SLOTS, t_hi + VOX_SLOTS, i) / n);
-          const float cz = __double2float_rn((double)vox_get64(t_lo + 2 * VOX_SLOTS, t_hi + 2 * VOX_SLOTS, i) / n);
+          const double rn = 1.0 / ((double)t_cnt[i] * 16777216.0);  // one FP64 division per voxel, three multiplications
+          const float cx = __double2float_rn(__dmul_rn((double)vox_get64(t_lo, t_hi, i), rn));
+          const float cy = __double2float_rn(__dmul_rn((double)vox_get64(t_lo + VOX_SLOTS, t_hi + VOX_SLOTS, i), rn));
+          const float cz = __double2float_rn(__dmul_rn((double)vox_get64(t_lo + 2 * VOX_SLOTS, t_hi + 2 * VOX_SLOTS, i), rn));
           float h;
-          const int b = bin_point_exact(p.bc, cx, cy, cz, h);
+          const int b = bin_point<true, false>(p.bc, cx, cy, cz, h);  // FP32 front end + exact fallback: the reference's bin
           if (b >= 0) atomicMax(&s_bins[b], enc_float(h));
           if (want_out) {
             const unsigned o = atomicAdd(out_count, 1u);
@@ -330,6 +353,7 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
   }
   cluster.sync();  // nobody leaves while CTA 0 still reads its shared memory
   if (rank != 0) return;
+  if (threadIdx.x == 0 && !refuse && any_point) atomicMax(p.passes_hint, passes);
   if (threadIdx.x == 0 && p.info) {
     VoxInfo* vi = &p.info[scan];
     for (int a = 0; a < 3; ++a) vi->min_b[a] = min_b[a], vi->div_b[a] = div_b[a];
