@@ -208,7 +208,7 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
   unsigned* out_count = p.info ? &p.info[scan].n_out : nullptr;  // global counter (zeroed by the host)
 
   // key partitions to start with: what recent scans needed (all CTAs of the cluster must agree: CTA 0's reading)
-  int passes = max(1, min(64, reinterpret_cast<const int*>(cluster.map_shared_rank(s_mm, 0))[6]));
+  int passes = max(1, min(64, reinterpret_cast<const int*>(cluster.map_shared_rank(s_mm, 0))[6]));  // 1, 2, 4, ...: only ever doubled
   unsigned* keys = p.keys + (unsigned long long)scan * p.n_pts;
   if (refuse) {
     // ---- PCL: "Leaf size is too small for the input dataset" -> output = input: bin the raw points ----------------
@@ -299,7 +299,7 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
           for (int u = 0; u < VOX_UNROLL; ++u) {
             const unsigned key = kk[u];
             bool own = key != VOX_EMPTY && (vox_hash(key) >> 29) == rank;  // VOX_CLUSTER == 8: owner = top three hash bits
-            if (passes > 1) own = own && (int)(vox_hash2(key) % (unsigned)passes) == part;
+            own = own && (int)(vox_hash2(key) & (unsigned)(passes - 1)) == part;  // passes is a power of two
             const unsigned m = __ballot_sync(FULL, own);
             if (own) myq[qn + __popc(m & ((1u << lane) - 1u))] = make_uint2(i0 + lane + u * VOX_THREADS, key);
             qn += __popc(m);
