@@ -110,6 +110,11 @@ class SCManager {
     ok(scgpu_append_scan(h(), points(_scan_down), _scan_down.points.size(), sizeof(SCPointType)), "makeAndSaveScancontextAndKeys");
   }
 
+  // Extension (not in the reference class): take over the voxel-grid filter the caller runs in front of this class --
+  // downSizeFilterScancontext.setLeafSize(0.5, 0.5, 0.5) / .filter() (mapOptmization.cpp:264, 1235-1237).  With a leaf
+  // set, makeAndSaveScancontextAndKeys / makeScancontext expect the RAW scan and filter it on the device.
+  void setDownsampleLeaf(float leaf) { ok(scgpu_set_downsample_leaf(h(), leaf), "setDownsampleLeaf"); }
+
   std::pair<int, float> detectLoopClosureID(void) {  // int: nearest node index, float: relative yaw
     int loop_id = -1, nn_idx = 0, nn_align = 0;
     float yaw = 0.f;
