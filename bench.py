@@ -420,6 +420,14 @@ def run_multi_gpu(args):
         return ms.item() * 1e-3, m.launch_count() - l0, r
 
     dt_dev, launches, r = timed(False)
+    # roofline of the dominant kernel (k_build_tma: every rank bins its own B scans): CUDA events around the build
+    # launch of each step of one more device-leg pass, on the stream it is launched on; max over ranks
+    search.build_events = []
+    timed(False)
+    ms_build = torch.tensor([sum(a.elapsed_time(b) for a, b in search.build_events[-args.steps:]) / args.steps], device="cuda")
+    search.build_events = None
+    dist.all_reduce(ms_build, op=dist.ReduceOp.MAX)
+    ms_build = ms_build.item()
     dt_e2e, _, r2 = timed(True)
     same = all(torch.equal(r[k].cpu(), r2[k]) for k in ("loop_id", "nn_idx", "nn_shift"))
     if rank == 0:
@@ -435,7 +443,11 @@ def run_multi_gpu(args):
             "e2e": {"value": nq * args.steps / dt_e2e, "unit": "queries/s", "h2d_bytes_per_step": nq * PTS * 16 + nq * 8,
                     "d2h_bytes_per_step": nq * 24 * G, "ms_per_step": 1e3 * dt_e2e / args.steps, "results_equal_device_leg": bool(same)},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "stages": {"loops_found": int((r["loop_id"] >= 0).sum().item())},
+            "roofline": {"kernel": "k_build_tma", "bound": "hbm", "achieved": ALGO_BYTES_PER_SCAN * B / (ms_build * 1e-3) / 1e9,
+                         "peak": measured_peak()[0], "unit": "GB/s", "frac": ALGO_BYTES_PER_SCAN * B / (ms_build * 1e-3) / 1e9 / measured_peak()[0],
+                         "traffic": NCU_TRAFFIC_BYTES_PER_SCAN * B, "peak_source": measured_peak()[1], "per": "gpu (max over ranks of the build launch time)",
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SCAN * B, "ms_per_launch": ms_build},
+            "stages": {"loops_found": int((r["loop_id"] >= 0).sum().item()), "build_ms_per_step": ms_build},
         }
         print(json.dumps(line))
     dist.destroy_process_group()

@@ -73,7 +73,14 @@ class ShardedSearch:
         global entry size + j*G + r.  Returns the detect results of all G*B new entries in global order
         (identical on every rank): dict(loop_id, yaw, min_dist, nn_idx, nn_shift)."""
         G, B = self.world, scans_local.shape[0]
+        ev = getattr(self, "build_events", None)      # bench.py: CUDA events around the build launch (roofline.achieved)
+        if ev is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rec_local = self.st.build(scans_local)                                   # [B, rec]
+        if ev is not None:
+            e1.record()
+            ev.append((e0, e1))
         gathered = self._all_gather(rec_local)                                   # [G, B, rec]   exchange 1
         rec_global = gathered.transpose(0, 1).reshape(G * B, -1).contiguous()    # query q = j*G + r
         first = self.size
