@@ -730,7 +730,7 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
     if (h->exh_cfg == 1)
       k_exh_screen<20, 60, 3, 1, 20><<<dim3(grid, (unsigned)rows), 20 * 32, exh_smem_bytes<20, 60, 3, 20>(), st>>>(sp);
     else
-      k_exh_screen<40, 120, 6, 2, 4><<<dim3(grid, (unsigned)rows), 4 * 32, exh_smem_bytes<40, 120, 6, 4>(), st>>>(sp);
+      k_exh_screen<40, 120, 6, 1, 4, 2><<<dim3(grid, (unsigned)rows), 4 * 2 * 32, exh_smem_bytes<40, 120, 6, 4, 2>(), st>>>(sp);
     if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
     CK(cudaGetLastError());
     const unsigned rb = (unsigned)((n_max + 1023) / 1024 < 296 ? (n_max + 1023) / 1024 : 296);
@@ -841,8 +841,8 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   if (e == cudaSuccess && h->exh)
     e = h->exh_cfg == 1 ? cudaFuncSetAttribute(k_exh_screen<20, 60, 3, 1, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)exh_smem_bytes<20, 60, 3, 20>())
-                        : cudaFuncSetAttribute(k_exh_screen<40, 120, 6, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)exh_smem_bytes<40, 120, 6, 4>());
+                        : cudaFuncSetAttribute(k_exh_screen<40, 120, 6, 1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)exh_smem_bytes<40, 120, 6, 4, 2>());
   if (e == cudaSuccess && h->exh && h->exh_cfg == 1)
     e = cudaFuncSetAttribute(k_cand_screen<20, 60, 3, 1, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem_bytes<20, 60, 3, 10, 1>());
   if (e == cudaSuccess && h->exh && h->exh_cfg == 2)

@@ -393,16 +393,21 @@ struct ExhWarpRing {
   ExhVkRec<S> vk[2];
 };
 
-template <int R, int S, int RAD, int EW>
+template <int R, int S, int RAD, int EW, int WPE = 1>
 constexpr size_t exh_smem_bytes() {
-  return sizeof(ExhWarpRing<R, S>) * EW + (size_t)EW * 4 * sizeof(uint64_t) + qtab_bytes<R, S, 2 * RAD + 1>();
+  return sizeof(ExhWarpRing<R, S>) * EW + (size_t)EW * 4 * sizeof(uint64_t) + qtab_bytes<R, S, 2 * RAD + 1>() +
+         (WPE > 1 ? (size_t)EW * 2 * WPE * 16 * sizeof(float) : 0);
 }
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// R x S descriptor, search radius RAD, RPL descriptor rows per lane, EW consumer warps per block
-template <int R, int S, int RAD, int RPL, int EW>
-__global__ void __launch_bounds__(EW * 32, 1) k_exh_screen(const ExhScreenParams pp) {
+// R x S descriptor, search radius RAD, RPL descriptor rows per lane, EW entry streams (rings) per block, WPE warps per
+// entry.  WPE = 2 (the 40 x 120 instantiation: a 19.2 KB descriptor leaves room for only four rings per SM): the two warps
+// of a team share a ring, each takes half of the rows, both compute the (cheap) alignment redundantly, and they exchange
+// their per-shift partial sums through shared memory around ONE named barrier per entry -- after which the slots are
+// free, so the same barrier also orders the next TMA request.  Twice the warps per SM for the same shared memory.
+template <int R, int S, int RAD, int RPL, int EW, int WPE = 1>
+__global__ void __launch_bounds__(EW * WPE * 32, 1) k_exh_screen(const ExhScreenParams pp) {
   // this block's query
   struct {
     ExhDb db;
@@ -419,21 +424,25 @@ __global__ void __launch_bounds__(EW * 32, 1) k_exh_screen(const ExhScreenParams
   p.d32 = pp.d32 + blockIdx.y * pp.d32_pitch;
   p.min_bits = pp.min_bits + qi;
   constexpr int W = 2 * RAD + 1;
-  constexpr int ROW_LANES = R / RPL;
+  constexpr int ROWS_PER_WARP = R / WPE;
+  constexpr int ROW_LANES = ROWS_PER_WARP / RPL;
   constexpr int ALIGN_LANES = (S + W - 1) / W;
   constexpr int PITCH = 2 * qtab_pairs(S, W);  // floats per table row
-  static_assert(R % RPL == 0 && ROW_LANES + ALIGN_LANES <= 32, "rows + alignment lanes must fit one warp");
+  static_assert(R % WPE == 0 && ROWS_PER_WARP % RPL == 0 && ROW_LANES + ALIGN_LANES <= 32, "rows + alignment lanes must fit one warp");
   static_assert(S <= 128 && S % 4 == 0, "valid-column masks are 128 bits; rows are read with 16-byte loads");
   static_assert(sizeof(ExhWarpRing<R, S>) % 16 == 0, "TMA destinations are 16-byte aligned");
+  static_assert(WPE == 1 || EW + 1 <= 15, "one named barrier per team");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  ExhWarpRing<R, S>& ring = reinterpret_cast<ExhWarpRing<R, S>*>(smem_raw)[warp];
-  uint64_t* full_sc = reinterpret_cast<uint64_t*>(smem_raw + sizeof(ExhWarpRing<R, S>) * EW) + warp * 4;  // [2]
+  const int team = warp / WPE, half = warp % WPE;  // team = entry stream; half = which share of the rows
+  ExhWarpRing<R, S>& ring = reinterpret_cast<ExhWarpRing<R, S>*>(smem_raw)[team];
+  uint64_t* full_sc = reinterpret_cast<uint64_t*>(smem_raw + sizeof(ExhWarpRing<R, S>) * EW) + team * 4;  // [2]
   uint64_t* full_vk = full_sc + 2;                                                                        // [2]
   float* qtable = reinterpret_cast<float*>(smem_raw + sizeof(ExhWarpRing<R, S>) * EW + (size_t)EW * 4 * sizeof(uint64_t));  // pair table
+  float* xbuf = qtable + (R + 1) * PITCH + team * 2 * WPE * 16;  // [2][WPE][16] partial sums of the team (WPE > 1)
 
-  // consecutive warps of the grid take consecutive entries: warp gw scores gw, gw + TW, gw + 2 TW, ...
-  const unsigned long long TW = (unsigned long long)gridDim.x * EW, gw = (unsigned long long)blockIdx.x * EW + warp;
+  // consecutive teams of the grid take consecutive entries: team gw scores gw, gw + TW, gw + 2 TW, ...
+  const unsigned long long TW = (unsigned long long)gridDim.x * EW, gw = (unsigned long long)blockIdx.x * EW + team;
   const unsigned long long my_n = p.n_local > gw ? (p.n_local - 1 - gw) / TW + 1 : 0;
   auto issue_sc = [&](unsigned long long j) {  // descriptor of my j-th entry -> slot j & 1
     const int slot = (int)(j & 1);
@@ -445,7 +454,7 @@ __global__ void __launch_bounds__(EW * 32, 1) k_exh_screen(const ExhScreenParams
     mbar_arrive_expect_tx(&full_vk[slot], (unsigned)sizeof(ExhVkRec<S>));
     tma_bulk_g2s(&ring.vk[slot], p.db.vk + (gw + j * TW) * sizeof(ExhVkRec<S>), (unsigned)sizeof(ExhVkRec<S>), &full_vk[slot]);
   };
-  if (lane == 0) {
+  if (lane == 0 && half == 0) {
     for (int s = 0; s < 4; ++s) mbar_init(&full_sc[s], 1);
     fence_barrier_init();
     if (my_n > 0) {  // the copies do not touch the query table: start them before it is built
@@ -492,7 +501,7 @@ __global__ void __launch_bounds__(EW * 32, 1) k_exh_screen(const ExhScreenParams
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       const bool on = rw || (i == 0 && al);
-      const int r = rw ? lane + i * ROW_LANES : R;
+      const int r = rw ? half * ROWS_PER_WARP + lane + i * ROW_LANES : R;
       const float* held = rw ? &ring.sc_hat[sc_w][r * S] : &ring.vk[vk_a].vkey[0];
       const float* qrow = qtable + r * PITCH;
       __syncwarp();
@@ -501,29 +510,63 @@ __global__ void __launch_bounds__(EW * 32, 1) k_exh_screen(const ExhScreenParams
         else window_fma<S, W, false>(reinterpret_cast<const float4*>(held), qrow, base, acc);
       }
     }
-    // ---- window result of entry k-1 ------------------------------------------------------------------
-    if (has_win) {
-      int d_mine;
-      const float total = transpose_reduce<W>(acc, row_lane, lane, &d_mine);
-      ExhAux ax = ax_cur;
-      if (rev) reverse_mask<S>(ax.vmask);
-      const float out = screened_distance<S, RAD>(total, d_mine, a_cur, qmask, ax, amb_cur, q_flag);
-      if (lane == 0) {
-        p.d32[gw + (k - 1) * TW] = out;
-        if (out >= 0.f) my_min = min(my_min, __float_as_uint(out));
+    if (WPE == 1) {
+      // ---- window result of entry k-1 ------------------------------------------------------------------
+      if (has_win) {
+        int d_mine;
+        const float total = transpose_reduce<W>(acc, row_lane, lane, &d_mine);
+        ExhAux ax = ax_cur;
+        if (rev) reverse_mask<S>(ax.vmask);
+        const float out = screened_distance<S, RAD>(total, d_mine, a_cur, qmask, ax, amb_cur, q_flag);
+        if (lane == 0) {
+          p.d32[gw + (k - 1) * TW] = out;
+          if (out >= 0.f) my_min = min(my_min, __float_as_uint(out));
+        }
       }
-    }
-    // ---- alignment result of entry k (becomes a_cur of the next iteration) -------------------------------
-    if (has_al) {
-      ax_cur = ring.vk[vk_a].aux;
-      align_argmax<S, W>(acc, align_lane, base, v1norm * ax_cur.vnorm, &a_cur, &amb_cur);
-    }
-    // ---- both slots read in this iteration are free: request what they hold next ---------------------------
-    __syncwarp();
-    if (lane == 0) {
-      fence_proxy_async();  // the warp's generic-proxy reads of the slots precede the async-proxy writes
-      if (k + 1 < my_n) issue_sc(k + 1);  // -> slot sc_w (k = 0: the still unused second slot)
-      if (k + 2 < my_n) issue_vk(k + 2);  // -> slot vk_a
+      // ---- alignment result of entry k (becomes a_cur of the next iteration) -------------------------------
+      if (has_al) {
+        ax_cur = ring.vk[vk_a].aux;
+        align_argmax<S, W>(acc, align_lane, base, v1norm * ax_cur.vnorm, &a_cur, &amb_cur);
+      }
+      // ---- both slots read in this iteration are free: request what they hold next ---------------------------
+      __syncwarp();
+      if (lane == 0) {
+        fence_proxy_async();  // the warp's generic-proxy reads of the slots precede the async-proxy writes
+        if (k + 1 < my_n) issue_sc(k + 1);  // -> slot sc_w (k = 0: the still unused second slot)
+        if (k + 2 < my_n) issue_vk(k + 2);  // -> slot vk_a
+      }
+    } else {
+      // ---- team of WPE warps: publish my partial sums, meet the others ONCE, then everything runs on registers ----
+      ExhAux ax_new = ax_cur;
+      if (has_al) ax_new = ring.vk[vk_a].aux;  // last read of the sector-key slot
+      int d_mine = 0;
+      float total = 0.f;
+      float* xb = xbuf + (int)(k & 1) * WPE * 16;
+      if (has_win) {
+        total = transpose_reduce<W>(acc, row_lane, lane, &d_mine);
+        xb[half * 16 + d_mine] = total;  // (lanes sharing a shift index write the same value)
+      }
+      __syncwarp();
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + team), "r"(WPE * 32) : "memory");
+      if (lane == 0 && half == 0) {  // every warp of the team has finished reading both slots
+        fence_proxy_async();
+        if (k + 1 < my_n) issue_sc(k + 1);
+        if (k + 2 < my_n) issue_vk(k + 2);
+      }
+      if (has_win) {
+        total = 0.f;
+#pragma unroll
+        for (int w = 0; w < WPE; ++w) total += xb[w * 16 + d_mine];  // same order in every warp of the team
+        ExhAux ax = ax_cur;
+        if (rev) reverse_mask<S>(ax.vmask);
+        const float out = screened_distance<S, RAD>(total, d_mine, a_cur, qmask, ax, amb_cur, q_flag);
+        if (lane == 0 && half == 0) {
+          p.d32[gw + (k - 1) * TW] = out;
+          if (out >= 0.f) my_min = min(my_min, __float_as_uint(out));
+        }
+      }
+      ax_cur = ax_new;
+      if (has_al) align_argmax<S, W>(acc, align_lane, base, v1norm * ax_cur.vnorm, &a_cur, &amb_cur);
     }
   }
   if (lane == 0 && my_min != 0x7f800000u) atomicMin(p.min_bits, my_min);
