@@ -331,6 +331,16 @@ def db_size_sweep(torch):
             ts.append(m.timing()[2])
         ms = float(np.median(ts))
         out["top10"].append({"db": n, "queries_per_sec": nq / (ms * 1e-3), "ms_per_256_queries": ms})
+        # the same search with as many queries per launch sequence as an offline relocalisation run would submit
+        nb = min(4096, n - 64)
+        for _ in range(2):
+            m.query_batched(n - nb, nb)
+        ts = []
+        for _ in range(5):
+            m.query_batched(n - nb, nb)
+            ts.append(m.timing()[2])
+        msb = float(np.median(ts))
+        out.setdefault("top10_large_batches", []).append({"db": n, "queries_per_launch": nb, "queries_per_sec": nb / (msb * 1e-3), "ms": msb})
     n = sizes[-1]
     qs = [n - 1 - 37 * i for i in range(32)]
     m.exhaustive_batched(qs, n - 50)
