@@ -36,7 +36,7 @@ namespace scgpu {
 namespace cg = cooperative_groups;
 
 constexpr int VOX_CLUSTER = 8;
-constexpr int VOX_THREADS = 512;
+constexpr int VOX_THREADS = 1024;
 constexpr int VOX_SLOTS = 6144;           // per CTA
 constexpr int VOX_MAX_PROBE = 96;
 constexpr int VOX_UNROLL = 8;             // independent point loads in flight per thread
