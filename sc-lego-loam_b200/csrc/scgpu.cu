@@ -223,11 +223,11 @@ int launch_build_voxel(scgpu_handle* h, const void* d_pts, size_t n_scans, size_
   p.L = h->L;
   p.out_cap = out_cap;
   // scratch for the leaf indices: launches are cut so that it stays below ~512 MB
-  size_t per_launch = pts_per_scan ? (size_t)(512u << 20) / (pts_per_scan * 4) : 65535;
+  size_t per_launch = pts_per_scan ? (size_t)(512u << 20) / (pts_per_scan * 8) : 65535;
   if (per_launch < 1) per_launch = 1;
   if (per_launch > 65535) per_launch = 65535;  // gridDim.y limit
   if (per_launch > n_scans) per_launch = n_scans;
-  RET(h->vox_keys.reserve(per_launch * pts_per_scan * 4 + 16));
+  RET(h->vox_keys.reserve(per_launch * pts_per_scan * 8 + 16));
   if (!h->vox_hint.p) {
     RET(h->vox_hint.reserve(16));
     CK(cudaMemsetAsync(h->vox_hint.p, 0, 16, st));
