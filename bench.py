@@ -301,10 +301,30 @@ def run_single_gpu(args):
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single(m, scans, res_dev, n0)
     if not args.no_sweep:
+        line["voxel_grid"] = voxel_extra(d_scans.data_ptr(), min(B, 1184))
         del d_scans, m
         torch.cuda.empty_cache()
         line["db_size_sweep"] = db_size_sweep(torch)
     print(json.dumps(line))
+
+
+def voxel_extra(ptr, n_scans):
+    """SURVEY 8(f) rank 2: the caller's pcl::VoxelGrid (leaf 0.5 m) moved in front of the descriptor build on the device
+    (k_build_voxel), on the first n_scans resident scans of the run."""
+    from sc_lego_loam_b200.scgpu import SCManager
+    m = SCManager(device=0, capacity_hint=n_scans * 6 + 8)
+    m.set_downsample_leaf(0.5)
+    ms = []
+    for _ in range(5):
+        m.truncate(0)
+        m.append_scans((ptr, n_scans, PTS, 16, 1))
+        ms.append(m.timing()[1])
+    m.close()
+    t = float(np.median(ms[2:]))
+    peak, _ = measured_peak()
+    return {"kernel": "k_build_voxel", "leaf_m": 0.5, "scans": n_scans, "ms": t, "scans_per_sec": n_scans / (t * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": n_scans * PTS * 16 / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": n_scans * PTS * 16 / (t * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": n_scans * PTS * 16}}
 
 
 def db_size_sweep(torch):
