@@ -391,7 +391,17 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
   if (nq > 65535) return fail(SCGPU_E_INVALID, "at most 65535 queries per call");
   unsigned chunk, chunks;
   const uint64_t n_local = local_count(h, h->n_global);
-  choose_chunks(n_local, nq, chunk, chunks);
+  // large batches over a large shard: groups of TOPK_QT queries share every key they load (k_topk_tile) -- only when each
+  // warp's stream stays long (>= 8k keys), see the kernel's header.  SCGPU_TOPK_TILE=1/0 forces / forbids it (tests).
+  bool tile = nq >= 16 && h->slots <= 2 && (h->L.R == 20 || h->L.R == 40);
+  const size_t groups = (nq + TOPK_QT - 1) / TOPK_QT;
+  if (tile) {
+    choose_chunks(n_local, groups, chunk, chunks);
+    static const char* force = getenv("SCGPU_TOPK_TILE");
+    tile = force ? atoi(force) != 0 : (uint64_t)chunk / TOPK_TILE_WARPS >= 8192;
+  }
+  const size_t units = tile ? groups : nq;
+  choose_chunks(n_local, units, chunk, chunks);
   RET(query_reserve(h, nq, chunks, st));
   TopkParams p;
   p.qrecords = static_cast<const unsigned char*>(d_qrec);
@@ -404,6 +414,17 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
   p.partial = h->partial.as<unsigned long long>();
   p.tickets = h->ttickets.as<unsigned>();
   p.keys_out = reinterpret_cast<unsigned long long*>(d_keys_out);
+  if (tile) {
+    dim3 tgrid(chunks, (unsigned)units);
+    const unsigned n = (unsigned)nq;
+    if (h->slots == 1 && h->L.R == 20) k_topk_tile<1, 20><<<tgrid, TOPK_TILE_WARPS * 32, 0, st>>>(p, n);
+    else if (h->slots == 1) k_topk_tile<1, 40><<<tgrid, TOPK_TILE_WARPS * 32, 0, st>>>(p, n);
+    else if (h->L.R == 20) k_topk_tile<2, 20><<<tgrid, TOPK_TILE_WARPS * 32, 0, st>>>(p, n);
+    else k_topk_tile<2, 40><<<tgrid, TOPK_TILE_WARPS * 32, 0, st>>>(p, n);
+    h->launches++;
+    CK(cudaGetLastError());
+    return SCGPU_OK;
+  }
   dim3 grid(chunks, (unsigned)nq);
   const bool many = (uint64_t)chunks * nq >= 4096;  // enough blocks to fill the GPU with 2-warp blocks
   if (h->slots == 1) {

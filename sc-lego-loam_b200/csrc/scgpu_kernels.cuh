@@ -725,6 +725,136 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32) k_topk(const TopkParams p) {
   if (lane == 0) p.tickets[q] = 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// k_topk_tile: the form for LARGE databases searched by LARGE query batches.  A block takes one chunk of the database
+// and a GROUP of QT queries: every ring key is loaded from L2 once per group instead of once per query (k_topk at 4,096
+// queries x 100k keys moves 33 GB through L2 in 3.5 ms: L2-bandwidth-bound), the loads of the next 32 keys are issued
+// before the current ones are used, and the K-th key of every list is cached in a register so that the common case (no
+// insertion) costs one vote.  Same arithmetic, same (dist2, index) order, same partial-list / last-block-done merge as
+// k_topk; one ticket per group.  Only used when every warp's stream is long (>= 8k keys): each (warp, query) list pays
+// ~K(1 + ln(n/K)) warm-up insertions, which on short streams costs more than the saved L2 traffic (measured: the
+// 4,541-keyframe run's query stage 0.40 -> 0.51 ms when this kernel was used unconditionally).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TOPK_QT = 8;        // queries per group
+constexpr int TOPK_TILE_WARPS = 4;
+
+template <int RC>
+__device__ __forceinline__ float ringkey_dist2_regs(const float* q, const float (&kv)[RC]) {
+  float result = 0.f;
+  int d = 0;
+#pragma unroll
+  for (; d + 3 < RC; d += 4) {
+    const float d0 = __fsub_rn(q[d], kv[d]), d1 = __fsub_rn(q[d + 1], kv[d + 1]);
+    const float d2 = __fsub_rn(q[d + 2], kv[d + 2]), d3 = __fsub_rn(q[d + 3], kv[d + 3]);
+    const float t = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
+    result = __fadd_rn(result, t);
+  }
+#pragma unroll
+  for (; d < RC; ++d) {
+    const float d0 = __fsub_rn(q[d], kv[d]);
+    result = __fadd_rn(result, __fmul_rn(d0, d0));
+  }
+  return result;
+}
+
+template <int SLOTS, int RC>
+__global__ void __launch_bounds__(TOPK_TILE_WARPS * 32) k_topk_tile(const TopkParams p, unsigned nq) {
+  constexpr int QT = TOPK_QT, TW = TOPK_TILE_WARPS;
+  __shared__ __align__(16) float s_q[QT][RC];
+  __shared__ unsigned long long s_vis[QT];
+  __shared__ unsigned long long s_lists[TW][QT][32 * SLOTS];
+  __shared__ bool s_last;
+  const int K = p.K;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned q0 = blockIdx.y * QT;
+  const int nqg = (int)min((unsigned)QT, nq - q0);  // queries in this group
+  for (int i = threadIdx.x; i < QT * RC; i += blockDim.x) {
+    const int q = i / RC, d = i - q * RC;
+    s_q[q][d] = q < nqg ? reinterpret_cast<const float*>(p.qrecords + (size_t)(q0 + q) * p.L.rec_bytes + p.L.off_ring)[d] : 0.f;
+  }
+  if (threadIdx.x < QT) {
+    unsigned long long vis = 0;
+    if ((int)threadIdx.x < nqg) {
+      const unsigned long long ns = p.n_search[q0 + threadIdx.x];
+      if (ns > (unsigned long long)p.db.rank) vis = (ns - 1 - p.db.rank) / p.db.G + 1;  // local entries l with l*G + rank < ns
+      if (vis > p.n_local) vis = p.n_local;
+    }
+    s_vis[threadIdx.x] = vis;
+  }
+  __syncthreads();
+  unsigned long long vmax = 0;
+#pragma unroll
+  for (int q = 0; q < QT; ++q) vmax = s_vis[q] > vmax ? s_vis[q] : vmax;
+  const unsigned long long start = (unsigned long long)blockIdx.x * p.chunk;
+  unsigned long long end = start + p.chunk;
+  if (end > vmax) end = vmax;
+
+  WarpList<SLOTS> list[QT];
+  unsigned long long wk[QT];  // K-th key of every list (warp-uniform)
+#pragma unroll
+  for (int q = 0; q < QT; ++q) {
+    list[q].init();
+    wk[q] = KEY_NONE;
+  }
+  float kv[RC], kn[RC];
+  const float* col = p.db.ringT;
+  const unsigned long long cap = p.db.cap;
+  {
+    const unsigned long long l = start + (unsigned long long)warp * 32 + lane;
+#pragma unroll
+    for (int d = 0; d < RC; ++d) kn[d] = l < end ? __ldg(col + (size_t)d * cap + l) : 0.f;
+  }
+  for (unsigned long long base = start + (unsigned long long)warp * 32; base < end; base += TW * 32) {
+#pragma unroll
+    for (int d = 0; d < RC; ++d) kv[d] = kn[d];
+    const unsigned long long lcur = base + lane, lnext = lcur + TW * 32;
+#pragma unroll
+    for (int d = 0; d < RC; ++d) kn[d] = lnext < end ? __ldg(col + (size_t)d * cap + lnext) : 0.f;  // in flight during the work below
+    const unsigned long long idx = lcur * p.db.G + p.db.rank;
+#pragma unroll
+    for (int q = 0; q < QT; ++q) {
+      const float d2 = ringkey_dist2_regs<RC>(s_q[q], kv);
+      const unsigned long long key = lcur < s_vis[q] ? (((unsigned long long)__float_as_uint(d2) << 32) | idx) : KEY_NONE;
+      if (__any_sync(FULL, key < wk[q])) {
+        list[q].offer(key, K);
+        wk[q] = list[q].kth(K);
+      }
+    }
+  }
+  // block merge: every warp publishes its QT lists, warp w then owns queries w, w + TW, ...
+#pragma unroll
+  for (int q = 0; q < QT; ++q) list[q].store(&s_lists[warp][q][0], K);
+  __syncthreads();
+  const unsigned chunks = gridDim.x;
+  for (int q = warp; q < nqg; q += TW) {
+    WarpList<SLOTS> m;
+    m.init();
+    for (int w = 0; w < TW; ++w) m.offer_from(&s_lists[w][q][0], K, K);
+    if (chunks == 1) m.store(p.keys_out + (size_t)(q0 + q) * K, K);
+    else m.store(p.partial + ((size_t)(q0 + q) * chunks + blockIdx.x) * K, K);
+  }
+  if (chunks == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(&p.tickets[blockIdx.y], 1u) == chunks - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last block of this group: merge every chunk's list of each of its queries (reads through L2)
+  for (int q = warp; q < nqg; q += TW) {
+    WarpList<SLOTS> m;
+    m.init();
+    const unsigned long long* all = p.partial + (size_t)(q0 + q) * chunks * K;
+    const int total = (int)chunks * K;
+    for (int b = 0; b < total; b += 32) {
+      const int i = b + lane;
+      m.offer(i < total ? __ldcg(all + i) : KEY_NONE, K);
+    }
+    m.store(p.keys_out + (size_t)(q0 + q) * K, K);
+  }
+  if (threadIdx.x == 0) p.tickets[blockIdx.y] = 0;
+}
+
 // merge `parts` lists per query: in [parts][nq][K] -> out [nq][K]; one warp per query
 template <int SLOTS>
 __global__ void __launch_bounds__(128) k_merge(const unsigned long long* in, int parts, unsigned nq, int K, unsigned long long* out) {

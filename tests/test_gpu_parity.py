@@ -454,3 +454,40 @@ def test_kitti00_scale_properties():
     assert np.array_equal(r1["loop_id"], [d["loop_id"] for d in got])
     assert np.array_equal(r1["yaw"], np.array([d["yaw"] for d in got], np.float32))
     assert np.array_equal(r1["min_dist"], [d["min_dist"] for d in got])
+
+
+@pytest.mark.parametrize("force", ["1", "0"])
+def test_tiled_topk_kernel_matches_port(force):
+    """k_topk_tile (groups of 8 queries sharing every key load; chosen by itself only for large batches over large
+    shards) forced on / off through SCGPU_TOPK_TILE in a fresh process: candidate indices and squared distances of 40
+    batched queries equal the oracle's brute force bit for bit, K = 10 and K = 50, ragged last group, growing n_search."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, %r)
+from oracle import oracle as orc
+from sc_lego_loam_b200.scgpu import SCManager
+from sc_lego_loam_b200.synth import ScanGen
+n, nq = 20000, 43
+descs = ScanGen("hdl64", seed=12, n_places=9000).descs(0, n)
+for K in (10, 50):
+    p = orc.Params(num_candidates=K)
+    port = orc.Port(p)
+    m = SCManager(num_candidates=K, capacity_hint=n + 8)
+    m.append_descs(descs)
+    allkeys = np.stack([port.ringkey(d.astype(np.float64)).astype(np.float32) for d in descs])
+    m.query_batched(n - nq, nq)
+    for q in range(nq):
+        qi = n - nq + q
+        ns = qi + 1 - 50
+        cnt, idx, d2 = port.knn(allkeys[:ns], allkeys[qi])
+        c = m.candidates(q)
+        assert c["n_tree"] == ns
+        assert np.array_equal(c["cand_d2"].view(np.uint32), d2.view(np.uint32)), (K, q)
+        assert np.array_equal(c["cand_idx"], idx), (K, q)
+print("tiled-ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SCGPU_TOPK_TILE=force)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "tiled-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
