@@ -342,8 +342,8 @@ __device__ __forceinline__ float screened_distance(float total, int d_mine, int 
   float dist = __int_as_float(0x7f800000);  // +inf: no valid column pair at this shift -> the reference yields NaN there
   bool nan_here = false;
   if (d_mine < W) {
-    int sft = (a_cur + d_mine - RAD) % S;
-    if (sft < 0) sft += S;
+    int sft = a_cur + d_mine - RAD;  // a_cur in [0, S), d_mine - RAD in [-RAD, RAD]: one conditional wrap, no division
+    sft = sft < 0 ? sft + S : (sft >= S ? sft - S : sft);
     const int n = valid_pairs<S>(qmask, ax.vmask, sft);
     if (n > 0) {
       dist = 1.0f - __fdividef(total, (float)n);  // n <= 128: the approximate reciprocal costs < 2.4e-7 absolute
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(EW * WPE * 32, 1) k_exh_screen(const ExhScreen
     // Selects, not branches: with an if / else-if here the compiler lets the two lane groups run the window code one
     // after the other (every FFMA2 issued twice per entry).
     const bool rw = row_lane && has_win, al = align_lane && has_al;
-    const int base = rw ? ((a_cur - RAD) % S + S) % S : (al ? (lane - ROW_LANES) * W : 0);
+    const int base = rw ? (a_cur >= RAD ? a_cur - RAD : a_cur - RAD + S) : (al ? (lane - ROW_LANES) * W : 0);
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       const bool on = rw || (i == 0 && al);
@@ -729,6 +729,12 @@ __global__ void __launch_bounds__(CW * 32) k_cand_screen(const CandScreenParams 
   }
   __syncwarp();
   fetch_more();
+  // sharded database: a rank that owns none of this query's candidates has nothing to score -- skip the table build
+  if (!__syncthreads_or(issued > 0)) {
+    for (int k = warp; k < p.K; k += CW)
+      if (lane == 0) p.d32[(size_t)q * p.K + k] = __int_as_float(0x7f800000);
+    return;
+  }
 
   if (threadIdx.x == 0) {
     s_mask[0] = s_mask[1] = 0;
@@ -783,7 +789,7 @@ __global__ void __launch_bounds__(CW * 32) k_cand_screen(const CandScreenParams 
     float acc[W];
 #pragma unroll
     for (int d = 0; d < W; ++d) acc[d] = 0.f;
-    const int base = ((a_cur - RAD) % S + S) % S;
+    const int base = a_cur >= RAD ? a_cur - RAD : a_cur - RAD + S;
     if (row_lane) {
 #pragma unroll
       for (int i = 0; i < RPL; ++i) {
