@@ -4,8 +4,8 @@
 // mapOptmization.cpp:264 (setLeafSize), 1235-1237 (filter), 1628-1630 (makeAndSaveScancontextAndKeys of the result).
 // k_build_voxel does both steps for a batch of scans: points -> voxel centroids -> polar max-height bins -> record.
 //
-// One thread-block CLUSTER of 8 CTAs per scan.  The voxel table of the scan is spread over the cluster's shared memories
-// (8 x 6,144 slots x 32 B = 1.5 MB): voxel index -> hash -> (owner CTA, slot).  Every CTA walks ALL points of the scan
+// One thread-block CLUSTER of 8 CTAs per scan, two CTAs resident per SM (one scan's barriers overlap another's work).
+// The voxel table of the scan is spread over the cluster's shared memories (8 x 3,072 slots x 32 B = 768 KB): voxel index -> hash -> (owner CTA, slot).  Every CTA walks ALL points of the scan
 // (the scan is L2-resident: phase 1 has just read it) and accumulates the points whose voxel it owns with LOCAL
 // shared-memory atomics; distributed shared memory carries the min/max exchange, the overflow flag and the final merge
 // of the eight partial polar grids.  (First version: every CTA read 1/8 of the points and updated the owner's table
@@ -36,8 +36,8 @@ namespace scgpu {
 namespace cg = cooperative_groups;
 
 constexpr int VOX_CLUSTER = 8;
-constexpr int VOX_THREADS = 1024;
-constexpr int VOX_SLOTS = 6144;           // per CTA
+constexpr int VOX_THREADS = 512;
+constexpr int VOX_SLOTS = 3072;           // per CTA
 constexpr int VOX_MAX_PROBE = 96;
 constexpr int VOX_UNROLL = 8;             // independent point loads in flight per thread
 constexpr unsigned VOX_EMPTY = 0xffffffffu;
@@ -103,7 +103,7 @@ __device__ __forceinline__ void vox_load(const unsigned char* p, float& x, float
 }
 
 template <int STRIDE>
-__global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREADS, 1) k_build_voxel(const VoxelBuildParams p) {
+__global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREADS, 2) k_build_voxel(const VoxelBuildParams p) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
   extern __shared__ __align__(16) unsigned char smem_raw[];

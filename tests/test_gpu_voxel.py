@@ -82,14 +82,14 @@ def test_voxel_grid_edges(mgr):
 
 
 def test_table_overflow_takes_more_passes(mgr):
-    """More occupied voxels than the cluster's table holds (8 x 6,144 slots): the scan is redone in key partitions."""
+    """More occupied voxels than the cluster's table holds (8 x 3,072 slots): the scan is redone in key partitions."""
     from oracle import oracle as orc
     rng = np.random.default_rng(9)
     s = rng.uniform(-100, 100, (120000, 4)).astype(np.float32)   # ~every point its own voxel
     s[:, 2] = rng.uniform(-5, 5, 120000)
     want = orc.Voxel().downsample(s, 0.5)
     got = mgr.voxel_downsample(s, 0.5)
-    assert len(want["idx"]) > 8 * 6144 and got["passes"] > 1
+    assert len(want["idx"]) > 8 * 3072 and got["passes"] > 1
     _compare(got, want, 100.0)
 
 
