@@ -211,6 +211,7 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
   unsigned* out_count = p.info ? &p.info[scan].n_out : nullptr;  // global counter (zeroed by the host)
 
   // key partitions to start with: what recent scans needed (all CTAs of the cluster must agree: CTA 0's reading)
+  unsigned gen = 0;
   int passes = max(1, min(64, reinterpret_cast<const int*>(cluster.map_shared_rank(s_mm, 0))[6]));  // 1, 2, 4, ...: only ever doubled
   if (refuse) {
     // ---- PCL: "Leaf size is too small for the input dataset" -> output = input: bin the raw points ----------------
@@ -303,6 +304,7 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
       if (want_out && rank == 0 && threadIdx.x == 0) atomicExch(out_count, 0u);
       bool overflow = false;
       for (int part = 0; part < passes && !overflow; ++part) {
+        ++gen;  // generation of this (attempt, partition): the overflow flag carries the generation that overflowed
         // ---- clear my table
         for (int i = threadIdx.x; i < VOX_SLOTS; i += VOX_THREADS) {
           t_key[i] = VOX_EMPTY;
@@ -335,7 +337,7 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
             slot = slot + 1 == VOX_SLOTS ? 0 : slot + 1;
           }
           if (!placed) {
-            *flag0 = 1u;  // (remote store; rare)
+            *flag0 = gen;  // (remote store; rare)
             return;
           }
           atomicAdd(&t_cnt[slot], 1u);
@@ -370,12 +372,11 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
         __syncwarp();
         if (lane < qn) insert(myq[lane]);
         cluster.sync();
-        overflow = *flag0 != 0;  // every CTA reads the same value: the flag is only written before the sync above
-        cluster.sync();          // ... and only cleared after this one
-        if (overflow) {
-          if (rank == 0 && threadIdx.x == 0) s_flag[0] = 0;
-          break;
-        }
+        // ONE barrier per partition: the flag is never cleared.  It equals `gen` iff some CTA overflowed in this
+        // generation; a CTA that is already in a later generation can only write a larger value, and it can only be
+        // there if this generation did not overflow -- so every CTA takes the same decision.
+        overflow = *reinterpret_cast<volatile unsigned*>(flag0) == gen;
+        if (overflow) break;
         // ---- phase 3: my slots -> centroids -> my copy of the polar grid
         for (int i = threadIdx.x; i < VOX_SLOTS; i += VOX_THREADS) {
           const unsigned key = t_key[i];
@@ -395,7 +396,6 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
         __syncthreads();
       }
       if (!overflow) break;
-      cluster.sync();  // the cleared flag is visible before the next attempt can set it
     }
   }
   // ---- the eight partial grids -> CTA 0 (plain remote loads, coalesced)
