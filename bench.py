@@ -301,11 +301,28 @@ def run_single_gpu(args):
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_single(m, scans, res_dev, n0)
     if not args.no_sweep:
+        line["online_latency"] = online_latency(m, scans)
         line["voxel_grid"] = voxel_extra(d_scans.data_ptr(), min(B, 1184))
         del d_scans, m
         torch.cuda.empty_cache()
         line["db_size_sweep"] = db_size_sweep(torch)
     print(json.dumps(line))
+
+
+def online_latency(m, scans, n=96):
+    """The reference's own call pattern (mapOptmization.cpp:1630 + 916): ONE makeAndSaveScancontextAndKeys of a host scan
+    followed by ONE detectLoopClosureID, per keyframe, on top of the database the run has built (4,541+ keyframes);
+    wall-clock per keyframe including the H2D copy of the scan and both host synchronisations."""
+    ts = []
+    for i in range(n):
+        t0 = time.perf_counter()
+        m.makeAndSaveScancontextAndKeys(scans[i % len(scans)])
+        m.detectLoopClosureID()
+        ts.append(time.perf_counter() - t0)
+    ts = np.array(ts[16:]) * 1e3
+    return {"calls": "scgpu_append_scan (120k-point pinned host scan) + scgpu_detect", "keyframes": int(ts.size), "db_keyframes": int(m.size()),
+            "ms_per_keyframe_median": float(np.median(ts)), "ms_per_keyframe_p99": float(np.percentile(ts, 99)),
+            "keyframes_per_sec": float(1e3 / np.median(ts))}
 
 
 def voxel_extra(ptr, n_scans):
