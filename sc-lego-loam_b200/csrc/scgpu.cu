@@ -785,7 +785,11 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
 extern "C" {
 
 const char* scgpu_last_error(void) { return g_err; }
-const char* scgpu_version(void) { return "scgpu 0.1 (sm_100a; kernels: k_build k_append k_topk k_merge k_score k_best k_finalize k_pair_api)"; }
+const char* scgpu_version(void) {
+  return "scgpu 0.1 (sm_100a; kernels: k_build k_build_tma k_build_voxel k_append k_gather k_topk k_topk_tile k_merge k_cand_screen "
+         "k_cand_select k_score k_score_pairs k_score_list k_best k_finalize k_pair_api k_exh_prep k_exh_append k_exh_screen k_exh_compact "
+         "k_exh_final)";
+}
 
 int scgpu_default_config(scgpu_config* c) {
   if (!c) return fail(SCGPU_E_INVALID, "null config");
