@@ -211,7 +211,7 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
   unsigned* out_count = p.info ? &p.info[scan].n_out : nullptr;  // global counter (zeroed by the host)
 
   // key partitions to start with: what recent scans needed (all CTAs of the cluster must agree: CTA 0's reading)
-  unsigned gen = 0;
+  unsigned attempt = 0, gen = 0;  // gen = (attempt << 16 | partition + 1): the value the overflow flag takes
   int passes = max(1, min(64, reinterpret_cast<const int*>(cluster.map_shared_rank(s_mm, 0))[6]));  // 1, 2, 4, ...: only ever doubled
   if (refuse) {
     // ---- PCL: "Leaf size is too small for the input dataset" -> output = input: bin the raw points ----------------
@@ -303,8 +303,9 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
     for (;; passes *= 2) {  // retried with twice the key partitions when a table overflows
       if (want_out && rank == 0 && threadIdx.x == 0) atomicExch(out_count, 0u);
       bool overflow = false;
+      ++attempt;
       for (int part = 0; part < passes && !overflow; ++part) {
-        ++gen;  // generation of this (attempt, partition): the overflow flag carries the generation that overflowed
+        gen = (attempt << 16) | (unsigned)(part + 1);  // what the overflow flag is set to in this (attempt, partition)
         // ---- clear my table
         for (int i = threadIdx.x; i < VOX_SLOTS; i += VOX_THREADS) {
           t_key[i] = VOX_EMPTY;
@@ -372,10 +373,14 @@ __global__ void __cluster_dims__(VOX_CLUSTER, 1, 1) __launch_bounds__(VOX_THREAD
         __syncwarp();
         if (lane < qn) insert(myq[lane]);
         cluster.sync();
-        // ONE barrier per partition: the flag is never cleared.  It equals `gen` iff some CTA overflowed in this
-        // generation; a CTA that is already in a later generation can only write a larger value, and it can only be
-        // there if this generation did not overflow -- so every CTA takes the same decision.
-        overflow = *reinterpret_cast<volatile unsigned*>(flag0) == gen;
+        // ONE barrier per partition: the flag is never cleared.  All writes of this (attempt, partition) precede the
+        // barrier above; what a CTA that is already further along may have written since tells the same story: a later
+        // partition of the same attempt means this one did not overflow, a later ATTEMPT exists only because it did.
+        // So every CTA of the cluster takes the same decision whatever it reads.
+        {
+          const unsigned v = *reinterpret_cast<volatile unsigned*>(flag0);
+          overflow = v == gen || (v >> 16) > attempt;
+        }
         if (overflow) break;
         // ---- phase 3: my slots -> centroids -> my copy of the polar grid
         for (int i = threadIdx.x; i < VOX_SLOTS; i += VOX_THREADS) {
