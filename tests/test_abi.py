@@ -78,6 +78,7 @@ int main() {
     Eigen::MatrixXd sk = n.scManager.makeSectorkeyFromScancontext(sc);
     std::pair<double,int> d = n.scManager.distanceBtnScanContext(sc, sc);
     (void)n.scManager.fastAlignUsingVkey(sk, sk); (void)n.scManager.distDirectSC(sc, sc); (void)d; (void)rk;
+    n.scManager.setDownsampleLeaf(0.5f);   // extension: the caller's pcl::VoxelGrid moved in front of the build
   }
   return n.scManager.PC_NUM_RING == 20 && n.scManager.NUM_CANDIDATES_FROM_TREE == 10 ? 0 : 1;
 }
