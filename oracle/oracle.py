@@ -2,8 +2,10 @@
 
 ctypes loaders for (a) the plain-C restatement ``oracle/_build/libscoracle.so`` (class ``Port``) and
 (b) the reference's own Scancontext.cpp compiled verbatim, ``oracle/_ref/libscref*.so`` (class ``Ref``).
-Only tests/, ``__graft_entry__.smoke()`` and bench.py's cpu_baseline / ``--impl reference`` legs may
-import this module; it is the checker, never the thing measured as the product.
+Only tests/, ``__graft_entry__.smoke()``, bench.py's cpu_baseline / ``--impl reference`` legs and the cpu_baseline legs
+of the per-config bench tools (tools/bench_configs.py, bench_exhaustive.py, bench_voxel.py) may import this module; it is
+the checker and the CPU baseline, never the thing measured as the product.  The product package (sc-lego-loam_b200/,
+include/) never imports, links or executes anything under oracle/.
 """
 import ctypes as C
 import os
