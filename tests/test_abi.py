@@ -90,3 +90,19 @@ int main() {
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing in the product package or the public headers imports, links or
+    executes anything under oracle/ (there is no CPU fallback to route through)."""
+    bad = []
+    for base in ("sc-lego-loam_b200", "sc_lego_loam_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or re.search(r'#include\s+["<][^">]*oracle', text) \
+                        or "libscoracle" in text or "libscref" in text or "libvoxoracle" in text:
+                    bad.append(os.path.join(base, f))
+    assert not bad, bad
