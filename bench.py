@@ -350,7 +350,7 @@ def db_size_sweep(torch):
     from sc_lego_loam_b200.scgpu import SCManager
     from sc_lego_loam_b200.synth import ScanGen
     gen = ScanGen("hdl64", seed=SEED + 1, n_places=80000)
-    sizes = (1000, 10000, 100000)
+    sizes = (1000, 2000, 5000, 10000, 20000, 50000, 100000)
     descs = gen.descs(0, sizes[-1], R, S, threads=min(16, os.cpu_count() or 1))
     m = SCManager(device=0, capacity_hint=sizes[-1] + 8)
     peak, _ = measured_peak()
