@@ -16,6 +16,7 @@
 // polarcontexts_.size().
 #pragma once
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,15 +28,38 @@
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 
+// The reference header pulls in nanoflann and its vector-of-vectors adaptor (Scancontext.h:25-26) and opens the namespace;
+// with the reference's include directory behind this one they are found and the same names stay visible to the caller.
+// (The KD-tree itself is not used: retrieval is exact brute force on the device.)
+#if defined(__has_include)
+#if __has_include("nanoflann.hpp") && __has_include("KDTreeVectorOfVectorsAdaptor.h")
+#include "nanoflann.hpp"
+#include "KDTreeVectorOfVectorsAdaptor.h"
+#define SCGPU_HAVE_NANOFLANN 1
+#endif
+#endif
+
 #include "scgpu.h"
 
+// the global using-directives and -declarations mapOptmization.cpp is compiled under (Scancontext.h:30-39)
 using namespace Eigen;
+#ifdef SCGPU_HAVE_NANOFLANN
+using namespace nanoflann;
+#endif
 
 using std::cout;
 using std::endl;
 using std::make_pair;
 
+using std::atan2;
+using std::cos;
+using std::sin;
+
 using SCPointType = pcl::PointXYZI;  // x, y, z are read; stride = sizeof(SCPointType)
+using KeyMat = std::vector<std::vector<float> >;  // Scancontext.h:42
+#ifdef SCGPU_HAVE_NANOFLANN
+using InvKeyTree = KDTreeVectorOfVectorsAdaptor<KeyMat, float>;  // Scancontext.h:43 (type kept; no tree is ever built)
+#endif
 
 // -- helpers the reference declares at namespace scope (Scancontext.h:49-55) ---------------------
 inline void coreImportTest(void) { cout << "scancontext lib is successfully imported (scgpu, sm_100a)." << endl; }
@@ -165,7 +189,10 @@ class SCManager {
  private:
   scgpu_handle* handle_ = nullptr;
 
-  // the handle is created on first use (device from $SCGPU_DEVICE, default 0) from the constants above
+  // the handle is created on first use from the constants above.  $SCGPU_DEVICES=0,1,... : the database is sharded over
+  // those GPUs (entry i on the (i % n)-th; one process drives them all, NVLink peer access between the shards);
+  // otherwise the single device $SCGPU_DEVICE (default 0).  $SCGPU_CAPACITY: keyframes to reserve (a sharded database has
+  // a fixed capacity; default 65536).
   scgpu_handle* h() {
     if (!handle_) {
       scgpu_config c;
@@ -180,6 +207,19 @@ class SCManager {
       c.dist_thres = SC_DIST_THRES;
       c.tree_period = TREE_MAKING_PERIOD_;
       if (const char* d = std::getenv("SCGPU_DEVICE")) c.device = std::atoi(d);
+      if (const char* cap = std::getenv("SCGPU_CAPACITY")) c.capacity_hint = std::strtoull(cap, nullptr, 10);
+      if (const char* list = std::getenv("SCGPU_DEVICES")) {
+        int n = 0;
+        for (const char* p = list; *p && n < SCGPU_MAX_DEVICES;) {
+          char* end = nullptr;
+          const long v = std::strtol(p, &end, 10);
+          if (end == p) break;
+          c.devices[n++] = static_cast<int>(v);
+          p = (*end == ',') ? end + 1 : end;
+        }
+        c.n_devices = n;
+        if (n > 1 && !std::getenv("SCGPU_CAPACITY")) c.capacity_hint = 65536;
+      }
       ok(scgpu_create(&c, &handle_), "SCManager");
     }
     return handle_;

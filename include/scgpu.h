@@ -45,6 +45,10 @@ extern "C" {
 #define SCGPU_FLAG_NO_SCREENING 4u /* exhaustive search scores every entry with the FP64 pair kernel (no FP32 screening
                                       pass, no second copy of the database); results are identical, for A/B timing */
 #define SCGPU_FLAG_NO_TMA_BUILD 8u /* bin with the register-staged k_build instead of the TMA-staged k_build_tma (A/B) */
+#define SCGPU_FLAG_PEER 16u /* this handle (shard_rank of shard_count > 1) is one shard of a PEER-SHARDED database: fixed
+                                capacity (capacity_hint), one device allocation per shard that the other shards map over
+                                NVLink (scgpu_peer_export / scgpu_peer_attach), ring keys replicated on every shard, candidate
+                                rows fetched from their owner inside the scoring kernels.  See "peer-sharded database" below. */
 #define SCGPU_FLAG_FRESH_TREE 1u /* search keys [0, size - exclude_recent) on EVERY detect instead of emulating the
                                     reference's periodically rebuilt KD-tree snapshot (SC.cpp:264-276) */
 
@@ -64,8 +68,12 @@ typedef struct scgpu_config {
   int32_t shard_count;     /* 1 = whole database on this device */
   uint64_t capacity_hint;  /* database entries (global) to reserve up front; storage grows on demand */
   uint32_t flags;          /* SCGPU_FLAG_* */
-  uint32_t reserved;
+  int32_t n_devices;       /* > 1: ONE handle (one host process) drives a database sharded over devices[0 .. n_devices):
+                              entry i lives on devices[i % n_devices]; every call below works on such a handle.  0 / 1: the
+                              single device `device`.  (SURVEY.md 8(b) "device list".)  At most SCGPU_MAX_DEVICES. */
+  int32_t devices[8];      /* CUDA ordinals; the same ordinal may appear more than once (shards sharing a device) */
 } scgpu_config;
+#define SCGPU_MAX_DEVICES 8
 
 typedef struct scgpu_handle scgpu_handle;
 
@@ -120,6 +128,14 @@ int scgpu_append_descs(scgpu_handle* h, const float* sc, size_t n);
 int scgpu_replay_batched(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan,
                          size_t stride_bytes, int location, int* loop_id, float* yaw_rad, double* nearest_dist,
                          int* nearest_idx, int* nearest_shift);
+/* Asynchronous form of scgpu_replay_batched: the whole step is enqueued and the call returns; scgpu_replay_results waits for
+ * the LAST enqueued step and copies its results out.  Steps may be enqueued back to back: the binning of a step overlaps the
+ * query stage of the one before (two streams; its append waits until those queries are done).  Host scans (location 0) are
+ * consumed before the call returns only as far as staging goes -- keep them valid until scgpu_replay_results. */
+int scgpu_replay_async(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride_bytes,
+                       int location);
+int scgpu_replay_results(scgpu_handle* h, size_t n, int* loop_id, float* yaw_rad, double* nearest_dist, int* nearest_idx,
+                         int* nearest_shift);
 /* Detect for n_queries already-stored entries [first, first+n_queries) as if each had just been appended
  * (database truncated to first+i+1 for query i) with a FRESH snapshot (n_search = first+i+1-exclude_recent). */
 int scgpu_query_batched(scgpu_handle* h, uint64_t first, size_t n_queries, int* loop_id, float* yaw_rad,
@@ -212,6 +228,40 @@ int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_query_records, size_t 
 int scgpu_stage_finalize(scgpu_handle* h, const void* d_best_parts, int parts, size_t n_queries,
                          const uint64_t* d_n_search, int32_t* d_loop_id, float* d_yaw, double* d_nearest_dist,
                          int32_t* d_nearest_idx, int32_t* d_nearest_shift, void* stream);
+/* Fallback of scgpu_stage_exhaustive: when a result's n_rescored exceeds SCGPU_EXH_LIST_CAP the rescoring list of its batch
+ * overflowed (a database of near-duplicates: the list is shared by the <= 64 queries of a batch) and the reported winner is
+ * NOT reliable; this call scores every local entry of the shard exactly for that one query record (host-synchronous) and
+ * writes the shard's true winner to d_best_out (same 24-byte layout). */
+#define SCGPU_EXH_LIST_CAP 65536
+int scgpu_stage_exhaustive_exact(scgpu_handle* h, const void* d_query_record, uint64_t n_search, void* d_best_out);
+
+/* ---- peer-sharded database: the shards read and write each other's memory over NVLink ---------------------------------
+ * (replaces the three all_gathers of the staged API above.)  Entry i lives on shard i % G.  Every shard keeps
+ * a replica of ALL ring keys (80 B per entry: k_append stores a new entry's key into every replica with peer stores), so the
+ * retrieval for a query runs on ONE device with no merge; the queries are partitioned -- the shard that binned a scan also
+ * searches for it -- and the candidates' rows are fetched from their owner shards inside the scoring kernels (the per-warp TMA
+ * bulk copy of k_cand_screen and the loads of the FP64 pair kernel address peer memory).  Per-query work divides by G.
+ *
+ *   one process, several GPUs : scgpu_config.n_devices / devices -- scgpu_create returns ONE handle for the whole database and
+ *                               every call of this header works on it (cudaDeviceEnablePeerAccess, events between the streams);
+ *   one process per GPU       : every rank creates its shard with SCGPU_FLAG_PEER (same configuration, capacity_hint = the
+ *                               fixed global capacity), exchanges scgpu_peer_export blobs (e.g. torch.distributed all_gather)
+ *                               and calls scgpu_peer_attach (cudaIpcOpenMemHandle); steps are then collective calls of
+ *                               scgpu_peer_replay_async, synchronised by in-kernel flag barriers over peer memory -- no NCCL
+ *                               call on the data path.  One GPU per process (a cross-process barrier cannot share a GPU). */
+#define SCGPU_PEER_BLOB_BYTES 128
+int scgpu_peer_export(scgpu_handle* h, void* blob, size_t blob_bytes);
+/* blobs: n * SCGPU_PEER_BLOB_BYTES bytes, blob s exported by shard s (this shard's own included). */
+int scgpu_peer_attach(scgpu_handle* h, const void* blobs, int n);
+/* COLLECTIVE replay step: a batch of n_total scans is appended and a detect is run after each, exactly as
+ * scgpu_replay_batched would on one device; scan i becomes global entry size + i and belongs to shard (size + i) % G.  Every
+ * rank passes ITS scans of the batch (those i with (size + i) % G == shard_rank, in order, contiguous; host or device memory)
+ * and the same n_total.  Asynchronous; scgpu_replay_results then returns the results of ALL n_total scans on every rank. */
+int scgpu_peer_replay_async(scgpu_handle* h, const void* pts, size_t n_total, size_t pts_per_scan, size_t stride_bytes,
+                            int location);
+/* The cross-process barrier by itself on `stream` (all ranks call it the same number of times). */
+int scgpu_peer_barrier(scgpu_handle* h, void* stream);
+
 /* Host helper: the n_search sequence a run of n consecutive detects produces (one detect after each append,
  * database size first_size, first_size+1, ...), advancing the handle's snapshot state (SC.cpp:257-276). */
 int scgpu_plan_n_search(scgpu_handle* h, uint64_t first_size, size_t n, uint64_t* out_n_search);

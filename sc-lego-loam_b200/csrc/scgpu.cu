@@ -10,6 +10,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "scgpu_exhaustive.cuh"
@@ -131,23 +138,125 @@ struct scgpu_handle {
   size_t last_nq = 0;
   std::vector<uint64_t> last_nsearch;
   uint64_t launches = 0;
+  uint64_t mutation = 0, last_mutation = 0;  // candidate dumps are valid only while nothing has changed since the pipeline ran
+  DevBuf records2[2];      // record buffers of asynchronous replays (alternating: the next build overlaps this query stage)
+  int rec_turn = 0;
+  DevBuf res_buf;          // result block of replays on a handle without a slab
+  ResultBlock res_rb{};
+  size_t replay_nq = 0;    // results held by the last asynchronous replay
+  bool replay_ipc = false;
+  uint64_t n_written = 0;  // local slots [0, n_written) have been stored at some point (scgpu_stage_set_size validates against it)
+  // ---- peer-sharded mode (SCGPU_FLAG_PEER, or a shard of a device-list handle) ---------------------------------------
+  bool peer = false;      // one fixed-capacity slab holds every array the other shards read or write
+  bool attached = false;  // the other shards' slabs are mapped
+  void* slab = nullptr;
+  size_t slab_bytes = 0;
+  struct SlabOff {
+    size_t sc, sector, colnorm, hat, vk, ring, flags, results, total;
+  } so{};
+  PeerTab peers{};                          // every shard's arrays as seen from this device
+  float* ring_of[MAX_SHARDS] = {};          // every shard's ring-key replica
+  unsigned* flags_of[MAX_SHARDS] = {};      // every shard's barrier cells
+  void* results_of[MAX_SHARDS] = {};        // every shard's result block
+  void* ipc_base[MAX_SHARDS] = {};          // slabs opened with cudaIpcOpenMemHandle (closed in scgpu_destroy)
+  ResultBlock rb{};
+  unsigned epoch[2] = {0, 0};               // barrier generations: channel 0 = "appended", 1 = "queries done"
+  cudaStream_t qstream = nullptr;           // query stage of chunk c runs here while chunk c+1 is binned on `stream`
+  cudaEvent_t ev_app = nullptr, ev_qdone = nullptr, ev_side = nullptr;
+  PinBuf h_ns_ring[4];                      // n_search staging of asynchronous replays (rotating, guarded by events)
+  cudaEvent_t ev_ns_ring[4] = {nullptr, nullptr, nullptr, nullptr};
+  int ns_turn = 0;
+  DevBuf q_idx;
+  // ---- device-list handle (cfg.n_devices > 1): this object only routes to its shards ------------------------------------
+  std::vector<scgpu_handle*> shards;
+  bool is_group = false;
+  scgpu_handle* parent = nullptr;
 };
 
+extern "C" {
+static int create_one(const scgpu_config* cfg, scgpu_handle** out);
+}
+
 namespace {
+
+// a public call on a device-list handle that only needs "a device": use the first shard
+#define GROUP_FIRST(h) ((h)->is_group ? (h)->shards[0] : (h))
 
 uint64_t local_count(const scgpu_handle* h, uint64_t n_global) {
   const uint64_t G = (uint64_t)h->cfg.shard_count, r = (uint64_t)h->cfg.shard_rank;
   return n_global > r ? (n_global - 1 - r) / G + 1 : 0;
 }
 
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr uint64_t PEER_RESULT_CAP = 65536;  // queries per replay batch whose results a shard's slab can hold
+
+// Peer-sharded mode: ONE allocation per shard (so that one cudaIpcMemHandle maps everything the other shards touch) laid out
+// identically on every shard: sc | sector | colnorm | sc_hat | vk | ring-key replica [R][cap * G] | barrier cells | results.
+int slab_alloc(scgpu_handle* h, uint64_t cap) {
+  const Layout& L = h->L;
+  const uint64_t G = (uint64_t)h->cfg.shard_count;
+  scgpu_handle::SlabOff o{};
+  size_t at = 0;
+  auto take = [&](size_t bytes) {
+    const size_t r = at;
+    at = align_up(at + bytes, 256);
+    return r;
+  };
+  o.sc = take(cap * L.RS * sizeof(float));
+  o.sector = take(cap * L.S * sizeof(double));
+  o.colnorm = take(cap * L.S * sizeof(double));
+  o.hat = take(h->exh ? cap * L.RS * sizeof(float) : 0);
+  o.vk = take(h->exh ? (cap + 8) * exh_vk_bytes(L.S) : 0);
+  o.ring = take((size_t)L.R * cap * G * sizeof(float));
+  o.flags = take(1024);
+  h->rb.cap_q = PEER_RESULT_CAP;
+  o.results = take(h->rb.bytes());
+  o.total = at;
+  CK(cudaMalloc(&h->slab, o.total));
+  CK(cudaMemsetAsync(h->slab, 0, o.total, h->stream));  // barrier cells start at generation 0
+  CK(cudaStreamSynchronize(h->stream));
+  h->slab_bytes = o.total;
+  h->so = o;
+  unsigned char* b = static_cast<unsigned char*>(h->slab);
+  h->db.sc = reinterpret_cast<float*>(b + o.sc);
+  h->db.sector = reinterpret_cast<double*>(b + o.sector);
+  h->db.colnorm = reinterpret_cast<double*>(b + o.colnorm);
+  h->db.ringT = reinterpret_cast<float*>(b + o.ring);
+  h->db.cap = cap;
+  h->db.ring_cap = cap * G;
+  h->db.ring_global = 1;
+  h->x_sc_hat = h->exh ? reinterpret_cast<float*>(b + o.hat) : nullptr;
+  h->x_vk = h->exh ? b + o.vk : nullptr;
+  return SCGPU_OK;
+}
+
+// the arrays of shard s as seen from h's device, given the base of s's slab in h's address space
+void peer_fill(scgpu_handle* h, int s, void* base) {
+  unsigned char* b = static_cast<unsigned char*>(base);
+  h->peers.sc[s] = reinterpret_cast<const float*>(b + h->so.sc);
+  h->peers.sector[s] = reinterpret_cast<const double*>(b + h->so.sector);
+  h->peers.colnorm[s] = reinterpret_cast<const double*>(b + h->so.colnorm);
+  h->peers.sc_hat[s] = reinterpret_cast<const float*>(b + h->so.hat);
+  h->peers.vk[s] = b + h->so.vk;
+  h->ring_of[s] = reinterpret_cast<float*>(b + h->so.ring);
+  h->flags_of[s] = reinterpret_cast<unsigned*>(b + h->so.flags);
+  h->results_of[s] = b + h->so.results;
+}
+
 int db_reserve(scgpu_handle* h, uint64_t want_local) {
   if (want_local <= h->db.cap) return SCGPU_OK;
+  if (h->peer)
+    return fail(SCGPU_E_INVALID, "a peer-sharded database has a fixed capacity (capacity_hint = %llu entries): %llu local slots wanted, %llu there",
+                (unsigned long long)h->cfg.capacity_hint, (unsigned long long)want_local, (unsigned long long)h->db.cap);
   CK(cudaDeviceSynchronize());  // rare: the shard moves to a larger allocation; nothing may still be reading the old one
   uint64_t cap = h->db.cap ? h->db.cap * 2 : 1024;
   while (cap < want_local) cap *= 2;
   const Layout& L = h->L;
   Db nd = h->db;
   nd.cap = cap;
+  nd.ring_cap = cap;
+  nd.ring_global = 0;
   CK(cudaMalloc(&nd.sc, cap * L.RS * sizeof(float)));
   CK(cudaMalloc(&nd.ringT, cap * L.R * sizeof(float)));
   CK(cudaMalloc(&nd.sector, cap * L.S * sizeof(double)));
@@ -257,25 +366,30 @@ int launch_build_voxel(scgpu_handle* h, const void* d_pts, size_t n_scans, size_
 
 // Stage 1+2 on device-resident points.
 int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_per_scan, size_t stride, void* d_records,
-                 cudaStream_t st) {
+                 cudaStream_t st, size_t scan_pitch = 0) {  // scan_pitch: bytes between scans (0 = contiguous)
   if (n_scans == 0) return SCGPU_OK;
-  if (h->voxel_leaf > 0.f && pts_per_scan > 0)
+  if (scan_pitch == 0) scan_pitch = pts_per_scan * stride;
+  if (h->voxel_leaf > 0.f && pts_per_scan > 0) {
+    if (scan_pitch != pts_per_scan * stride) return fail(SCGPU_E_INVALID, "the voxel-grid path takes contiguous scans");
     return launch_build_voxel(h, d_pts, n_scans, pts_per_scan, stride, h->voxel_leaf, d_records, nullptr, nullptr, nullptr, 0, st);
+  }
   if (stride < 12 || (stride & 3) || ((uintptr_t)d_pts & 3)) return fail(SCGPU_E_INVALID, "points must be 4-byte aligned, stride >= 12 and a multiple of 4");
   if (pts_per_scan > 0xfffffff0ull || n_scans > 65535ull * 1024) return fail(SCGPU_E_INVALID, "scan too large");
   RET(build_reserve(h, n_scans, st));
   BuildParams p;
   p.pts = static_cast<const unsigned char*>(d_pts);
-  p.scan_pitch = (unsigned long long)pts_per_scan * stride;
+  p.scan_pitch = (unsigned long long)scan_pitch;
   p.n_pts = (unsigned)pts_per_scan;
   p.stride = (unsigned)stride;
   // tile: enough blocks for two full waves of the GPU (4 resident blocks per SM), otherwise as large as possible -- a
   // scan binned by ONE block needs no global merge (atomics, fences, ticket) and starts / drains its TMA ring once
-  // (4,541 HDL-64 scans: 16k-point tiles 1.71 ms, whole-scan tiles 1.56 ms)
+  // (4,541 HDL-64 scans: 16k-point tiles 1.71 ms, whole-scan tiles 1.56 ms).  From ~3/4 of one wave of scans on, whole-scan
+  // tiles also win over splitting (568 scans per GPU of the 8-GPU run: three tiles per scan 0.72 of roofline).
   unsigned ppb = 256;
   if (pts_per_scan) {
     const uint64_t want = (uint64_t)h->sm_count * 8;
     uint64_t tiles = (want + n_scans - 1) / n_scans;
+    if (n_scans >= (uint64_t)h->sm_count * 3) tiles = 1;
     const uint64_t max_tiles = (pts_per_scan + 2047) / 2048;
     if (tiles > max_tiles) tiles = max_tiles;
     if (tiles < 1) tiles = 1;
@@ -300,15 +414,24 @@ int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_
     q.records = p.records + s0 * h->L.rec_bytes;
     q.gbins = p.gbins;  // per-launch scan index restarts at 0: workspace rows [0, ns)
     dim3 grid(tiles, (unsigned)ns);
-    const bool al16 = (((uintptr_t)q.pts & 15) == 0);
-    const int sk = (stride == 16 && al16) ? 16 : ((stride == 32 && al16) ? 32 : 0);
-    if (sk && q.bc.fast && !(h->cfg.flags & SCGPU_FLAG_NO_TMA_BUILD)) {
+    const bool al16 = (((uintptr_t)q.pts & 15) == 0) && (scan_pitch & 15) == 0;
+    int sk = (stride == 16 && al16) ? 16 : ((stride == 32 && al16) ? 32 : 0);
+    // packed xyz (12 bytes per point, what the host packer ships over PCIe): TMA copies are multiples of 16 bytes, so
+    // every tile must hold a multiple of 4 points
+    const bool tma12 = stride == 12 && al16 && (pts_per_scan & 3) == 0;
+    if ((sk || tma12) && q.bc.fast && !(h->cfg.flags & SCGPU_FLAG_NO_TMA_BUILD)) {
       // TMA-staged variant (tile start offsets are multiples of 16 bytes because pts_per_block * stride is)
-      const size_t sm = sk == 16 ? build_tma_smem<16>(h->L.RS) : build_tma_smem<32>(h->L.RS);
-      if (sk == 16 && q.bc.lh_is_float) k_build_tma<16, true, true><<<grid, 256, sm, st>>>(q);
-      else if (sk == 16) k_build_tma<16, true, false><<<grid, 256, sm, st>>>(q);
-      else if (q.bc.lh_is_float) k_build_tma<32, true, true><<<grid, 256, sm, st>>>(q);
-      else k_build_tma<32, true, false><<<grid, 256, sm, st>>>(q);
+      if (tma12) {
+        const size_t sm = build_tma_smem<12>(h->L.RS);
+        if (q.bc.lh_is_float) k_build_tma<12, true, true><<<grid, 256, sm, st>>>(q);
+        else k_build_tma<12, true, false><<<grid, 256, sm, st>>>(q);
+      } else {
+        const size_t sm = sk == 16 ? build_tma_smem<16>(h->L.RS) : build_tma_smem<32>(h->L.RS);
+        if (sk == 16 && q.bc.lh_is_float) k_build_tma<16, true, true><<<grid, 256, sm, st>>>(q);
+        else if (sk == 16) k_build_tma<16, true, false><<<grid, 256, sm, st>>>(q);
+        else if (q.bc.lh_is_float) k_build_tma<32, true, true><<<grid, 256, sm, st>>>(q);
+        else k_build_tma<32, true, false><<<grid, 256, sm, st>>>(q);
+      }
       h->launches++;
       CK(cudaGetLastError());
       continue;
@@ -335,16 +458,32 @@ int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_
   return SCGPU_OK;
 }
 
-int launch_append(scgpu_handle* h, const void* d_records, uint64_t first_global, uint64_t step, size_t n, cudaStream_t st) {
+int exh_sync(scgpu_handle* h, cudaStream_t st);
+
+// push: (peer-sharded) also store the records' ring keys into the other shards' replicas -- peer stores over NVLink
+int launch_append(scgpu_handle* h, const void* d_records, uint64_t first_global, uint64_t step, size_t n, cudaStream_t st, bool push = false) {
   if (n == 0) return SCGPU_OK;
   if (step < 1) return fail(SCGPU_E_INVALID, "global_step must be >= 1");
   const uint64_t new_size = first_global + (n - 1) * step + 1;
   if (new_size > 0xffffffffull) return fail(SCGPU_E_INVALID, "database index space is 32 bits");
   RET(db_reserve(h, local_count(h, new_size)));
-  k_append<<<(unsigned)n, 128, 0, st>>>(static_cast<const unsigned char*>(d_records), h->L, h->db, first_global, step);
+  if (h->peer && new_size > h->db.ring_cap) return fail(SCGPU_E_INVALID, "peer-sharded database is full (%llu entries)", (unsigned long long)h->db.ring_cap);
+  PushList pl{};
+  if (push) {
+    if (!h->attached) return fail(SCGPU_E_INVALID, "peer-sharded handle is not attached to its peers (scgpu_peer_attach)");
+    for (int s = 0; s < h->cfg.shard_count; ++s)
+      if (s != h->cfg.shard_rank) pl.dst[pl.n++] = h->ring_of[s];
+  }
+  // entries below the current size are being overwritten: their screening copies are stale
+  const uint64_t first_local = first_global / (uint64_t)h->cfg.shard_count;
+  if (first_global < h->n_global && h->x_upto > first_local) h->x_upto = first_local;
+  k_append<<<(unsigned)n, 128, 0, st>>>(static_cast<const unsigned char*>(d_records), h->L, h->db, first_global, step, pl);
   h->launches++;
   CK(cudaGetLastError());
   if (new_size > h->n_global) h->n_global = new_size;
+  const uint64_t have = local_count(h, h->n_global);
+  if (have > h->n_written) h->n_written = have;
+  if (h->peer && h->exh) RET(exh_sync(h, st));  // the other shards fetch screening rows from here: keep them current
   return SCGPU_OK;
 }
 
@@ -390,7 +529,8 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
   if (nq == 0) return SCGPU_OK;
   if (nq > 65535) return fail(SCGPU_E_INVALID, "at most 65535 queries per call");
   unsigned chunk, chunks;
-  const uint64_t n_local = local_count(h, h->n_global);
+  // peer-sharded: retrieval runs over this shard's replica of ALL ring keys (global indices): one device, no merge
+  const uint64_t n_local = h->peer ? h->n_global : local_count(h, h->n_global);
   // large batches over a large shard: groups of TOPK_QT queries share every key they load (k_topk_tile) -- only when each
   // warp's stream stays long (>= 8k keys), see the kernel's header.  SCGPU_TOPK_TILE=1/0 forces / forbids it (tests).
   bool tile = nq >= 16 && h->slots <= 2 && (h->L.R == 20 || h->L.R == 40);
@@ -407,6 +547,11 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
   p.qrecords = static_cast<const unsigned char*>(d_qrec);
   p.L = h->L;
   p.db = h->db;
+  if (h->peer) {
+    p.db.cap = h->db.ring_cap;
+    p.db.rank = 0;
+    p.db.G = 1;
+  }
   p.n_search = reinterpret_cast<const unsigned long long*>(d_ns);
   p.n_local = n_local;
   p.chunk = chunk;
@@ -471,6 +616,7 @@ int launch_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t*
   p.pair_shift = d_pair_shift;
   p.flip = flip;
   p.active = nullptr;
+  p.peers = h->peers;
   const size_t smem = pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float));
   dim3 grid((unsigned)K_eff, (unsigned)nq);
   k_score<<<grid, 128, smem, st>>>(p);
@@ -509,6 +655,7 @@ int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const 
   cp.n_search = reinterpret_cast<const unsigned long long*>(d_ns);
   cp.K = h->K;
   cp.d32 = h->c_d32.as<float>();
+  cp.peers = h->peers;
   // warps per block, staging slots per warp.  One slot: three blocks fit an SM and cover each other's fetch latency
   // (two slots = one block per SM measured slower at K = 50).
   if (h->exh_cfg == 1) k_cand_screen<20, 60, 3, 1, 10, 1><<<(unsigned)nq, 10 * 32, cand_smem_bytes<20, 60, 3, 10, 1>(), st>>>(cp);
@@ -527,6 +674,7 @@ int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const 
   p.pair_shift = h->pair_shift.as<int>();
   p.flip = 0;
   p.active = nullptr;
+  p.peers = h->peers;
   k_score_pairs<<<(unsigned)h->sm_count * 8, 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p, h->c_list.as<unsigned long long>(),
                                                                                                             h->c_count.as<unsigned>());
   h->launches += 3;
@@ -544,10 +692,14 @@ int launch_best(scgpu_handle* h, size_t nq, const uint64_t* d_keys, Best* d_best
 }
 
 int launch_finalize(scgpu_handle* h, const Best* d_parts, int parts, size_t nq, const uint64_t* d_ns, int* d_loop, float* d_yaw,
-                    double* d_dist, int* d_idx, int* d_shift, cudaStream_t st) {
+                    double* d_dist, int* d_idx, int* d_shift, cudaStream_t st, unsigned out_off = 0, unsigned out_step = 1,
+                    const PushList* push = nullptr) {
   if (nq == 0) return SCGPU_OK;
+  PushList pl{};
+  if (push) pl = *push;
   k_finalize<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(d_parts, parts, (unsigned)nq, reinterpret_cast<const unsigned long long*>(d_ns),
-                                                           h->K, h->L.S, h->cfg.dist_thres, d_loop, d_yaw, d_dist, d_idx, d_shift);
+                                                           h->K, h->L.S, h->cfg.dist_thres, d_loop, d_yaw, d_dist, d_idx, d_shift, out_off,
+                                                           out_step, h->rb, pl);
   h->launches++;
   CK(cudaGetLastError());
   return SCGPU_OK;
@@ -570,26 +722,49 @@ void plan(scgpu_handle* h, uint64_t first_size, size_t n, uint64_t* out) {
 }
 
 // full single-shard query pipeline for nq query records already on the device; results land in h->o_*.
-int run_pipeline(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* h_ns) {
-  cudaStream_t st = h->stream;
-  RET(h->nsearch.reserve(nq * sizeof(uint64_t)));
-  RET(h->h_ns.reserve(nq * sizeof(uint64_t)));
-  memcpy(h->h_ns.p, h_ns, nq * sizeof(uint64_t));
-  CK(cudaMemcpyAsync(h->nsearch.p, h->h_ns.p, nq * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+// Query stage (stages 3 + 4 + decision) for nq query records on the device, enqueued on st.  Result q goes to slot
+// out_off + q * out_step of the given arrays (and of the result blocks in `push`).
+int query_stage(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* d_ns, cudaStream_t st, int* d_loop, float* d_yaw, double* d_dist,
+                int* d_idx, int* d_shift, unsigned out_off, unsigned out_step, const PushList* push) {
+  if (nq == 0) return SCGPU_OK;
+  if (h->peer && !h->attached) return fail(SCGPU_E_INVALID, "peer-sharded handle is not attached to its peers (scgpu_peer_attach)");
   unsigned chunk, chunks;
-  choose_chunks(local_count(h, h->n_global), nq, chunk, chunks);
+  choose_chunks(h->peer ? h->n_global : local_count(h, h->n_global), nq, chunk, chunks);
   RET(query_reserve(h, nq, chunks, st));
-  const uint64_t* d_ns = h->nsearch.as<uint64_t>();
   RET(launch_topk(h, d_qrec, nq, d_ns, h->keys.as<uint64_t>(), st));
   h->last_screened = h->exh && !(h->cfg.flags & SCGPU_FLAG_NO_SCREENING);
   h->last_qrec = d_qrec;
   if (h->last_screened) RET(launch_score_screened(h, d_qrec, nq, h->keys.as<uint64_t>(), d_ns, st));
   else RET(launch_score(h, d_qrec, nq, h->keys.as<uint64_t>(), d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
   RET(launch_best(h, nq, h->keys.as<uint64_t>(), h->best.as<Best>(), st));
-  RET(launch_finalize(h, h->best.as<Best>(), 1, nq, d_ns, h->o_loop.as<int>(), h->o_yaw.as<float>(), h->o_dist.as<double>(),
-                      h->o_idx.as<int>(), h->o_shift.as<int>(), st));
+  return launch_finalize(h, h->best.as<Best>(), 1, nq, d_ns, d_loop, d_yaw, d_dist, d_idx, d_shift, st, out_off, out_step, push);
+}
+
+// a public call is about to use the per-handle query workspace on h->stream: order it after an asynchronous replay's
+// query stage (which runs on h->qstream)
+int join_replay(scgpu_handle* h) {
+  CK(cudaStreamWaitEvent(h->stream, h->ev_qdone, 0));
+  return SCGPU_OK;
+}
+
+// full query pipeline for nq query records already on the device (the shard's own stream); results land in h->o_*.
+int run_pipeline(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* h_ns) {
+  cudaStream_t st = h->stream;
+  RET(join_replay(h));
+  RET(h->nsearch.reserve(nq * sizeof(uint64_t)));
+  RET(h->h_ns.reserve(nq * sizeof(uint64_t)));
+  CK(cudaEventSynchronize(h->ev_nl));  // the previous copy out of the pinned staging cell has finished
+  memcpy(h->h_ns.p, h_ns, nq * sizeof(uint64_t));
+  CK(cudaMemcpyAsync(h->nsearch.p, h->h_ns.p, nq * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(h->ev_nl, st));
+  unsigned chunk, chunks;
+  choose_chunks(h->peer ? h->n_global : local_count(h, h->n_global), nq, chunk, chunks);
+  RET(query_reserve(h, nq, chunks, st));
+  RET(query_stage(h, d_qrec, nq, h->nsearch.as<uint64_t>(), st, h->o_loop.as<int>(), h->o_yaw.as<float>(), h->o_dist.as<double>(),
+                  h->o_idx.as<int>(), h->o_shift.as<int>(), 0, 1, nullptr));
   h->last_nq = nq;
   h->last_nsearch.assign(h_ns, h_ns + nq);
+  h->last_mutation = h->mutation;
   return SCGPU_OK;
 }
 
@@ -632,46 +807,187 @@ bool is_pinned_or_device(const void* p, int* is_device) {
   return a.type == cudaMemoryTypeHost;
 }
 
-// Host points -> records, double-buffered H2D on the copy stream overlapped with k_build on the compute stream.
-int build_from_host(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, void* d_records) {
+// ---- host thread pool: packs x, y, z of host scans into pinned staging (12 bytes per point) ---------------------------
+// The caller's clouds are pcl::PointXYZI records (32 bytes; mapOpt.cpp:1628-1630 passes a pageable cloud) or float4: only
+// 12 of those bytes are read by the path, and the PCIe link is what bounds the end-to-end rate -- so pageable sources,
+// which have to be staged through pinned memory anyway, are packed on the way (2.67x / 1.33x fewer bytes over the link),
+// by a few host threads instead of one memcpy.  Pinned sources go straight to the DMA engine unless SCGPU_PACK_PINNED=1.
+class HostPool {
+ public:
+  static HostPool& get() {
+    static HostPool p;
+    return p;
+  }
+  int threads() const { return (int)workers_.size() + 1; }
+  // fn(i) for i in [0, n); the calling thread takes part; returns when every item is done
+  void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
+    if (n == 0) return;
+    if (workers_.empty() || n == 1) {
+      for (size_t i = 0; i < n; ++i) fn(i);
+      return;
+    }
+    auto job = std::make_shared<Job>();
+    job->fn = &fn;
+    job->n = n;
+    job->left = n;
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      job_ = job;
+      ++gen_;
+    }
+    cv_.notify_all();
+    run(*job);
+    std::unique_lock<std::mutex> g(job->mu);
+    job->done.wait(g, [&] { return job->left == 0; });
+  }
+
+ private:
+  struct Job {  // workers hold a reference to the job they joined: a late worker never touches a newer job's counters
+    const std::function<void(size_t)>* fn = nullptr;
+    size_t n = 0, left = 0;
+    std::atomic<size_t> next{0};
+    std::mutex mu;
+    std::condition_variable done;
+  };
+  HostPool() {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 4;
+    int local_world = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = atoi(e) > 0 ? atoi(e) : 1;  // one process per GPU: share the cores
+    int n = (int)(hw / (unsigned)local_world);
+    if (n > 16) n = 16;
+    if (const char* e = getenv("SCGPU_HOST_THREADS")) n = atoi(e);
+    if (n < 1) n = 1;
+    for (int i = 1; i < n; ++i) workers_.emplace_back([this] { loop(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  static void run(Job& j) {
+    size_t did = 0;
+    for (;;) {
+      const size_t i = j.next.fetch_add(1);
+      if (i >= j.n) break;
+      (*j.fn)(i);  // valid: the caller of parallel_for cannot return before `left` reaches 0
+      ++did;
+    }
+    if (did) {
+      std::lock_guard<std::mutex> g(j.mu);
+      j.left -= did;
+      if (j.left == 0) j.done.notify_all();
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      std::shared_ptr<Job> job;
+      {
+        std::unique_lock<std::mutex> g(mu_);
+        cv_.wait(g, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        job = job_;
+      }
+      run(*job);
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::shared_ptr<Job> job_;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
+// x, y, z of points [0, n) at `stride` bytes -> 12 bytes per point
+void pack_xyz(const unsigned char* src, size_t stride, size_t n, float* dst) {
+  if (stride == 12) {
+    memcpy(dst, src, n * 12);
+    return;
+  }
+  for (size_t i = 0; i < n; ++i) {
+    const float* p = reinterpret_cast<const float*>(src + i * stride);
+    dst[3 * i] = p[0];
+    dst[3 * i + 1] = p[1];
+    dst[3 * i + 2] = p[2];
+  }
+}
+
+// Host points -> records.  Scans at `src_pitch` bytes (0 = contiguous).  Chunks of scans are staged double-buffered: while
+// chunk c is on the link (copy stream) and chunk c-1 is being binned (compute stream), the host threads pack chunk c+1.
+int build_from_host(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, void* d_records, size_t src_pitch = 0) {
   const size_t scan_bytes = pts_per_scan * stride;
+  if (src_pitch == 0) src_pitch = scan_bytes;
   if (scan_bytes == 0) return launch_build(h, h->d_pts[0].p ? h->d_pts[0].p : d_records, n_scans, 0, stride ? stride : 16, d_records, h->stream);
-  size_t per_chunk = (size_t)(32u << 20) / scan_bytes;
-  if (per_chunk < 1) per_chunk = 1;
-  if (per_chunk > n_scans) per_chunk = n_scans;
-  RET(h->d_pts[0].reserve(per_chunk * scan_bytes));
-  if (per_chunk < n_scans) RET(h->d_pts[1].reserve(per_chunk * scan_bytes));
+  if (stride < 12 || (stride & 3) || ((uintptr_t)pts & 3) || (src_pitch & 3))
+    return fail(SCGPU_E_INVALID, "points must be 4-byte aligned, stride >= 12 and a multiple of 4");
   int dev;
   const bool pinned = is_pinned_or_device(pts, &dev) && !dev;
+  static const bool pack_pinned = getenv("SCGPU_PACK_PINNED") && atoi(getenv("SCGPU_PACK_PINNED")) != 0;
+  static const bool no_pack = getenv("SCGPU_NO_PACK") && atoi(getenv("SCGPU_NO_PACK")) != 0;
+  // the voxel path wants its input as given (it carries no restriction on stride, but keeps the code path of round 1)
+  const bool pack = !no_pack && (!pinned || pack_pinned) && !(h->voxel_leaf > 0.f);
+  const size_t out_stride = pack ? 12 : stride;
+  // staged bytes per scan, padded so that every scan starts 16-byte aligned on the device (TMA)
+  const size_t out_scan = h->voxel_leaf > 0.f ? pts_per_scan * out_stride : ((pts_per_scan * out_stride + 15) & ~(size_t)15);
+  size_t per_chunk = (size_t)(24u << 20) / out_scan;
+  if (per_chunk < 1) per_chunk = 1;
+  if (per_chunk > n_scans) per_chunk = n_scans;
+  RET(h->d_pts[0].reserve(per_chunk * out_scan));
+  if (per_chunk < n_scans) RET(h->d_pts[1].reserve(per_chunk * out_scan));
   const unsigned char* src = static_cast<const unsigned char*>(pts);
+  const bool direct = pinned && !pack;
   int turn = 0;
   for (size_t s0 = 0; s0 < n_scans; s0 += per_chunk, turn ^= 1) {
     const size_t ns = n_scans - s0 < per_chunk ? n_scans - s0 : per_chunk;
-    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[turn], 0));
-    if (pinned) {
-      CK(cudaMemcpyAsync(h->d_pts[turn].p, src + s0 * scan_bytes, ns * scan_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+    if (direct) {
+      CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[turn], 0));
+      if (src_pitch == scan_bytes && out_scan == scan_bytes)
+        CK(cudaMemcpyAsync(h->d_pts[turn].p, src + s0 * src_pitch, ns * scan_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+      else
+        CK(cudaMemcpy2DAsync(h->d_pts[turn].p, out_scan, src + s0 * src_pitch, src_pitch, scan_bytes, ns, cudaMemcpyHostToDevice, h->copy_stream));
     } else {
-      // pageable source: stage through our own pinned buffer so the copy is truly asynchronous
-      RET(h->h_pts[turn].reserve(per_chunk * scan_bytes));
-      CK(cudaEventSynchronize(h->ev_pin[turn]));
-      memcpy(h->h_pts[turn].p, src + s0 * scan_bytes, ns * scan_bytes);
-      CK(cudaMemcpyAsync(h->d_pts[turn].p, h->h_pts[turn].p, ns * scan_bytes, cudaMemcpyHostToDevice, h->copy_stream));
+      // pageable (or packed) source: through our own pinned buffer so that the copy is truly asynchronous
+      RET(h->h_pts[turn].reserve(per_chunk * out_scan));
+      CK(cudaEventSynchronize(h->ev_pin[turn]));  // the previous copy out of this staging buffer has finished
+      unsigned char* stage = static_cast<unsigned char*>(h->h_pts[turn].p);
+      // work items: slices of scans, so that one scan (the online call) also spreads over the threads
+      const size_t slice = 16384;
+      const size_t slices_per_scan = (pts_per_scan + slice - 1) / slice;
+      HostPool::get().parallel_for(ns * slices_per_scan, [&](size_t w) {
+        const size_t sc = w / slices_per_scan, p0 = (w % slices_per_scan) * slice;
+        const size_t np = pts_per_scan - p0 < slice ? pts_per_scan - p0 : slice;
+        const unsigned char* from = src + (s0 + sc) * src_pitch + p0 * stride;
+        unsigned char* to = stage + sc * out_scan + p0 * out_stride;
+        if (pack) pack_xyz(from, stride, np, reinterpret_cast<float*>(to));
+        else memcpy(to, from, np * stride);
+      });
+      CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[turn], 0));
+      CK(cudaMemcpyAsync(h->d_pts[turn].p, stage, ns * out_scan, cudaMemcpyHostToDevice, h->copy_stream));
       CK(cudaEventRecord(h->ev_pin[turn], h->copy_stream));
     }
     CK(cudaEventRecord(h->ev_copied[turn], h->copy_stream));
     CK(cudaStreamWaitEvent(h->stream, h->ev_copied[turn], 0));
-    RET(launch_build(h, h->d_pts[turn].p, ns, pts_per_scan, stride, static_cast<unsigned char*>(d_records) + s0 * h->L.rec_bytes, h->stream));
+    RET(launch_build(h, h->d_pts[turn].p, ns, pts_per_scan, out_stride, static_cast<unsigned char*>(d_records) + s0 * h->L.rec_bytes, h->stream,
+                     out_scan));
     CK(cudaEventRecord(h->ev_consumed[turn], h->stream));
   }
   return SCGPU_OK;
 }
 
-int build_any(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location, void* d_records) {
-  if (location == 1) return launch_build(h, pts, n_scans, pts_per_scan, stride, d_records, h->stream);
-  return build_from_host(h, pts, n_scans, pts_per_scan, stride, d_records);
+int build_any(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location, void* d_records,
+              size_t src_pitch = 0) {
+  if (location == 1) return launch_build(h, pts, n_scans, pts_per_scan, stride, d_records, h->stream, src_pitch);
+  return build_from_host(h, pts, n_scans, pts_per_scan, stride, d_records, src_pitch);
 }
 
 int pair_api(scgpu_handle* h, const double* a, size_t na, const double* b, size_t nb, int mode, double* out_d, size_t nd, int* out_i) {
+  h = GROUP_FIRST(h);
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->stream;
   RET(h->api_in.reserve((na + nb) * sizeof(double)));
@@ -769,6 +1085,7 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
     p.pair_shift = h->x_ps.as<int>();
     p.flip = 0;
     p.active = d_count;
+    p.peers = PeerTab{};  // every shard rescores its own entries
     k_score_list<<<dim3((unsigned)h->sm_count * 4, 1), 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p);
     h->launches += 3;
     CK(cudaGetLastError());
@@ -779,7 +1096,264 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
   return SCGPU_OK;
 }
 
+
+// ======================================================================================================================
+// Replay engine: "append n scans, detect after each" for one shard, for the G shards of a device-list handle (one host
+// process), or for one shard of a database whose other shards are driven by other processes (torchrun, one per GPU).
+//
+//   build stream (h->stream)    : [H2D] -> k_build(chunk c) -> k_append (+ ring keys pushed into every shard's replica)
+//                                  -> barrier "appended" -> event
+//   query stream (h->qstream)   : wait event -> k_topk over the replica -> k_cand_screen / k_score_pairs (candidate rows read
+//                                  from their owner shards) -> k_best -> k_finalize (results pushed to every shard)
+//                                  ... after the last chunk: barrier "queries done"
+// Queries are PARTITIONED: shard r scores the scans it binned itself (global entries first + j*G + r), so per-query work
+// divides by G, no record leaves its device, and nothing is merged.  The build of chunk c+1 -- and of the NEXT replay call --
+// runs while the query stage of chunk c is in flight; the next call's append waits for "queries done" (its writes would
+// race with peers still reading).
+// ======================================================================================================================
+struct ReplayShard {
+  scgpu_handle* h;
+  const void* pts;  // this shard's scans: scan j at pts + j * pitch
+  size_t pitch;     // bytes between this shard's consecutive scans (0 = contiguous)
+};
+
+int barrier_timeout_flag(scgpu_handle* h, unsigned* out) {
+  *out = 0;
+  if (!h->peer) return SCGPU_OK;
+  CK(cudaMemcpyAsync(out, h->flags_of[h->cfg.shard_rank] + 2 * MAX_SHARDS, sizeof(unsigned), cudaMemcpyDeviceToHost, h->qstream));
+  return SCGPU_OK;
+}
+
+int launch_peer_barrier(scgpu_handle* h, int channel, cudaStream_t st) {
+  BarrierCells bc{};
+  for (int s = 0; s < h->cfg.shard_count; ++s) bc.cells[s] = h->flags_of[s];
+  const unsigned e = ++h->epoch[channel];
+  k_peer_barrier<<<1, 32, 0, st>>>(bc, h->cfg.shard_count, h->cfg.shard_rank, channel, e);
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
+
+void* result_base(scgpu_handle* h) { return h->peer ? h->results_of[h->cfg.shard_rank] : h->res_buf.p; }
+const ResultBlock& result_rb(scgpu_handle* h) { return h->peer ? h->rb : h->res_rb; }
+
+// sh: the shards this process drives (all G of a device-list handle, or the one shard of this rank).  The batch is n_total
+// scans; scan i becomes global entry first + i and belongs to shard (first + i) % G; x.pts is the shard's FIRST scan of the
+// batch, its following ones x.pitch bytes apart.  ipc: the other shards live in other processes -> cross-device flag
+// barriers instead of events (every process makes the same sequence of barrier calls).
+int replay_enqueue(std::vector<ReplayShard>& sh, uint64_t first, size_t n_total, size_t P, size_t stride, int location, bool ipc) {
+  scgpu_handle* h0 = sh[0].h;
+  const uint64_t G = h0->peer ? (uint64_t)h0->cfg.shard_count : 1;
+  if (n_total == 0) return SCGPU_OK;
+  if (n_total > 65535 || (h0->peer && n_total > PEER_RESULT_CAP)) return fail(SCGPU_E_INVALID, "at most 65535 scans per replay call");
+  if (!ipc && sh.size() != G) return fail(SCGPU_E_INVALID, "internal: shard list does not cover the database");
+  const size_t B = (n_total + G - 1) / G;  // scans per shard (the last ones of some shards may be missing)
+  // chunks: the query stage of chunk c overlaps the binning of chunk c+1; only worth it while a chunk still fills the GPU
+  // with whole-scan tiles (>= two waves of one-block-per-scan)
+  size_t C = 1;
+  {
+    const size_t per = (size_t)h0->sm_count * 8;
+    if (B >= 2 * per) C = B / per;
+    if (const char* e = getenv("SCGPU_REPLAY_CHUNKS")) C = (size_t)std::max(1, atoi(e));
+    if (C > B) C = B;
+  }
+  auto shard_off = [&](scgpu_handle* h) {  // index within the batch of the shard's first scan
+    const uint64_t r = h->peer ? (uint64_t)h->cfg.shard_rank : 0;
+    return (size_t)((r + G - first % G) % G);
+  };
+  auto shard_cnt = [&](size_t off) { return n_total > off ? (n_total - 1 - off) / G + 1 : 0; };
+  std::vector<uint64_t> plan_all(n_total);
+  for (auto& x : sh) {
+    scgpu_handle* h = x.h;
+    CK(cudaSetDevice(h->cfg.device));
+    plan(h, first + 1, n_total, plan_all.data());  // every shard advances the same snapshot state
+    h->mutation++;
+    h->rec_turn ^= 1;
+    RET(h->records2[h->rec_turn].reserve(B * h->L.rec_bytes));
+    RET(h->nsearch.reserve(B * sizeof(uint64_t)));
+    if (!h->peer && h->res_rb.cap_q < n_total) {
+      CK(cudaStreamSynchronize(h->qstream));
+      RET(h->res_buf.reserve((n_total + n_total / 4 + 64) * 24));
+      h->res_rb.cap_q = h->res_buf.bytes / 24;
+    }
+    // n_search of this shard's queries through a rotating pinned cell (several replays may be in flight)
+    const int slot = h->ns_turn++ & 3;
+    RET(h->h_ns_ring[slot].reserve(B * sizeof(uint64_t)));
+    CK(cudaEventSynchronize(h->ev_ns_ring[slot]));
+    uint64_t* hn = static_cast<uint64_t*>(h->h_ns_ring[slot].p);
+    const size_t off = shard_off(h), Bx = shard_cnt(off);
+    for (size_t j = 0; j < Bx; ++j) hn[j] = plan_all[off + j * G];
+    if (Bx) CK(cudaMemcpyAsync(h->nsearch.p, hn, Bx * sizeof(uint64_t), cudaMemcpyHostToDevice, h->qstream));
+    CK(cudaEventRecord(h->ev_ns_ring[slot], h->qstream));
+    h->last_nsearch.assign(hn, hn + Bx);
+  }
+  for (size_t c = 0; c < C; ++c) {
+    for (auto& x : sh) {
+      scgpu_handle* h = x.h;
+      CK(cudaSetDevice(h->cfg.device));
+      const size_t off = shard_off(h), Bx = shard_cnt(off);
+      const size_t j0 = std::min(Bx, B * c / C), j1 = std::min(Bx, B * (c + 1) / C), nj = j1 - j0;
+      unsigned char* rec = h->records2[h->rec_turn].as<unsigned char>() + j0 * h->L.rec_bytes;
+      const size_t pitch = x.pitch ? x.pitch : P * stride;
+      if (c == 0) CK(cudaEventRecord(h->ev_t0, h->stream));
+      if (nj) RET(build_any(h, static_cast<const unsigned char*>(x.pts) + j0 * pitch, nj, P, stride, location, rec, x.pitch));
+      if (c == C - 1) CK(cudaEventRecord(h->ev_t1, h->stream));
+      if (c == 0)  // the previous replay's query stage (on every shard) may still be reading what the append overwrites
+        for (auto& y : sh) CK(cudaStreamWaitEvent(h->stream, y.h->ev_qdone, 0));
+      if (nj) RET(launch_append(h, rec, first + off + j0 * G, G, nj, h->stream, G > 1));
+      if (ipc && G > 1) RET(launch_peer_barrier(h, 0, h->stream));
+      CK(cudaEventRecord(h->ev_app, h->stream));
+    }
+    const uint64_t present = first + std::min<uint64_t>(n_total, (uint64_t)(B * (c + 1) / C) * G);  // entries in place after this chunk
+    for (auto& x : sh) {
+      scgpu_handle* h = x.h;
+      CK(cudaSetDevice(h->cfg.device));
+      const size_t off = shard_off(h), Bx = shard_cnt(off);
+      const size_t j0 = std::min(Bx, B * c / C), j1 = std::min(Bx, B * (c + 1) / C), nj = j1 - j0;
+      for (auto& y : sh) CK(cudaStreamWaitEvent(h->qstream, y.h->ev_app, 0));
+      h->n_global = present;
+      const uint64_t have = local_count(h, h->n_global);
+      if (have > h->n_written) h->n_written = have;
+      PushList pl{};
+      if (G > 1)
+        for (int s2 = 0; s2 < (int)G; ++s2)
+          if (s2 != h->cfg.shard_rank) pl.dst[pl.n++] = h->results_of[s2];
+      void* rbase = result_base(h);
+      const ResultBlock& rb = result_rb(h);
+      const unsigned char* rec = h->records2[h->rec_turn].as<unsigned char>() + j0 * h->L.rec_bytes;
+      if (nj)
+        RET(query_stage(h, rec, nj, h->nsearch.as<uint64_t>() + j0, h->qstream, rb.loop(rbase), rb.yaw(rbase), rb.dist(rbase), rb.idx(rbase),
+                        rb.shift(rbase), (unsigned)(off + j0 * G), (unsigned)G, &pl));
+    }
+  }
+  for (auto& x : sh) {
+    scgpu_handle* h = x.h;
+    CK(cudaSetDevice(h->cfg.device));
+    if (ipc && G > 1) RET(launch_peer_barrier(h, 1, h->qstream));
+    CK(cudaEventRecord(h->ev_qdone, h->qstream));
+    CK(cudaEventRecord(h->ev_t2, h->qstream));
+    h->timing_valid = true;
+    h->replay_nq = n_total;
+    h->replay_ipc = ipc;
+    // candidate dumps (scgpu_get_batch_candidates) need the whole batch in the query workspace: one chunk, one shard
+    h->last_nq = (C == 1 && !h->peer) ? n_total : 0;
+    h->last_mutation = h->mutation;
+  }
+  return SCGPU_OK;
+}
+
+// results of the last replay_enqueue -> caller arrays.  Device-list handle: wait for every shard, read shard 0's block.
+int replay_fetch(std::vector<scgpu_handle*>& hs, size_t nq, int* loop_id, float* yaw, double* dist, int* idx, int* shift) {
+  for (scgpu_handle* h : hs) {
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaEventSynchronize(h->ev_qdone));
+    CK(cudaStreamSynchronize(h->copy_stream));
+  }
+  scgpu_handle* h = hs[0];
+  CK(cudaSetDevice(h->cfg.device));
+  if (nq > h->replay_nq) return fail(SCGPU_E_INVALID, "the last replay produced %zu results", h->replay_nq);
+  RET(h->h_out.reserve(nq * 24 + 64));
+  unsigned char* b = static_cast<unsigned char*>(h->h_out.p);
+  void* rbase = result_base(h);
+  const ResultBlock& rb = result_rb(h);
+  cudaStream_t st = h->qstream;
+  CK(cudaMemcpyAsync(b, rb.dist(rbase), nq * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b + nq * 8, rb.loop(rbase), nq * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b + nq * 12, rb.yaw(rbase), nq * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b + nq * 16, rb.idx(rbase), nq * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(b + nq * 20, rb.shift(rbase), nq * 4, cudaMemcpyDeviceToHost, st));
+  unsigned timed_out = 0;
+  if (h->replay_ipc) RET(barrier_timeout_flag(h, &timed_out));
+  CK(cudaStreamSynchronize(st));
+  if (timed_out) return fail(SCGPU_E_CUDA, "peer barrier timed out: a shard of the database did not reach the step");
+  if (dist) memcpy(dist, b, nq * 8);
+  if (loop_id) memcpy(loop_id, b + nq * 8, nq * 4);
+  if (yaw) memcpy(yaw, b + nq * 12, nq * 4);
+  if (idx) memcpy(idx, b + nq * 16, nq * 4);
+  if (shift) memcpy(shift, b + nq * 20, nq * 4);
+  return SCGPU_OK;
+}
+
+// ---- device-list handle: one host process, G shards -----------------------------------------------------------------
+int group_attach(std::vector<scgpu_handle*>& hs) {
+  const int G = (int)hs.size();
+  for (int a = 0; a < G; ++a) {
+    scgpu_handle* h = hs[a];
+    CK(cudaSetDevice(h->cfg.device));
+    for (int b = 0; b < G; ++b) {
+      const int db = hs[b]->cfg.device;
+      if (db != h->cfg.device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, h->cfg.device, db));
+        if (!can) return fail(SCGPU_E_CUDA, "device %d cannot access device %d's memory (no peer path)", h->cfg.device, db);
+        const cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(SCGPU_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      peer_fill(h, b, hs[b]->slab);
+    }
+    h->peers.G = G;
+    h->peers.rank = a;
+    h->peers.cap = h->db.cap;
+    h->attached = true;
+  }
+  return SCGPU_OK;
+}
+
+// every shard's appends so far are visible to `h`'s stream `st` (device-list handle: events instead of flag barriers)
+int group_wait_appends(scgpu_handle* g, scgpu_handle* h, cudaStream_t st) {
+  for (scgpu_handle* s : g->shards) CK(cudaStreamWaitEvent(st, s->ev_app, 0));
+  return SCGPU_OK;
+}
+
+void group_set_size(scgpu_handle* g, uint64_t n) {
+  g->n_global = n;
+  for (scgpu_handle* s : g->shards) {
+    s->n_global = n;
+    const uint64_t have = local_count(s, n);
+    if (have > s->n_written) s->n_written = have;
+  }
+}
+
 }  // namespace
+
+static int group_create(const scgpu_config* cfg, scgpu_handle** out) {
+  const int G = cfg->n_devices;
+  *out = nullptr;
+  if (G > SCGPU_MAX_DEVICES || G > MAX_SHARDS) return fail(SCGPU_E_INVALID, "at most %d devices", SCGPU_MAX_DEVICES);
+  if (cfg->shard_count != 1) return fail(SCGPU_E_INVALID, "a device-list handle is the whole database: shard_count must be 1");
+  scgpu_handle* g = new scgpu_handle();
+  g->is_group = true;
+  g->cfg = *cfg;
+  g->L = make_layout(cfg->num_ring, cfg->num_sector);
+  g->K = cfg->num_candidates;
+  for (int r = 0; r < G; ++r) {
+    scgpu_config c = *cfg;
+    c.n_devices = 0;
+    c.device = cfg->devices[r];
+    c.shard_rank = r;
+    c.shard_count = G;
+    c.flags |= SCGPU_FLAG_PEER;
+    scgpu_handle* s = nullptr;
+    const int rc = create_one(&c, &s);
+    if (rc != SCGPU_OK) {
+      scgpu_destroy(g);
+      return rc;
+    }
+    s->parent = g;
+    g->shards.push_back(s);
+  }
+  const int rc = group_attach(g->shards);
+  if (rc != SCGPU_OK) {
+    scgpu_destroy(g);
+    return rc;
+  }
+  g->radius = g->shards[0]->radius;
+  g->W = g->shards[0]->W;
+  g->exh = g->shards[0]->exh;
+  *out = g;
+  return SCGPU_OK;
+}
 
 // =================================================================================================
 extern "C" {
@@ -813,6 +1387,18 @@ int scgpu_default_config(scgpu_config* c) {
 int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   if (!cfg || !out) return fail(SCGPU_E_INVALID, "null argument");
   *out = nullptr;
+  if (cfg->n_devices > 1) return group_create(cfg, out);
+  if (cfg->n_devices == 1) {
+    scgpu_config c = *cfg;
+    c.device = cfg->devices[0];
+    c.n_devices = 0;
+    return create_one(&c, out);
+  }
+  return create_one(cfg, out);
+}
+
+static int create_one(const scgpu_config* cfg, scgpu_handle** out) {
+  *out = nullptr;
   if (cfg->num_ring < 1 || cfg->num_ring > 64 || cfg->num_sector < 1 || cfg->num_sector > 1024)
     return fail(SCGPU_E_INVALID, "num_ring must be in [1,64], num_sector in [1,1024]");
   if (cfg->num_candidates < 1 || cfg->num_candidates > 128) return fail(SCGPU_E_INVALID, "num_candidates must be in [1,128]");
@@ -835,6 +1421,11 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   h->W = 2 * h->radius + 1;
   h->db.rank = cfg->shard_rank;
   h->db.G = cfg->shard_count;
+  h->peer = (cfg->flags & SCGPU_FLAG_PEER) && cfg->shard_count > 1;
+  if (h->peer && cfg->shard_count > MAX_SHARDS) {
+    delete h;
+    return fail(SCGPU_E_INVALID, "at most %d peer shards", MAX_SHARDS);
+  }
   // FP32 screening kernels are instantiated for the reference's 20x60 (radius 3) and BASELINE's 40x120 (radius 6)
   h->exh_cfg = (h->L.R == 20 && h->L.S == 60 && h->radius == 3) ? 1 : ((h->L.R == 40 && h->L.S == 120 && h->radius == 6) ? 2 : 0);
   h->exh = h->exh_cfg != 0 && !(cfg->flags & SCGPU_FLAG_NO_SCREENING);
@@ -847,6 +1438,15 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   }
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  {  // the query stage of a pipelined replay: latency-bound kernels that should win SM slots whenever the binning frees any
+    int lo = 0, hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->qstream, cudaStreamNonBlocking, hi);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_app, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_qdone, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming);
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&h->ev_ns_ring[i], cudaEventDisableTiming);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming);
@@ -860,6 +1460,8 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<16>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<12, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<12>(h->L.RS));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<12, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<12>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_voxel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vox_smem_bytes(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_voxel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vox_smem_bytes(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_voxel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vox_smem_bytes(h->L.RS));
@@ -882,7 +1484,8 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
   }
   uint64_t cap = cfg->capacity_hint / (uint64_t)cfg->shard_count + 1;
   if (cap < 1024) cap = 1024;
-  int r = db_reserve(h, cap);
+  cap = (cap + 63) & ~63ull;
+  int r = h->peer ? slab_alloc(h, cap) : db_reserve(h, cap);
   if (r == SCGPU_OK) r = h->rec_single.reserve(h->L.rec_bytes);
   if (r != SCGPU_OK) {
     delete h;
@@ -894,9 +1497,21 @@ int scgpu_create(const scgpu_config* cfg, scgpu_handle** out) {
 
 int scgpu_destroy(scgpu_handle* h) {
   if (!h) return SCGPU_OK;
+  if (h->is_group) {
+    for (scgpu_handle* s : h->shards) {
+      cudaSetDevice(s->cfg.device);
+      cudaDeviceSynchronize();
+    }
+    for (scgpu_handle* s : h->shards) scgpu_destroy(s);
+    delete h;
+    return SCGPU_OK;
+  }
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+  if (h->qstream) cudaStreamSynchronize(h->qstream);
+  for (int s = 0; s < MAX_SHARDS; ++s)
+    if (h->ipc_base[s]) cudaIpcCloseMemHandle(h->ipc_base[s]);
   DevBuf* bufs[] = {&h->gbins, &h->btickets, &h->d_pts[0], &h->d_pts[1], &h->records, &h->rec_single, &h->nsearch, &h->keys, &h->partial,
                     &h->ttickets, &h->pair_dist, &h->pair_shift, &h->best, &h->o_loop, &h->o_yaw, &h->o_dist, &h->o_idx, &h->o_shift,
                     &h->api_in, &h->api_out, &h->vox_info, &h->vox_pts, &h->vox_idx, &h->vox_in, &h->vox_keys, &h->vox_hint};
@@ -905,7 +1520,18 @@ int scgpu_destroy(scgpu_handle* h) {
   h->h_pts[1].release();
   h->h_out.release();
   h->h_ns.release();
-  if (h->db.cap) {
+  h->q_idx.release();
+  for (int i = 0; i < 4; ++i) {
+    h->h_ns_ring[i].release();
+    if (h->ev_ns_ring[i]) cudaEventDestroy(h->ev_ns_ring[i]);
+  }
+  if (h->ev_app) cudaEventDestroy(h->ev_app);
+  if (h->ev_qdone) cudaEventDestroy(h->ev_qdone);
+  if (h->ev_side) cudaEventDestroy(h->ev_side);
+  if (h->qstream) cudaStreamDestroy(h->qstream);
+  if (h->peer) {
+    if (h->slab) cudaFree(h->slab);
+  } else if (h->db.cap) {
     cudaFree(h->db.sc);
     cudaFree(h->db.ringT);
     cudaFree(h->db.sector);
@@ -941,11 +1567,26 @@ int scgpu_size(scgpu_handle* h, uint64_t* out_n) {
 int scgpu_launch_count(scgpu_handle* h, uint64_t* out) {
   if (!h || !out) return fail(SCGPU_E_INVALID, "null argument");
   *out = h->launches;
+  for (scgpu_handle* s : h->shards) *out += s->launches;
   return SCGPU_OK;
 }
 
 int scgpu_get_timing(scgpu_handle* h, double* ms_total, double* ms_build, double* ms_query) {
   if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->is_group) {  // the slowest shard of each phase
+    double t[3] = {0, 0, 0};
+    for (scgpu_handle* s : h->shards) {
+      double a, b, c;
+      RET(scgpu_get_timing(s, &a, &b, &c));
+      t[0] = std::max(t[0], a);
+      t[1] = std::max(t[1], b);
+      t[2] = std::max(t[2], c);
+    }
+    if (ms_total) *ms_total = t[0];
+    if (ms_build) *ms_build = t[1];
+    if (ms_query) *ms_query = t[2];
+    return SCGPU_OK;
+  }
   if (!h->timing_valid) return fail(SCGPU_E_INVALID, "no timed call yet");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaEventSynchronize(h->ev_t2));
@@ -969,7 +1610,10 @@ int scgpu_record_bytes(scgpu_handle* h, size_t* out) {
 
 int scgpu_make_sc(scgpu_handle* h, const void* pts, size_t n, size_t stride, double* out_sc) {
   if (!h || !out_sc || (!pts && n)) return fail(SCGPU_E_INVALID, "null argument");
+  h = GROUP_FIRST(h);
   CK(cudaSetDevice(h->cfg.device));
+  RET(join_replay(h));
+  h->mutation++;
   RET(build_from_host(h, pts, 1, n, stride ? stride : 16, h->rec_single.p));
   std::vector<float> sc(h->L.RS);
   CK(cudaMemcpyAsync(sc.data(), h->rec_single.p, sizeof(float) * h->L.RS, cudaMemcpyDeviceToHost, h->stream));
@@ -1009,17 +1653,47 @@ int scgpu_distance(scgpu_handle* h, const double* sc1, const double* sc2, double
   return pair_api(h, sc1, h->L.RS, sc2, h->L.RS, 0, out_dist, 1, out_shift);
 }
 
+// scans [0, n) of this shard's share of a batch: scan j is global entry first_global + j * step, its points at pts + j * pitch
+static int append_scans_one(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location,
+                            uint64_t first_global, uint64_t step, size_t pitch, bool push) {
+  CK(cudaSetDevice(h->cfg.device));
+  RET(join_replay(h));
+  h->mutation++;
+  CK(cudaEventRecord(h->ev_t0, h->stream));
+  if (n_scans) {
+    RET(h->records.reserve(n_scans * h->L.rec_bytes));
+    RET(build_any(h, pts, n_scans, pts_per_scan, stride, location, h->records.p, pitch));
+  }
+  CK(cudaEventRecord(h->ev_t1, h->stream));
+  if (n_scans) RET(launch_append(h, h->records.p, first_global, step, n_scans, h->stream, push));
+  CK(cudaEventRecord(h->ev_t2, h->stream));
+  CK(cudaEventRecord(h->ev_app, h->stream));
+  h->timing_valid = true;
+  return SCGPU_OK;
+}
+
 int scgpu_append_scans_batched(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location) {
   if (!h || (!pts && n_scans && pts_per_scan)) return fail(SCGPU_E_INVALID, "null argument");
   if (n_scans == 0) return SCGPU_OK;
-  CK(cudaSetDevice(h->cfg.device));
-  RET(h->records.reserve(n_scans * h->L.rec_bytes));
-  CK(cudaEventRecord(h->ev_t0, h->stream));
-  RET(build_any(h, pts, n_scans, pts_per_scan, stride, location, h->records.p));
-  CK(cudaEventRecord(h->ev_t1, h->stream));
-  RET(launch_append(h, h->records.p, h->n_global, 1, n_scans, h->stream));
-  CK(cudaEventRecord(h->ev_t2, h->stream));
-  h->timing_valid = true;
+  if (h->is_group) {  // scan i -> shard (size + i) % G, binned on that shard's device; ring keys pushed to every replica
+    const uint64_t G = h->shards.size(), first = h->n_global;
+    const size_t scan_bytes = pts_per_scan * stride;
+    for (scgpu_handle* s : h->shards) {
+      const size_t off = (size_t)(((uint64_t)s->cfg.shard_rank + G - first % G) % G);
+      const size_t cnt = n_scans > off ? (n_scans - 1 - off) / G + 1 : 0;
+      RET(append_scans_one(s, static_cast<const unsigned char*>(pts) + off * scan_bytes, cnt, pts_per_scan, stride, location, first + off, G,
+                           G * scan_bytes, true));
+    }
+    if (location == 0)
+      for (scgpu_handle* s : h->shards) {
+        CK(cudaSetDevice(s->cfg.device));
+        CK(cudaStreamSynchronize(s->copy_stream));
+      }
+    group_set_size(h, first + n_scans);
+    return SCGPU_OK;
+  }
+  if (h->peer) return fail(SCGPU_E_INVALID, "a shard of a peer-sharded database appends through scgpu_peer_replay_async / the staged API");
+  RET(append_scans_one(h, pts, n_scans, pts_per_scan, stride, location, h->n_global, 1, 0, false));
   if (location == 0) CK(cudaStreamSynchronize(h->copy_stream));  // the caller's buffer is not retained
   return SCGPU_OK;
 }
@@ -1028,10 +1702,12 @@ int scgpu_append_scan(scgpu_handle* h, const void* pts, size_t n, size_t stride)
   return scgpu_append_scans_batched(h, pts, 1, n, stride, 0);
 }
 
-int scgpu_append_descs(scgpu_handle* h, const float* sc, size_t n) {
-  if (!h || (!sc && n)) return fail(SCGPU_E_INVALID, "null argument");
-  if (n == 0) return SCGPU_OK;
+// Ready-made descriptors.  A shard of a sharded database is given ALL n descriptors (every rank / shard the same ones): it
+// keeps the entries it owns and, peer-sharded, the ring key of every entry in its replica -- nothing crosses devices.
+static int append_descs_one(scgpu_handle* h, const float* sc, size_t n) {
   CK(cudaSetDevice(h->cfg.device));
+  RET(join_replay(h));
+  h->mutation++;
   const size_t batch = 8192;
   DevBuf tmp;
   RET(tmp.reserve(batch * h->L.RS * sizeof(float)));
@@ -1050,17 +1726,88 @@ int scgpu_append_descs(scgpu_handle* h, const float* sc, size_t n) {
     rc = launch_append(h, h->records.p, h->n_global, 1, m, h->stream);
     if (rc == SCGPU_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) rc = fail(SCGPU_E_CUDA, "append_descs sync failed");
   }
+  if (rc == SCGPU_OK && cudaEventRecord(h->ev_app, h->stream) != cudaSuccess) rc = fail(SCGPU_E_CUDA, "event record failed");
   tmp.release();
   return rc;
 }
 
+int scgpu_append_descs(scgpu_handle* h, const float* sc, size_t n) {
+  if (!h || (!sc && n)) return fail(SCGPU_E_INVALID, "null argument");
+  if (n == 0) return SCGPU_OK;
+  if (h->is_group) {
+    for (scgpu_handle* s : h->shards) RET(append_descs_one(s, sc, n));
+    group_set_size(h, h->n_global + n);
+    return SCGPU_OK;
+  }
+  return append_descs_one(h, sc, n);
+}
+
+// detect for the stored entries [first, first + nq) of a device-list handle: shard r gathers and scores the queries it
+// owns (candidate rows come from whichever shard holds them), results land in shard 0's block
+static int group_query_range(scgpu_handle* g, uint64_t first, size_t nq, const uint64_t* ns, int* loop_id, float* yaw, double* nearest_dist,
+                             int* nearest_idx, int* nearest_shift) {
+  const uint64_t G = g->shards.size();
+  if (nq > PEER_RESULT_CAP) return fail(SCGPU_E_INVALID, "at most %llu queries per call", (unsigned long long)PEER_RESULT_CAP);
+  for (scgpu_handle* h : g->shards) {
+    CK(cudaSetDevice(h->cfg.device));
+    RET(join_replay(h));
+    const size_t off = (size_t)(((uint64_t)h->cfg.shard_rank + G - first % G) % G);
+    const size_t cnt = nq > off ? (nq - 1 - off) / G + 1 : 0;
+    CK(cudaEventRecord(h->ev_t0, h->stream));
+    CK(cudaEventRecord(h->ev_t1, h->stream));
+    if (cnt) {
+      RET(group_wait_appends(g, h, h->stream));
+      RET(h->records.reserve(cnt * h->L.rec_bytes));
+      RET(h->q_idx.reserve(cnt * sizeof(uint64_t)));
+      RET(h->nsearch.reserve(cnt * sizeof(uint64_t)));
+      RET(h->h_ns.reserve(2 * cnt * sizeof(uint64_t)));
+      CK(cudaEventSynchronize(h->ev_nl));
+      uint64_t* hq = static_cast<uint64_t*>(h->h_ns.p);
+      for (size_t j = 0; j < cnt; ++j) {
+        hq[j] = first + off + j * G;
+        hq[cnt + j] = ns[off + j * G];
+      }
+      CK(cudaMemcpyAsync(h->q_idx.p, hq, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaMemcpyAsync(h->nsearch.p, hq + cnt, cnt * 8, cudaMemcpyHostToDevice, h->stream));
+      CK(cudaEventRecord(h->ev_nl, h->stream));
+      k_gather<<<(unsigned)cnt, 128, 0, h->stream>>>(h->records.as<unsigned char>(), h->L, h->db, h->peers, 0, h->q_idx.as<unsigned long long>());
+      h->launches++;
+      CK(cudaGetLastError());
+      PushList pl{};
+      if (h->cfg.shard_rank != 0) pl.dst[pl.n++] = h->results_of[0];
+      void* rbase = result_base(h);
+      RET(query_stage(h, h->records.p, cnt, h->nsearch.as<uint64_t>(), h->stream, h->rb.loop(rbase), h->rb.yaw(rbase), h->rb.dist(rbase),
+                      h->rb.idx(rbase), h->rb.shift(rbase), (unsigned)off, (unsigned)G, &pl));
+      h->last_nq = cnt;
+      h->last_nsearch.assign(hq + cnt, hq + 2 * cnt);
+      h->last_mutation = h->mutation;
+    }
+    CK(cudaEventRecord(h->ev_t2, h->stream));
+    CK(cudaEventRecord(h->ev_qdone, h->stream));
+    h->timing_valid = true;
+    h->replay_nq = nq;
+    h->replay_ipc = false;
+  }
+  std::vector<scgpu_handle*> hs(g->shards);
+  for (scgpu_handle* h : hs) {
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return replay_fetch(hs, nq, loop_id, yaw, nearest_dist, nearest_idx, nearest_shift);
+}
+
 int scgpu_detect(scgpu_handle* h, int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift) {
   if (!h || !loop_id || !yaw) return fail(SCGPU_E_INVALID, "null argument");
-  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "scgpu_detect needs the whole database on one device; use the staged API for shards");
+  if (!h->is_group && h->cfg.shard_count != 1)
+    return fail(SCGPU_E_INVALID, "scgpu_detect needs the whole database behind the handle (one device, or a device list); use the staged API for shards");
   if (h->n_global == 0) return fail(SCGPU_E_EMPTY, "detect on an empty database");
-  CK(cudaSetDevice(h->cfg.device));
   uint64_t ns;
-  plan(h, h->n_global, 1, &ns);
+  if (h->is_group) {
+    for (scgpu_handle* s : h->shards) plan(s, h->n_global, 1, &ns);  // every shard carries the same snapshot state
+  } else {
+    CK(cudaSetDevice(h->cfg.device));
+    plan(h, h->n_global, 1, &ns);
+  }
   if (ns == 0) {  // SC.cpp:257-261
     *loop_id = -1;
     *yaw = 0.0f;
@@ -1068,55 +1815,89 @@ int scgpu_detect(scgpu_handle* h, int* loop_id, float* yaw, double* nearest_dist
     if (nearest_idx) *nearest_idx = 0;
     if (nearest_shift) *nearest_shift = 0;
     h->last_nq = 0;
+    for (scgpu_handle* s : h->shards) s->last_nq = 0;
     return SCGPU_OK;
   }
-  k_gather<<<1, 128, 0, h->stream>>>(h->rec_single.as<unsigned char>(), h->L, h->db, h->n_global - 1);
+  if (h->is_group) {
+    for (scgpu_handle* s : h->shards) s->last_nq = 0;
+    return group_query_range(h, h->n_global - 1, 1, &ns, loop_id, yaw, nearest_dist, nearest_idx, nearest_shift);
+  }
+  RET(join_replay(h));
+  k_gather<<<1, 128, 0, h->stream>>>(h->rec_single.as<unsigned char>(), h->L, h->db, h->peers, h->n_global - 1, nullptr);
   h->launches++;
   CK(cudaGetLastError());
   RET(run_pipeline(h, h->rec_single.p, 1, &ns));
   return fetch_results(h, 1, loop_id, yaw, nearest_dist, nearest_idx, nearest_shift);
 }
 
-int scgpu_replay_batched(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location,
-                         int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift) {
-  if (!h || (!pts && n_scans && pts_per_scan) || !loop_id || !yaw) return fail(SCGPU_E_INVALID, "null argument");
-  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "scgpu_replay_batched is single-shard; use the staged API for shards");
+// the shards (and their first scans) of a replay over host / device scans laid out contiguously
+static void replay_shards(scgpu_handle* h, const void* pts, size_t scan_bytes, uint64_t first, std::vector<ReplayShard>& sh) {
+  if (!h->is_group) {
+    sh.push_back({h, pts, 0});
+    return;
+  }
+  const uint64_t G = h->shards.size();
+  for (scgpu_handle* s : h->shards) {
+    const size_t off = (size_t)(((uint64_t)s->cfg.shard_rank + G - first % G) % G);
+    sh.push_back({s, static_cast<const unsigned char*>(pts) + off * scan_bytes, G * scan_bytes});
+  }
+}
+
+int scgpu_replay_async(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location) {
+  if (!h || (!pts && n_scans && pts_per_scan)) return fail(SCGPU_E_INVALID, "null argument");
+  if (!h->is_group && h->cfg.shard_count != 1)
+    return fail(SCGPU_E_INVALID, "scgpu_replay_* needs the whole database behind the handle; shards of other processes use scgpu_peer_replay_async");
   if (n_scans == 0) return SCGPU_OK;
   if (n_scans > 65535) return fail(SCGPU_E_INVALID, "at most 65535 scans per call");
-  CK(cudaSetDevice(h->cfg.device));
   const uint64_t first = h->n_global;
-  std::vector<uint64_t> ns(n_scans);
-  plan(h, first + 1, n_scans, ns.data());
-  RET(h->records.reserve(n_scans * h->L.rec_bytes));
-  CK(cudaEventRecord(h->ev_t0, h->stream));
-  RET(build_any(h, pts, n_scans, pts_per_scan, stride, location, h->records.p));
-  CK(cudaEventRecord(h->ev_t1, h->stream));
-  RET(launch_append(h, h->records.p, first, 1, n_scans, h->stream));
-  RET(run_pipeline(h, h->records.p, n_scans, ns.data()));
-  CK(cudaEventRecord(h->ev_t2, h->stream));
-  h->timing_valid = true;
-  RET(fetch_results(h, n_scans, loop_id, yaw, nearest_dist, nearest_idx, nearest_shift));
-  if (location == 0) CK(cudaStreamSynchronize(h->copy_stream));
+  std::vector<ReplayShard> sh;
+  replay_shards(h, pts, pts_per_scan * stride, first, sh);
+  RET(replay_enqueue(sh, first, n_scans, pts_per_scan, stride, location, false));
+  if (h->is_group) group_set_size(h, first + n_scans);
+  h->replay_nq = n_scans;
   return SCGPU_OK;
+}
+
+int scgpu_replay_results(scgpu_handle* h, size_t n, int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift) {
+  if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  std::vector<scgpu_handle*> hs;
+  if (h->is_group) hs = h->shards;
+  else hs.push_back(h);
+  return replay_fetch(hs, n, loop_id, yaw, nearest_dist, nearest_idx, nearest_shift);
+}
+
+int scgpu_replay_batched(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location,
+                         int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift) {
+  if (!loop_id || !yaw) return fail(SCGPU_E_INVALID, "null argument");
+  RET(scgpu_replay_async(h, pts, n_scans, pts_per_scan, stride, location));
+  if (n_scans == 0) return SCGPU_OK;
+  return scgpu_replay_results(h, n_scans, loop_id, yaw, nearest_dist, nearest_idx, nearest_shift);
 }
 
 int scgpu_query_batched(scgpu_handle* h, uint64_t first, size_t nq, int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx,
                         int* nearest_shift) {
   if (!h || !loop_id || !yaw) return fail(SCGPU_E_INVALID, "null argument");
-  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "scgpu_query_batched is single-shard; use the staged API for shards");
+  if (!h->is_group && h->cfg.shard_count != 1)
+    return fail(SCGPU_E_INVALID, "scgpu_query_batched needs the whole database behind the handle; use the staged API for shards");
   if (nq == 0) return SCGPU_OK;
   if (first + nq > h->n_global || nq > 65535) return fail(SCGPU_E_INVALID, "query range outside the database");
-  CK(cudaSetDevice(h->cfg.device));
   std::vector<uint64_t> ns(nq);
   const uint64_t excl = (uint64_t)h->cfg.exclude_recent;
   for (size_t i = 0; i < nq; ++i) {
     const uint64_t size = first + i + 1;
     ns[i] = size >= excl + 1 ? size - excl : 0;
   }
+  if (h->is_group) {
+    for (scgpu_handle* s : h->shards) s->last_nq = 0;
+    return group_query_range(h, first, nq, ns.data(), loop_id, yaw, nearest_dist, nearest_idx, nearest_shift);
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  RET(join_replay(h));
+  h->mutation++;
   RET(h->records.reserve(nq * h->L.rec_bytes));
   CK(cudaEventRecord(h->ev_t0, h->stream));
   CK(cudaEventRecord(h->ev_t1, h->stream));
-  k_gather<<<(unsigned)nq, 128, 0, h->stream>>>(h->records.as<unsigned char>(), h->L, h->db, first);
+  k_gather<<<(unsigned)nq, 128, 0, h->stream>>>(h->records.as<unsigned char>(), h->L, h->db, h->peers, first, nullptr);
   h->launches++;
   CK(cudaGetLastError());
   RET(run_pipeline(h, h->records.p, nq, ns.data()));
@@ -1128,8 +1909,17 @@ int scgpu_query_batched(scgpu_handle* h, uint64_t first, size_t nq, int* loop_id
 int scgpu_get_batch_candidates(scgpu_handle* h, size_t q, uint64_t* cand_idx, float* cand_d2, double* cand_dist, int* cand_shift,
                                uint64_t* n_search) {
   if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->is_group) {  // the last detect ran on one shard: that shard holds the candidate table
+    for (scgpu_handle* s : h->shards)
+      if (s->last_nq) return scgpu_get_batch_candidates(s, q, cand_idx, cand_d2, cand_dist, cand_shift, n_search);
+    return fail(SCGPU_E_INVALID, "no such query in the last call");
+  }
   if (q >= h->last_nq) return fail(SCGPU_E_INVALID, "no such query in the last call");
+  // the dump re-reads the query records and the candidate table of the last pipeline: anything that ran since then may have
+  // overwritten them
+  if (h->last_mutation != h->mutation) return fail(SCGPU_E_INVALID, "the database or the query workspace changed since the last detect / replay / query call");
   CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->ev_qdone));
   if (h->last_screened) {
     // the pipeline scored exactly only the candidates that could win; complete the table for the dump
     RET(launch_score(h, h->last_qrec, h->last_nq, h->keys.as<uint64_t>(), h->nsearch.as<uint64_t>(), h->K, h->pair_dist.as<double>(),
@@ -1168,18 +1958,28 @@ int scgpu_get_candidates(scgpu_handle* h, uint64_t* cand_idx, float* cand_d2, do
 int scgpu_get_entry(scgpu_handle* h, uint64_t i, float* sc, float* ring, double* sector) {
   if (!h) return fail(SCGPU_E_INVALID, "null argument");
   if (i >= h->n_global) return fail(SCGPU_E_INVALID, "entry out of range");
+  if (h->is_group) return scgpu_get_entry(h->shards[i % h->shards.size()], i, sc, ring, sector);
   if ((int)(i % (uint64_t)h->cfg.shard_count) != h->cfg.shard_rank) return fail(SCGPU_E_INVALID, "entry lives on another shard");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
+  CK(cudaStreamSynchronize(h->qstream));
   const uint64_t l = i / (uint64_t)h->cfg.shard_count;
   if (sc) CK(cudaMemcpy(sc, h->db.sc + l * h->L.RS, sizeof(float) * h->L.RS, cudaMemcpyDeviceToHost));
-  if (ring) CK(cudaMemcpy2D(ring, sizeof(float), h->db.ringT + l, h->db.cap * sizeof(float), sizeof(float), h->L.R, cudaMemcpyDeviceToHost));
+  if (ring)
+    CK(cudaMemcpy2D(ring, sizeof(float), h->db.ringT + ring_slot(h->db, i, l), h->db.ring_cap * sizeof(float), sizeof(float), h->L.R,
+                    cudaMemcpyDeviceToHost));
   if (sector) CK(cudaMemcpy(sector, h->db.sector + l * h->L.S, sizeof(double) * h->L.S, cudaMemcpyDeviceToHost));
   return SCGPU_OK;
 }
 
 int scgpu_truncate(scgpu_handle* h, uint64_t n) {
   if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->is_group) {
+    for (scgpu_handle* s : h->shards) RET(scgpu_truncate(s, n));
+    if (n < h->n_global) h->n_global = n;
+    return SCGPU_OK;
+  }
+  h->mutation++;
   if (n < h->n_global) h->n_global = n;
   if (h->x_upto > local_count(h, h->n_global)) h->x_upto = local_count(h, h->n_global);
   // the snapshot may reference forgotten entries: the next detect takes a fresh one (counter % period == 0)
@@ -1190,53 +1990,48 @@ int scgpu_truncate(scgpu_handle* h, uint64_t n) {
 
 int scgpu_plan_n_search(scgpu_handle* h, uint64_t first_size, size_t n, uint64_t* out) {
   if (!h || (!out && n)) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->is_group) {
+    for (scgpu_handle* s : h->shards) plan(s, first_size, n, out);
+    return SCGPU_OK;
+  }
   plan(h, first_size, n, out);
   return SCGPU_OK;
 }
 
-// Exhaustive scoring with the exact FP64 pair kernel (every entry is a "candidate").
-int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped, double* best_dist, int* best_shift, int64_t* best_idx,
-                     int* best_flip) {
-  if (!h || !best_dist || !best_shift || !best_idx) return fail(SCGPU_E_INVALID, "null argument");
-  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "scgpu_exhaustive is single-shard; use the staged API for shards");
-  if (q >= h->n_global || n_search > h->n_global) return fail(SCGPU_E_INVALID, "range outside the database");
-  CK(cudaSetDevice(h->cfg.device));
-  cudaStream_t st = h->stream;
-  *best_dist = 10000000.0;
-  *best_shift = 0;
-  *best_idx = 0;
-  if (best_flip) *best_flip = 0;
-  if (n_search == 0) return SCGPU_OK;
-  k_gather<<<1, 128, 0, st>>>(h->rec_single.as<unsigned char>(), h->L, h->db, q);
-  h->launches++;
-  if (h->exh) {
-    RET(h->x_best.reserve(sizeof(Best)));
-    CK(cudaEventRecord(h->ev_t0, st));
-    RET(launch_exhaustive_fast(h, h->rec_single.as<unsigned char>(), 1, &n_search, h->x_best.as<Best>(), st, h->ev_t0, h->ev_t1, flipped));
-    CK(cudaEventRecord(h->ev_t2, st));
-    h->timing_valid = true;
-    Best b;
-    CK(cudaMemcpyAsync(&b, h->x_best.p, sizeof b, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if ((unsigned)b.rank <= EXH_CAND_CAP) {
-      *best_dist = b.dist;
-      *best_shift = b.shift & 0x3fffffff;
-      *best_idx = b.idx;
-      if (best_flip) *best_flip = (b.shift >> 30) & 1;
-      h->last_exh_rescored = (unsigned)b.rank;
-      return SCGPU_OK;
-    }
-    // more near-ties than the rescoring list holds (e.g. a database of duplicates): score everything exactly
+// ---- exhaustive search: shard-local core + reduction over the shards behind the handle -------------------------------
+struct ExhWin {
+  double dist = 10000000.0;
+  int shift = 0;
+  int64_t idx = 0;
+  int flip = 0;
+  bool found = false;
+};
+// the loop of SC.cpp:296-311 over every entry: strict-min in (index, forward-before-flipped) order
+static void exh_take(ExhWin& w, double d, int shift, int64_t idx, int flip) {
+  if (!(d < 10000000.0)) return;
+  if (!w.found || d < w.dist || (d == w.dist && (idx < w.idx || (idx == w.idx && flip < w.flip)))) {
+    w.dist = d;
+    w.shift = shift;
+    w.idx = idx;
+    w.flip = flip;
+    w.found = true;
   }
-  h->last_exh_rescored = (unsigned)n_search;
-  const size_t n = (size_t)n_search;
+}
+
+// Every local entry with global index < n_search scored by the exact FP64 pair kernel (no screening); query record on the device.
+static int exhaustive_exact_local(scgpu_handle* h, const unsigned char* d_qrec, uint64_t n_search, int flipped, ExhWin* out) {
+  cudaStream_t st = h->stream;
+  const size_t n = (size_t)local_count(h, n_search);
+  *out = ExhWin();
+  if (n == 0) return SCGPU_OK;
+  const uint64_t G = (uint64_t)h->cfg.shard_count, r = (uint64_t)h->cfg.shard_rank;
   DevBuf keys, pd, ps, ns;
   RET(keys.reserve(n * 8));
   RET(pd.reserve(n * 8 * 2));
   RET(ps.reserve(n * 4 * 2));
   RET(ns.reserve(8));
   std::vector<uint64_t> hk(n);
-  for (size_t i = 0; i < n; ++i) hk[i] = i;
+  for (size_t i = 0; i < n; ++i) hk[i] = i * G + r;
   uint64_t one = n_search;
   CK(cudaMemcpyAsync(keys.p, hk.data(), n * 8, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ns.p, &one, 8, cudaMemcpyHostToDevice, st));
@@ -1247,7 +2042,7 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
       const size_t m = n - s0 < slab ? n - s0 : slab;
       // one "query" with m candidate slots per launch (grid.x = slots)
       ScoreParams p;
-      p.qrecords = h->rec_single.as<unsigned char>();
+      p.qrecords = d_qrec;
       p.L = h->L;
       p.db = h->db;
       p.keys = keys.as<unsigned long long>() + s0;
@@ -1258,6 +2053,7 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
       p.pair_shift = ps.as<int>() + f * n + s0;
       p.flip = f;
       p.active = nullptr;
+      p.peers = PeerTab{};
       k_score<<<dim3((unsigned)m, 1), 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p);
       h->launches++;
       if (cudaGetLastError() != cudaSuccess) rc = fail(SCGPU_E_CUDA, "k_score launch failed");
@@ -1272,61 +2068,105 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
   ps.release();
   ns.release();
   if (rc != SCGPU_OK) return rc;
-  // strict-min in (index, forward-before-flipped) order: the argmin reduction of SC.cpp:296-311 over all entries
   for (size_t i = 0; i < n; ++i)
-    for (int f = 0; f <= (flipped ? 1 : 0); ++f) {
-      const double d = hd[f * n + i];
-      if (d < *best_dist) {
-        *best_dist = d;
-        *best_shift = hs[f * n + i];
-        *best_idx = (int64_t)i;
-        if (best_flip) *best_flip = f;
-      }
+    for (int f = 0; f <= (flipped ? 1 : 0); ++f) exh_take(*out, hd[f * n + i], hs[f * n + i], (int64_t)hk[i], f);
+  return SCGPU_OK;
+}
+
+// phase 1 (asynchronous): gather the query records of stored entries q[0..nq) (from whichever shard holds them), screen +
+// rescore this shard's entries; per-query Best -> h->x_best
+static int exh_enqueue(scgpu_handle* h, scgpu_handle* group, const uint64_t* q, const uint64_t* n_search, size_t nq, int flipped) {
+  CK(cudaSetDevice(h->cfg.device));
+  RET(join_replay(h));
+  h->mutation++;
+  cudaStream_t st = h->stream;
+  if (group) RET(group_wait_appends(group, h, st));
+  RET(h->records.reserve(nq * h->L.rec_bytes));
+  RET(h->x_best.reserve(nq * sizeof(Best)));
+  RET(h->q_idx.reserve(nq * sizeof(uint64_t)));
+  CK(cudaMemcpyAsync(h->q_idx.p, q, nq * 8, cudaMemcpyHostToDevice, st));  // (pageable source: staged by the runtime before it returns)
+  CK(cudaEventRecord(h->ev_t0, st));
+  k_gather<<<(unsigned)nq, 128, 0, st>>>(h->records.as<unsigned char>(), h->L, h->db, h->peers, 0, h->q_idx.as<unsigned long long>());
+  h->launches++;
+  CK(cudaGetLastError());
+  if (h->exh) {
+    const size_t per = flipped ? EXH_MAX_BATCH / 2 : EXH_MAX_BATCH;
+    for (size_t i0 = 0; i0 < nq; i0 += per) {
+      const size_t m = nq - i0 < per ? nq - i0 : per;
+      RET(launch_exhaustive_fast(h, h->records.as<unsigned char>() + i0 * h->L.rec_bytes, m, n_search + i0, h->x_best.as<Best>() + i0, st,
+                                 nq == 1 ? h->ev_t0 : nullptr, nq == 1 ? h->ev_t1 : nullptr, flipped));
     }
+  }
+  if (nq != 1 || !h->exh) CK(cudaEventRecord(h->ev_t1, st));
+  CK(cudaEventRecord(h->ev_t2, st));
+  h->timing_valid = true;
+  return SCGPU_OK;
+}
+
+// phase 2: wait, read the shard's winners; a query whose rescoring list overflowed (more near-ties than EXH_CAND_CAP, e.g. a
+// database of duplicates -- the list is shared by the queries of a batch) is redone exactly over every local entry
+static int exh_collect(scgpu_handle* h, const uint64_t* n_search, size_t nq, int flipped, std::vector<ExhWin>& out) {
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  out.assign(nq, ExhWin());
+  std::vector<Best> b(nq);
+  if (h->exh) CK(cudaMemcpyAsync(b.data(), h->x_best.p, nq * sizeof(Best), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h->last_exh_rescored = 0;
+  for (size_t i = 0; i < nq; ++i) {
+    if (local_count(h, n_search[i]) == 0) continue;
+    if (h->exh && (unsigned)b[i].rank <= EXH_CAND_CAP) {
+      if (b[i].dist < 10000000.0) exh_take(out[i], b[i].dist, b[i].shift & 0x3fffffff, b[i].idx, (b[i].shift >> 30) & 1);
+      h->last_exh_rescored = (unsigned)b[i].rank;
+      continue;
+    }
+    RET(exhaustive_exact_local(h, h->records.as<unsigned char>() + i * h->L.rec_bytes, n_search[i], flipped, &out[i]));
+    h->last_exh_rescored = (unsigned)local_count(h, n_search[i]);
+  }
+  return SCGPU_OK;
+}
+
+static int exhaustive_any(scgpu_handle* h, const uint64_t* q, const uint64_t* n_search, size_t nq, int flipped, std::vector<ExhWin>& win) {
+  if (!h->is_group && h->cfg.shard_count != 1)
+    return fail(SCGPU_E_INVALID, "scgpu_exhaustive* needs the whole database behind the handle; use scgpu_stage_exhaustive for shards");
+  for (size_t i = 0; i < nq; ++i)
+    if (q[i] >= h->n_global || n_search[i] > h->n_global) return fail(SCGPU_E_INVALID, "range outside the database");
+  win.assign(nq, ExhWin());
+  if (nq == 0) return SCGPU_OK;
+  std::vector<scgpu_handle*> hs;
+  if (h->is_group) hs = h->shards;
+  else hs.push_back(h);
+  for (scgpu_handle* s : hs) RET(exh_enqueue(s, h->is_group ? h : nullptr, q, n_search, nq, flipped));
+  std::vector<ExhWin> part;
+  for (scgpu_handle* s : hs) {
+    RET(exh_collect(s, n_search, nq, flipped, part));
+    for (size_t i = 0; i < nq; ++i)
+      if (part[i].found) exh_take(win[i], part[i].dist, part[i].shift, part[i].idx, part[i].flip);
+  }
+  return SCGPU_OK;
+}
+
+int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped, double* best_dist, int* best_shift, int64_t* best_idx,
+                     int* best_flip) {
+  if (!h || !best_dist || !best_shift || !best_idx) return fail(SCGPU_E_INVALID, "null argument");
+  std::vector<ExhWin> w;
+  RET(exhaustive_any(h, &q, &n_search, 1, flipped, w));
+  *best_dist = w[0].dist;
+  *best_shift = w[0].shift;
+  *best_idx = w[0].idx;
+  if (best_flip) *best_flip = w[0].flip;
   return SCGPU_OK;
 }
 
 int scgpu_exhaustive_batched(scgpu_handle* h, const uint64_t* q, const uint64_t* n_search, size_t nq, double* best_dist, int* best_shift,
                              int64_t* best_idx) {
   if (!h || ((!q || !n_search || !best_dist || !best_shift || !best_idx) && nq)) return fail(SCGPU_E_INVALID, "null argument");
-  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "scgpu_exhaustive_batched is single-shard; use the staged API for shards");
-  for (size_t i = 0; i < nq; ++i)
-    if (q[i] >= h->n_global || n_search[i] > h->n_global) return fail(SCGPU_E_INVALID, "range outside the database");
-  if (nq == 0) return SCGPU_OK;
-  if (!h->exh) {
-    for (size_t i = 0; i < nq; ++i) RET(scgpu_exhaustive(h, q[i], n_search[i], 0, best_dist + i, best_shift + i, best_idx + i, nullptr));
-    return SCGPU_OK;
-  }
-  CK(cudaSetDevice(h->cfg.device));
-  cudaStream_t st = h->stream;
-  RET(h->records.reserve(nq * h->L.rec_bytes));
-  RET(h->x_best.reserve(nq * sizeof(Best)));
-  CK(cudaEventRecord(h->ev_t0, st));
-  CK(cudaEventRecord(h->ev_t1, st));
+  std::vector<ExhWin> w;
+  RET(exhaustive_any(h, q, n_search, nq, 0, w));
   for (size_t i = 0; i < nq; ++i) {
-    unsigned char* rec = h->records.as<unsigned char>() + i * h->L.rec_bytes;
-    k_gather<<<1, 128, 0, st>>>(rec, h->L, h->db, q[i]);
-    h->launches++;
-  }
-  for (size_t i0 = 0; i0 < nq; i0 += EXH_MAX_BATCH) {
-    const size_t m = nq - i0 < EXH_MAX_BATCH ? nq - i0 : EXH_MAX_BATCH;
-    RET(launch_exhaustive_fast(h, h->records.as<unsigned char>() + i0 * h->L.rec_bytes, m, n_search + i0, h->x_best.as<Best>() + i0, st, nullptr,
-                               nullptr));
-  }
-  CK(cudaEventRecord(h->ev_t2, st));
-  h->timing_valid = true;
-  std::vector<Best> b(nq);
-  CK(cudaMemcpyAsync(b.data(), h->x_best.p, nq * sizeof(Best), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  for (size_t i = 0; i < nq; ++i) {
-    if (n_search[i] == 0 || (unsigned)b[i].rank > EXH_CAND_CAP) {
-      RET(scgpu_exhaustive(h, q[i], n_search[i], 0, best_dist + i, best_shift + i, best_idx + i, nullptr));
-      continue;
-    }
-    best_dist[i] = b[i].dist;
-    best_shift[i] = b[i].shift & 0x3fffffff;
-    best_idx[i] = b[i].idx;
-    h->last_exh_rescored = (unsigned)b[i].rank;
+    best_dist[i] = w[i].dist;
+    best_shift[i] = w[i].shift;
+    best_idx[i] = w[i].idx;
   }
   return SCGPU_OK;
 }
@@ -1334,48 +2174,110 @@ int scgpu_exhaustive_batched(scgpu_handle* h, const uint64_t* q, const uint64_t*
 int scgpu_exhaustive_stats(scgpu_handle* h, uint64_t* rescored) {
   if (!h || !rescored) return fail(SCGPU_E_INVALID, "null argument");
   *rescored = h->last_exh_rescored;
+  for (scgpu_handle* s : h->shards) *rescored += s->last_exh_rescored;
   return SCGPU_OK;
 }
 
+// Flat binary database file: header | float descriptors (column-major R*S each), entry 0 first.
+struct SaveHeader {
+  char magic[8];  // "SCGPUDB2"
+  uint64_t R, S, n;
+  uint64_t counter, n_tree;  // tree-snapshot state (SC.cpp:264-276): detects after a load continue the saved run's sequence
+  double lidar_height, max_radius;  // the constants that shaped the stored descriptors: a handle with others must not load them
+};
+
 int scgpu_save(scgpu_handle* h, const char* path) {
   if (!h || !path) return fail(SCGPU_E_INVALID, "null argument");
-  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "save is single-shard");
-  CK(cudaSetDevice(h->cfg.device));
-  CK(cudaStreamSynchronize(h->stream));
-  const uint64_t n = h->n_global;
-  std::vector<float> sc((size_t)n * h->L.RS);
-  if (n) CK(cudaMemcpy(sc.data(), h->db.sc, sc.size() * sizeof(float), cudaMemcpyDeviceToHost));
-  FILE* f = fopen(path, "wb");
-  if (!f) return fail(SCGPU_E_IO, "cannot open %s for writing", path);
-  const char magic[8] = {'S', 'C', 'G', 'P', 'U', 'D', 'B', '1'};
-  uint64_t hdr[4] = {(uint64_t)h->L.R, (uint64_t)h->L.S, n, 0};
-  bool ok = fwrite(magic, 1, 8, f) == 8 && fwrite(hdr, 8, 4, f) == 4 && fwrite(&h->cfg, sizeof h->cfg, 1, f) == 1 &&
-            (sc.empty() || fwrite(sc.data(), sizeof(float), sc.size(), f) == sc.size());
-  ok = (fclose(f) == 0) && ok;
-  return ok ? SCGPU_OK : fail(SCGPU_E_IO, "short write to %s", path);
+  if (!h->is_group && h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "save needs the whole database behind the handle");
+  std::vector<scgpu_handle*> hs;
+  if (h->is_group) hs = h->shards;
+  else hs.push_back(h);
+  const uint64_t n = h->n_global, G = hs.size();
+  const size_t RS = (size_t)h->L.RS;
+  try {
+    std::vector<std::vector<float>> part(G);
+    for (uint64_t r = 0; r < G; ++r) {
+      scgpu_handle* s = hs[r];
+      CK(cudaSetDevice(s->cfg.device));
+      CK(cudaStreamSynchronize(s->stream));
+      CK(cudaStreamSynchronize(s->qstream));
+      part[r].resize((size_t)local_count(s, n) * RS);
+      if (!part[r].empty()) CK(cudaMemcpy(part[r].data(), s->db.sc, part[r].size() * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(SCGPU_E_IO, "cannot open %s for writing", path);
+    SaveHeader hd{};
+    memcpy(hd.magic, "SCGPUDB2", 8);
+    hd.R = (uint64_t)h->L.R;
+    hd.S = (uint64_t)h->L.S;
+    hd.n = n;
+    hd.counter = (uint64_t)hs[0]->counter;
+    hd.n_tree = hs[0]->n_tree;
+    hd.lidar_height = h->cfg.lidar_height;
+    hd.max_radius = h->cfg.max_radius;
+    bool ok = fwrite(&hd, sizeof hd, 1, f) == 1;
+    if (G == 1) {
+      ok = ok && (part[0].empty() || fwrite(part[0].data(), sizeof(float), part[0].size(), f) == part[0].size());
+    } else {
+      for (uint64_t i = 0; i < n && ok; ++i) ok = fwrite(part[i % G].data() + (size_t)(i / G) * RS, sizeof(float), RS, f) == RS;
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? SCGPU_OK : fail(SCGPU_E_IO, "short write to %s", path);
+  } catch (const std::exception& e) {
+    return fail(SCGPU_E_IO, "save: %s", e.what());
+  }
 }
 
 int scgpu_load(scgpu_handle* h, const char* path) {
   if (!h || !path) return fail(SCGPU_E_INVALID, "null argument");
-  if (h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "load is single-shard");
+  if (!h->is_group && h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "load needs the whole database behind the handle");
+  if (h->n_global != 0) return fail(SCGPU_E_INVALID, "load replaces the database: the handle must be empty (scgpu_truncate(h, 0) first)");
   FILE* f = fopen(path, "rb");
   if (!f) return fail(SCGPU_E_IO, "cannot open %s", path);
-  char magic[8];
-  uint64_t hdr[4];
-  scgpu_config saved;
-  if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "SCGPUDB1", 8) != 0 || fread(hdr, 8, 4, f) != 4 || fread(&saved, sizeof saved, 1, f) != 1) {
+  SaveHeader hd{};
+  if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "SCGPUDB2", 8) != 0) {
     fclose(f);
     return fail(SCGPU_E_IO, "%s is not a scgpu database", path);
   }
-  if ((int)hdr[0] != h->L.R || (int)hdr[1] != h->L.S) {
+  if ((int)hd.R != h->L.R || (int)hd.S != h->L.S || hd.lidar_height != h->cfg.lidar_height || hd.max_radius != h->cfg.max_radius) {
     fclose(f);
-    return fail(SCGPU_E_INVALID, "database is %llux%llu, handle is %dx%d", (unsigned long long)hdr[0], (unsigned long long)hdr[1], h->L.R, h->L.S);
+    return fail(SCGPU_E_INVALID, "database was built with %llux%llu, lidar height %g, radius %g; the handle has %dx%d, %g, %g",
+                (unsigned long long)hd.R, (unsigned long long)hd.S, hd.lidar_height, hd.max_radius, h->L.R, h->L.S, h->cfg.lidar_height,
+                h->cfg.max_radius);
   }
-  std::vector<float> sc((size_t)hdr[2] * h->L.RS);
-  const bool ok = sc.empty() || fread(sc.data(), sizeof(float), sc.size(), f) == sc.size();
+  // the entry count comes from an untrusted file: check it against the file's size and the 32-bit index space before sizing anything
+  const size_t RS = (size_t)h->L.RS;
+  long here = ftell(f);
+  fseek(f, 0, SEEK_END);
+  const long end = ftell(f);
+  fseek(f, here, SEEK_SET);
+  if (hd.n > 0xffffffffull || here < 0 || end < here || (uint64_t)(end - here) != hd.n * RS * sizeof(float)) {
+    fclose(f);
+    return fail(SCGPU_E_IO, "%s: header says %llu entries, the file holds %lld bytes of descriptors", path, (unsigned long long)hd.n,
+                (long long)(end - here));
+  }
+  int rc = SCGPU_OK;
+  try {
+    const size_t batch = 8192;
+    std::vector<float> buf(std::min<size_t>(batch, (size_t)hd.n) * RS);
+    for (uint64_t i0 = 0; i0 < hd.n && rc == SCGPU_OK; i0 += batch) {
+      const size_t m = (size_t)std::min<uint64_t>(batch, hd.n - i0);
+      if (fread(buf.data(), sizeof(float), m * RS, f) != m * RS) rc = fail(SCGPU_E_IO, "short read from %s", path);
+      else rc = scgpu_append_descs(h, buf.data(), m);
+    }
+  } catch (const std::exception& e) {
+    rc = fail(SCGPU_E_IO, "load: %s", e.what());
+  }
   fclose(f);
-  if (!ok) return fail(SCGPU_E_IO, "short read from %s", path);
-  return scgpu_append_descs(h, sc.data(), (size_t)hdr[2]);
+  if (rc != SCGPU_OK) return rc;
+  std::vector<scgpu_handle*> hs;
+  if (h->is_group) hs = h->shards;
+  else hs.push_back(h);
+  for (scgpu_handle* s : hs) {
+    s->counter = (long long)hd.counter;
+    s->n_tree = hd.n_tree;
+  }
+  return SCGPU_OK;
 }
 
 int scgpu_probe_atanf(const float* x, size_t n, float* out) {
@@ -1397,6 +2299,7 @@ int scgpu_probe_atanf(const float* x, size_t n, float* out) {
 int scgpu_probe_bins(scgpu_handle* h, const float* xyz, size_t n, int32_t* bin, float* height, float* theta) {
   if (!h || ((!xyz || !bin || !height || !theta) && n)) return fail(SCGPU_E_INVALID, "null argument");
   if (n == 0) return SCGPU_OK;
+  h = GROUP_FIRST(h);
   CK(cudaSetDevice(h->cfg.device));
   float *dx = nullptr, *dh = nullptr, *dt = nullptr;
   int* db = nullptr;
@@ -1422,6 +2325,7 @@ int scgpu_probe_bins(scgpu_handle* h, const float* xyz, size_t n, int32_t* bin, 
 
 int scgpu_probe_selfcheck(scgpu_handle* h, uint64_t n, uint64_t seed, int mode, uint64_t* mismatches, uint64_t* fallbacks, float* first_bad) {
   if (!h || !mismatches || !fallbacks) return fail(SCGPU_E_INVALID, "null argument");
+  h = GROUP_FIRST(h);
   CK(cudaSetDevice(h->cfg.device));
   unsigned long long* d = nullptr;
   float* db = nullptr;
@@ -1491,6 +2395,10 @@ int scgpu_stage_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t
 
 int scgpu_set_downsample_leaf(scgpu_handle* h, float leaf) {
   if (!h) return fail(SCGPU_E_INVALID, "null handle");
+  if (h->is_group) {
+    for (scgpu_handle* s : h->shards) RET(scgpu_set_downsample_leaf(s, leaf));
+    return SCGPU_OK;
+  }
   if (!(leaf >= 0.f) || !(leaf < 1e30f)) return fail(SCGPU_E_INVALID, "leaf size must be >= 0 (0 = no downsampling) and finite");
   if (leaf > 0.f && vox_smem_bytes(h->L.RS) > 227 * 1024) return fail(SCGPU_E_INVALID, "descriptor too large for the voxel kernel's shared memory");
   h->voxel_leaf = leaf;
@@ -1501,6 +2409,7 @@ int scgpu_voxel_downsample(scgpu_handle* h, const void* pts, size_t n, size_t st
                            size_t cap, size_t* out_n, int32_t* min_b, int32_t* div_b, int32_t* status) {
   if (!h || !out_n || (n && !pts)) return fail(SCGPU_E_INVALID, "null argument");
   if (stride_bytes < 12 || (stride_bytes & 3)) return fail(SCGPU_E_INVALID, "stride must be >= 12 and a multiple of 4");
+  h = GROUP_FIRST(h);
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = h->stream;
   const unsigned ocap = (unsigned)(n ? n : 1);  // a voxel per point at most
@@ -1539,7 +2448,16 @@ int scgpu_stage_append(scgpu_handle* h, const void* d_records, uint64_t first_gl
 
 int scgpu_stage_set_size(scgpu_handle* h, uint64_t n_global) {
   if (!h) return fail(SCGPU_E_INVALID, "null argument");
-  if (local_count(h, n_global) > h->db.cap) return fail(SCGPU_E_INVALID, "size beyond this shard's stored entries");
+  if (h->is_group) return fail(SCGPU_E_INVALID, "the staged API addresses one shard, not a device-list handle");
+  // only slots that have been written may become searchable
+  if (local_count(h, n_global) > h->n_written) return fail(SCGPU_E_INVALID, "size beyond this shard's stored entries");
+  if (n_global < h->n_global) {  // shrinking = scgpu_truncate: screening copies above the cut and the snapshot state are void
+    const uint64_t keep = local_count(h, n_global);
+    if (h->x_upto > keep) h->x_upto = keep;
+    h->counter = 0;
+    h->n_tree = 0;
+  }
+  h->mutation++;
   h->n_global = n_global;
   return SCGPU_OK;
 }
@@ -1570,9 +2488,10 @@ int scgpu_stage_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint
 int scgpu_stage_gather(scgpu_handle* h, uint64_t global_idx, void* d_record, void* stream) {
   if (!h || !d_record) return fail(SCGPU_E_INVALID, "null argument");
   if (global_idx >= h->n_global) return fail(SCGPU_E_INVALID, "entry out of range");
-  if ((int)(global_idx % (uint64_t)h->cfg.shard_count) != h->cfg.shard_rank) return fail(SCGPU_E_INVALID, "entry lives on another shard");
+  if (!(h->peer && h->attached) && (int)(global_idx % (uint64_t)h->cfg.shard_count) != h->cfg.shard_rank)
+    return fail(SCGPU_E_INVALID, "entry lives on another shard");
   CK(cudaSetDevice(h->cfg.device));
-  k_gather<<<1, 128, 0, ST(stream)>>>(static_cast<unsigned char*>(d_record), h->L, h->db, global_idx / (uint64_t)h->cfg.shard_count);
+  k_gather<<<1, 128, 0, ST(stream)>>>(static_cast<unsigned char*>(d_record), h->L, h->db, h->peers, global_idx, nullptr);
   h->launches++;
   CK(cudaGetLastError());
   return SCGPU_OK;
@@ -1596,6 +2515,99 @@ int scgpu_stage_finalize(scgpu_handle* h, const void* d_best_parts, int parts, s
   CK(cudaSetDevice(h->cfg.device));
   return launch_finalize(h, static_cast<const Best*>(d_best_parts), parts, nq, d_ns, d_loop_id, d_yaw, d_nearest_dist, d_nearest_idx,
                          d_nearest_shift, ST(stream));
+}
+
+// The exhaustive search of this shard for ONE query record, every local entry scored exactly (no screening): what a caller of
+// scgpu_stage_exhaustive falls back to when a result reports more rescored candidates than the list holds (n_rescored >
+// SCGPU_EXH_LIST_CAP).  Synchronises the handle's own stream; d_query_record must be complete when called.
+int scgpu_stage_exhaustive_exact(scgpu_handle* h, const void* d_query_record, uint64_t n_search, void* d_best_out) {
+  if (!h || !d_query_record || !d_best_out) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->is_group) return fail(SCGPU_E_INVALID, "the staged API addresses one shard, not a device-list handle");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  ExhWin w;
+  RET(exhaustive_exact_local(h, static_cast<const unsigned char*>(d_query_record), n_search, 0, &w));
+  Best b;
+  b.dist = w.found ? w.dist : 10000000.0;
+  b.rank = 0;
+  b.shift = w.shift;
+  b.idx = w.idx;
+  CK(cudaMemcpy(d_best_out, &b, sizeof b, cudaMemcpyHostToDevice));
+  return SCGPU_OK;
+}
+
+// ---- peer-sharded database, one process per GPU -------------------------------------------------------------------------
+
+int scgpu_peer_export(scgpu_handle* h, void* blob, size_t blob_bytes) {
+  if (!h || !blob) return fail(SCGPU_E_INVALID, "null argument");
+  if (!h->peer || h->is_group) return fail(SCGPU_E_INVALID, "not a peer-sharded shard handle (SCGPU_FLAG_PEER)");
+  if (blob_bytes < SCGPU_PEER_BLOB_BYTES) return fail(SCGPU_E_INVALID, "blob must hold %d bytes", SCGPU_PEER_BLOB_BYTES);
+  CK(cudaSetDevice(h->cfg.device));
+  memset(blob, 0, SCGPU_PEER_BLOB_BYTES);
+  cudaIpcMemHandle_t mh;
+  CK(cudaIpcGetMemHandle(&mh, h->slab));
+  static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  unsigned char* b = static_cast<unsigned char*>(blob);
+  memcpy(b, &mh, 64);
+  uint64_t meta[4] = {h->slab_bytes, h->db.cap, (uint64_t)h->cfg.shard_rank, (uint64_t)h->cfg.shard_count};
+  memcpy(b + 64, meta, sizeof meta);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->cfg.device));
+  memcpy(b + 96, &prop.uuid, 16);  // lets the peers see whether two shards share a physical GPU
+  return SCGPU_OK;
+}
+
+int scgpu_peer_attach(scgpu_handle* h, const void* blobs, int n) {
+  if (!h || !blobs) return fail(SCGPU_E_INVALID, "null argument");
+  if (!h->peer || h->is_group) return fail(SCGPU_E_INVALID, "not a peer-sharded shard handle (SCGPU_FLAG_PEER)");
+  if (n != h->cfg.shard_count) return fail(SCGPU_E_INVALID, "%d blobs for %d shards", n, h->cfg.shard_count);
+  if (h->attached) return fail(SCGPU_E_INVALID, "already attached");
+  CK(cudaSetDevice(h->cfg.device));
+  const unsigned char* b = static_cast<const unsigned char*>(blobs);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->cfg.device));
+  for (int s = 0; s < n; ++s) {
+    const unsigned char* bs = b + (size_t)s * SCGPU_PEER_BLOB_BYTES;
+    uint64_t meta[4];
+    memcpy(meta, bs + 64, sizeof meta);
+    if (meta[0] != h->slab_bytes || meta[1] != h->db.cap || meta[2] != (uint64_t)s || meta[3] != (uint64_t)n)
+      return fail(SCGPU_E_INVALID, "shard %d was created with a different configuration (slab %llu vs %llu bytes)", s,
+                  (unsigned long long)meta[0], (unsigned long long)h->slab_bytes);
+    if (s == h->cfg.shard_rank) {
+      peer_fill(h, s, h->slab);
+      continue;
+    }
+    if (memcmp(bs + 96, &prop.uuid, 16) == 0)
+      return fail(SCGPU_E_INVALID, "shards %d and %d are on the same GPU: the cross-process barrier needs one GPU per process", s, h->cfg.shard_rank);
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, bs, 64);
+    void* base = nullptr;
+    CK(cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_base[s] = base;
+    peer_fill(h, s, base);
+  }
+  h->peers.G = n;
+  h->peers.rank = h->cfg.shard_rank;
+  h->peers.cap = h->db.cap;
+  h->attached = true;
+  return SCGPU_OK;
+}
+
+int scgpu_peer_replay_async(scgpu_handle* h, const void* pts, size_t n_total, size_t pts_per_scan, size_t stride, int location) {
+  if (!h || (!pts && n_total && pts_per_scan)) return fail(SCGPU_E_INVALID, "null argument");
+  if (!h->peer || h->is_group || !h->attached) return fail(SCGPU_E_INVALID, "needs an attached peer-sharded shard handle");
+  if (n_total == 0) return SCGPU_OK;
+  const uint64_t first = h->n_global;
+  std::vector<ReplayShard> sh;
+  sh.push_back({h, pts, 0});
+  return replay_enqueue(sh, first, n_total, pts_per_scan, stride, location, true);
+}
+
+int scgpu_peer_barrier(scgpu_handle* h, void* stream) {
+  if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (!h->peer || h->is_group || !h->attached) return fail(SCGPU_E_INVALID, "needs an attached peer-sharded shard handle");
+  CK(cudaSetDevice(h->cfg.device));
+  return launch_peer_barrier(h, 0, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -659,6 +659,8 @@ struct CandScreenParams {
   const unsigned long long* n_search;   // [nq]
   int K;
   float* d32;                           // [nq][K] out: approx distance; -1 = rescore; +inf = cannot win / not mine
+  PeerTab peers;                        // peers.G > 0: every candidate is screened here; its screening copy is fetched from the
+                                        // owner shard by the same TMA bulk copy, over NVLink peer memory
 };
 
 // one candidate staged in shared memory: screening copy of the descriptor + its sector key / aux record
@@ -700,23 +702,28 @@ __global__ void __launch_bounds__(CW * 32) k_cand_screen(const CandScreenParams 
   const double* qnorm = reinterpret_cast<const double*>(qrec + p.L.off_norm);
   const unsigned long long* qkeys = p.keys + (size_t)q * p.K;
 
-  // candidate k of this query: is it this shard's, and which local entry (warp-uniform)
-  auto owned = [&](int k, unsigned long long* l) {
+  // candidate k of this query: is it scored here, which shard holds it and which local entry (warp-uniform)
+  const unsigned long long nshards = p.peers.G ? (unsigned long long)p.peers.G : (unsigned long long)p.db.G;
+  auto owned = [&](int k, unsigned long long* l, int* owner) {
     const unsigned long long key = qkeys[k];
     const unsigned long long g = (key == KEY_NONE) ? 0ull : (key & 0xffffffffull);
-    *l = g / (unsigned long long)p.db.G;
-    return !early && (int)(g % (unsigned long long)p.db.G) == p.db.rank;
+    *l = g / nshards;
+    *owner = (int)(g % nshards);
+    return !early && (p.peers.G != 0 || *owner == p.db.rank);
   };
   int issued = 0, consumed = 0, k_issue = warp;  // fetches requested / used so far; next candidate to look at for a fetch
   auto fetch_more = [&]() {
     while (issued - consumed < NS && k_issue < p.K) {
       unsigned long long l;
-      if (owned(k_issue, &l)) {
+      int owner;
+      if (owned(k_issue, &l, &owner)) {
         if (lane == 0) {
           const int s = issued % NS;
+          const float* src_hat = p.peers.G ? p.peers.sc_hat[owner] : p.xdb.sc_hat;
+          const unsigned char* src_vk = p.peers.G ? p.peers.vk[owner] : p.xdb.vk;
           mbar_arrive_expect_tx(&full[s], (unsigned)sizeof(CandSlot<R, S>));
-          tma_bulk_g2s(slots[s].sc_hat, p.xdb.sc_hat + l * (R * S), R * S * 4u, &full[s]);
-          tma_bulk_g2s(&slots[s].vk, p.xdb.vk + l * sizeof(ExhVkRec<S>), (unsigned)sizeof(ExhVkRec<S>), &full[s]);
+          tma_bulk_g2s(slots[s].sc_hat, src_hat + l * (R * S), R * S * 4u, &full[s]);
+          tma_bulk_g2s(&slots[s].vk, src_vk + l * sizeof(ExhVkRec<S>), (unsigned)sizeof(ExhVkRec<S>), &full[s]);
         }
         ++issued;
       }
@@ -766,7 +773,8 @@ __global__ void __launch_bounds__(CW * 32) k_cand_screen(const CandScreenParams 
   for (int k = warp; k < p.K; k += CW) {
     const size_t o = (size_t)q * p.K + k;
     unsigned long long l;
-    if (!owned(k, &l)) {
+    int owner;
+    if (!owned(k, &l, &owner)) {
       if (lane == 0) p.d32[o] = __int_as_float(0x7f800000);
       continue;
     }
@@ -853,7 +861,7 @@ constexpr int BUILD_UNROLL = 4;
 constexpr int BUILD_CHUNK = 256 * BUILD_UNROLL;  // points per chunk
 constexpr int BUILD_QCAP = 128;                  // undecided points parked per block (overflow: decided on the spot)
 
-template <int STRIDE, bool FAST, bool LH_FLOAT>  // STRIDE = 16 or 32 (bytes per point, 16-byte aligned base)
+template <int STRIDE, bool FAST, bool LH_FLOAT>  // STRIDE = 12, 16 or 32 (bytes per point, 16-byte aligned scan starts)
 __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* ring = smem_raw;                                             // [BUILD_STAGES][BUILD_CHUNK * STRIDE]
@@ -904,24 +912,29 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
     const unsigned pts = min((unsigned)BUILD_CHUNK, end - start - c * BUILD_CHUNK);
     const unsigned char* sp = ring + (size_t)slot * BUILD_CHUNK * STRIDE + (size_t)threadIdx.x * STRIDE;
     float px[BUILD_UNROLL], py[BUILD_UNROLL], pz[BUILD_UNROLL];
-    if (pts == BUILD_CHUNK) {  // full chunk: no bounds checks
-#pragma unroll
-      for (int u = 0; u < BUILD_UNROLL; ++u) {
+    // STRIDE 16 / 32: one 16-byte load per point; STRIDE 12 (packed xyz): three 4-byte loads, lane stride 3 words -- both
+    // conflict-free
+    auto take = [&](int u) {
+      if (STRIDE == 12) {
+        const float* f = reinterpret_cast<const float*>(sp + (size_t)u * 256 * STRIDE);
+        px[u] = f[0];
+        py[u] = f[1];
+        pz[u] = f[2];
+      } else {
         const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)u * 256 * STRIDE);
         px[u] = v.x;
         py[u] = v.y;
         pz[u] = v.z;
       }
+    };
+    if (pts == BUILD_CHUNK) {  // full chunk: no bounds checks
+#pragma unroll
+      for (int u = 0; u < BUILD_UNROLL; ++u) take(u);
     } else {
 #pragma unroll
       for (int u = 0; u < BUILD_UNROLL; ++u) {
         px[u] = py[u] = pz[u] = __int_as_float(0x7fc00000);  // NaN: dropped
-        if (u * 256 + threadIdx.x < pts) {
-          const float4 v = *reinterpret_cast<const float4*>(sp + (size_t)u * 256 * STRIDE);
-          px[u] = v.x;
-          py[u] = v.y;
-          pz[u] = v.z;
-        }
+        if (u * 256 + threadIdx.x < pts) take(u);
       }
     }
     __syncwarp();

@@ -497,15 +497,55 @@ struct Db {
   double* colnorm;
   unsigned long long cap;  // local capacity
   int rank, G;
+  // ring-key matrix addressing.  Sharded-by-all_gather / single shard: ringT is [R][cap] over LOCAL slots (ring_global = 0,
+  // ring_cap = cap).  Peer-sharded (PeerTab below): ringT is this shard's REPLICA of every shard's ring keys, [R][ring_cap]
+  // over GLOBAL indices (ring_global = 1), so that retrieval for a query runs on one device without a merge.
+  unsigned long long ring_cap;
+  int ring_global;
+};
+
+__host__ __device__ __forceinline__ unsigned long long ring_slot(const Db& db, unsigned long long g, unsigned long long l) {
+  return db.ring_global ? g : l;
+}
+
+// Peer-sharded database: every shard's arrays as seen from THIS device -- its own allocations and the other shards'
+// through NVLink peer mappings (cudaIpcOpenMemHandle between processes, cudaDeviceEnablePeerAccess inside one).  Global entry g
+// lives on shard g % G, local slot g / G.  G == 0: table unused.
+constexpr int MAX_SHARDS = 8;
+struct PeerTab {
+  int G, rank;
+  unsigned long long cap;  // local capacity, identical on every shard
+  const float* sc[MAX_SHARDS];
+  const double* sector[MAX_SHARDS];
+  const double* colnorm[MAX_SHARDS];
+  const float* sc_hat[MAX_SHARDS];          // screening copies (scgpu_exhaustive.cuh)
+  const unsigned char* vk[MAX_SHARDS];
+};
+
+// where a kernel that produces per-entry / per-query values also delivers them on other devices (peer stores)
+struct PushList {
+  int n;
+  void* dst[MAX_SHARDS];
 };
 
 // records [0,n) -> entries first_global + i*step (kept when owned)
+// push: the other shards' ring-key replicas (peer stores over NVLink); the ring key of a record is written there too
 __global__ void __launch_bounds__(128) k_append(const unsigned char* records, Layout L, Db db, unsigned long long first_global,
-                                                unsigned long long step) {
+                                                unsigned long long step, PushList push) {
   const unsigned long long g = first_global + blockIdx.x * step;
-  if ((int)(g % (unsigned long long)db.G) != db.rank) return;
   const unsigned long long l = g / (unsigned long long)db.G;
   const unsigned char* rec = records + (size_t)blockIdx.x * L.rec_bytes;
+  const bool mine = (int)(g % (unsigned long long)db.G) == db.rank;
+  if (db.ring_global) {  // every shard keeps every ring key
+    const float* ring = reinterpret_cast<const float*>(rec + L.off_ring);
+    for (int i = threadIdx.x; i < L.R; i += blockDim.x) {
+      const float v = ring[i];
+      const size_t o = (size_t)i * db.ring_cap + g;
+      db.ringT[o] = v;
+      for (int s = 0; s < push.n; ++s) static_cast<float*>(push.dst[s])[o] = v;
+    }
+  }
+  if (!mine) return;
   const float4* src4 = reinterpret_cast<const float4*>(rec);
   float4* dst4 = reinterpret_cast<float4*>(db.sc + l * L.RS);
   if ((L.RS & 3) == 0) {
@@ -516,22 +556,33 @@ __global__ void __launch_bounds__(128) k_append(const unsigned char* records, La
   const float* ring = reinterpret_cast<const float*>(rec + L.off_ring);
   const double* sector = reinterpret_cast<const double*>(rec + L.off_sector);
   const double* norm = reinterpret_cast<const double*>(rec + L.off_norm);
-  for (int i = threadIdx.x; i < L.R; i += blockDim.x) db.ringT[(size_t)i * db.cap + l] = ring[i];
+  if (!db.ring_global)
+    for (int i = threadIdx.x; i < L.R; i += blockDim.x) db.ringT[(size_t)i * db.cap + l] = ring[i];
   for (int i = threadIdx.x; i < L.S; i += blockDim.x) {
     db.sector[l * L.S + i] = sector[i];
     db.colnorm[l * L.S + i] = norm[i];
   }
 }
 
-// entries first_global + i -> records (single shard only): query records for stored entries
-__global__ void __launch_bounds__(128) k_gather(unsigned char* records, Layout L, Db db, unsigned long long first_global) {
-  const unsigned long long l = first_global + blockIdx.x;
+// stored entries -> records (query records for stored entries).  Block b takes global entry idx[b] (idx != null) or
+// first_global + b.  Single shard: the entry is local.  Peer-sharded (peers.G > 0): the entry is read from its owner
+// shard through the peer table, whichever shard that is.
+__global__ void __launch_bounds__(128) k_gather(unsigned char* records, Layout L, Db db, PeerTab peers, unsigned long long first_global,
+                                                const unsigned long long* idx) {
+  const unsigned long long g = idx ? idx[blockIdx.x] : first_global + blockIdx.x;
+  const unsigned long long G = peers.G ? (unsigned long long)peers.G : (unsigned long long)db.G;
+  const unsigned long long l = g / G;
+  const int o = (int)(g % G);
+  const float* sc = peers.G ? peers.sc[o] : db.sc;
+  const double* sector = peers.G ? peers.sector[o] : db.sector;
+  const double* colnorm = peers.G ? peers.colnorm[o] : db.colnorm;
   unsigned char* rec = records + (size_t)blockIdx.x * L.rec_bytes;
-  for (int i = threadIdx.x; i < L.RS; i += blockDim.x) reinterpret_cast<float*>(rec)[i] = db.sc[l * L.RS + i];
-  for (int i = threadIdx.x; i < L.R; i += blockDim.x) reinterpret_cast<float*>(rec + L.off_ring)[i] = db.ringT[(size_t)i * db.cap + l];
+  for (int i = threadIdx.x; i < L.RS; i += blockDim.x) reinterpret_cast<float*>(rec)[i] = sc[l * L.RS + i];
+  for (int i = threadIdx.x; i < L.R; i += blockDim.x)
+    reinterpret_cast<float*>(rec + L.off_ring)[i] = db.ringT[(size_t)i * db.ring_cap + ring_slot(db, g, l)];
   for (int i = threadIdx.x; i < L.S; i += blockDim.x) {
-    reinterpret_cast<double*>(rec + L.off_sector)[i] = db.sector[l * L.S + i];
-    reinterpret_cast<double*>(rec + L.off_norm)[i] = db.colnorm[l * L.S + i];
+    reinterpret_cast<double*>(rec + L.off_sector)[i] = sector[l * L.S + i];
+    reinterpret_cast<double*>(rec + L.off_norm)[i] = colnorm[l * L.S + i];
   }
 }
 
@@ -1022,6 +1073,7 @@ struct ScoreParams {
   int* pair_shift;    // [nq][K]; -1 = candidate not owned by this shard
   int flip;           // score the candidate with its columns reversed (composed "reverse loop" search)
   const unsigned* active;  // optional: only slots k < *active are scored (fixed-size grid over a device-side count)
+  PeerTab peers;      // peers.G > 0: every candidate is scored here, its data read from the owner shard (NVLink peer loads)
 };
 
 template <bool LIST>  // LIST: slot k of one flat list whose keys are (query index << 32 | global entry index)
@@ -1038,19 +1090,23 @@ __device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, in
   }
   const unsigned long long key = p.keys[o];
   const unsigned long long g = (!LIST && key == KEY_NONE) ? 0ull : (key & 0xffffffffull);
-  if ((int)(g % (unsigned long long)p.db.G) != p.db.rank) {
+  const unsigned long long G = p.peers.G ? (unsigned long long)p.peers.G : (unsigned long long)p.db.G;
+  const int owner = (int)(g % G);
+  if (!p.peers.G && owner != p.db.rank) {
     if (threadIdx.x == 0) {
       p.pair_dist[o] = 10000000.0;
       p.pair_shift[o] = -1;
     }
     return;
   }
-  const unsigned long long l = g / (unsigned long long)p.db.G;
+  const unsigned long long l = g / G;
   float *a, *b;
   PairSmem m = carve_pair_smem<float>(smem_raw, R, S, W, a, b);
   const unsigned char* qrec = p.qrecords + (size_t)q * p.L.rec_bytes;
   const float* qsc = reinterpret_cast<const float*>(qrec);
-  const float* csc = p.db.sc + l * p.L.RS;
+  const float* csc = (p.peers.G ? p.peers.sc[owner] : p.db.sc) + l * p.L.RS;
+  const double* csector = (p.peers.G ? p.peers.sector[owner] : p.db.sector) + l * S;
+  const double* cnorm = (p.peers.G ? p.peers.colnorm[owner] : p.db.colnorm) + l * S;
   const int RP = pair_pitch(R);
   const bool flip = LIST ? (key >> 63) != 0 : p.flip != 0;
   for (int i = threadIdx.x; i < p.L.RS; i += blockDim.x) {
@@ -1064,8 +1120,8 @@ __device__ __forceinline__ void score_pair(const ScoreParams& p, const int k, in
     const int ci = flip ? (S - 1 - i) : i;
     m.vk1[i] = qv[i];
     m.n1[i] = qn[i];
-    m.vk2[i] = p.db.sector[l * S + ci];
-    m.n2[i] = p.db.colnorm[l * S + ci];
+    m.vk2[i] = csector[ci];
+    m.n2[i] = cnorm[ci];
   }
   __syncthreads();
   const int align = fast_align_block(m, S);
@@ -1186,8 +1242,22 @@ __global__ void k_best(const double* pair_dist, const int* pair_shift, const uns
 
 // SC.cpp:317-336 over `parts` shard results: threshold and yaw.  yaw = deg2rad(float(shift * 360/S)) with
 // deg2rad(d) = float(double(d) * M_PI / 180.0) (SC.cpp:17-20, 333).
+// Result placement (peer-sharded replay: the queries of one shard are every G-th entry of the batch, and every shard gets every
+// result): query q goes to slot out_off + q * out_step of the local arrays and of the same arrays on the devices in `push`,
+// whose dst[s] is the base of a result block laid out like ResultBlock below.
+struct ResultBlock {  // capacity cap_q queries: double dist[cap_q] | int loop[cap_q] | float yaw[cap_q] | int idx[cap_q] | int shift[cap_q]
+  unsigned long long cap_q;
+  __host__ __device__ double* dist(void* base) const { return static_cast<double*>(base); }
+  __host__ __device__ int* loop(void* base) const { return reinterpret_cast<int*>(static_cast<unsigned char*>(base) + cap_q * 8); }
+  __host__ __device__ float* yaw(void* base) const { return reinterpret_cast<float*>(static_cast<unsigned char*>(base) + cap_q * 12); }
+  __host__ __device__ int* idx(void* base) const { return reinterpret_cast<int*>(static_cast<unsigned char*>(base) + cap_q * 16); }
+  __host__ __device__ int* shift(void* base) const { return reinterpret_cast<int*>(static_cast<unsigned char*>(base) + cap_q * 20); }
+  __host__ __device__ size_t bytes() const { return (size_t)cap_q * 24; }
+};
+
 __global__ void k_finalize(const Best* parts_in, int parts, unsigned nq, const unsigned long long* n_search, int K, int S,
-                           double thres, int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift) {
+                           double thres, int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift,
+                           unsigned out_off, unsigned out_step, ResultBlock rb, PushList push) {
   const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   double dist = 10000000.0;
@@ -1213,11 +1283,56 @@ __global__ void k_finalize(const Best* parts_in, int parts, unsigned nq, const u
     const float deg = __double2float_rn(__dmul_rn((double)shift, unit));           // SC.cpp:333 argument narrowing
     y = __double2float_rn(__ddiv_rn(__dmul_rn((double)deg, 3.14159265358979323846), 180.0));  // SC.cpp:17-20
   }
-  loop_id[q] = lid;
-  yaw[q] = y;
-  if (nearest_dist) nearest_dist[q] = dist;
-  if (nearest_idx) nearest_idx[q] = (int)idx;
-  if (nearest_shift) nearest_shift[q] = shift;
+  const unsigned o = out_off + q * out_step;
+  loop_id[o] = lid;
+  yaw[o] = y;
+  if (nearest_dist) nearest_dist[o] = dist;
+  if (nearest_idx) nearest_idx[o] = (int)idx;
+  if (nearest_shift) nearest_shift[o] = shift;
+  for (int s = 0; s < push.n; ++s) {
+    void* b = push.dst[s];
+    rb.loop(b)[o] = lid;
+    rb.yaw(b)[o] = y;
+    rb.dist(b)[o] = dist;
+    rb.idx(b)[o] = (int)idx;
+    rb.shift(b)[o] = shift;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-device barrier of a peer-sharded database whose shards are driven by DIFFERENT processes (one per GPU): thread t
+// announces "this shard reached generation `epoch`" in shard t's cell block (a peer store), then waits until shard t's
+// announcement has arrived in its own block.  cells: [channel][MAX_SHARDS] generations + cell 2*MAX_SHARDS = timeout flag.
+// Everything a shard stored into peer memory before the barrier (ring keys by k_append, results by k_finalize) is
+// ordered before its announcement by the system-scope fence.  Generations only grow; comparison is wrap-safe.
+// The wait is bounded (~2 s of globaltimer): a missing peer turns into an error code, not a hung GPU.
+// Only for shards on DISTINCT devices: kernels that wait on one another must not share a GPU.
+// ------------------------------------------------------------------------------------------------
+struct BarrierCells {
+  unsigned* cells[MAX_SHARDS];
+};
+__global__ void k_peer_barrier(BarrierCells peers, int G, int rank, int channel, unsigned epoch) {
+  const int t = threadIdx.x;
+  if (t < G) {
+    __threadfence_system();
+    volatile unsigned* theirs = peers.cells[t] + channel * MAX_SHARDS + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(epoch) : "memory");
+    const unsigned* mine = peers.cells[rank] + channel * MAX_SHARDS + t;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      unsigned v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 2000000000ull) {
+        peers.cells[rank][2 * MAX_SHARDS] = 1u;
+        break;
+      }
+      __nanosleep(200);
+    }
+    __threadfence_system();
+  }
 }
 
 // device-side probes used by the parity tests (tests/test_gpu_parity.py): atanf / xy2theta / bin of many points

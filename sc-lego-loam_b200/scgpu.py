@@ -16,6 +16,7 @@ FLAG_FRESH_TREE = 1
 FLAG_EXACT_BINNING = 2
 FLAG_NO_SCREENING = 4
 FLAG_NO_TMA_BUILD = 8
+FLAG_PEER = 16
 
 
 class ScgpuError(RuntimeError):
@@ -28,7 +29,8 @@ class Config(C.Structure):
                 ("max_radius", C.c_double), ("exclude_recent", C.c_int32), ("num_candidates", C.c_int32),
                 ("search_ratio", C.c_double), ("dist_thres", C.c_double), ("tree_period", C.c_int32),
                 ("device", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
-                ("capacity_hint", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("capacity_hint", C.c_uint64), ("flags", C.c_uint32), ("n_devices", C.c_int32),
+                ("devices", C.c_int32 * 8)]
 
 
 _vp, _sz, _i, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
@@ -52,6 +54,13 @@ _SIGNATURES = {
     "scgpu_append_descs": [_vp, _vp, _sz],
     "scgpu_replay_batched": [_vp, _vp, _sz, _sz, _sz, _i, _vp, _vp, _vp, _vp, _vp],
     "scgpu_query_batched": [_vp, _u64, _sz, _vp, _vp, _vp, _vp, _vp],
+    "scgpu_replay_async": [_vp, _vp, _sz, _sz, _sz, _i],
+    "scgpu_replay_results": [_vp, _sz, _vp, _vp, _vp, _vp, _vp],
+    "scgpu_peer_export": [_vp, _vp, _sz],
+    "scgpu_peer_attach": [_vp, _vp, _i],
+    "scgpu_peer_replay_async": [_vp, _vp, _sz, _sz, _sz, _i],
+    "scgpu_peer_barrier": [_vp, _vp],
+    "scgpu_stage_exhaustive_exact": [_vp, _vp, _u64, _vp],
     "scgpu_get_candidates": [_vp, _vp, _vp, _vp, _vp, C.POINTER(_u64)],
     "scgpu_get_batch_candidates": [_vp, _sz, _vp, _vp, _vp, _vp, C.POINTER(_u64)],
     "scgpu_get_entry": [_vp, _u64, _vp, _vp, _vp],
@@ -138,10 +147,18 @@ class SCManager:
         self.lib = load_library()
         self.cfg = Config()
         _check(self.lib.scgpu_default_config(C.byref(self.cfg)))
+        devices = cfg.pop("devices", None)
         for k, v in cfg.items():
             if not hasattr(self.cfg, k):
                 raise TypeError(f"unknown config field {k}")
             setattr(self.cfg, k, v)
+        if devices is not None:      # device list: ONE handle drives a database sharded over these GPUs (entry i on devices[i % n])
+            devices = [int(d) for d in devices]
+            if not 1 <= len(devices) <= 8:
+                raise ValueError("1 to 8 devices")
+            self.cfg.n_devices = len(devices)
+            for i, d in enumerate(devices):
+                self.cfg.devices[i] = d
         self.h = _vp()
         _check(self.lib.scgpu_create(C.byref(self.cfg), C.byref(self.h)))
         self.R, self.S, self.K = self.cfg.num_ring, self.cfg.num_sector, self.cfg.num_candidates
@@ -260,6 +277,38 @@ class SCManager:
                                              out["yaw"].ctypes.data, out["min_dist"].ctypes.data,
                                              out["nn_idx"].ctypes.data, out["nn_shift"].ctypes.data))
         return out
+
+    def replay_async(self, scans):
+        """Enqueue the bench step and return; ``replay_results`` waits for the last enqueued step.  Device-resident
+        scans (tuple form, location 1) must stay valid until then; host scans too."""
+        keep, (ptr, n, pts, stride, loc) = self._scans(scans)
+        self._keep = keep
+        _check(self.lib.scgpu_replay_async(self.h, ptr, n, pts, stride, loc))
+        return n
+
+    def replay_results(self, n, out=None):
+        if out is None:
+            out = dict(loop_id=np.empty(n, np.int32), yaw=np.empty(n, np.float32), min_dist=np.empty(n, np.float64),
+                       nn_idx=np.empty(n, np.int32), nn_shift=np.empty(n, np.int32))
+        _check(self.lib.scgpu_replay_results(self.h, n, out["loop_id"].ctypes.data, out["yaw"].ctypes.data,
+                                             out["min_dist"].ctypes.data, out["nn_idx"].ctypes.data, out["nn_shift"].ctypes.data))
+        return out
+
+    # ---- peer-sharded database, one process per GPU (include/scgpu.h "peer-sharded database") ----------------------
+    def peer_export(self):
+        blob = np.zeros(128, np.uint8)
+        _check(self.lib.scgpu_peer_export(self.h, blob.ctypes.data, blob.size))
+        return blob
+
+    def peer_attach(self, blobs):
+        blobs = np.ascontiguousarray(blobs, np.uint8).reshape(-1, 128)
+        _check(self.lib.scgpu_peer_attach(self.h, blobs.ctypes.data, blobs.shape[0]))
+
+    def peer_replay_async(self, scans_local, n_total):
+        """Collective: this rank's scans of a batch of n_total (see scgpu_peer_replay_async)."""
+        keep, (ptr, n, pts, stride, loc) = self._scans(scans_local)
+        self._keep = keep
+        _check(self.lib.scgpu_peer_replay_async(self.h, ptr, n_total, pts, stride, loc))
 
     def query_batched(self, first, n):
         out = dict(loop_id=np.empty(n, np.int32), yaw=np.empty(n, np.float32), min_dist=np.empty(n, np.float64),

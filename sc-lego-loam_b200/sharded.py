@@ -52,7 +52,8 @@ class ShardedSearch:
         rec = self.st.gather(global_idx) if self.rank == owner else torch.empty(self.st.rec_bytes, dtype=torch.uint8, device=self.st.device)
         if self.world > 1:
             dist.broadcast(rec, src=owner, group=self.group)
-        return reduce_exhaustive(self._all_gather(self.st.exhaustive(rec, n_search).unsqueeze(0)).reshape(self.world, 3))
+        d, s, i = self.exhaustive_records(rec.unsqueeze(0), n_search)
+        return float(d[0].item()), int(s[0].item()), int(i[0].item())
 
     def exhaustive_stored(self, first_idx, nq, n_search):
         """Exhaustive search for the stored entries first_idx .. first_idx+nq-1 as queries (first_idx and nq multiples
@@ -65,8 +66,19 @@ class ShardedSearch:
 
     def exhaustive_records(self, qrecs, n_search):
         """The same for a batch of query records present on every rank ([nq, rec]); returns device tensors
-        (dist, shift, idx) per query.  One all_gather of 24 bytes per query per rank."""
-        return reduce_exhaustive_batch(self._all_gather(self.st.exhaustive(qrecs, n_search)))
+        (dist, shift, idx) per query.  One all_gather of 24 bytes per query per rank.  A shard whose rescoring list
+        overflowed (n_rescored > EXH_LIST_CAP: a database of near-duplicates) reports an unreliable winner; those
+        queries are redone exactly on that shard (scgpu_stage_exhaustive_exact) and gathered again."""
+        local = self.st.exhaustive(qrecs, n_search)
+        parts = self._all_gather(local)
+        over = (parts[..., 1] & 0xffffffff) > EXH_LIST_CAP                        # [G, nq]
+        if bool(over.any().item()):
+            mine = over[self.rank].nonzero().flatten().tolist()
+            ns = np.broadcast_to(np.asarray(n_search, np.uint64), (qrecs.shape[0],))
+            for q in mine:
+                local[q] = self.st.exhaustive_exact(qrecs[q], int(ns[q]))
+            parts = self._all_gather(local)
+        return reduce_exhaustive_batch(parts)
 
     def step(self, scans_local):
         """scans_local: this rank's B scans ([B, P, k] float32 on the stage device).  Scan j of rank r becomes
@@ -92,6 +104,9 @@ class ShardedSearch:
         keys = self.st.merge(self._all_gather(keys_local))                       # exchange 2
         best_local = self.st.score(rec_global, keys, n_search)                   # [GB, 3] int64
         return self.st.finalize(self._all_gather(best_local), n_search)          # exchange 3
+
+
+EXH_LIST_CAP = 65536      # SCGPU_EXH_LIST_CAP (include/scgpu.h)
 
 
 def reduce_exhaustive_batch(parts):
@@ -205,6 +220,13 @@ class GpuStages:
         self._check(self.lib.scgpu_stage_exhaustive(self.h, qrec.data_ptr(), nq, ns.ctypes.data, best.data_ptr(), self._stream()))
         return best[0] if single else best
 
+    def exhaustive_exact(self, qrec, n_search):
+        """Every local entry scored exactly for one query record (overflow fallback): [3] int64."""
+        best = torch.empty(3, dtype=torch.int64, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()
+        self._check(self.lib.scgpu_stage_exhaustive_exact(self.h, qrec.data_ptr(), int(n_search), best.data_ptr()))
+        return best
+
     def finalize(self, parts, n_search):
         G, nq, _ = parts.shape
         dev = self.device
@@ -215,3 +237,44 @@ class GpuStages:
                                                   out["loop_id"].data_ptr(), out["yaw"].data_ptr(), out["min_dist"].data_ptr(),
                                                   out["nn_idx"].data_ptr(), out["nn_shift"].data_ptr(), self._stream()))
         return out
+
+
+class PeerShardedSearch:
+    """The database sharded over the ranks with the shards reading and writing each other's HBM over NVLink
+    (include/scgpu.h "peer-sharded database").  torch.distributed is used ONCE, to exchange the shards' IPC handles;
+    after that a step is one collective C call per rank -- ring keys are pushed into every shard's replica by k_append,
+    queries are partitioned (the rank that binned a scan searches for it), candidate rows are fetched from their owners
+    inside k_cand_screen / k_score_pairs, results are pushed to every rank by k_finalize, and the two synchronisation
+    points of a step are in-kernel flag barriers over peer memory.  No NCCL call on the data path."""
+
+    def __init__(self, manager, rank=None, world=None, group=None):
+        self.m = manager
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        dev = torch.device("cuda", manager.cfg.device)
+        mine = torch.from_numpy(manager.peer_export()).to(dev)
+        blobs = torch.empty((self.world, mine.numel()), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(blobs, mine, group=group)
+        manager.peer_attach(blobs.cpu().numpy())
+        dist.barrier(group=group)          # every rank has mapped every shard before anyone stores into a peer
+
+    def prefill_descs(self, descs):
+        """Every rank passes the SAME descriptors; each keeps the entries it owns and every ring key."""
+        self.m.append_descs(descs)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def truncate(self, n):
+        self.m.truncate(n)
+
+    def step_async(self, scans_local, n_total):
+        """scans_local: this rank's scans of the batch ((ptr, n, pts, stride, location) tuple or numpy array)."""
+        self.m.peer_replay_async(scans_local, n_total)
+
+    def results(self, n_total, out=None):
+        return self.m.replay_results(n_total, out)
+
+    def step(self, scans_local, n_total):
+        self.step_async(scans_local, n_total)
+        return self.results(n_total)

@@ -12,7 +12,8 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def test_same_caller_same_output(tmp_path):
+@pytest.mark.parametrize("devices", [None, "0,0", "0,0,0,0,0,0,0,0"])
+def test_same_caller_same_output(tmp_path, devices):
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "dropin_ref")
     if not os.path.exists(ref_bin):
         pytest.skip("oracle/_ref/dropin_ref not built (needs /root/reference at build time)")
@@ -27,7 +28,10 @@ def test_same_caller_same_output(tmp_path):
     assert r.returncode == 0, r.stderr
     n = "150"
     want = subprocess.run([ref_bin, n], capture_output=True, text=True, timeout=300)
-    got = subprocess.run([exe, n], capture_output=True, text=True, timeout=300)
+    env = dict(os.environ)
+    if devices:      # the database sharded over a device list behind the same class (here: shards sharing the one GPU)
+        env["SCGPU_DEVICES"] = devices
+    got = subprocess.run([exe, n], capture_output=True, text=True, timeout=300, env=env)
     assert want.returncode == 0 and got.returncode == 0, got.stderr
     wl, gl = want.stdout.splitlines(), got.stdout.splitlines()
     assert len(wl) == len(gl)
