@@ -6,25 +6,29 @@ makeAndSaveScancontextAndKeys + detectLoopClosureID), next to the reference CPU 
 
 Workload (BASELINE.json configs[1]): KITTI-00-shaped synthetic run -- 4,541 keyframes, HDL-64 scans (64 x 1875 =
 120,000 points, float4 records), 20x60 descriptor, 10 candidates, exclude-recent 50.  One "step" replays the
-WHOLE run from an empty database: for every keyframe descriptor build (k_build) + keys + append + exact ring-key
+WHOLE run from an empty database: for every keyframe descriptor build (k_build_tma) + keys + append + exact ring-key
 top-10 over the keyframes visible at that moment (k_topk) + column-shifted cosine distance of the 10 candidates
-(k_score) + argmin, threshold and yaw -- with the reference's periodic tree-snapshot semantics, i.e. exactly the
-results of 4,541 x { makeAndSaveScancontextAndKeys; detectLoopClosureID }.  (--batch N replays only the last N
-keyframes on top of a pre-filled database; used for quick runs.)
+(k_cand_screen + k_score_pairs) + argmin, threshold and yaw -- with the reference's periodic tree-snapshot semantics,
+i.e. exactly the results of 4,541 x { makeAndSaveScancontextAndKeys; detectLoopClosureID }.  (--batch N replays only
+the last N keyframes on top of a pre-filled database; used for quick runs.)
 
-  value   : keyframes(queries)/s with the scans already resident in HBM (device leg)
-  e2e     : the same through the C ABI with HOST (pinned) scan buffers: H2D of the scans and D2H of the results
-            inside the timed region
-  roofline: k_build, the dominant kernel: algorithmic bytes (16 B/point + descriptor record) / CUDA-event time
+  value   : keyframes(queries)/s with the scans already resident in HBM.  K steps are enqueued back to back
+            (scgpu_replay_async; results stay on the device until the end) and timed with CUDA events on the library's
+            own streams (scgpu_timer_start/stop); the host wall clock around the same region is reported beside it.
+  e2e     : the same through the C ABI with HOST scan buffers, one synchronous call per step: H2D of the scans and D2H of
+            the results inside the timed region.  Headline e2e = pinned float4 scans; `e2e.pageable_xyzi` = pageable
+            32-byte pcl::PointXYZI records, the input mapOptmization.cpp:1628-1630 really passes.
+  roofline: k_build_tma, the dominant kernel: algorithmic bytes (16 B/point + descriptor record) / CUDA-event time
             of the k_build launches, against the measured copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the reference's own Scancontext.cpp compiled verbatim (oracle/_ref), or the
             oracle port when that library is absent, on the host cores of this box.
+N > 1 (torchrun, one process per GPU): the database is PEER-SHARDED (include/scgpu.h): entry i on rank i % N, every rank
+bins and searches for its own scans, ring keys / candidate rows / results cross NVLink inside the kernels.
 Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -38,11 +42,9 @@ DB_SIZE = 4541
 PTS = 120000
 R, S, K_CAND = 20, 60, 10
 ALGO_BYTES_PER_SCAN = 16 * PTS + 4 * R * S + 4 * R + 8 * S   # 1,925,360 B
-# dram__bytes_read.sum + dram__bytes_write.sum of the bench's own k_build_tma launch (4,541 scans), one `ncu --set full`
-# capture, profiles/r1_k_build_tma_final_ncu_summary.txt: 8.718801 GB read + 0.029917 GB written (= 1.00 x algorithmic)
-NCU_TRAFFIC_BYTES_PER_SCAN = (8.718801e9 + 0.029917184e9) / 4541
 SEED = 20181002
 WORKLOAD = "kitti00_shaped_4541kf_hdl64_120kpts_sc20x60_k10_excl50"
+KEYS = ("loop_id", "yaw", "min_dist", "nn_idx", "nn_shift")
 
 
 def parse():
@@ -51,10 +53,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="scgpu", choices=["scgpu", "reference"])
-    ap.add_argument("--batch", type=int, default=DB_SIZE, help="keyframes replayed per step (per GPU); default = the whole run")
-    ap.add_argument("--no-sweep", action="store_true", help="skip the query-only database-size sweep / exhaustive 100k extras")
+    ap.add_argument("--batch", type=int, default=DB_SIZE, help="keyframes replayed per step; default = the whole run")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the extras (database-size sweep, exhaustive 100k, configs 3 / 5, voxel grid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device leg only (profiling runs: the ncu launch list then is the step's)")
+    ap.add_argument("--mode", default="peer", choices=["peer", "allgather"],
+                    help="N > 1: peer-sharded database (default) or round 1's three NCCL all_gathers per step")
     return ap.parse_args()
 
 
@@ -108,8 +112,25 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(kernel="k_build_tma"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per scan of the dominant kernel, from the newest committed `ncu --set
+    full` summary under profiles/ (tools/prof_summary.py writes the machine-readable line this reads)."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_{kernel}*ncu_summary.txt"))):
+        try:
+            txt = open(path).read()
+        except OSError:
+            continue
+        m = re.search(r"BENCH_TRAFFIC\s+bytes=([0-9.eE+]+)\s+scans=(\d+)", txt)
+        if m:
+            best = (float(m.group(1)) / int(m.group(2)), os.path.relpath(path, ROOT))
+    return best
+
+
 def gen_scans(indices, out):
-    """out[j] = scan indices[j] (float4 records); scangen releases the GIL, so threads scale over the host cores."""
+    """out[j] = scan indices[j] (out.shape[2] floats per point); scangen releases the GIL, so threads scale over the cores."""
     from concurrent.futures import ThreadPoolExecutor
     from sc_lego_loam_b200.synth import ScanGen
     gen = ScanGen("hdl64", seed=SEED, n_places=3500)
@@ -187,22 +208,21 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def cpu_baseline_single(m, scans, gpu_res, n0, budget_keyframes=1491):
-    """One thread of the reference itself (oracle/_ref; else the oracle port) on a bounded sample of the SAME run:
-    its database is pre-filled with the descriptors of keyframes [0, i0) exactly as the GPU run stored them, then
-    keyframes [i0, end) go through makeAndSaveScancontextAndKeys + detectLoopClosureID.  i0 is chosen so that the
-    reference's first timed detect rebuilds its tree ((i0 - 50) % 10 == 0), i.e. both sides see the same
-    snapshots, and the loop ids / yaws of the sample are compared with the GPU's."""
+def reference_sample(get_entry, scans, first_scan_index, gpu_res, total, budget_keyframes):
+    """One thread of the reference itself (oracle/_ref; else the oracle port) on a bounded sample of the SAME run: its
+    database is pre-filled with the descriptors of keyframes [0, i0) exactly as the GPU run stored them, then keyframes
+    [i0, total) go through makeAndSaveScancontextAndKeys + detectLoopClosureID.  i0 is chosen so that the reference's
+    first timed detect rebuilds its tree ((i0 - 50) % 10 == 0), i.e. both sides see the same snapshots; the loop ids and
+    yaw bit patterns of the sample are compared with the GPU's.  scans[j] = keyframe first_scan_index + j."""
     from oracle import oracle as orc
     kind = "reference" if orc.ref_available("default") else "port"
     obj = orc.Ref("default") if kind == "reference" else orc.Port()
-    total = n0 + len(scans)
-    i0 = max(n0, total - budget_keyframes)
+    i0 = max(first_scan_index, total - budget_keyframes)
     while i0 < total - 1 and (i0 < 50 or (i0 - 50) % 10 != 0):
         i0 += 1
     for i in range(i0):
-        obj.append_desc(m.get_entry(i)[0].astype(np.float64))
-    sample = scans[i0 - n0:]
+        obj.append_desc(get_entry(i)[0].astype(np.float64))
+    sample = scans[i0 - first_scan_index:]
     if kind == "reference":
         tb, td, ids, yaws = obj.time_run(sample, want_results=True)
     else:
@@ -216,13 +236,43 @@ def cpu_baseline_single(m, scans, gpu_res, n0, budget_keyframes=1491):
             tb, td = tb + (t1 - t0), td + (time.perf_counter() - t1)
             ids[j], yaws[j] = d["loop_id"], d["yaw"]
     n = len(sample)
-    match = bool(np.array_equal(ids, gpu_res["loop_id"][i0 - n0:]) and
-                 np.array_equal(yaws.view(np.uint32), gpu_res["yaw"][i0 - n0:].view(np.uint32)))
+    match = bool(np.array_equal(ids, gpu_res["loop_id"][i0:total]) and
+                 np.array_equal(yaws.view(np.uint32), gpu_res["yaw"][i0:total].view(np.uint32)))
     return {"value": n / (tb + td), "unit": "queries/s", "cores": 1, "kind": kind,
             "sample": f"keyframes [{i0}, {total}) of the same run ({n} keyframes, database {i0}->{total}, pre-filled with the "
                       f"descriptors the GPU run stored); build {1e3 * tb / n:.2f} ms + detect {1e3 * td / n:.2f} ms per keyframe; "
                       f"host has {os.cpu_count()} cores",
             "loop_ids_and_yaws_equal_gpu": match}
+
+
+def new_out(n):
+    return dict(loop_id=np.empty(n, np.int32), yaw=np.empty(n, np.float32), min_dist=np.empty(n, np.float64),
+                nn_idx=np.empty(n, np.int32), nn_shift=np.empty(n, np.int32))
+
+
+def h2d_probe(torch, device):
+    """What the host side can deliver: pinned -> device copy rate of this GPU's link, and one core's memcpy rate."""
+    n = 1 << 28
+    h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    d = torch.empty(n, dtype=torch.uint8, device=device)
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        d.copy_(h, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbs = 4 * n / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    a = np.ones(1 << 27, np.uint8)
+    b = np.empty_like(a)
+    np.copyto(b, a)
+    t0 = time.perf_counter()
+    for _ in range(4):
+        np.copyto(b, a)
+    mem = 4 * a.size / (time.perf_counter() - t0) / 1e9
+    return {"pinned_h2d_gbs": gbs, "one_core_memcpy_gbs": mem,
+            "note": "keyframes/s from host scans <= pinned_h2d_gbs / bytes shipped per scan (1.92 MB float4 as given, 1.44 MB packed xyz)"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -241,65 +291,118 @@ def run_single_gpu(args):
     if n0:
         m.append_descs(gen.descs(0, n0, R, S))
     d_scans = h_scans.cuda()
-    out = dict(loop_id=np.empty(B, np.int32), yaw=np.empty(B, np.float32), min_dist=np.empty(B, np.float64),
-               nn_idx=np.empty(B, np.int32), nn_shift=np.empty(B, np.int32))
-
-    def step(ptr, loc):
-        m.truncate(n0)
-        m.replay((ptr, B, PTS, 16, loc), out)
-
+    dev = (d_scans.data_ptr(), B, PTS, 16, 1)
+    host = (h_scans.data_ptr(), B, PTS, 16, 0)
+    out = new_out(B)
     clocks = ClockSampler(0)
     clocks.start()
 
-    def timed(ptr, loc):
-        for _ in range(args.warmup):
-            step(ptr, loc)
-        torch.cuda.synchronize()
-        l0 = m.launch_count()
-        tb = tq = 0.0
-        clocks.active = True
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step(ptr, loc)          # returns after the results are on the host (stream synchronised inside)
-            _, b, q = m.timing()
-            tb, tq = tb + b, tq + q
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        clocks.active = False
-        return dt, tb / args.steps, tq / args.steps, m.launch_count() - l0
-
-    dt_dev, ms_build, ms_query, launches = timed(d_scans.data_ptr(), 1)
+    # ---- device leg: K steps in flight, device stopwatch --------------------------------------------------------------
+    for _ in range(args.warmup):
+        m.truncate(n0)
+        m.replay_async(dev)
+    m.replay_results(B, out)
+    torch.cuda.synchronize()
+    l0 = m.launch_count()
+    clocks.active = True
+    m.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.truncate(n0)
+        m.replay_async(dev)
+    ms_dev = m.timer_stop()
+    wall_dev = time.perf_counter() - t0
+    clocks.active = False
+    launches = m.launch_count() - l0
+    m.replay_results(B, out)
     res_dev = {k: v.copy() for k, v in out.items()}
-    if args.no_e2e:
-        dt_e2e, same = float("nan"), True
-    else:
-        dt_e2e, ms_build_e2e, _, _ = timed(h_scans.data_ptr(), 0)
-        same = all(np.array_equal(res_dev[k], out[k], equal_nan=True) for k in out)
+
+    # ---- the dominant kernel by itself: one synchronous step at a time, CUDA events around the k_build launches ----------
+    tb = tq = 0.0
+    clocks.active = True
+    for _ in range(args.steps):
+        m.truncate(n0)
+        m.replay(dev, out)
+        _, b, q = m.timing()
+        tb, tq = tb + b, tq + q
+    clocks.active = False
+    ms_build, ms_query = tb / args.steps, tq / args.steps
+    same_sync = all(np.array_equal(res_dev[k], out[k], equal_nan=True) for k in out)
+
+    # ---- e2e legs ---------------------------------------------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def timed_host(src, n, first):
+            for _ in range(args.warmup):
+                m.truncate(first)
+                m.replay(src, o2)
+            torch.cuda.synchronize()
+            clocks.active = True
+            t = time.perf_counter()
+            for _ in range(args.steps):
+                m.truncate(first)
+                m.replay(src, o2)          # returns after the results are on the host
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t
+            clocks.active = False
+            return dt / args.steps
+        o2 = new_out(B)
+        s_pinned = timed_host(host, B, n0)
+        same = all(np.array_equal(res_dev[k], o2[k], equal_nan=True) for k in o2)
+        e2e = {"value": B / s_pinned, "unit": "queries/s", "h2d_bytes_per_step": B * PTS * 16 + B * 8, "d2h_bytes_per_step": B * 24,
+               "ms_per_step": 1e3 * s_pinned, "results_equal_device_leg": bool(same), "h2d_gbs": (B * PTS * 16) / s_pinned / 1e9,
+               "input": "pinned host float4 scans, DMA straight from the caller's buffer"}
+        # the input the drop-in really gets: pageable pcl::PointXYZI records (32 bytes); a tail of the run on top of the
+        # database the full step left behind (the cut keeps the reference's snapshot schedule: (first - 50) % 10 == 0)
+        first = max(n0, (DB_SIZE - 1024 - 50) // 10 * 10 + 50)
+        nt = DB_SIZE - first
+        xyzi = np.zeros((nt, PTS, 8), np.float32)
+        xyzi[:, :, :3] = scans[first - n0:, :, :3]
+        xyzi[:, :, 4] = 0.5                                    # intensity lane
+        o2 = new_out(nt)
+        m.truncate(n0)
+        m.replay(dev, out)                                     # the database of the full run
+        s_page = timed_host(xyzi, nt, first)
+        same_p = all(np.array_equal(res_dev[k][first - n0:], o2[k], equal_nan=True) for k in o2)
+        e2e["pageable_xyzi"] = {"value": nt / s_page, "unit": "queries/s", "keyframes_per_step": nt, "db_keyframes": DB_SIZE,
+                                "ms_per_step": 1e3 * s_page, "results_equal_device_leg": bool(same_p),
+                                "host_bytes_read_per_step": nt * PTS * 32, "h2d_bytes_per_step": nt * PTS * 12,
+                                "host_gbs": nt * PTS * 32 / s_page / 1e9,
+                                "input": "pageable 32-byte pcl::PointXYZI records (mapOptmization.cpp:1628-1630): x, y, z packed to 12 B/point "
+                                         "by the library's host threads into pinned staging, double-buffered against the H2D copy"}
+        del xyzi
+        e2e["host_probe"] = h2d_probe(torch, "cuda:0")
+        o2 = new_out(B)
     clocks.stop()
 
     peak, peak_src = measured_peak()
     achieved = ALGO_BYTES_PER_SCAN * B / (ms_build * 1e-3) / 1e9
+    traffic = ncu_traffic()
     line = {
-        "metric": "sc_loop_queries_per_sec", "value": B * args.steps / dt_dev, "unit": "queries/s", "n_gpus": 1,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_dev / args.steps, "higher_is_better": True,
+        "metric": "sc_loop_queries_per_sec", "value": B * args.steps / (ms_dev * 1e-3), "unit": "queries/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32 binning + f64 keys/distance", "data": "synthetic",
         "config": {"workload": WORKLOAD, "db_keyframes": DB_SIZE, "keyframes_per_step": B, "points_per_scan": PTS,
                    "point_stride_bytes": 16, "l2": f"inputs larger than L2 ({B * PTS * 16 >> 20} MiB of points per step)",
-                   "parallelism": "1 gpu"},
-        "e2e": {"value": B * args.steps / dt_e2e, "unit": "queries/s", "h2d_bytes_per_step": B * PTS * 16 + B * 8,
-                "d2h_bytes_per_step": B * 24, "ms_per_step": 1e3 * dt_e2e / args.steps, "results_equal_device_leg": bool(same),
-                "h2d_gbs": (B * PTS * 16) / (dt_e2e / args.steps) / 1e9},
+                   "parallelism": "1 gpu", "timing": "CUDA events on the library's streams over K steps enqueued back to back "
+                                                     "(binning of step n+1 overlaps the query stage of step n); wall clock beside it"},
+        "wall_ms_per_step": 1e3 * wall_dev / args.steps,
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_build_tma", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES_PER_SCAN * B, "traffic_source": "ncu --set full capture of this launch (profiles/r1_k_build_tma_final_ncu_summary.txt)",
+                     "traffic": traffic[0] * B if traffic else None, "traffic_source": traffic[1] if traffic else None,
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SCAN * B,
-                     "ms_per_launch": ms_build},
-        "stages": {"build_ms_per_step": ms_build, "query_ms_per_step": ms_query, "builds_per_sec": B / (ms_build * 1e-3),
-                   "queries_only_per_sec": B / (ms_query * 1e-3), "loops_found": int((res_dev["loop_id"] >= 0).sum())},
+                     "ms_per_launch": ms_build, "timed": "CUDA events around the k_build launches of K synchronous steps",
+                     "whole_step_frac": ALGO_BYTES_PER_SCAN * B / (ms_dev / args.steps * 1e-3) / 1e9 / peak},
+        "stages": {"build_ms_per_step": ms_build, "query_ms_per_step_serial": ms_query, "builds_per_sec": B / (ms_build * 1e-3),
+                   "queries_only_per_sec": B / (ms_query * 1e-3), "loops_found": int((res_dev["loop_id"] >= 0).sum()),
+                   "sync_step_results_equal_async": bool(same_sync)},
         "clocks": clocks.summary(),
     }
+    if e2e:
+        line["e2e"] = e2e
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_single(m, scans, res_dev, n0)
+        line["cpu_baseline"] = reference_sample(m.get_entry, scans, n0, {k: np.concatenate([np.zeros(n0, v.dtype), v]) for k, v in res_dev.items()},
+                                                DB_SIZE, 1491)
     if not args.no_sweep:
         line["online_latency"] = online_latency(m, scans)
         line["voxel_grid"] = voxel_extra(d_scans.data_ptr(), min(B, 1184))
@@ -312,22 +415,28 @@ def run_single_gpu(args):
 def online_latency(m, scans, n=96):
     """The reference's own call pattern (mapOptmization.cpp:1630 + 916): ONE makeAndSaveScancontextAndKeys of a host scan
     followed by ONE detectLoopClosureID, per keyframe, on top of the database the run has built (4,541+ keyframes);
-    wall-clock per keyframe including the H2D copy of the scan and both host synchronisations."""
-    ts = []
-    for i in range(n):
-        t0 = time.perf_counter()
-        m.makeAndSaveScancontextAndKeys(scans[i % len(scans)])
-        m.detectLoopClosureID()
-        ts.append(time.perf_counter() - t0)
-    ts = np.array(ts[16:]) * 1e3
-    return {"calls": "scgpu_append_scan (120k-point pinned host scan) + scgpu_detect", "keyframes": int(ts.size), "db_keyframes": int(m.size()),
-            "ms_per_keyframe_median": float(np.median(ts)), "ms_per_keyframe_p99": float(np.percentile(ts, 99)),
-            "keyframes_per_sec": float(1e3 / np.median(ts))}
+    wall-clock per keyframe including the H2D copy of the scan and both host synchronisations.  Input as the caller
+    passes it: a PAGEABLE cloud of 32-byte pcl::PointXYZI records."""
+    out = {}
+    for name, k in (("pageable_xyzi_32B", 8), ("pageable_float4_16B", 4)):
+        ts = []
+        src = np.zeros((8, scans.shape[1], k), np.float32)
+        src[:, :, :3] = scans[:8, :, :3]
+        for i in range(n):
+            t0 = time.perf_counter()
+            m.makeAndSaveScancontextAndKeys(src[i % 8])
+            m.detectLoopClosureID()
+            ts.append(time.perf_counter() - t0)
+        ts = np.array(ts[16:]) * 1e3
+        out[name] = {"ms_per_keyframe_median": float(np.median(ts)), "ms_per_keyframe_p99": float(np.percentile(ts, 99)),
+                     "keyframes_per_sec": float(1e3 / np.median(ts))}
+    out.update({"calls": "scgpu_append_scan (120k-point pageable host scan) + scgpu_detect", "keyframes": n - 16, "db_keyframes": int(m.size())})
+    return out
 
 
 def voxel_extra(ptr, n_scans):
     """SURVEY 8(f) rank 2: the caller's pcl::VoxelGrid (leaf 0.5 m) moved in front of the descriptor build on the device
-    (k_build_voxel), on the first n_scans resident scans of the run."""
+    (k_build_voxel), on the first n_scans resident scans of the run.  PARITY UNPINNED: PCL is absent here."""
     from sc_lego_loam_b200.scgpu import SCManager
     m = SCManager(device=0, capacity_hint=n_scans * 6 + 8)
     m.set_downsample_leaf(0.5)
@@ -340,13 +449,35 @@ def voxel_extra(ptr, n_scans):
     t = float(np.median(ms[2:]))
     peak, _ = measured_peak()
     return {"kernel": "k_build_voxel", "leaf_m": 0.5, "scans": n_scans, "ms": t, "scans_per_sec": n_scans / (t * 1e-3),
+            "parity": "unpinned (restated pcl::VoxelGrid; PCL absent)",
             "roofline": {"bound": "hbm", "achieved": n_scans * PTS * 16 / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": n_scans * PTS * 16 / (t * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": n_scans * PTS * 16}}
 
 
+def exhaustive_extra(m, n, peak, qs):
+    """Config 4 on one handle (one GPU or a device list): Q = 1 and Q = len(qs) per call."""
+    m.exhaustive_batched(qs, n - 50)
+    m.exhaustive_batched(qs, n - 50)
+    ms = m.timing()[0] / len(qs)
+    single, screen = [], []
+    for q in qs[:8]:
+        m.exhaustive(q, n - 50)
+        t = m.timing()
+        single.append(t[0])
+        screen.append(t[1])
+    ms_screen, ms_single = float(np.median(screen)), float(np.median(single))
+    algo = 4 * R * S * (n - 50)
+    return {"queries_per_sec_batched": 1e3 / ms, "ms_per_query_batched": ms, "batch": len(qs), "ms_per_query_single": ms_single,
+            "queries_per_sec": 1e3 / ms, "rescored_last": m.exhaustive_rescored(),
+            "roofline": {"kernel": "k_exh_screen", "bound": "hbm", "achieved": algo / (ms_screen * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": algo / (ms_screen * 1e-3) / 1e9 / peak, "ms_per_launch": ms_screen,
+                         "algorithmic_bytes_per_launch": algo, "whole_query_frac_single": algo / (ms_single * 1e-3) / 1e9 / peak}}
+
+
 def db_size_sweep(torch):
     """BASELINE's "queries/sec vs DB size": (a) the reference's top-10 search (k_topk + k_score + argmin) for 256 stored
-    keyframes against databases of 1k..100k keyframes, and (b) the exhaustive every-entry search at 100k (config 4)."""
+    keyframes against databases of 1k..100k keyframes, with the achieved ring-key stream of k_topk (4*R*N bytes per
+    query), and (b) the exhaustive every-entry search at 100k (config 4)."""
     from sc_lego_loam_b200.scgpu import SCManager
     from sc_lego_loam_b200.synth import ScanGen
     gen = ScanGen("hdl64", seed=SEED + 1, n_places=80000)
@@ -367,7 +498,11 @@ def db_size_sweep(torch):
             m.query_batched(n - nq, nq)
             ts.append(m.timing()[2])
         ms = float(np.median(ts))
-        out["top10"].append({"db": n, "queries_per_sec": nq / (ms * 1e-3), "ms_per_256_queries": ms})
+        key_bytes = 4 * R * (n - 50 - nq / 2)                  # ring keys one query compares against (4*R*N_search)
+        out["top10"].append({"db": n, "queries_per_sec": nq / (ms * 1e-3), "ms_per_256_queries": ms,
+                             "retrieval_stream_gbs": nq * key_bytes / (ms * 1e-3) / 1e9,
+                             "retrieval_stream_note": "4*R*N_search bytes per query / whole query-stage time; the key matrix "
+                                                      "(80 B x N) is L2-resident, so this is an L2 stream, not HBM"})
         # the same search with as many queries per launch sequence as an offline relocalisation run would submit
         nb = min(4096, n - 64)
         for _ in range(2):
@@ -377,127 +512,291 @@ def db_size_sweep(torch):
             m.query_batched(n - nb, nb)
             ts.append(m.timing()[2])
         msb = float(np.median(ts))
-        out.setdefault("top10_large_batches", []).append({"db": n, "queries_per_launch": nb, "queries_per_sec": nb / (msb * 1e-3), "ms": msb})
+        out.setdefault("top10_large_batches", []).append({"db": n, "queries_per_launch": nb, "queries_per_sec": nb / (msb * 1e-3), "ms": msb,
+                                                          "retrieval_stream_gbs": nb * 4 * R * (n - 50 - nb / 2) / (msb * 1e-3) / 1e9})
     n = sizes[-1]
-    qs = [n - 1 - 37 * i for i in range(32)]
-    m.exhaustive_batched(qs, n - 50)
-    m.exhaustive_batched(qs, n - 50)
-    ms = m.timing()[0] / len(qs)
-    single = []
-    for q in qs[:8]:
-        m.exhaustive(q, n - 50)
-        single.append(m.timing()[1])
-    ms_screen = float(np.median(single))
-    algo = 4 * R * S * (n - 50)
-    out["exhaustive_100k"] = {"queries_per_sec": 1e3 / ms, "ms_per_query": ms, "rescored_last": m.exhaustive_rescored(),
-                              "roofline": {"kernel": "k_exh_screen", "bound": "hbm", "achieved": algo / (ms_screen * 1e-3) / 1e9, "peak": peak,
-                                           "unit": "GB/s", "frac": algo / (ms_screen * 1e-3) / 1e9 / peak, "ms_per_launch": ms_screen,
-                                           "algorithmic_bytes_per_launch": algo}}
+    qs = [n - 1 - 37 * i for i in range(64)]
+    out["exhaustive_100k"] = exhaustive_extra(m, n, peak, qs)
     return out
 
 
+# ------------------------------------------------------------------------------------------------------
 def run_multi_gpu(args):
-    """STRONG scaling of the same job: the 4,541-keyframe run (rounded up to a multiple of G) replayed from an
-    empty database, keyframe i built by and stored on rank i % G; every query searches all shards."""
+    """STRONG scaling of the same job: the 4,541-keyframe run replayed from an empty database, keyframe i binned by, stored
+    on and searched for by rank i % G."""
     import torch
     import torch.distributed as dist
-    from sc_lego_loam_b200.scgpu import SCManager
-    from sc_lego_loam_b200.sharded import GpuStages, ShardedSearch
+    from sc_lego_loam_b200.scgpu import FLAG_PEER, SCManager, ScgpuError
+    from sc_lego_loam_b200.sharded import PeerShardedSearch
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     G = world
     total = min(args.batch, DB_SIZE)
-    B = (total + G - 1) // G                     # keyframes per rank per step
-    n0 = (DB_SIZE - total) // G * G              # pre-filled part when --batch < the whole run
+    n0 = DB_SIZE - total
+    mine = np.array([i for i in range(total) if (n0 + i) % G == rank])     # this rank's keyframes of the batch
+    B = len(mine)
     h_scans = torch.empty((B, PTS, 4), dtype=torch.float32, pin_memory=True)
-    gen = gen_scans(n0 + np.arange(B) * G + rank, h_scans.numpy())
-    m = SCManager(device=local, shard_rank=rank, shard_count=G, capacity_hint=n0 + G * B + 64)
-    search = ShardedSearch(GpuStages(m, f"cuda:{local}"), rank, world)
+    gen = gen_scans(n0 + mine, h_scans.numpy())
+    m = SCManager(device=local, shard_rank=rank, shard_count=G, flags=FLAG_PEER, capacity_hint=DB_SIZE + 64)
+    search = PeerShardedSearch(m, rank, world)
     if n0:
         search.prefill_descs(gen.descs(0, n0, R, S))
     d_scans = h_scans.cuda()
-    d_stage = torch.empty_like(d_scans)
-
-    ns_cache = {}
-    plan_uncached = search.st.plan_n_search
-
-    def plan_cached(first_size, n):
-        """Every step restarts from the same database size (truncate resets the snapshot state), so the n_search
-        plan is the same device tensor each time: computing it once keeps the step free of host synchronisation."""
-        if (first_size, n) not in ns_cache:
-            ns_cache[(first_size, n)] = plan_uncached(first_size, n)
-        return ns_cache[(first_size, n)]
-
-    search.st.plan_n_search = plan_cached
-
-    def step(e2e):
-        m.truncate(n0)
-        search.size = n0
-        src = d_scans
-        if e2e:
-            d_stage.copy_(h_scans, non_blocking=True)
-            src = d_stage
-        r = search.step(src)
-        if e2e:
-            return {k: v.cpu() for k, v in r.items()}
-        return r
-
+    dev = (d_scans.data_ptr(), B, PTS, 16, 1)
+    host = (h_scans.data_ptr(), B, PTS, 16, 0)
+    out = new_out(total)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
 
-    def timed(e2e):
-        for _ in range(args.warmup):
-            step(e2e)
-        torch.cuda.synchronize()
-        dist.barrier()
-        l0 = m.launch_count()
-        clocks.active = True
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            r = step(e2e)
-        e1.record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        clocks.active = False
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item() * 1e-3, m.launch_count() - l0, r
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    dt_dev, launches, r = timed(False)
-    # roofline of the dominant kernel (k_build_tma: every rank bins its own B scans): CUDA events around the build
-    # launch of each step of one more device-leg pass, on the stream it is launched on; max over ranks
-    search.build_events = []
-    timed(False)
-    ms_build = torch.tensor([sum(a.elapsed_time(b) for a, b in search.build_events[-args.steps:]) / args.steps], device="cuda")
-    search.build_events = None
-    dist.all_reduce(ms_build, op=dist.ReduceOp.MAX)
-    ms_build = ms_build.item()
-    dt_e2e, _, r2 = timed(True)
-    same = all(torch.equal(r[k].cpu(), r2[k]) for k in ("loop_id", "nn_idx", "nn_shift"))
+    # ---- device leg ------------------------------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        search.truncate(n0)
+        search.step_async(dev, total)
+    search.results(total, out)
+    torch.cuda.synchronize()
+    dist.barrier()
+    l0 = m.launch_count()
+    clocks.active = True
+    m.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        search.truncate(n0)
+        search.step_async(dev, total)
+    ms_dev = allmax(m.timer_stop())
+    wall_dev = allmax(time.perf_counter() - t0)
+    clocks.active = False
+    launches = m.launch_count() - l0
+    search.results(total, out)
+    res_dev = {k: v.copy() for k, v in out.items()}
+    # the dominant kernel by itself (k_build_tma: every rank bins its own scans): synchronous steps, events around the build
+    tb = 0.0
+    dist.barrier()
+    for _ in range(args.steps):
+        search.truncate(n0)
+        search.step_async(dev, total)
+        search.results(total, out)
+        tb += m.timing()[1]
+    ms_build = allmax(tb / args.steps)
+    # ---- e2e leg: pinned host scans in, results on the host of every rank -----------------------------------------------------
+    for _ in range(args.warmup):
+        search.truncate(n0)
+        search.step_async(host, total)
+        search.results(total, out)
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks.active = True
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        search.truncate(n0)
+        search.step_async(host, total)
+        search.results(total, out)
+    s_e2e = allmax(time.perf_counter() - t0) / args.steps
+    clocks.active = False
+    same = all(np.array_equal(res_dev[k], out[k], equal_nan=True) for k in out)
+    line = None
     if rank == 0:
         clocks.stop()
-        nq = G * B
+        peak, peak_src = measured_peak()
+        traffic = ncu_traffic()
+        ach = ALGO_BYTES_PER_SCAN * B / (ms_build * 1e-3) / 1e9
         line = {
-            "metric": "sc_loop_queries_per_sec", "value": nq * args.steps / dt_dev, "unit": "queries/s", "n_gpus": G,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_dev / args.steps, "higher_is_better": True,
+            "metric": "sc_loop_queries_per_sec", "value": total * args.steps / (ms_dev * 1e-3), "unit": "queries/s", "n_gpus": G,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32 binning + f64 keys/distance", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "db_keyframes": n0 + nq, "keyframes_per_step": nq, "keyframes_per_gpu_per_step": B,
+            "config": {"workload": WORKLOAD, "db_keyframes": DB_SIZE, "keyframes_per_step": total, "keyframes_per_gpu_per_step": B,
                        "points_per_scan": PTS, "point_stride_bytes": 16, "l2": "inputs larger than L2",
-                       "parallelism": f"database sharded i%{G} over {G} gpus; each rank bins its own scans; 3 NCCL all_gathers per step"},
-            "e2e": {"value": nq * args.steps / dt_e2e, "unit": "queries/s", "h2d_bytes_per_step": nq * PTS * 16 + nq * 8,
-                    "d2h_bytes_per_step": nq * 24 * G, "ms_per_step": 1e3 * dt_e2e / args.steps, "results_equal_device_leg": bool(same)},
-            "gpu_launches": int(launches), "clocks": clocks.summary(),
-            "roofline": {"kernel": "k_build_tma", "bound": "hbm", "achieved": ALGO_BYTES_PER_SCAN * B / (ms_build * 1e-3) / 1e9,
-                         "peak": measured_peak()[0], "unit": "GB/s", "frac": ALGO_BYTES_PER_SCAN * B / (ms_build * 1e-3) / 1e9 / measured_peak()[0],
-                         "traffic": NCU_TRAFFIC_BYTES_PER_SCAN * B, "peak_source": measured_peak()[1], "per": "gpu (max over ranks of the build launch time)",
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SCAN * B, "ms_per_launch": ms_build},
-            "stages": {"loops_found": int((r["loop_id"] >= 0).sum().item()), "build_ms_per_step": ms_build},
+                       "parallelism": f"database peer-sharded i%{G} over {G} gpus (one process each): every rank bins, stores and searches for its "
+                                      "own scans; ring keys pushed into every rank's replica and candidate rows fetched from their owners over "
+                                      "NVLink peer memory inside the kernels; two in-kernel flag barriers per step; no NCCL call on the data path",
+                       "timing": "CUDA events on the library's streams over K steps enqueued back to back, max over ranks"},
+            "wall_ms_per_step": 1e3 * wall_dev / args.steps,
+            "e2e": {"value": total / s_e2e, "unit": "queries/s", "h2d_bytes_per_step": total * PTS * 16 + total * 8,
+                    "d2h_bytes_per_step": total * 24 * G, "ms_per_step": 1e3 * s_e2e, "results_equal_device_leg": bool(same),
+                    "h2d_gbs_aggregate": total * PTS * 16 / s_e2e / 1e9, "input": "pinned host float4 scans, one synchronous collective call per step"},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "k_build_tma", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": traffic[0] * B if traffic else None, "traffic_source": traffic[1] if traffic else None, "peak_source": peak_src,
+                         "per": "gpu (max over ranks of the build launch time)", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SCAN * B,
+                         "ms_per_launch": ms_build,
+                         "whole_step_frac_aggregate": ALGO_BYTES_PER_SCAN * total / (ms_dev / args.steps * 1e-3) / 1e9 / (peak * G)},
+            "stages": {"loops_found": int((res_dev["loop_id"] >= 0).sum()), "build_ms_per_step": ms_build},
         }
+        if not args.no_cpu_baseline:
+            # rank 0 cross-checks a sample of the run against the reference itself (the scans of the sample are regenerated here;
+            # the database prefix is read out of the shards through the peer mappings)
+            budget = 160
+            i0 = max(n0, DB_SIZE - budget)
+            while i0 < DB_SIZE - 1 and (i0 < 50 or (i0 - 50) % 10 != 0):
+                i0 += 1
+            sample = np.empty((DB_SIZE - i0, PTS, 4), np.float32)
+            gen_scans(np.arange(i0, DB_SIZE), sample)
+            full = {k: np.concatenate([np.zeros(n0, v.dtype), v]) for k, v in res_dev.items()}
+            cb = reference_sample(m.get_entry, sample, i0, full, DB_SIZE, DB_SIZE - i0)
+            cb["loop_ids_and_yaws_equal_reference"] = cb["loop_ids_and_yaws_equal_gpu"]
+            line["cpu_baseline"] = cb
+    dist.barrier()
+    del d_scans
+    m.close()
+    torch.cuda.empty_cache()
+    if not args.no_sweep:
+        extras = multi_gpu_extras(torch, dist, rank, world, local)
+        if rank == 0:
+            line.update(extras)
+    clocks.active = False
+    if rank == 0:
+        clocks.stop()
+        line["clocks"] = clocks.summary()
         print(json.dumps(line))
+    dist.barrier()
     dist.destroy_process_group()
+
+
+def multi_gpu_extras(torch, dist, rank, world, local):
+    """BASELINE configs 3, 4 and 5 on the sharded database, under the same clock as the headline."""
+    from sc_lego_loam_b200.scgpu import FLAG_PEER, SCManager
+    from sc_lego_loam_b200.sharded import GpuStages, PeerShardedSearch, ShardedSearch
+    from sc_lego_loam_b200.synth import ScanGen
+    G = world
+    peak, _ = measured_peak()
+    out = {}
+
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- config 4: exhaustive every-entry search over 100k keyframes, 20x60 ------------------------------------------------------
+    n = 100000
+    gen = ScanGen("hdl64", seed=SEED + 1, n_places=80000)
+    descs = gen.descs(0, n, R, S, threads=max(1, min(16, (os.cpu_count() or 1) // G)))
+    m = SCManager(device=local, shard_rank=rank, shard_count=G, flags=FLAG_PEER, capacity_hint=n + 64)
+    peer = PeerShardedSearch(m, rank, world)
+    peer.prefill_descs(descs)
+    st = GpuStages(m, f"cuda:{local}")
+    search = ShardedSearch(st, rank, world)
+    qs = [n - 1 - 37 * i for i in range(64)]
+    recs = torch.stack([st.gather(q) for q in qs])           # every rank reads the query records out of their owner shards
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def timed(fn, reps):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev[0].record()
+        for _ in range(reps):
+            r = fn()
+        ev[1].record()
+        torch.cuda.synchronize()
+        return allmax(ev[0].elapsed_time(ev[1]) / reps), r
+
+    ms64, r64 = timed(lambda: search.exhaustive_records(recs, n - 50), 5)
+    ms1, r1 = timed(lambda: search.exhaustive_records(recs[:1], n - 50), 20)
+    shard_bytes = 4 * R * S * ((n - 50) // G)
+    res4 = {"db_keyframes": n, "gpus": G, "q64": {"ms_per_query": ms64 / 64, "queries_per_sec": 64e3 / ms64},
+            "q1": {"ms_per_query": ms1, "queries_per_sec": 1e3 / ms1},
+            "roofline": {"bound": "hbm", "per_gpu_bytes_per_query": shard_bytes, "peak_per_gpu": peak, "unit": "GB/s",
+                         "q64_per_gpu_achieved": shard_bytes / (ms64 / 64 * 1e-3) / 1e9, "q64_frac_aggregate": shard_bytes / (ms64 / 64 * 1e-3) / 1e9 / peak,
+                         "q1_per_gpu_achieved": shard_bytes / (ms1 * 1e-3) / 1e9, "q1_frac_aggregate": shard_bytes / (ms1 * 1e-3) / 1e9 / peak,
+                         "note": "every GPU streams its shard once per query; aggregate fraction = per-GPU fraction (equal shards); one NCCL "
+                                 "all_gather of 24 B per query per rank"}}
+    if rank == 0:
+        # parity of a sample against the oracle port restricted to a prefix (the reference needs 41 us per pair: 4 s per full query)
+        from oracle import oracle as orc
+        port = orc.Port()
+        nchk = 3000
+        for d in descs[:nchk]:
+            port.append_desc(d.astype(np.float64))
+    d3, s3, i3 = search.exhaustive_records(recs[:4], 3000)
+    if rank == 0:
+        ok = True
+        for j in range(4):
+            want = port.exhaustive(descs[qs[j]].astype(np.float64), 3000, False)
+            ok &= (int(i3[j]) == want[2] and int(s3[j]) == want[1] and abs(float(d3[j]) - want[0]) <= 1e-5 * abs(want[0]) + 1e-9)
+        res4["winners_equal_oracle_on_3000_entry_prefix"] = bool(ok)
+    out["exhaustive_100k"] = res4
+    m.close()
+    del descs, recs
+    torch.cuda.empty_cache()
+    dist.barrier()
+
+    # ---- config 3: 40k OS1-64 keyframes, K = 50: a batch of 64 scans per GPU replayed on top --------------------------------------
+    n_db, per = 40000, 64
+    gen = ScanGen("os1", seed=20181003, n_places=30000)
+    descs = gen.descs(0, n_db, R, S, threads=max(1, min(16, (os.cpu_count() or 1) // G)))
+    total = per * G
+    m = SCManager(device=local, shard_rank=rank, shard_count=G, flags=FLAG_PEER, num_candidates=50, capacity_hint=n_db + total + 64)
+    peer = PeerShardedSearch(m, rank, world)
+    peer.prefill_descs(descs)
+    mine = [i for i in range(total) if (n_db + i) % G == rank]
+    scans = np.stack([gen.scan(n_db + i, 4) for i in mine])
+    d = torch.from_numpy(scans).cuda()
+    devt = (d.data_ptr(), len(mine), scans.shape[1], 16, 1)
+    for _ in range(3):
+        peer.truncate(n_db)
+        peer.step_async(devt, total)
+    res = peer.results(total)
+    dist.barrier()
+    m.timer_start()
+    for _ in range(10):
+        peer.truncate(n_db)
+        peer.step_async(devt, total)
+    ms = allmax(m.timer_stop()) / 10
+    res3 = {"db_keyframes": n_db, "candidates": 50, "points_per_scan": int(scans.shape[1]), "keyframes_per_step": total, "ms_per_step": ms,
+            "queries_per_sec": total / (ms * 1e-3), "loops_found": int((res["loop_id"] >= 0).sum())}
+    if rank == 0:
+        from oracle import oracle as orc
+        kind = "reference" if orc.ref_available("k50") else "port"
+        ref = orc.Ref("k50") if kind == "reference" else orc.Port(orc.Params(num_candidates=50))
+        for dd in descs:
+            ref.append_desc(dd.astype(np.float64))
+        chk = 24
+        ids, yaws = [], []
+        t0 = time.perf_counter()
+        for i in range(chk):
+            ref.append_scan(gen.scan(n_db + i, 4))
+            r = ref.detect(details=False) if kind == "reference" else ref.detect()
+            ids.append(r["loop_id"])
+            yaws.append(r["yaw"])
+        sec = time.perf_counter() - t0
+        res3["cpu"] = {"kind": kind, "cores": 1, "keyframes": chk, "queries_per_sec": chk / sec}
+        res3[f"first_{chk}_equal_reference"] = bool(np.array_equal(ids, res["loop_id"][:chk]) and
+                                                    np.array_equal(np.array(yaws, np.float32).view(np.uint32), res["yaw"][:chk].view(np.uint32)))
+    out["config3_40k_k50"] = res3
+    m.close()
+    del descs, d
+    torch.cuda.empty_cache()
+    dist.barrier()
+
+    # ---- config 5: 40x120, 20k keyframes, forward + column-reversed exhaustive search ---------------------------------------------
+    R5, S5, n5 = 40, 120, 20000
+    gen = ScanGen("hdl64", seed=20181005, n_places=15000)
+    descs = gen.descs(0, n5, R5, S5, threads=max(1, min(16, (os.cpu_count() or 1) // G)))
+    descs[n5 - 1] = descs[4242].reshape(S5, R5)[::-1].ravel()       # the query is a column-reversed revisit of entry 4242
+    m = SCManager(device=local, shard_rank=rank, shard_count=G, flags=FLAG_PEER, num_ring=R5, num_sector=S5, capacity_hint=n5 + 64)
+    peer = PeerShardedSearch(m, rank, world)
+    peer.prefill_descs(descs)
+    st = GpuStages(m, f"cuda:{local}")
+    search = ShardedSearch(st, rank, world)
+    rec = st.gather(n5 - 1).unsqueeze(0)
+    ms_f, rf = timed(lambda: search.exhaustive_records(rec, n5 - 50), 20)
+    ms_b, rb = timed(lambda: search.exhaustive_records(rec, n5 - 50, flipped=True), 20)
+    sb = 4 * R5 * S5 * ((n5 - 50) // G)
+    out["config5_40x120_flipped"] = {"db_keyframes": n5, "gpus": G, "ms_per_query_forward": ms_f, "ms_per_query_forward_plus_flipped": ms_b,
+                                     "winner_forward_plus_flipped": [float(rb[0][0]), int(rb[1][0]), int(rb[2][0])],
+                                     "finds_reversed_revisit": bool(int(rb[2][0]) == 4242 and float(rb[0][0]) < 1e-9),
+                                     "roofline": {"bound": "hbm", "per_gpu_bytes_per_pass": sb, "forward_frac_aggregate": sb / (ms_f * 1e-3) / 1e9 / peak,
+                                                  "peak_per_gpu": peak}}
+    m.close()
+    dist.barrier()
+    return out
 
 
 def main():
@@ -513,7 +812,11 @@ def main():
             run_reference_arm(args)
         return
     if world > 1:
-        run_multi_gpu(args)
+        if args.mode == "allgather":
+            from tools.bench_allgather import run_multi_gpu_allgather
+            run_multi_gpu_allgather(args)
+        else:
+            run_multi_gpu(args)
     else:
         run_single_gpu(args)
 

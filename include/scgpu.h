@@ -228,6 +228,10 @@ int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_query_records, size_t 
 int scgpu_stage_finalize(scgpu_handle* h, const void* d_best_parts, int parts, size_t n_queries,
                          const uint64_t* d_n_search, int32_t* d_loop_id, float* d_yaw, double* d_nearest_dist,
                          int32_t* d_nearest_idx, int32_t* d_nearest_shift, void* stream);
+/* The same with the column-reversed ("flipped") pass of BASELINE config 5 (flipped != 0: every entry is also scored with its
+ * columns reversed, forward first); a flipped winner is flagged in bit 30 of the shift field. */
+int scgpu_stage_exhaustive2(scgpu_handle* h, const void* d_query_records, size_t nq, const uint64_t* n_search, int flipped,
+                            void* d_best_out, void* stream);
 /* Fallback of scgpu_stage_exhaustive: when a result's n_rescored exceeds SCGPU_EXH_LIST_CAP the rescoring list of its batch
  * overflowed (a database of near-duplicates: the list is shared by the <= 64 queries of a batch) and the reported winner is
  * NOT reliable; this call scores every local entry of the shard exactly for that one query record (host-synchronous) and
@@ -273,6 +277,11 @@ int scgpu_probe_bins(scgpu_handle* h, const float* xyz, size_t n, int32_t* bin, 
 /* Device time (CUDA events on the handle's stream) of the last scgpu_replay_batched / scgpu_append_scans_batched /
  * scgpu_query_batched call: whole call, its k_build launches only, and everything after them. */
 int scgpu_get_timing(scgpu_handle* h, double* ms_total, double* ms_build, double* ms_query);
+/* Device-side stopwatch over a sequence of calls (asynchronous ones included): CUDA events on the handle's own streams --
+ * start behind everything enqueued so far, stop behind everything enqueued since; a device-list handle reports its slowest
+ * shard.  scgpu_timer_stop waits for the work to finish. */
+int scgpu_timer_start(scgpu_handle* h);
+int scgpu_timer_stop(scgpu_handle* h, double* ms);
 /* On-device self check of the binning front end: n pseudo-random points (mode 0: uniform over the ROI square;
  * mode 1: on / next to ring and sector boundaries), fast-path+fallback bin vs the exact restatement.
  * first_bad (optional, 5 floats): x, y, z, fast bin, exact bin of the first mismatch. */

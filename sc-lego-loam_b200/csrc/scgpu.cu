@@ -163,6 +163,7 @@ struct scgpu_handle {
   unsigned epoch[2] = {0, 0};               // barrier generations: channel 0 = "appended", 1 = "queries done"
   cudaStream_t qstream = nullptr;           // query stage of chunk c runs here while chunk c+1 is binned on `stream`
   cudaEvent_t ev_app = nullptr, ev_qdone = nullptr, ev_side = nullptr;
+  cudaEvent_t ev_b0 = nullptr, ev_b1 = nullptr;  // scgpu_timer_start / stop
   PinBuf h_ns_ring[4];                      // n_search staging of asynchronous replays (rotating, guarded by events)
   cudaEvent_t ev_ns_ring[4] = {nullptr, nullptr, nullptr, nullptr};
   int ns_turn = 0;
@@ -1528,6 +1529,8 @@ int scgpu_destroy(scgpu_handle* h) {
   if (h->ev_app) cudaEventDestroy(h->ev_app);
   if (h->ev_qdone) cudaEventDestroy(h->ev_qdone);
   if (h->ev_side) cudaEventDestroy(h->ev_side);
+  if (h->ev_b0) cudaEventDestroy(h->ev_b0);
+  if (h->ev_b1) cudaEventDestroy(h->ev_b1);
   if (h->qstream) cudaStreamDestroy(h->qstream);
   if (h->peer) {
     if (h->slab) cudaFree(h->slab);
@@ -1597,6 +1600,48 @@ int scgpu_get_timing(scgpu_handle* h, double* ms_total, double* ms_build, double
   if (ms_total) *ms_total = a;
   if (ms_build) *ms_build = b;
   if (ms_query) *ms_query = c;
+  return SCGPU_OK;
+}
+
+// Device-side stopwatch over a sequence of (asynchronous) calls: start is an event on the build stream behind everything
+// enqueued so far, stop an event behind everything enqueued on both streams; device-list handle: the slowest shard.
+int scgpu_timer_start(scgpu_handle* h) {
+  if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->is_group) {
+    for (scgpu_handle* s : h->shards) RET(scgpu_timer_start(s));
+    return SCGPU_OK;
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  if (!h->ev_b0) {
+    CK(cudaEventCreate(&h->ev_b0));
+    CK(cudaEventCreate(&h->ev_b1));
+  }
+  CK(cudaEventRecord(h->ev_side, h->qstream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_side, 0));
+  CK(cudaEventRecord(h->ev_b0, h->stream));
+  return SCGPU_OK;
+}
+
+int scgpu_timer_stop(scgpu_handle* h, double* ms) {
+  if (!h || !ms) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->is_group) {
+    *ms = 0;
+    for (scgpu_handle* s : h->shards) {
+      double t;
+      RET(scgpu_timer_stop(s, &t));
+      *ms = std::max(*ms, t);
+    }
+    return SCGPU_OK;
+  }
+  if (!h->ev_b0) return fail(SCGPU_E_INVALID, "scgpu_timer_start first");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventRecord(h->ev_side, h->stream));
+  CK(cudaStreamWaitEvent(h->qstream, h->ev_side, 0));
+  CK(cudaEventRecord(h->ev_b1, h->qstream));
+  CK(cudaEventSynchronize(h->ev_b1));
+  float t = 0;
+  CK(cudaEventElapsedTime(&t, h->ev_b0, h->ev_b1));
+  *ms = t;
   return SCGPU_OK;
 }
 
@@ -1959,11 +2004,22 @@ int scgpu_get_entry(scgpu_handle* h, uint64_t i, float* sc, float* ring, double*
   if (!h) return fail(SCGPU_E_INVALID, "null argument");
   if (i >= h->n_global) return fail(SCGPU_E_INVALID, "entry out of range");
   if (h->is_group) return scgpu_get_entry(h->shards[i % h->shards.size()], i, sc, ring, sector);
-  if ((int)(i % (uint64_t)h->cfg.shard_count) != h->cfg.shard_rank) return fail(SCGPU_E_INVALID, "entry lives on another shard");
+  const int owner = (int)(i % (uint64_t)h->cfg.shard_count);
+  const bool remote = owner != h->cfg.shard_rank;
+  // an attached peer shard reads other shards' entries through its mapping of their memory (the caller makes sure the owner
+  // has finished writing: scgpu_replay_results / a barrier)
+  if (remote && !(h->peer && h->attached)) return fail(SCGPU_E_INVALID, "entry lives on another shard");
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaStreamSynchronize(h->qstream));
   const uint64_t l = i / (uint64_t)h->cfg.shard_count;
+  if (remote) {
+    if (sc) CK(cudaMemcpy(sc, h->peers.sc[owner] + l * h->L.RS, sizeof(float) * h->L.RS, cudaMemcpyDeviceToHost));
+    if (ring)
+      CK(cudaMemcpy2D(ring, sizeof(float), h->db.ringT + i, h->db.ring_cap * sizeof(float), sizeof(float), h->L.R, cudaMemcpyDeviceToHost));
+    if (sector) CK(cudaMemcpy(sector, h->peers.sector[owner] + l * h->L.S, sizeof(double) * h->L.S, cudaMemcpyDeviceToHost));
+    return SCGPU_OK;
+  }
   if (sc) CK(cudaMemcpy(sc, h->db.sc + l * h->L.RS, sizeof(float) * h->L.RS, cudaMemcpyDeviceToHost));
   if (ring)
     CK(cudaMemcpy2D(ring, sizeof(float), h->db.ringT + ring_slot(h->db, i, l), h->db.ring_cap * sizeof(float), sizeof(float), h->L.R,
@@ -2497,16 +2553,23 @@ int scgpu_stage_gather(scgpu_handle* h, uint64_t global_idx, void* d_record, voi
   return SCGPU_OK;
 }
 
-int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_qrecords, size_t nq, const uint64_t* n_search, void* d_best_out, void* stream) {
+int scgpu_stage_exhaustive2(scgpu_handle* h, const void* d_qrecords, size_t nq, const uint64_t* n_search, int flipped, void* d_best_out,
+                            void* stream) {
   if (!h || !d_qrecords || !d_best_out || (!n_search && nq)) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->is_group) return fail(SCGPU_E_INVALID, "the staged API addresses one shard, not a device-list handle");
   if (!h->exh) return fail(SCGPU_E_INVALID, "screening kernels are instantiated for 20x60 (radius 3) and 40x120 (radius 6) only");
   CK(cudaSetDevice(h->cfg.device));
-  for (size_t i0 = 0; i0 < nq; i0 += EXH_MAX_BATCH) {
-    const size_t m = nq - i0 < EXH_MAX_BATCH ? nq - i0 : EXH_MAX_BATCH;
+  const size_t per = flipped ? EXH_MAX_BATCH / 2 : EXH_MAX_BATCH;
+  for (size_t i0 = 0; i0 < nq; i0 += per) {
+    const size_t m = nq - i0 < per ? nq - i0 : per;
     RET(launch_exhaustive_fast(h, static_cast<const unsigned char*>(d_qrecords) + i0 * h->L.rec_bytes, m, n_search + i0,
-                               static_cast<Best*>(d_best_out) + i0, ST(stream), nullptr, nullptr));
+                               static_cast<Best*>(d_best_out) + i0, ST(stream), nullptr, nullptr, flipped));
   }
   return SCGPU_OK;
+}
+
+int scgpu_stage_exhaustive(scgpu_handle* h, const void* d_qrecords, size_t nq, const uint64_t* n_search, void* d_best_out, void* stream) {
+  return scgpu_stage_exhaustive2(h, d_qrecords, nq, n_search, 0, d_best_out, stream);
 }
 
 int scgpu_stage_finalize(scgpu_handle* h, const void* d_best_parts, int parts, size_t nq, const uint64_t* d_ns, int32_t* d_loop_id,

@@ -56,6 +56,8 @@ _SIGNATURES = {
     "scgpu_query_batched": [_vp, _u64, _sz, _vp, _vp, _vp, _vp, _vp],
     "scgpu_replay_async": [_vp, _vp, _sz, _sz, _sz, _i],
     "scgpu_replay_results": [_vp, _sz, _vp, _vp, _vp, _vp, _vp],
+    "scgpu_timer_start": [_vp],
+    "scgpu_timer_stop": [_vp, _pd],
     "scgpu_peer_export": [_vp, _vp, _sz],
     "scgpu_peer_attach": [_vp, _vp, _i],
     "scgpu_peer_replay_async": [_vp, _vp, _sz, _sz, _sz, _i],
@@ -69,6 +71,7 @@ _SIGNATURES = {
     "scgpu_exhaustive_batched": [_vp, _vp, _vp, _sz, _vp, _vp, _vp],
     "scgpu_exhaustive_stats": [_vp, C.POINTER(_u64)],
     "scgpu_stage_exhaustive": [_vp, _vp, _sz, _vp, _vp, _vp],
+    "scgpu_stage_exhaustive2": [_vp, _vp, _sz, _vp, _i, _vp, _vp],
     "scgpu_stage_gather": [_vp, _u64, _vp, _vp],
     "scgpu_set_downsample_leaf": [_vp, C.c_float],
     "scgpu_voxel_downsample": [_vp, _vp, _sz, _sz, C.c_float, _vp, _vp, _sz, C.POINTER(_sz), _vp, _vp, _pi],
@@ -396,6 +399,15 @@ class SCManager:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _check(self.lib.scgpu_get_timing(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def timer_start(self):
+        _check(self.lib.scgpu_timer_start(self.h))
+
+    def timer_stop(self):
+        """Device milliseconds since timer_start (waits for everything enqueued)."""
+        ms = C.c_double()
+        _check(self.lib.scgpu_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def selfcheck_binning(self, n, seed=1, mode=0):
         """(mismatches, fallbacks, first_bad) of the binning front end vs the exact path over n device-generated points."""

@@ -64,12 +64,12 @@ class ShardedSearch:
         recs = self._all_gather(mine).transpose(0, 1).reshape(nq, -1).contiguous()                      # query i = j*G + r
         return self.exhaustive_records(recs, n_search)
 
-    def exhaustive_records(self, qrecs, n_search):
+    def exhaustive_records(self, qrecs, n_search, flipped=False):
         """The same for a batch of query records present on every rank ([nq, rec]); returns device tensors
         (dist, shift, idx) per query.  One all_gather of 24 bytes per query per rank.  A shard whose rescoring list
         overflowed (n_rescored > EXH_LIST_CAP: a database of near-duplicates) reports an unreliable winner; those
         queries are redone exactly on that shard (scgpu_stage_exhaustive_exact) and gathered again."""
-        local = self.st.exhaustive(qrecs, n_search)
+        local = self.st.exhaustive(qrecs, n_search, flipped)
         parts = self._all_gather(local)
         over = (parts[..., 1] & 0xffffffff) > EXH_LIST_CAP                        # [G, nq]
         if bool(over.any().item()):
@@ -123,7 +123,7 @@ def reduce_exhaustive_batch(parts):
     none = ~cand.any(dim=0)
     take = lambda t: t.gather(0, g.unsqueeze(0)).squeeze(0)                 # noqa: E731
     out_d = torch.where(none, torch.full_like(dmin, 1e7), take(d))
-    out_s = torch.where(none, torch.zeros_like(g), take(shift)).to(torch.int32)
+    out_s = torch.where(none, torch.zeros_like(g), take(shift) & 0x3fffffff).to(torch.int32)       # bit 30: flipped winner
     out_i = torch.where(none, torch.zeros_like(g), take(idx))
     return out_d, out_s, out_i
 
@@ -211,13 +211,15 @@ class GpuStages:
         self._check(self.lib.scgpu_stage_gather(self.h, global_idx, rec.data_ptr(), self._stream()))
         return rec
 
-    def exhaustive(self, qrec, n_search):
-        """This shard's exhaustive winners for the query record(s) qrec ([rec] or [nq, rec]): [3] / [nq, 3] int64."""
+    def exhaustive(self, qrec, n_search, flipped=False):
+        """This shard's exhaustive winners for the query record(s) qrec ([rec] or [nq, rec]): [3] / [nq, 3] int64.
+        flipped: also score every entry with its columns reversed (a flipped winner has bit 30 of the shift set)."""
         single = qrec.dim() == 1
         nq = 1 if single else qrec.shape[0]
         ns = np.ascontiguousarray(np.broadcast_to(np.asarray(n_search, np.uint64), (nq,)))
         best = torch.empty((nq, 3), dtype=torch.int64, device=self.device)
-        self._check(self.lib.scgpu_stage_exhaustive(self.h, qrec.data_ptr(), nq, ns.ctypes.data, best.data_ptr(), self._stream()))
+        self._check(self.lib.scgpu_stage_exhaustive2(self.h, qrec.data_ptr(), nq, ns.ctypes.data, int(bool(flipped)), best.data_ptr(),
+                                                     self._stream()))
         return best[0] if single else best
 
     def exhaustive_exact(self, qrec, n_search):
