@@ -476,18 +476,50 @@ int launch_append(scgpu_handle* h, const void* d_records, uint64_t first_global,
       if (s != h->cfg.shard_rank) pl.dst[pl.n++] = h->ring_of[s];
   }
   // entries below the current size are being overwritten: their screening copies are stale
-  const uint64_t first_local = first_global / (uint64_t)h->cfg.shard_count;
+  const uint64_t first_local = local_count(h, first_global);  // this shard's entries below first_global = the first slot written
   if (first_global < h->n_global && h->x_upto > first_local) h->x_upto = first_local;
-  k_append<<<(unsigned)n, 128, 0, st>>>(static_cast<const unsigned char*>(d_records), h->L, h->db, first_global, step, pl);
+  // with the screening kernels in use, the screening copy of the new entries is written by the same launch -- provided the
+  // entries before them already have theirs (otherwise exh_sync catches up lazily, before the first search that needs it)
+  const bool fused_hat = h->exh && (step == 1 || step == (uint64_t)h->cfg.shard_count) && h->x_upto >= first_local;
+  if (fused_hat)
+    k_append_hat<<<(unsigned)n, 128, 0, st>>>(static_cast<const unsigned char*>(d_records), h->L, h->db, first_global, step, pl, h->x_sc_hat, h->x_vk);
+  else
+    k_append<<<(unsigned)n, 128, 0, st>>>(static_cast<const unsigned char*>(d_records), h->L, h->db, first_global, step, pl);
   h->launches++;
   CK(cudaGetLastError());
   if (new_size > h->n_global) h->n_global = new_size;
   const uint64_t have = local_count(h, h->n_global);
   if (have > h->n_written) h->n_written = have;
+  if (fused_hat && have > h->x_upto) h->x_upto = have;
   if (h->peer && h->exh) RET(exh_sync(h, st));  // the other shards fetch screening rows from here: keep them current
   return SCGPU_OK;
 }
 
+// Launch shape of k_topk: `warps` (2, 4 or 8) per block share one (query, chunk).  Every warp keeps its own sorted list, which
+// costs ~K(1 + ln(n_warp / K)) warm-up insertions plus a merge per warp -- so a warp's stream should be long (>= ~1k keys) --
+// while the launch as a whole wants ~16 warps per SM to cover the L2 latency of the key loads.  (A 568-query step over 4,541
+// keys: 2 chunks x 8 warps = 288 keys per warp took 59 us; 1 chunk x 4 warps = 1,135 keys per warp is the shape chosen now.)
+void choose_topk_shape(uint64_t n_local, size_t nq, int sm_count, unsigned& chunk, unsigned& chunks, int& warps) {
+  if (n_local == 0 || nq == 0) {
+    chunk = 256;
+    chunks = 1;
+    warps = 2;
+    return;
+  }
+  uint64_t wq = ((uint64_t)sm_count * 16 + nq - 1) / nq;  // warps per query the grid would like
+  const uint64_t by_stream = n_local / 1024;              // ... and what keeps every stream >= 1,024 keys
+  if (wq > by_stream) wq = by_stream;
+  if (wq < 2) wq = 2;
+  warps = wq <= 2 ? 2 : (wq <= 4 ? 4 : 8);
+  uint64_t c = (wq + warps - 1) / warps;
+  if (c < 1) c = 1;
+  uint64_t ch = (n_local + c - 1) / c;
+  ch = (ch + 255) / 256 * 256;
+  chunk = (unsigned)ch;
+  chunks = (unsigned)((n_local + ch - 1) / ch);
+}
+
+// k_topk_tile's shape (groups of TOPK_QT queries per block, TOPK_TILE_WARPS warps): as many chunks as fill the GPU
 void choose_chunks(uint64_t n_local, size_t nq, unsigned& chunk, unsigned& chunks) {
   if (n_local == 0) {
     chunk = 256;
@@ -541,8 +573,10 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
     static const char* force = getenv("SCGPU_TOPK_TILE");
     tile = force ? atoi(force) != 0 : (uint64_t)chunk / TOPK_TILE_WARPS >= 8192;
   }
+  int warps = 8;
+  if (tile) choose_chunks(n_local, groups, chunk, chunks);
+  else choose_topk_shape(n_local, nq, h->sm_count, chunk, chunks, warps);
   const size_t units = tile ? groups : nq;
-  choose_chunks(n_local, units, chunk, chunks);
   RET(query_reserve(h, nq, chunks, st));
   TopkParams p;
   p.qrecords = static_cast<const unsigned char*>(d_qrec);
@@ -572,17 +606,18 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
     return SCGPU_OK;
   }
   dim3 grid(chunks, (unsigned)nq);
-  const bool many = (uint64_t)chunks * nq >= 4096;  // enough blocks to fill the GPU with 2-warp blocks
+#define SCGPU_TOPK_CASE(SL)                                         \
+  if (warps == 2) k_topk<SL, 2><<<grid, 64, 0, st>>>(p);            \
+  else if (warps == 4) k_topk<SL, 4><<<grid, 128, 0, st>>>(p);      \
+  else k_topk<SL, 8><<<grid, 256, 0, st>>>(p);
   if (h->slots == 1) {
-    if (many) k_topk<1, 2><<<grid, 64, 0, st>>>(p);
-    else k_topk<1, 8><<<grid, 256, 0, st>>>(p);
+    SCGPU_TOPK_CASE(1)
   } else if (h->slots == 2) {
-    if (many) k_topk<2, 2><<<grid, 64, 0, st>>>(p);
-    else k_topk<2, 8><<<grid, 256, 0, st>>>(p);
+    SCGPU_TOPK_CASE(2)
   } else {
-    if (many) k_topk<4, 2><<<grid, 64, 0, st>>>(p);
-    else k_topk<4, 8><<<grid, 256, 0, st>>>(p);
+    SCGPU_TOPK_CASE(4)
   }
+#undef SCGPU_TOPK_CASE
   h->launches++;
   CK(cudaGetLastError());
   return SCGPU_OK;
@@ -639,13 +674,16 @@ int exh_sync(scgpu_handle* h, cudaStream_t st) {
 }
 
 // Stage 4 for the top-K path: FP32 screening of all K candidates, exact FP64 scoring of those that can be the minimum.
+// The rescoring list's counter is armed (zero) on entry: zeroed at allocation, re-armed by k_best / k_best_finalize.
 int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* d_keys, const uint64_t* d_ns, cudaStream_t st) {
   if (nq == 0) return SCGPU_OK;
   RET(exh_sync(h, st));
   RET(h->c_d32.reserve(nq * h->K * sizeof(float)));
   RET(h->c_list.reserve(nq * h->K * sizeof(uint64_t)));
-  RET(h->c_count.reserve(16));
-  CK(cudaMemsetAsync(h->c_count.p, 0, 4, st));
+  if (!h->c_count.p) {
+    RET(h->c_count.reserve(16));
+    CK(cudaMemsetAsync(h->c_count.p, 0, 16, st));
+  }
   CandScreenParams cp;
   cp.qrecords = static_cast<const unsigned char*>(d_qrec);
   cp.L = h->L;
@@ -657,12 +695,14 @@ int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const 
   cp.K = h->K;
   cp.d32 = h->c_d32.as<float>();
   cp.peers = h->peers;
+  cp.list = h->c_list.as<unsigned long long>();
+  cp.count = h->c_count.as<unsigned>();
+  cp.pair_dist = h->pair_dist.as<double>();
+  cp.pair_shift = h->pair_shift.as<int>();
   // warps per block, staging slots per warp.  One slot: three blocks fit an SM and cover each other's fetch latency
   // (two slots = one block per SM measured slower at K = 50).
   if (h->exh_cfg == 1) k_cand_screen<20, 60, 3, 1, 10, 1><<<(unsigned)nq, 10 * 32, cand_smem_bytes<20, 60, 3, 10, 1>(), st>>>(cp);
   else k_cand_screen<40, 120, 6, 2, 5, 1><<<(unsigned)nq, 5 * 32, cand_smem_bytes<40, 120, 6, 5, 1>(), st>>>(cp);
-  k_cand_select<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(h->c_d32.as<float>(), (unsigned)nq, h->K, h->c_list.as<unsigned long long>(),
-                                                             h->c_count.as<unsigned>(), h->pair_dist.as<double>(), h->pair_shift.as<int>());
   ScoreParams p;
   p.qrecords = static_cast<const unsigned char*>(d_qrec);
   p.L = h->L;
@@ -678,7 +718,7 @@ int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const 
   p.peers = h->peers;
   k_score_pairs<<<(unsigned)h->sm_count * 8, 128, pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float)), st>>>(p, h->c_list.as<unsigned long long>(),
                                                                                                             h->c_count.as<unsigned>());
-  h->launches += 3;
+  h->launches += 2;
   CK(cudaGetLastError());
   return SCGPU_OK;
 }
@@ -686,7 +726,8 @@ int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const 
 int launch_best(scgpu_handle* h, size_t nq, const uint64_t* d_keys, Best* d_best, cudaStream_t st) {
   if (nq == 0) return SCGPU_OK;
   k_best<<<(unsigned)((nq + 127) / 128), 128, 0, st>>>(h->pair_dist.as<double>(), h->pair_shift.as<int>(),
-                                                       reinterpret_cast<const unsigned long long*>(d_keys), (unsigned)nq, h->K, d_best);
+                                                       reinterpret_cast<const unsigned long long*>(d_keys), (unsigned)nq, h->K, d_best,
+                                                       h->c_count.as<unsigned>());
   h->launches++;
   CK(cudaGetLastError());
   return SCGPU_OK;
@@ -737,8 +778,16 @@ int query_stage(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
   h->last_qrec = d_qrec;
   if (h->last_screened) RET(launch_score_screened(h, d_qrec, nq, h->keys.as<uint64_t>(), d_ns, st));
   else RET(launch_score(h, d_qrec, nq, h->keys.as<uint64_t>(), d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
-  RET(launch_best(h, nq, h->keys.as<uint64_t>(), h->best.as<Best>(), st));
-  return launch_finalize(h, h->best.as<Best>(), 1, nq, d_ns, d_loop, d_yaw, d_dist, d_idx, d_shift, st, out_off, out_step, push);
+  // decision: strict-min in retrieval order, threshold, yaw -- one launch (every candidate's score is on this device)
+  PushList pl{};
+  if (push) pl = *push;
+  k_best_finalize<<<(unsigned)((nq + 3) / 4), 128, 0, st>>>(h->pair_dist.as<double>(), h->pair_shift.as<int>(), h->keys.as<unsigned long long>(),
+                                                            (unsigned)nq, h->K, reinterpret_cast<const unsigned long long*>(d_ns), h->L.S,
+                                                            h->cfg.dist_thres, d_loop, d_yaw, d_dist, d_idx, d_shift, out_off, out_step, h->rb, pl,
+                                                            h->c_count.as<unsigned>());
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
 }
 
 // a public call is about to use the per-handle query workspace on h->stream: order it after an asynchronous replay's
@@ -838,8 +887,14 @@ class HostPool {
     }
     cv_.notify_all();
     run(*job);
-    std::unique_lock<std::mutex> g(job->mu);
-    job->done.wait(g, [&] { return job->left == 0; });
+    // the caller has nothing else to do: poll (a sleeping caller would add a wake-up latency to every chunk)
+    for (int spins = 0;; ++spins) {
+      {
+        std::lock_guard<std::mutex> g(job->mu);
+        if (job->left == 0) break;
+      }
+      if (spins > 2000) std::this_thread::yield();
+    }
   }
 
  private:
@@ -960,7 +1015,16 @@ int build_from_host(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts
       // work items: slices of scans, so that one scan (the online call) also spreads over the threads
       const size_t slice = 16384;
       const size_t slices_per_scan = (pts_per_scan + slice - 1) / slice;
-      HostPool::get().parallel_for(ns * slices_per_scan, [&](size_t w) {
+      // One online scan (a few MB) is packed by the calling thread alone: waking sleeping workers costs more than they return
+      // (measured on the B200 host, 120k-point PointXYZI scan: 200 us with 1 thread, 240 / 310 / 370 us with 2 / 4 / 16 --
+      // idle cores take ~100 us to come back); batches go to the pool (16 threads: 100 GB/s of host reads).
+      const bool pooled = ns * pts_per_scan * stride >= ((size_t)16 << 20);
+      auto each = [&](size_t n_items, const std::function<void(size_t)>& fn) {
+        if (pooled) HostPool::get().parallel_for(n_items, fn);
+        else
+          for (size_t w = 0; w < n_items; ++w) fn(w);
+      };
+      each(ns * slices_per_scan, [&](size_t w) {
         const size_t sc = w / slices_per_scan, p0 = (w % slices_per_scan) * slice;
         const size_t np = pts_per_scan - p0 < slice ? pts_per_scan - p0 : slice;
         const unsigned char* from = src + (s0 + sc) * src_pitch + p0 * stride;
@@ -1149,15 +1213,13 @@ int replay_enqueue(std::vector<ReplayShard>& sh, uint64_t first, size_t n_total,
   if (n_total > 65535 || (h0->peer && n_total > PEER_RESULT_CAP)) return fail(SCGPU_E_INVALID, "at most 65535 scans per replay call");
   if (!ipc && sh.size() != G) return fail(SCGPU_E_INVALID, "internal: shard list does not cover the database");
   const size_t B = (n_total + G - 1) / G;  // scans per shard (the last ones of some shards may be missing)
-  // chunks: the query stage of chunk c overlaps the binning of chunk c+1; only worth it while a chunk still fills the GPU
-  // with whole-scan tiles (>= two waves of one-block-per-scan)
+  // chunks (SCGPU_REPLAY_CHUNKS, default 1): the query stage of chunk c may run while chunk c+1 is binned.  Measured on the
+  // 4,541-keyframe run (B200): 1.88 / 2.01 / 2.15 / 2.01 ms per step with 1 / 2 / 3 / 4 chunks -- the binning kernel fills every
+  // SM (4 blocks x 256 threads x 64 registers), so the query kernels only get slots in its tail and the smaller launches lose
+  // more to partial waves than the overlap returns.  One chunk it is.
   size_t C = 1;
-  {
-    const size_t per = (size_t)h0->sm_count * 8;
-    if (B >= 2 * per) C = B / per;
-    if (const char* e = getenv("SCGPU_REPLAY_CHUNKS")) C = (size_t)std::max(1, atoi(e));
-    if (C > B) C = B;
-  }
+  if (const char* e = getenv("SCGPU_REPLAY_CHUNKS")) C = (size_t)std::max(1, atoi(e));
+  if (C > B) C = B;
   auto shard_off = [&](scgpu_handle* h) {  // index within the batch of the shard's first scan
     const uint64_t r = h->peer ? (uint64_t)h->cfg.shard_rank : 0;
     return (size_t)((r + G - first % G) % G);
@@ -1361,9 +1423,9 @@ extern "C" {
 
 const char* scgpu_last_error(void) { return g_err; }
 const char* scgpu_version(void) {
-  return "scgpu 0.1 (sm_100a; kernels: k_build k_build_tma k_build_voxel k_append k_gather k_topk k_topk_tile k_merge k_cand_screen "
-         "k_cand_select k_score k_score_pairs k_score_list k_best k_finalize k_pair_api k_exh_prep k_exh_append k_exh_screen k_exh_compact "
-         "k_exh_final)";
+  return "scgpu 0.2 (sm_100a; kernels: k_build k_build_tma k_build_voxel k_append k_append_hat k_gather k_topk k_topk_tile k_merge "
+         "k_cand_screen k_score k_score_pairs k_score_list k_best k_finalize k_best_finalize k_pair_api k_exh_prep k_exh_append k_exh_screen "
+         "k_exh_compact k_exh_final k_peer_barrier)";
 }
 
 int scgpu_default_config(scgpu_config* c) {

@@ -644,8 +644,9 @@ __global__ void __launch_bounds__(256) k_exh_final(const double* pair_dist, cons
 // Top-K path: the same FP32 screening applied to the K retrieved candidates of each query (SC.cpp:296-311).
 //   k_cand_screen : one block per query (query table built from its record), one warp per candidate slot; the
 //                   candidate's screening copy is read straight from global memory (L2-resident) into registers.
-//   k_cand_select : per query, candidates whose screened distance is within 2*EXH_EPS of the smallest certain one
-//                   (plus every flagged one) go on a list; the others cannot be the minimum and are marked skipped.
+//                   The same block then selects (cand_select_warp): candidates whose screened distance is within 2*EXH_EPS
+//                   of the smallest certain one (plus every flagged one) go on a list; the others cannot be the minimum
+//                   and are marked skipped.
 //   k_score_pairs : the exact FP64 pair kernel over that list (typically 1-2 of the K candidates per query).
 // The strict-min in candidate order (k_best) then runs over exactly-scored candidates only, so the result is the
 // reference's.  scgpu_get_candidates rescoring everything exactly on demand keeps the parity dumps complete.
@@ -661,7 +662,36 @@ struct CandScreenParams {
   float* d32;                           // [nq][K] out: approx distance; -1 = rescore; +inf = cannot win / not mine
   PeerTab peers;                        // peers.G > 0: every candidate is screened here; its screening copy is fetched from the
                                         // owner shard by the same TMA bulk copy, over NVLink peer memory
+  // fused selection (k_cand_select's job, done by the block that screened the query): slots that need the exact kernel go on
+  // `list` ((query << 32) | slot, counted in *count), the others are marked skipped in pair_dist / pair_shift
+  unsigned long long* list;
+  unsigned* count;
+  double* pair_dist;
+  int* pair_shift;
 };
+
+// which candidate slots of query q need the exact kernel: flagged ones and those within 2*EXH_EPS of the smallest certain value.
+// One warp; d32 of the query's K slots must be visible.
+__device__ __forceinline__ void cand_select_warp(const CandScreenParams& p, int q, int lane) {
+  const float INF = __int_as_float(0x7f800000);
+  float mn = INF;
+  for (int k = lane; k < p.K; k += 32) {
+    const float v = p.d32[(size_t)q * p.K + k];
+    if (v >= 0.f) mn = fminf(mn, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(FULL, mn, o));
+  const float thr = mn + 2.0f * EXH_EPS;
+  for (int k = lane; k < p.K; k += 32) {
+    const size_t o = (size_t)q * p.K + k;
+    const float v = p.d32[o];
+    if (v < 0.f || (v <= thr && v < INF)) {
+      p.list[atomicAdd(p.count, 1u)] = ((unsigned long long)q << 32) | (unsigned)k;
+    } else {  // cannot be the minimum (or not this shard's): skipped by k_best
+      p.pair_dist[o] = 10000000.0;
+      p.pair_shift[o] = -1;
+    }
+  }
+}
 
 // one candidate staged in shared memory: screening copy of the descriptor + its sector key / aux record
 template <int R, int S>
@@ -740,6 +770,10 @@ __global__ void __launch_bounds__(CW * 32) k_cand_screen(const CandScreenParams 
   if (!__syncthreads_or(issued > 0)) {
     for (int k = warp; k < p.K; k += CW)
       if (lane == 0) p.d32[(size_t)q * p.K + k] = __int_as_float(0x7f800000);
+    if (p.list) {
+      __syncthreads();
+      if (warp == 0) cand_select_warp(p, q, lane);
+    }
     return;
   }
 
@@ -815,28 +849,24 @@ __global__ void __launch_bounds__(CW * 32) k_cand_screen(const CandScreenParams 
     const float out = screened_distance<S, RAD>(total, d_mine, a_cur, qmask, ax, amb, q_flag);
     if (lane == 0) p.d32[o] = out;
   }
+  if (p.list) {
+    __syncthreads();  // every warp's d32 stores are visible to the block
+    if (warp == 0) cand_select_warp(p, q, lane);
+  }
 }
 
-// per query: which candidate slots need the exact kernel
-__global__ void k_cand_select(const float* d32, unsigned nq, int K, unsigned long long* list, unsigned* count, double* pair_dist, int* pair_shift) {
-  const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nq) return;
-  float mn = __int_as_float(0x7f800000);
-  for (int k = 0; k < K; ++k) {
-    const float v = d32[(size_t)q * K + k];
-    if (v >= 0.f) mn = fminf(mn, v);
-  }
-  const float thr = mn + 2.0f * EXH_EPS;
-  for (int k = 0; k < K; ++k) {
-    const size_t o = (size_t)q * K + k;
-    const float v = d32[o];
-    if (v < 0.f || (v <= thr && v < __int_as_float(0x7f800000))) {
-      list[atomicAdd(count, 1u)] = ((unsigned long long)q << 32) | (unsigned)k;
-    } else {  // cannot be the minimum (or not this shard's): skipped by k_best
-      pair_dist[o] = 10000000.0;
-      pair_shift[o] = -1;
-    }
-  }
+// Stage-2 storage + screening copy in one launch (peer-sharded / batched replays: the screening rows must be current before the
+// barrier that lets other shards fetch them).  The screening side data is derived from the RECORD (in hand), not re-read from
+// the database.
+__global__ void __launch_bounds__(128) k_append_hat(const unsigned char* records, Layout L, Db db, unsigned long long first_global,
+                                                    unsigned long long step, PushList push, float* sc_hat, unsigned char* vk) {
+  unsigned long long l;
+  const unsigned char* rec = records + (size_t)blockIdx.x * L.rec_bytes;
+  if (!append_entry(rec, L, db, first_global + blockIdx.x * step, push, &l)) return;
+  float* vkey32 = reinterpret_cast<float*>(vk + l * exh_vk_bytes(L.S));
+  ExhAux* aux = reinterpret_cast<ExhAux*>(vkey32 + L.S);
+  exh_normalise<true>(reinterpret_cast<const float*>(rec), reinterpret_cast<const double*>(rec + L.off_sector),
+                      reinterpret_cast<const double*>(rec + L.off_norm), L, sc_hat + l * L.RS, vkey32, aux->vmask, &aux->vnorm, &aux->flags);
 }
 
 // the exact pair kernel over a (query, slot) list; persistent grid

@@ -530,11 +530,11 @@ struct PushList {
 
 // records [0,n) -> entries first_global + i*step (kept when owned)
 // push: the other shards' ring-key replicas (peer stores over NVLink); the ring key of a record is written there too
-__global__ void __launch_bounds__(128) k_append(const unsigned char* records, Layout L, Db db, unsigned long long first_global,
-                                                unsigned long long step, PushList push) {
-  const unsigned long long g = first_global + blockIdx.x * step;
+// returns true (block-uniform) when the entry is stored on this shard; *l_out = its local slot
+__device__ __forceinline__ bool append_entry(const unsigned char* rec, const Layout& L, const Db& db, unsigned long long g, const PushList& push,
+                                             unsigned long long* l_out) {
   const unsigned long long l = g / (unsigned long long)db.G;
-  const unsigned char* rec = records + (size_t)blockIdx.x * L.rec_bytes;
+  *l_out = l;
   const bool mine = (int)(g % (unsigned long long)db.G) == db.rank;
   if (db.ring_global) {  // every shard keeps every ring key
     const float* ring = reinterpret_cast<const float*>(rec + L.off_ring);
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(128) k_append(const unsigned char* records, La
       for (int s = 0; s < push.n; ++s) static_cast<float*>(push.dst[s])[o] = v;
     }
   }
-  if (!mine) return;
+  if (!mine) return false;
   const float4* src4 = reinterpret_cast<const float4*>(rec);
   float4* dst4 = reinterpret_cast<float4*>(db.sc + l * L.RS);
   if ((L.RS & 3) == 0) {
@@ -562,6 +562,13 @@ __global__ void __launch_bounds__(128) k_append(const unsigned char* records, La
     db.sector[l * L.S + i] = sector[i];
     db.colnorm[l * L.S + i] = norm[i];
   }
+  return true;
+}
+
+__global__ void __launch_bounds__(128) k_append(const unsigned char* records, Layout L, Db db, unsigned long long first_global,
+                                                unsigned long long step, PushList push) {
+  unsigned long long l;
+  append_entry(records + (size_t)blockIdx.x * L.rec_bytes, L, db, first_global + blockIdx.x * step, push, &l);
 }
 
 // stored entries -> records (query records for stored entries).  Block b takes global entry idx[b] (idx != null) or
@@ -735,15 +742,21 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32) k_topk(const TopkParams p) {
 
   WarpList<SLOTS> list;
   list.init();
-  for (unsigned long long base = start + (unsigned long long)warp * 32; base < end; base += TOPK_THREADS) {
-    const unsigned long long l = base + lane;
+  // two keys per lane per iteration: both keys' loads (2 x R lines from L2) are in flight together, which halves the exposed
+  // latency per key (the kernel is latency-bound: ~15 warps per SM, long-scoreboard stalls on the key loads)
+  auto dist_key = [&](unsigned long long l) {
     unsigned long long key = KEY_NONE;
     if (l < end) {
       const float d2 = R == 20 ? ringkey_dist2<20>(s_q, p.db.ringT, p.db.cap, l, R)
                                : (R == 40 ? ringkey_dist2<40>(s_q, p.db.ringT, p.db.cap, l, R) : ringkey_dist2<0>(s_q, p.db.ringT, p.db.cap, l, R));
       key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(l * p.db.G + p.db.rank);
     }
-    list.offer(key, K);
+    return key;
+  };
+  for (unsigned long long base = start + (unsigned long long)warp * 64; base < end; base += 2 * TOPK_THREADS) {
+    const unsigned long long k0 = dist_key(base + lane), k1 = dist_key(base + 32 + lane);
+    list.offer(k0, K);
+    list.offer(k1, K);
   }
   // block merge: warps > 0 publish, warp 0 absorbs
   if (warp > 0) list.store(s_lists + warp * 32 * SLOTS, K);
@@ -1217,8 +1230,11 @@ struct Best {
   long long idx;
 };
 
-__global__ void k_best(const double* pair_dist, const int* pair_shift, const unsigned long long* keys, unsigned nq, int K, Best* out) {
+// count (optional): the rescoring list's counter, re-armed for the next batch
+__global__ void k_best(const double* pair_dist, const int* pair_shift, const unsigned long long* keys, unsigned nq, int K, Best* out,
+                       unsigned* count) {
   const unsigned q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (count && q == 0) *count = 0;
   if (q >= nq) return;
   Best b;
   b.dist = 10000000.0;
@@ -1332,6 +1348,72 @@ __global__ void k_peer_barrier(BarrierCells peers, int G, int rank, int channel,
       __nanosleep(200);
     }
     __threadfence_system();
+  }
+}
+
+// k_best + k_finalize in one launch for the paths where ONE device holds every candidate's score (single shard, peer-sharded):
+// one warp per query -- lanes take the candidate slots, the strict-min in retrieval order is a warp reduction by (dist, slot).
+// Also re-arms the rescoring list's counter for the next batch (count, optional).
+__global__ void __launch_bounds__(128) k_best_finalize(const double* pair_dist, const int* pair_shift, const unsigned long long* keys, unsigned nq,
+                                                       int K, const unsigned long long* n_search, int S, double thres, int* loop_id, float* yaw,
+                                                       double* nearest_dist, int* nearest_idx, int* nearest_shift, unsigned out_off,
+                                                       unsigned out_step, ResultBlock rb, PushList push, unsigned* count) {
+  const unsigned q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (count && blockIdx.x == 0 && threadIdx.x == 0) *count = 0;
+  if (q >= nq) return;
+  double dist = 10000000.0;
+  int rank = K;
+  for (int k = lane; k < K; k += 32) {  // ascending k within a lane: strict '<' keeps the earliest slot
+    const size_t o = (size_t)q * K + k;
+    if (pair_shift[o] < 0) continue;
+    const double d = pair_dist[o];
+    if (d < dist) {
+      dist = d;
+      rank = k;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double od = __shfl_xor_sync(FULL, dist, o);
+    const int orank = __shfl_xor_sync(FULL, rank, o);
+    if (orank < K && (rank >= K || od < dist || (od == dist && orank < rank))) {
+      dist = od;
+      rank = orank;
+    }
+  }
+  if (lane != 0) return;
+  int shift = 0;
+  long long idx = 0;
+  const bool live = n_search[q] != 0;
+  if (rank < K && live) {
+    const size_t o = (size_t)q * K + rank;
+    shift = pair_shift[o];
+    const unsigned long long key = keys[o];
+    idx = (key == KEY_NONE) ? 0 : (long long)(key & 0xffffffffull);
+  } else {
+    dist = 10000000.0;
+  }
+  int lid = -1;
+  float y = 0.0f;
+  if (live) {
+    if (dist < thres) lid = (int)idx;
+    const double unit = __ddiv_rn(360.0, (double)S);                               // SC.h:82
+    const float deg = __double2float_rn(__dmul_rn((double)shift, unit));           // SC.cpp:333 argument narrowing
+    y = __double2float_rn(__ddiv_rn(__dmul_rn((double)deg, 3.14159265358979323846), 180.0));  // SC.cpp:17-20
+  }
+  const unsigned o = out_off + q * out_step;
+  loop_id[o] = lid;
+  yaw[o] = y;
+  if (nearest_dist) nearest_dist[o] = dist;
+  if (nearest_idx) nearest_idx[o] = (int)idx;
+  if (nearest_shift) nearest_shift[o] = shift;
+  for (int s = 0; s < push.n; ++s) {
+    void* b = push.dst[s];
+    rb.loop(b)[o] = lid;
+    rb.yaw(b)[o] = y;
+    rb.dist(b)[o] = dist;
+    rb.idx(b)[o] = (int)idx;
+    rb.shift(b)[o] = shift;
   }
 }
 
