@@ -164,6 +164,11 @@ int scgpu_exhaustive_batched(scgpu_handle* h, const uint64_t* q, const uint64_t*
 /* How many entries the last scgpu_exhaustive had to rescore with the exact FP64 kernel (the rest was ruled out
  * by the FP32 screening pass with a proven margin). */
 int scgpu_exhaustive_stats(scgpu_handle* h, uint64_t* rescored);
+/* Parity probe of the exhaustive search's screening pass (FP32 SIMT kernels for the windowed search, the tcgen05 tensor-core
+ * kernel for the full-shift search): the screened distance of stored entry q against every entry [0, n_search) --
+ * d32[i] approximates distanceBtnScanContext(q, i) within the selection margin; -1 = "cannot tell, the exact kernel decides",
+ * +inf = no valid column pair.  shift (optional, full-shift configuration only): the argmin shift per entry. */
+int scgpu_probe_screen(scgpu_handle* h, uint64_t q, uint64_t n_search, float* d32, uint32_t* shift);
 /* ---- voxel-grid downsample in front of the path ---------------------------------------
  * The reference filters every raw scan with pcl::VoxelGrid before it reaches SCManager:
  * downSizeFilterScancontext.setLeafSize(0.5, 0.5, 0.5) (mapOpt.cpp:264), .filter() (mapOpt.cpp:1235-1237), and the

@@ -196,6 +196,8 @@ REF_VARIANTS = {
     "k50": "libscref_k50.so",          # K=50
     "40x120": "libscref_40x120.so",    # R=40, S=120
     "full": "libscref_full.so",        # 7x18, ratio 1.0, K=3, exclude 5, period 3, lidar_height 0, radius 33.3
+    "full60": "libscref_full60.so",    # 20x60, ratio 1.0 (every shift searched)
+    "intensity": "libscref_intensity.so",  # bin value = point intensity instead of z + LIDAR_HEIGHT (Scancontext.h:41)
 }
 
 

@@ -40,6 +40,7 @@ void fill_cloud(pcl::PointCloud<SCPointType>& cloud, const void* pts, size_t n, 
     q.y = xyz[1];
     q.z = xyz[2];
     q.intensity = 0.f;
+    if (stride >= 20) std::memcpy(&q.intensity, p + i * stride + 16, sizeof(float));  // pcl::PointXYZI layout: intensity at byte 16
     cloud.points[i] = q;
   }
 }

@@ -21,6 +21,7 @@
 
 #include "scgpu_exhaustive.cuh"
 #include "scgpu_kernels.cuh"
+#include "scgpu_tc.cuh"
 #include "scgpu_voxel.cuh"
 
 using namespace scgpu;
@@ -109,7 +110,13 @@ struct scgpu_handle {
   uint64_t n_global = 0;
   // screening copy for the exhaustive search (only for configurations k_exh_screen is instantiated for)
   bool exh = false;
-  int exh_cfg = 0;  // 1: 20x60 radius 3, 2: 40x120 radius 6
+  int exh_cfg = 0;  // 1: 20x60 radius 3, 2: 40x120 radius 6, 3: 20x60 full-shift search (tensor-core screening, scgpu_tc.cuh)
+  // full-shift search on the tensor cores: hi / lo split of the screening copy, the queries' circulant expansion, TMA maps
+  DevBuf tc_e_hi, tc_e_lo, tc_q_hi, tc_q_lo, tc_qaux, tc_shift;
+  uint64_t tc_rows = 0;    // rows the E buffers (and their tensor maps) were sized for
+  uint64_t tc_upto = 0;    // local entries [0, tc_upto) are split
+  CUtensorMap tc_maps[4];  // E_hi, E_lo, Q_hi, Q_lo
+  bool tc_want_shifts = false;
   float* x_sc_hat = nullptr;
   unsigned char* x_vk = nullptr;  // [cap] ExhVkRec: float sector key + aux
   DevBuf x_query, x_d32, x_keys, x_pd, x_ps, x_small, x_best;
@@ -774,7 +781,7 @@ int query_stage(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
   choose_chunks(h->peer ? h->n_global : local_count(h, h->n_global), nq, chunk, chunks);
   RET(query_reserve(h, nq, chunks, st));
   RET(launch_topk(h, d_qrec, nq, d_ns, h->keys.as<uint64_t>(), st));
-  h->last_screened = h->exh && !(h->cfg.flags & SCGPU_FLAG_NO_SCREENING);
+  h->last_screened = h->exh && h->exh_cfg != 3 && !(h->cfg.flags & SCGPU_FLAG_NO_SCREENING);
   h->last_qrec = d_qrec;
   if (h->last_screened) RET(launch_score_screened(h, d_qrec, nq, h->keys.as<uint64_t>(), d_ns, st));
   else RET(launch_score(h, d_qrec, nq, h->keys.as<uint64_t>(), d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
@@ -1076,6 +1083,61 @@ int pair_api(scgpu_handle* h, const double* a, size_t na, const double* b, size_
   return SCGPU_OK;
 }
 
+constexpr size_t EXH_MAX_BATCH_TC = 64;      // queries per tensor-core screening launch (16 groups of 4)
+// ---- tensor-core full-shift screening: host side ------------------------------------------------------------------------
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D FP32 tensor [rows][TC_K], box = box_rows x TC_BK floats, 128-byte swizzle (what the UMMA shared-memory descriptors expect)
+int tc_make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t box_rows) {
+  static TensorMapEncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(SCGPU_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = reinterpret_cast<TensorMapEncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)TC_K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)TC_K * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SCGPU_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return SCGPU_OK;
+}
+
+// hi / lo split of the screening copy up to date with the shard; (re)creates the buffers and maps when the capacity changed
+int tc_sync(scgpu_handle* h, cudaStream_t st) {
+  const uint64_t have = local_count(h, h->n_global);
+  if (h->tc_rows != h->db.cap) {
+    CK(cudaStreamSynchronize(st));
+    h->tc_e_hi.release();
+    h->tc_e_lo.release();
+    const size_t bytes = (size_t)h->db.cap * TC_K * sizeof(float);
+    RET(h->tc_e_hi.reserve(bytes));
+    RET(h->tc_e_lo.reserve(bytes));
+    RET(h->tc_q_hi.reserve((size_t)EXH_MAX_BATCH_TC * TC_S * TC_K * sizeof(float), true, st));
+    RET(h->tc_q_lo.reserve((size_t)EXH_MAX_BATCH_TC * TC_S * TC_K * sizeof(float), true, st));
+    RET(h->tc_qaux.reserve((size_t)EXH_MAX_BATCH_TC * sizeof(TcQueryAux), true, st));
+    RET(tc_make_map(&h->tc_maps[0], h->tc_e_hi.p, h->db.cap, TC_M));
+    RET(tc_make_map(&h->tc_maps[1], h->tc_e_lo.p, h->db.cap, TC_M));
+    RET(tc_make_map(&h->tc_maps[2], h->tc_q_hi.p, (uint64_t)EXH_MAX_BATCH_TC * TC_S, TC_N));
+    RET(tc_make_map(&h->tc_maps[3], h->tc_q_lo.p, (uint64_t)EXH_MAX_BATCH_TC * TC_S, TC_N));
+    h->tc_rows = h->db.cap;
+    h->tc_upto = 0;
+  }
+  if (h->tc_upto > h->x_upto) h->tc_upto = h->x_upto;
+  if (have > h->tc_upto) {
+    k_tc_split_db<<<(unsigned)(have - h->tc_upto), 256, 0, st>>>(h->x_sc_hat, h->tc_e_hi.as<float>(), h->tc_e_lo.as<float>(), h->tc_upto);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->tc_upto = have;
+  }
+  return SCGPU_OK;
+}
+
 constexpr unsigned EXH_CAND_CAP = 65536;   // rescoring list of one batch
 constexpr size_t EXH_MAX_BATCH = 64;       // queries per screening launch
 
@@ -1128,16 +1190,58 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
     const uint64_t ew = h->exh_cfg == 1 ? 20 : 4;  // consumer warps per block of the instantiation
     const uint64_t groups = (n_max + ew - 1) / ew;
     const unsigned grid = (unsigned)(groups < (uint64_t)h->sm_count ? groups : (uint64_t)h->sm_count);
-    if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
-    if (h->exh_cfg == 1)
-      k_exh_screen<20, 60, 3, 1, 20><<<dim3(grid, (unsigned)rows), 20 * 32, exh_smem_bytes<20, 60, 3, 20>(), st>>>(sp);
-    else
-      k_exh_screen<40, 120, 6, 1, 4, 2><<<dim3(grid, (unsigned)rows), 4 * 2 * 32, exh_smem_bytes<40, 120, 6, 4, 2>(), st>>>(sp);
-    if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
+    float eps = EXH_EPS;
+    if (h->exh_cfg == 3) {
+      // every shift is searched: the distance table of a (query, entry) pair is a GEMM tile -- tensor cores (scgpu_tc.cuh);
+      // SCGPU_FULLSHIFT_SIMT=1 runs the FFMA2 counterpart instead (A/B)
+      static const bool simt = getenv("SCGPU_FULLSHIFT_SIMT") && atoi(getenv("SCGPU_FULLSHIFT_SIMT")) != 0;
+      if (flipped) return fail(SCGPU_E_INVALID, "the column-reversed pass is not instantiated for the full-shift search");
+      RET(tc_sync(h, st));
+      unsigned* d_shift = nullptr;
+      if (h->tc_want_shifts) {
+        RET(h->tc_shift.reserve((rows * pitch + 16) * sizeof(unsigned)));
+        d_shift = h->tc_shift.as<unsigned>();
+      }
+      if (simt) {
+        if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
+        const unsigned gx = (unsigned)std::min<uint64_t>((n_max + 7) / 8, (uint64_t)h->sm_count * 8);
+        k_fullshift_simt<TC_R, TC_S><<<dim3(gx, (unsigned)nq), 256, qtab_bytes<TC_R, TC_S, 15>(), st>>>(
+            h->x_sc_hat, h->x_vk, h->x_query.as<ExhQuery>(), d_nl, pitch, h->x_d32.as<float>(), d_min, d_shift);
+        if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
+      } else {
+        k_tc_prep_queries<<<dim3(TC_S, (unsigned)nq), 128, 0, st>>>(h->x_query.as<ExhQuery>(), h->tc_q_hi.as<float>(), h->tc_q_lo.as<float>(),
+                                                                    h->tc_qaux.as<TcQueryAux>());
+        h->launches++;
+        TcParams tp;
+        tp.vk = h->x_vk;
+        tp.qaux = h->tc_qaux.as<TcQueryAux>();
+        tp.n_local = d_nl;
+        tp.nq = (unsigned)nq;
+        tp.n_groups = (unsigned)((nq + TC_QG - 1) / TC_QG);
+        tp.n_tiles = (unsigned)((n_max + TC_M - 1) / TC_M);
+        tp.d32_pitch = pitch;
+        tp.d32 = h->x_d32.as<float>();
+        tp.min_bits = d_min;
+        tp.shift_out = d_shift;
+        const uint64_t items = (uint64_t)tp.n_groups * tp.n_tiles;
+        const unsigned gx = (unsigned)std::min<uint64_t>(items, (uint64_t)h->sm_count);
+        if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
+        k_tc_fullshift<<<gx, TC_THREADS, tc_smem_bytes(), st>>>(h->tc_maps[0], h->tc_maps[1], h->tc_maps[2], h->tc_maps[3], tp);
+        if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
+        eps = TC_EPS;
+      }
+    } else {
+      if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
+      if (h->exh_cfg == 1)
+        k_exh_screen<20, 60, 3, 1, 20><<<dim3(grid, (unsigned)rows), 20 * 32, exh_smem_bytes<20, 60, 3, 20>(), st>>>(sp);
+      else
+        k_exh_screen<40, 120, 6, 1, 4, 2><<<dim3(grid, (unsigned)rows), 4 * 2 * 32, exh_smem_bytes<40, 120, 6, 4, 2>(), st>>>(sp);
+      if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
+    }
     CK(cudaGetLastError());
     const unsigned rb = (unsigned)((n_max + 1023) / 1024 < 296 ? (n_max + 1023) / 1024 : 296);
     k_exh_compact<<<dim3(rb, (unsigned)rows), 256, 0, st>>>(sp.d32, pitch, d_nl, d_min, h->db.rank, h->db.G, sp.flip_mode,
-                                                           h->x_keys.as<unsigned long long>(), d_count, EXH_CAND_CAP);
+                                                           h->x_keys.as<unsigned long long>(), d_count, EXH_CAND_CAP, eps);
     ScoreParams p;
     p.qrecords = d_qrecs;
     p.L = h->L;
@@ -1491,6 +1595,7 @@ static int create_one(const scgpu_config* cfg, scgpu_handle** out) {
   }
   // FP32 screening kernels are instantiated for the reference's 20x60 (radius 3) and BASELINE's 40x120 (radius 6)
   h->exh_cfg = (h->L.R == 20 && h->L.S == 60 && h->radius == 3) ? 1 : ((h->L.R == 40 && h->L.S == 120 && h->radius == 6) ? 2 : 0);
+  if (h->L.R == TC_R && h->L.S == TC_S && 2 * h->radius >= h->L.S) h->exh_cfg = 3;  // every shift is searched: tensor-core screening
   h->exh = h->exh_cfg != 0 && !(cfg->flags & SCGPU_FLAG_NO_SCREENING);
   cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   const size_t smem_f = pair_smem_bytes(h->L.R, h->L.S, h->W, sizeof(float));
@@ -1528,11 +1633,16 @@ static int create_one(const scgpu_config* cfg, scgpu_handle** out) {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_voxel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vox_smem_bytes(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_voxel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vox_smem_bytes(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_voxel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vox_smem_bytes(h->L.RS));
-  if (e == cudaSuccess && h->exh)
+  if (e == cudaSuccess && h->exh && h->exh_cfg != 3)
     e = h->exh_cfg == 1 ? cudaFuncSetAttribute(k_exh_screen<20, 60, 3, 1, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)exh_smem_bytes<20, 60, 3, 20>())
                         : cudaFuncSetAttribute(k_exh_screen<40, 120, 6, 1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)exh_smem_bytes<40, 120, 6, 4, 2>());
+  if (e == cudaSuccess && h->exh_cfg == 3) {
+    e = cudaFuncSetAttribute(k_tc_fullshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes());
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k_fullshift_simt<TC_R, TC_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qtab_bytes<TC_R, TC_S, 15>());
+  }
   if (e == cudaSuccess && h->exh && h->exh_cfg == 1)
     e = cudaFuncSetAttribute(k_cand_screen<20, 60, 3, 1, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem_bytes<20, 60, 3, 10, 1>());
   if (e == cudaSuccess && h->exh && h->exh_cfg == 2)
@@ -1606,7 +1716,9 @@ int scgpu_destroy(scgpu_handle* h) {
       cudaFree(h->x_vk);
     }
   }
-  DevBuf* xb[] = {&h->x_query, &h->x_d32, &h->x_keys, &h->x_pd, &h->x_ps, &h->x_small, &h->x_best, &h->c_d32, &h->c_list, &h->c_count};
+  DevBuf* xb[] = {&h->x_query, &h->x_d32, &h->x_keys, &h->x_pd,    &h->x_ps,    &h->x_small, &h->x_best,  &h->c_d32,
+                  &h->c_list,  &h->c_count, &h->tc_e_hi, &h->tc_e_lo, &h->tc_q_hi, &h->tc_q_lo, &h->tc_qaux, &h->tc_shift,
+                  &h->records2[0], &h->records2[1], &h->res_buf};
   for (DevBuf* b : xb) b->release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
@@ -2289,6 +2401,30 @@ int scgpu_exhaustive_batched(scgpu_handle* h, const uint64_t* q, const uint64_t*
   return SCGPU_OK;
 }
 
+int scgpu_probe_screen(scgpu_handle* h, uint64_t q, uint64_t n_search, float* d32, uint32_t* shift) {
+  if (!h || !d32) return fail(SCGPU_E_INVALID, "null argument");
+  if (h->is_group || h->cfg.shard_count != 1) return fail(SCGPU_E_INVALID, "the screening probe runs on a single-device handle");
+  if (!h->exh) return fail(SCGPU_E_INVALID, "no screening kernel is instantiated for this configuration");
+  if (q >= h->n_global || n_search > h->n_global) return fail(SCGPU_E_INVALID, "range outside the database");
+  if (n_search == 0) return SCGPU_OK;
+  if (shift && h->exh_cfg != 3) return fail(SCGPU_E_INVALID, "per-entry shifts are reported by the full-shift configuration only");
+  CK(cudaSetDevice(h->cfg.device));
+  RET(join_replay(h));
+  h->mutation++;
+  cudaStream_t st = h->stream;
+  k_gather<<<1, 128, 0, st>>>(h->rec_single.as<unsigned char>(), h->L, h->db, h->peers, q, nullptr);
+  h->launches++;
+  RET(h->x_best.reserve(sizeof(Best)));
+  h->tc_want_shifts = shift != nullptr;
+  const int rc = launch_exhaustive_fast(h, h->rec_single.as<unsigned char>(), 1, &n_search, h->x_best.as<Best>(), st, nullptr, nullptr, 0);
+  h->tc_want_shifts = false;
+  RET(rc);
+  CK(cudaMemcpyAsync(d32, h->x_d32.p, n_search * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (shift) CK(cudaMemcpyAsync(shift, h->tc_shift.p, n_search * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SCGPU_OK;
+}
+
 int scgpu_exhaustive_stats(scgpu_handle* h, uint64_t* rescored) {
   if (!h || !rescored) return fail(SCGPU_E_INVALID, "null argument");
   *rescored = h->last_exh_rescored;
@@ -2598,7 +2734,7 @@ int scgpu_stage_score(scgpu_handle* h, const void* d_qrec, size_t nq, const uint
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t st = ST(stream);
   RET(query_reserve(h, nq, 1, st));
-  if (h->exh && !(h->cfg.flags & SCGPU_FLAG_NO_SCREENING)) RET(launch_score_screened(h, d_qrec, nq, d_keys, d_ns, st));
+  if (h->exh && h->exh_cfg != 3 && !(h->cfg.flags & SCGPU_FLAG_NO_SCREENING)) RET(launch_score_screened(h, d_qrec, nq, d_keys, d_ns, st));
   else RET(launch_score(h, d_qrec, nq, d_keys, d_ns, h->K, h->pair_dist.as<double>(), h->pair_shift.as<int>(), 0, st));
   return launch_best(h, nq, d_keys, static_cast<Best*>(d_best_out), st);
 }

@@ -576,12 +576,12 @@ __global__ void __launch_bounds__(EW * WPE * 32, 1) k_exh_screen(const ExhScreen
 // candidates = flagged entries + entries within 2*EXH_EPS of the query's smallest certain value -> one flat key list
 // (flip << 63 | query index << 32 | global entry index); grid (blocks, rows)
 __global__ void k_exh_compact(const float* d32, unsigned long long d32_pitch, const unsigned long long* n_local, const unsigned* min_bits,
-                              int rank, int G, int flip_mode, unsigned long long* keys, unsigned* count, unsigned cap) {
+                              int rank, int G, int flip_mode, unsigned long long* keys, unsigned* count, unsigned cap, float eps) {
   const unsigned row = blockIdx.y, q = flip_mode ? row >> 1 : row;
   const unsigned long long fbit = (flip_mode && (row & 1)) ? (1ull << 63) : 0ull;
   const float* rowp = d32 + row * d32_pitch;
   const unsigned long long n = n_local[q];
-  const float thr = __uint_as_float(min_bits[q]) + 2.0f * EXH_EPS;
+  const float thr = __uint_as_float(min_bits[q]) + 2.0f * eps;
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
     const float v = rowp[i];
     if (v < 0.f || (v <= thr && v < __int_as_float(0x7f800000))) {

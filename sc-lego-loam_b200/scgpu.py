@@ -70,6 +70,7 @@ _SIGNATURES = {
     "scgpu_exhaustive": [_vp, _u64, _u64, _i, _pd, _pi, C.POINTER(C.c_int64), _pi],
     "scgpu_exhaustive_batched": [_vp, _vp, _vp, _sz, _vp, _vp, _vp],
     "scgpu_exhaustive_stats": [_vp, C.POINTER(_u64)],
+    "scgpu_probe_screen": [_vp, _u64, _u64, _vp, _vp],
     "scgpu_stage_exhaustive": [_vp, _vp, _sz, _vp, _vp, _vp],
     "scgpu_stage_exhaustive2": [_vp, _vp, _sz, _vp, _i, _vp, _vp],
     "scgpu_stage_gather": [_vp, _u64, _vp, _vp],
@@ -351,6 +352,13 @@ class SCManager:
         _check(self.lib.scgpu_exhaustive_batched(self.h, q.ctypes.data, ns.ctypes.data, q.size, d.ctypes.data, s.ctypes.data,
                                                  i.ctypes.data))
         return d, s, i
+
+    def probe_screen(self, q, n_search, shifts=False):
+        """Screened distances (float32; -1 = rescore, inf = no valid column pair) of entry q vs entries [0, n_search)."""
+        d = np.empty(n_search, np.float32)
+        s = np.empty(n_search, np.uint32) if shifts else None
+        _check(self.lib.scgpu_probe_screen(self.h, q, n_search, d.ctypes.data, s.ctypes.data if shifts else None))
+        return (d, s) if shifts else d
 
     def exhaustive_rescored(self):
         n = _u64()
