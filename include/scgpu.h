@@ -49,6 +49,9 @@ extern "C" {
                                 capacity (capacity_hint), one device allocation per shard that the other shards map over
                                 NVLink (scgpu_peer_export / scgpu_peer_attach), ring keys replicated on every shard, candidate
                                 rows fetched from their owner inside the scoring kernels.  See "peer-sharded database" below. */
+#define SCGPU_FLAG_INTENSITY 32u /* intensity descriptor (the variant the reference's own comment names, SC.h:41): a bin holds the
+                                    maximum point INTENSITY (the float at byte 16 of a pcl::PointXYZI record; stride >= 20)
+                                    instead of z + LIDAR_HEIGHT (SC.cpp:168); everything downstream is unchanged */
 #define SCGPU_FLAG_FRESH_TREE 1u /* search keys [0, size - exclude_recent) on EVERY detect instead of emulating the
                                     reference's periodically rebuilt KD-tree snapshot (SC.cpp:264-276) */
 

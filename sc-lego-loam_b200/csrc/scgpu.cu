@@ -378,6 +378,7 @@ int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_
   if (n_scans == 0) return SCGPU_OK;
   if (scan_pitch == 0) scan_pitch = pts_per_scan * stride;
   if (h->voxel_leaf > 0.f && pts_per_scan > 0) {
+    if (h->cfg.flags & SCGPU_FLAG_INTENSITY) return fail(SCGPU_E_INVALID, "the voxel-grid path carries no intensity");
     if (scan_pitch != pts_per_scan * stride) return fail(SCGPU_E_INVALID, "the voxel-grid path takes contiguous scans");
     return launch_build_voxel(h, d_pts, n_scans, pts_per_scan, stride, h->voxel_leaf, d_records, nullptr, nullptr, nullptr, 0, st);
   }
@@ -389,6 +390,11 @@ int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_
   p.scan_pitch = (unsigned long long)scan_pitch;
   p.n_pts = (unsigned)pts_per_scan;
   p.stride = (unsigned)stride;
+  // intensity descriptor (SCGPU_FLAG_INTENSITY): bin the float at byte 16 of a pcl::PointXYZI record.  Packed 12-byte points
+  // come from the host packer, which has put the intensity into the third slot already.
+  const bool intensity = (h->cfg.flags & SCGPU_FLAG_INTENSITY) != 0;
+  p.val_off = (intensity && stride != 12) ? 16u : 8u;
+  if (intensity && stride != 12 && stride < 20) return fail(SCGPU_E_INVALID, "the intensity descriptor needs pcl::PointXYZI-like records (stride >= 20 bytes)");
   // tile: enough blocks for two full waves of the GPU (4 resident blocks per SM), otherwise as large as possible -- a
   // scan binned by ONE block needs no global merge (atomics, fences, ticket) and starts / drains its TMA ring once
   // (4,541 HDL-64 scans: 16k-point tiles 1.71 ms, whole-scan tiles 1.56 ms).  From ~3/4 of one wave of scans on, whole-scan
@@ -408,7 +414,7 @@ int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_
     if (v >= 1024 && v % 1024 == 0) ppb = (unsigned)v;
   }
   p.pts_per_block = ppb;
-  p.bc = make_bin_const(h->L.R, h->L.S, h->cfg.lidar_height, h->cfg.max_radius, !(h->cfg.flags & SCGPU_FLAG_EXACT_BINNING));
+  p.bc = make_bin_const(h->L.R, h->L.S, intensity ? 0.0 : h->cfg.lidar_height, h->cfg.max_radius, !(h->cfg.flags & SCGPU_FLAG_EXACT_BINNING));
   p.L = h->L;
   p.gbins = h->gbins.as<int>();
   p.tickets = h->btickets.as<unsigned>();
@@ -424,6 +430,7 @@ int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_
     dim3 grid(tiles, (unsigned)ns);
     const bool al16 = (((uintptr_t)q.pts & 15) == 0) && (scan_pitch & 15) == 0;
     int sk = (stride == 16 && al16) ? 16 : ((stride == 32 && al16) ? 32 : 0);
+    if (p.val_off != 8 && stride == 16) sk = 0;  // (a 20..28-byte or odd layout goes through the generic loads)
     // packed xyz (12 bytes per point, what the host packer ships over PCIe): TMA copies are multiples of 16 bytes, so
     // every tile must hold a multiple of 4 points
     const bool tma12 = stride == 12 && al16 && (pts_per_scan & 3) == 0;
@@ -967,17 +974,18 @@ class HostPool {
   bool stop_ = false;
 };
 
-// x, y, z of points [0, n) at `stride` bytes -> 12 bytes per point
-void pack_xyz(const unsigned char* src, size_t stride, size_t n, float* dst) {
-  if (stride == 12) {
+// x, y and the binned value (z, or the intensity at byte 16) of points [0, n) at `stride` bytes -> 12 bytes per point
+void pack_xyz(const unsigned char* src, size_t stride, size_t n, float* dst, size_t val_off = 8) {
+  if (stride == 12 && val_off == 8) {
     memcpy(dst, src, n * 12);
     return;
   }
+  const size_t vi = val_off / 4;
   for (size_t i = 0; i < n; ++i) {
     const float* p = reinterpret_cast<const float*>(src + i * stride);
     dst[3 * i] = p[0];
     dst[3 * i + 1] = p[1];
-    dst[3 * i + 2] = p[2];
+    dst[3 * i + 2] = p[vi];
   }
 }
 
@@ -994,6 +1002,8 @@ int build_from_host(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts
   static const bool pack_pinned = getenv("SCGPU_PACK_PINNED") && atoi(getenv("SCGPU_PACK_PINNED")) != 0;
   static const bool no_pack = getenv("SCGPU_NO_PACK") && atoi(getenv("SCGPU_NO_PACK")) != 0;
   // the voxel path wants its input as given (it carries no restriction on stride, but keeps the code path of round 1)
+  const bool intensity = (h->cfg.flags & SCGPU_FLAG_INTENSITY) != 0;
+  if (intensity && stride < 20) return fail(SCGPU_E_INVALID, "the intensity descriptor needs pcl::PointXYZI-like records (stride >= 20 bytes)");
   const bool pack = !no_pack && (!pinned || pack_pinned) && !(h->voxel_leaf > 0.f);
   const size_t out_stride = pack ? 12 : stride;
   // staged bytes per scan, padded so that every scan starts 16-byte aligned on the device (TMA)
@@ -1036,7 +1046,7 @@ int build_from_host(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts
         const size_t np = pts_per_scan - p0 < slice ? pts_per_scan - p0 : slice;
         const unsigned char* from = src + (s0 + sc) * src_pitch + p0 * stride;
         unsigned char* to = stage + sc * out_scan + p0 * out_stride;
-        if (pack) pack_xyz(from, stride, np, reinterpret_cast<float*>(to));
+        if (pack) pack_xyz(from, stride, np, reinterpret_cast<float*>(to), intensity ? 16 : 8);
         else memcpy(to, from, np * stride);
       });
       CK(cudaStreamWaitEvent(h->copy_stream, h->ev_consumed[turn], 0));

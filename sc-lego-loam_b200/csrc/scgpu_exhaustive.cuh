@@ -955,6 +955,8 @@ __global__ void __launch_bounds__(256) k_build_tma(const BuildParams p) {
         px[u] = v.x;
         py[u] = v.y;
         pz[u] = v.z;
+        if (STRIDE == 32 && p.val_off != 8)  // intensity descriptor: the value sits in the record's second half (already staged)
+          pz[u] = *reinterpret_cast<const float*>(sp + (size_t)u * 256 * STRIDE + p.val_off);
       }
     };
     if (pts == BUILD_CHUNK) {  // full chunk: no bounds checks

@@ -363,6 +363,8 @@ struct BuildParams {
   unsigned long long scan_pitch;
   unsigned n_pts;     // points per scan
   unsigned stride;    // bytes between points
+  unsigned val_off;   // byte offset of the value that is binned: 8 = z (the reference), 16 = intensity of a pcl::PointXYZI
+                      // (the descriptor variant of Scancontext.h:41; lidar_height is then 0)
   unsigned pts_per_block;
   BinConst bc;
   Layout L;
@@ -372,7 +374,7 @@ struct BuildParams {
 };
 
 template <int STRIDE>  // 16 / 32: one aligned 16-byte load per point; 0: three 4-byte loads (any 4-aligned stride)
-__device__ __forceinline__ void load_point(const unsigned char* p, float& x, float& y, float& z) {
+__device__ __forceinline__ void load_point(const unsigned char* p, float& x, float& y, float& z, unsigned val_off = 8) {
   if (STRIDE == 16 || STRIDE == 32) {
     const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
     x = v.x;
@@ -384,6 +386,7 @@ __device__ __forceinline__ void load_point(const unsigned char* p, float& x, flo
     y = __ldcs(f + 1);
     z = __ldcs(f + 2);
   }
+  if (val_off != 8) z = __ldcs(reinterpret_cast<const float*>(p + val_off));  // (uniform branch) intensity instead of height
 }
 
 // One atomicMax per distinct bin per warp: consecutive points of a scan share a beam and neighbouring azimuths,
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(256) k_build(const BuildParams p) {
     for (int u = 0; u < UNROLL; ++u) {
       const unsigned iu = i + u * blockDim.x;
       px[u] = py[u] = pz[u] = __int_as_float(0x7fc00000);  // NaN: dropped
-      if (iu < end) load_point<STRIDE>(base + (unsigned long long)iu * p.stride, px[u], py[u], pz[u]);
+      if (iu < end) load_point<STRIDE>(base + (unsigned long long)iu * p.stride, px[u], py[u], pz[u], p.val_off);
     }
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {

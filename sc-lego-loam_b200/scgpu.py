@@ -17,6 +17,7 @@ FLAG_EXACT_BINNING = 2
 FLAG_NO_SCREENING = 4
 FLAG_NO_TMA_BUILD = 8
 FLAG_PEER = 16
+FLAG_INTENSITY = 32
 
 
 class ScgpuError(RuntimeError):

@@ -113,3 +113,47 @@ def test_simt_counterpart_gives_the_same_search():
             "d = m.probe_screen(n - 1, 700)\nassert (d >= 0).mean() > 0.99\nprint('simt-ok')\n") % (ROOT, os.path.join(ROOT, "tests"))
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SCGPU_FULLSHIFT_SIMT="1"), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "simt-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_intensity_descriptor_equals_reference_variant():
+    """the bin value is the point's intensity (Scancontext.h:41) instead of z + LIDAR_HEIGHT.  Oracle: the
+    reference with that one line changed (oracle/_ref/libscref_intensity.so), else the port fed (x, y, intensity) with
+    lidar_height = 0 -- the same arithmetic by construction."""
+    import torch
+    from oracle import oracle as orc
+    from sc_lego_loam_b200.scgpu import FLAG_INTENSITY, SCManager, ScgpuError
+    from sc_lego_loam_b200.synth import ScanGen
+    gen = ScanGen("hdl64", seed=99, n_places=90, n_azim=150)
+    xyz = gen.scans(0, 120, 4)
+    rng = np.random.default_rng(5)
+    scans = np.zeros((120, xyz.shape[1], 8), np.float32)
+    scans[:, :, :3] = xyz[:, :, :3]
+    # an intensity field that depends on the place (so that revisits match) plus a little noise; some negative / zero values
+    scans[:, :, 4] = np.abs(np.sin(xyz[:, :, 0] * 0.37) * 90 + xyz[:, :, 2] * 7).astype(np.float32) + rng.normal(0, 0.01, xyz.shape[:2]).astype(np.float32)
+    scans[::7, ::5, 4] = 0.0
+    scans[::11, ::13, 4] = -3.5
+    have_ref = orc.ref_available("intensity")
+    ref = orc.Ref("intensity") if have_ref else orc.Port(orc.Params(lidar_height=0.0))
+
+    def ref_in(s):
+        return s if have_ref else np.ascontiguousarray(np.stack([s[:, 0], s[:, 1], s[:, 4]], axis=1))
+
+    m = SCManager(flags=FLAG_INTENSITY)
+    for i in (0, 17):
+        assert np.array_equal(m.makeScancontext(scans[i]), ref.make_sc(ref_in(scans[i])))
+    out = m.replay(scans)                                           # pageable: host packer (x, y, intensity)
+    pinned = torch.from_numpy(scans).pin_memory()
+    out_p = SCManager(flags=FLAG_INTENSITY).replay((pinned.data_ptr(), 120, scans.shape[1], 32, 0))   # pinned: k_build_tma<32> reads byte 16
+    d = torch.from_numpy(scans).cuda()
+    out_d = SCManager(flags=FLAG_INTENSITY).replay((d.data_ptr(), 120, scans.shape[1], 32, 1))        # device-resident
+    n_loop = 0
+    for i, s in enumerate(scans):
+        ref.append_scan(ref_in(s))
+        r = ref.detect(details=False) if have_ref else ref.detect()
+        for o in (out, out_p, out_d):
+            assert r["loop_id"] == o["loop_id"][i] and np.float32(r["yaw"]).tobytes() == o["yaw"][i].tobytes(), i
+        n_loop += r["loop_id"] >= 0
+    assert n_loop > 0
+    assert not np.array_equal(SCManager().makeScancontext(scans[0]), m.makeScancontext(scans[0]))      # it is a different descriptor
+    with pytest.raises(ScgpuError):
+        m.makeScancontext(xyz[0])                                   # 16-byte points carry no intensity
