@@ -191,6 +191,31 @@ int scgpu_set_downsample_leaf(scgpu_handle* h, float leaf);
  * bits 8.. = number of key partitions the scan needed.  Intensity is not carried (the path reads x, y, z only). */
 int scgpu_voxel_downsample(scgpu_handle* h, const void* pts, size_t n, size_t stride_bytes, float leaf, float* out_xyzn,
                            uint32_t* out_idx, size_t cap, size_t* out_n, int32_t* min_b, int32_t* div_b, int32_t* status);
+/* ---- loop verification after the path ---------------------------------------------------------------
+ * mapOptmization.cpp:1053-1078: once Scan Context has named a loop candidate, the latest keyframe cloud is aligned to the
+ * history submap (+-25 keyframes around the candidate, mapOpt.cpp:928-949) with pcl::IterativeClosestPoint and the loop is
+ * accepted when the ICP converged with fitness <= historyKeyframeFitnessScore (utility.h:139).  scgpu_verify_loop runs that
+ * point-to-point ICP on the device (exact brute-force nearest neighbours, FP64 transform estimation; csrc/scgpu_icp.cuh).
+ * PARITY UNPINNED: PCL is absent from the reference tree and from this image; the kernels and oracle/icp_oracle.cpp restate
+ * PCL 1.8's published algorithm and defaults. */
+typedef struct scgpu_icp_params {
+  int32_t max_iterations;             /* icp.setMaximumIterations           (100)  mapOpt.cpp:1055 */
+  int32_t seed_axis;                  /* -1: identity initial guess (the reference, mapOpt.cpp:1066); 0/1/2: seed with a rotation of
+                                         seed_angle about x / y / z -- the yaw detectLoopClosureID returned (mapOpt.cpp:918, unused there) */
+  double max_correspondence_distance; /* icp.setMaxCorrespondenceDistance   (100)  mapOpt.cpp:1054 */
+  double transformation_epsilon;      /* icp.setTransformationEpsilon       (1e-6) mapOpt.cpp:1056 */
+  double euclidean_fitness_epsilon;   /* icp.setEuclideanFitnessEpsilon     (1e-6) mapOpt.cpp:1057 */
+  double fitness_threshold;           /* historyKeyframeFitnessScore        (1.5)  utility.h:139   */
+  float seed_angle;                   /* radians */
+  float reserved;
+} scgpu_icp_params;
+int scgpu_default_icp_params(scgpu_icp_params* p);
+/* src / tgt: host clouds (n points, `stride` bytes apart, x y z first) = icp.setInputSource / setInputTarget.  Outputs (each
+ * optional): T = icp.getFinalTransformation() (row-major 4x4, source -> target), fitness = icp.getFitnessScore(), converged =
+ * icp.hasConverged(), iterations run, accepted = converged && fitness <= fitness_threshold (the test of mapOpt.cpp:1068). */
+int scgpu_verify_loop(scgpu_handle* h, const void* src, size_t n_src, const void* tgt, size_t n_tgt, size_t stride_bytes,
+                      const scgpu_icp_params* prm, double* T_row_major_16, double* fitness, int* converged, int* iterations,
+                      int* accepted);
 /* Flat binary save / load of the descriptor database. */
 int scgpu_save(scgpu_handle* h, const char* path);
 int scgpu_load(scgpu_handle* h, const char* path);

@@ -226,6 +226,29 @@ class Voxel:
         return {"points": out[:m].copy(), "idx": idx[:m].copy(), "count": cnt[:m].copy(), "min_b": mb, "div_b": db}
 
 
+class Icp:
+    """pcl::IterativeClosestPoint restated (oracle/icp_oracle.cpp; parity unpinned: PCL is not in this image)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_build", "libicporacle.so")
+        if not os.path.exists(path):
+            build(ref=False)
+        self.L = C.CDLL(path)
+        self.L.icp_oracle.argtypes = [_vp, _sz, _vp, _sz, _sz, _i, _d, _d, _d, _vp, _vp, C.POINTER(_d), C.POINTER(_i), C.POINTER(_i)]
+
+    def align(self, src, tgt, T0=None, max_iter=100, max_corr=100.0, trans_eps=1e-6, fit_eps=1e-6):
+        src = np.ascontiguousarray(src, np.float32)
+        tgt = np.ascontiguousarray(tgt, np.float32)
+        assert src.shape[1] == tgt.shape[1] >= 3
+        T0 = np.eye(4) if T0 is None else np.asarray(T0, np.float64)
+        T0 = np.ascontiguousarray(T0.reshape(16))
+        T = np.empty(16, np.float64)
+        fit, conv, its = _d(), _i(), _i()
+        self.L.icp_oracle(src.ctypes.data, src.shape[0], tgt.ctypes.data, tgt.shape[0], src.shape[1], max_iter, max_corr, trans_eps, fit_eps,
+                          T0.ctypes.data, T.ctypes.data, C.byref(fit), C.byref(conv), C.byref(its))
+        return dict(T=T.reshape(4, 4), fitness=fit.value, converged=bool(conv.value), iterations=its.value)
+
+
 def ref_available(variant="default"):
     return os.path.exists(os.path.join(HERE, "_ref", REF_VARIANTS[variant]))
 

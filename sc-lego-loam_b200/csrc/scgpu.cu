@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "scgpu_exhaustive.cuh"
+#include "scgpu_icp.cuh"
 #include "scgpu_kernels.cuh"
 #include "scgpu_tc.cuh"
 #include "scgpu_voxel.cuh"
@@ -113,6 +114,7 @@ struct scgpu_handle {
   int exh_cfg = 0;  // 1: 20x60 radius 3, 2: 40x120 radius 6, 3: 20x60 full-shift search (tensor-core screening, scgpu_tc.cuh)
   // full-shift search on the tensor cores: hi / lo split of the screening copy, the queries' circulant expansion, TMA maps
   DevBuf tc_e_hi, tc_e_lo, tc_q_hi, tc_q_lo, tc_qaux, tc_shift;
+  DevBuf icp_src, icp_tgt, icp_state, icp_part;  // loop verification (scgpu_icp.cuh)
   uint64_t tc_rows = 0;    // rows the E buffers (and their tensor maps) were sized for
   uint64_t tc_upto = 0;    // local entries [0, tc_upto) are split
   CUtensorMap tc_maps[4];  // E_hi, E_lo, Q_hi, Q_lo
@@ -1728,7 +1730,7 @@ int scgpu_destroy(scgpu_handle* h) {
   }
   DevBuf* xb[] = {&h->x_query, &h->x_d32, &h->x_keys, &h->x_pd,    &h->x_ps,    &h->x_small, &h->x_best,  &h->c_d32,
                   &h->c_list,  &h->c_count, &h->tc_e_hi, &h->tc_e_lo, &h->tc_q_hi, &h->tc_q_lo, &h->tc_qaux, &h->tc_shift,
-                  &h->records2[0], &h->records2[1], &h->res_buf};
+                  &h->records2[0], &h->records2[1], &h->res_buf, &h->icp_src, &h->icp_tgt, &h->icp_state, &h->icp_part};
   for (DevBuf* b : xb) b->release();
   for (int i = 0; i < 2; ++i) {
     if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
@@ -2804,6 +2806,88 @@ int scgpu_stage_exhaustive_exact(scgpu_handle* h, const void* d_query_record, ui
   b.shift = w.shift;
   b.idx = w.idx;
   CK(cudaMemcpy(d_best_out, &b, sizeof b, cudaMemcpyHostToDevice));
+  return SCGPU_OK;
+}
+
+// ---- loop verification after the path ---------------------------------------------------------------
+int scgpu_default_icp_params(scgpu_icp_params* p) {
+  if (!p) return fail(SCGPU_E_INVALID, "null argument");
+  memset(p, 0, sizeof *p);
+  p->max_iterations = 100;               // icp.setMaximumIterations(100)            mapOpt.cpp:1055
+  p->max_correspondence_distance = 100;  // icp.setMaxCorrespondenceDistance(100)    mapOpt.cpp:1054
+  p->transformation_epsilon = 1e-6;      // icp.setTransformationEpsilon(1e-6)       mapOpt.cpp:1056
+  p->euclidean_fitness_epsilon = 1e-6;   // icp.setEuclideanFitnessEpsilon(1e-6)     mapOpt.cpp:1057
+  p->fitness_threshold = 1.5;            // historyKeyframeFitnessScore              utility.h:139
+  p->seed_axis = -1;                     // identity initial guess, as the reference runs it (mapOpt.cpp:1066)
+  p->seed_angle = 0.f;
+  return SCGPU_OK;
+}
+
+int scgpu_verify_loop(scgpu_handle* h, const void* src, size_t n_src, const void* tgt, size_t n_tgt, size_t stride, const scgpu_icp_params* prm,
+                      double* T16, double* fitness, int* converged, int* iterations, int* accepted) {
+  if (!h || !prm || (!src && n_src) || (!tgt && n_tgt)) return fail(SCGPU_E_INVALID, "null argument");
+  if (stride < 12 || (stride & 3)) return fail(SCGPU_E_INVALID, "stride must be >= 12 and a multiple of 4");
+  if (n_src > 0x7fffffffull || n_tgt > 0x7fffffffull || prm->max_iterations < 1) return fail(SCGPU_E_INVALID, "bad cloud size / iteration cap");
+  h = GROUP_FIRST(h);
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  IcpState s0;
+  memset(&s0, 0, sizeof s0);
+  for (int k = 0; k < 4; ++k) s0.T[5 * k] = 1.0;
+  if (prm->seed_axis >= 0 && prm->seed_axis <= 2) {  // seed with the yaw Scan Context reported, about the caller's vertical axis
+    const double c = cos((double)prm->seed_angle), sn = sin((double)prm->seed_angle);
+    const int a = (prm->seed_axis + 1) % 3, b = (prm->seed_axis + 2) % 3;
+    s0.T[4 * a + a] = c;
+    s0.T[4 * a + b] = -sn;
+    s0.T[4 * b + a] = sn;
+    s0.T[4 * b + b] = c;
+  }
+  s0.prev_mse = 1.79769313486231570e308;
+  s0.fitness = 1.79769313486231570e308;
+  IcpState out = s0;
+  if (n_src && n_tgt) {
+    const unsigned blocks = (unsigned)((n_src + ICP_BLOCK - 1) / ICP_BLOCK);
+    RET(h->icp_src.reserve(n_src * stride));
+    RET(h->icp_tgt.reserve(n_tgt * stride));
+    RET(h->icp_state.reserve(sizeof(IcpState)));
+    RET(h->icp_part.reserve((size_t)blocks * sizeof(IcpPartial)));
+    CK(cudaMemcpyAsync(h->icp_src.p, src, n_src * stride, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->icp_tgt.p, tgt, n_tgt * stride, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->icp_state.p, &s0, sizeof s0, cudaMemcpyHostToDevice, st));
+    IcpCriteria crit;
+    crit.max_iterations = prm->max_iterations;
+    crit.translation_threshold = prm->transformation_epsilon;
+    crit.rotation_threshold = 0.99999;
+    crit.mse_abs = prm->euclidean_fitness_epsilon;
+    crit.mse_rel = 0.00001;
+    const double md = prm->max_correspondence_distance;
+    const float max_d2 = (float)(md * md);
+    IcpState* d_st = h->icp_state.as<IcpState>();
+    for (int it = 0; it < prm->max_iterations; ++it) {
+      k_icp_nn<<<blocks, ICP_BLOCK, 0, st>>>(h->icp_src.as<unsigned char>(), (unsigned)n_src, (unsigned)stride, h->icp_tgt.as<unsigned char>(),
+                                             (unsigned)n_tgt, (unsigned)stride, d_st, max_d2, 0, h->icp_part.as<IcpPartial>());
+      k_icp_solve<<<1, 32, 0, st>>>(h->icp_part.as<IcpPartial>(), blocks, d_st, crit, 0);
+      h->launches += 2;
+      if ((it & 7) == 7) {  // peek at the flag now and then so that an early convergence does not cost the full launch list
+        int done = 0;
+        CK(cudaMemcpyAsync(&done, &d_st->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (done) break;
+      }
+    }
+    k_icp_nn<<<blocks, ICP_BLOCK, 0, st>>>(h->icp_src.as<unsigned char>(), (unsigned)n_src, (unsigned)stride, h->icp_tgt.as<unsigned char>(),
+                                           (unsigned)n_tgt, (unsigned)stride, d_st, max_d2, 1, h->icp_part.as<IcpPartial>());
+    k_icp_solve<<<1, 32, 0, st>>>(h->icp_part.as<IcpPartial>(), blocks, d_st, crit, 1);
+    h->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&out, d_st, sizeof out, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  if (T16) memcpy(T16, out.T, sizeof out.T);
+  if (fitness) *fitness = out.fitness;
+  if (converged) *converged = out.converged;
+  if (iterations) *iterations = out.iterations;
+  if (accepted) *accepted = out.converged && out.fitness <= prm->fitness_threshold;  // mapOpt.cpp:1068
   return SCGPU_OK;
 }
 

@@ -34,6 +34,13 @@ class Config(C.Structure):
                 ("devices", C.c_int32 * 8)]
 
 
+class IcpParams(C.Structure):
+    """scgpu_icp_params: pcl::IterativeClosestPoint settings of mapOptmization.cpp:1053-1058 + the acceptance threshold."""
+    _fields_ = [("max_iterations", C.c_int32), ("seed_axis", C.c_int32), ("max_correspondence_distance", C.c_double),
+                ("transformation_epsilon", C.c_double), ("euclidean_fitness_epsilon", C.c_double),
+                ("fitness_threshold", C.c_double), ("seed_angle", C.c_float), ("reserved", C.c_float)]
+
+
 _vp, _sz, _i, _u64 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint64
 _pi, _pf, _pd = C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double)
 
@@ -57,6 +64,8 @@ _SIGNATURES = {
     "scgpu_query_batched": [_vp, _u64, _sz, _vp, _vp, _vp, _vp, _vp],
     "scgpu_replay_async": [_vp, _vp, _sz, _sz, _sz, _i],
     "scgpu_replay_results": [_vp, _sz, _vp, _vp, _vp, _vp, _vp],
+    "scgpu_default_icp_params": [C.POINTER(IcpParams)],
+    "scgpu_verify_loop": [_vp, _vp, _sz, _vp, _sz, _sz, C.POINTER(IcpParams), _vp, _pd, _pi, _pi, _pi],
     "scgpu_timer_start": [_vp],
     "scgpu_timer_stop": [_vp, _pd],
     "scgpu_peer_export": [_vp, _vp, _sz],
@@ -408,6 +417,24 @@ class SCManager:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _check(self.lib.scgpu_get_timing(self.h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    def verify_loop(self, source, target, seed_axis=-1, seed_angle=0.0, **overrides):
+        """Point-to-point ICP of `source` onto `target` with the reference's settings (mapOptmization.cpp:1053-1078):
+        dict(T (4,4), fitness, converged, iterations, accepted).  seed_axis 0/1/2 seeds the rotation with the Scan Context yaw."""
+        prm = IcpParams()
+        _check(self.lib.scgpu_default_icp_params(C.byref(prm)))
+        prm.seed_axis, prm.seed_angle = int(seed_axis), float(seed_angle)
+        for k, v in overrides.items():
+            setattr(prm, k, v)
+        s, sp, sn, ss = _pts(source)
+        t, tp, tn, ts = _pts(target)
+        if ss != ts:
+            raise ValueError("source and target must have the same point stride")
+        T = np.empty(16, np.float64)
+        fit, conv, its, acc = C.c_double(), C.c_int(), C.c_int(), C.c_int()
+        _check(self.lib.scgpu_verify_loop(self.h, sp, sn, tp, tn, ss, C.byref(prm), T.ctypes.data, C.byref(fit), C.byref(conv),
+                                          C.byref(its), C.byref(acc)))
+        return dict(T=T.reshape(4, 4), fitness=fit.value, converged=bool(conv.value), iterations=its.value, accepted=bool(acc.value))
 
     def timer_start(self):
         _check(self.lib.scgpu_timer_start(self.h))
