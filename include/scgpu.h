@@ -286,6 +286,9 @@ int scgpu_stage_exhaustive_exact(scgpu_handle* h, const void* d_query_record, ui
  *                               and calls scgpu_peer_attach (cudaIpcOpenMemHandle); steps are then collective calls of
  *                               scgpu_peer_replay_async, synchronised by in-kernel flag barriers over peer memory -- no NCCL
  *                               call on the data path.  One GPU per process (a cross-process barrier cannot share a GPU). */
+/* The partition of a batch over the shards (host arithmetic, no device needed): shard `rank` of G handles the scans
+ * first_index, first_index + G, ... (count of them) of a batch whose first scan becomes global entry `first`. */
+int scgpu_peer_partition(uint64_t first, size_t n_total, int G, int rank, size_t* first_index, size_t* count);
 #define SCGPU_PEER_BLOB_BYTES 128
 int scgpu_peer_export(scgpu_handle* h, void* blob, size_t blob_bytes);
 /* blobs: n * SCGPU_PEER_BLOB_BYTES bytes, blob s exported by shard s (this shard's own included). */

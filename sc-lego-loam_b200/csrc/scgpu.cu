@@ -1201,7 +1201,14 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
     sp.flip_mode = flipped ? 1 : 0;
     const uint64_t ew = h->exh_cfg == 1 ? 20 : 4;  // consumer warps per block of the instantiation
     const uint64_t groups = (n_max + ew - 1) / ew;
-    const unsigned grid = (unsigned)(groups < (uint64_t)h->sm_count ? groups : (uint64_t)h->sm_count);
+    // One block per SM in total: with several screening rows (a batch of queries, or forward + column-reversed) every row gets
+    // sm_count / rows blocks, all resident at once and all walking the database in the same order -- an entry fetched from HBM
+    // for one row is an L2 hit for the others (rows x sm_count blocks would run the rows one after the other, each streaming
+    // the whole database from HBM again).
+    uint64_t per_row = (uint64_t)h->sm_count / rows;
+    if (per_row < 1) per_row = 1;
+    if (const char* e = getenv("SCGPU_EXH_BLOCKS_PER_ROW")) per_row = (uint64_t)std::max(1, atoi(e));
+    const unsigned grid = (unsigned)(groups < per_row ? groups : per_row);
     float eps = EXH_EPS;
     if (h->exh_cfg == 3) {
       // every shift is searched: the distance table of a (query, entry) pair is a GEMM tile -- tensor cores (scgpu_tc.cuh);
@@ -1336,7 +1343,7 @@ int replay_enqueue(std::vector<ReplayShard>& sh, uint64_t first, size_t n_total,
   size_t C = 1;
   if (const char* e = getenv("SCGPU_REPLAY_CHUNKS")) C = (size_t)std::max(1, atoi(e));
   if (C > B) C = B;
-  auto shard_off = [&](scgpu_handle* h) {  // index within the batch of the shard's first scan
+  auto shard_off = [&](scgpu_handle* h) {  // index within the batch of the shard's first scan (= scgpu_peer_partition)
     const uint64_t r = h->peer ? (uint64_t)h->cfg.shard_rank : 0;
     return (size_t)((r + G - first % G) % G);
   };
@@ -2892,6 +2899,17 @@ int scgpu_verify_loop(scgpu_handle* h, const void* src, size_t n_src, const void
 }
 
 // ---- peer-sharded database, one process per GPU -------------------------------------------------------------------------
+
+// Which scans of a batch a shard bins, stores and searches for: scan i of the batch becomes global entry first + i and belongs to
+// shard (first + i) % G.  Host arithmetic only (no device needed): *first_index = the shard's first scan in the batch, *count = how
+// many it has; its j-th scan is batch index first_index + j * G.  This is the partition scgpu_peer_replay_async applies.
+int scgpu_peer_partition(uint64_t first, size_t n_total, int G, int rank, size_t* first_index, size_t* count) {
+  if (!first_index || !count || G < 1 || rank < 0 || rank >= G) return fail(SCGPU_E_INVALID, "bad argument");
+  const size_t off = (size_t)(((uint64_t)rank + (uint64_t)G - first % (uint64_t)G) % (uint64_t)G);
+  *first_index = off;
+  *count = n_total > off ? (n_total - 1 - off) / (size_t)G + 1 : 0;
+  return SCGPU_OK;
+}
 
 int scgpu_peer_export(scgpu_handle* h, void* blob, size_t blob_bytes) {
   if (!h || !blob) return fail(SCGPU_E_INVALID, "null argument");

@@ -68,6 +68,7 @@ _SIGNATURES = {
     "scgpu_verify_loop": [_vp, _vp, _sz, _vp, _sz, _sz, C.POINTER(IcpParams), _vp, _pd, _pi, _pi, _pi],
     "scgpu_timer_start": [_vp],
     "scgpu_timer_stop": [_vp, _pd],
+    "scgpu_peer_partition": [_u64, _sz, _i, _i, C.POINTER(_sz), C.POINTER(_sz)],
     "scgpu_peer_export": [_vp, _vp, _sz],
     "scgpu_peer_attach": [_vp, _vp, _i],
     "scgpu_peer_replay_async": [_vp, _vp, _sz, _sz, _sz, _i],
@@ -456,6 +457,13 @@ class SCManager:
         n = _sz()
         _check(self.lib.scgpu_record_bytes(self.h, C.byref(n)))
         return n.value
+
+
+def peer_partition(first, n_total, G, rank):
+    """(first_index, count): the scans of a batch shard `rank` of G owns (include/scgpu.h scgpu_peer_partition).  No GPU needed."""
+    a, b = _sz(), _sz()
+    _check(load_library().scgpu_peer_partition(first, n_total, G, rank, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def probe_atanf(x):
