@@ -349,9 +349,14 @@ def run_single_gpu(args):
         o2 = new_out(B)
         s_pinned = timed_host(host, B, n0)
         same = all(np.array_equal(res_dev[k], o2[k], equal_nan=True) for k in o2)
-        e2e = {"value": B / s_pinned, "unit": "queries/s", "h2d_bytes_per_step": B * PTS * 16 + B * 8, "d2h_bytes_per_step": B * 24,
-               "ms_per_step": 1e3 * s_pinned, "results_equal_device_leg": bool(same), "h2d_gbs": (B * PTS * 16) / s_pinned / 1e9,
-               "input": "pinned host float4 scans, DMA straight from the caller's buffer"}
+        from sc_lego_loam_b200.scgpu import host_info
+        pool, packs = host_info()
+        shipped = 12 if packs else 16
+        e2e = {"value": B / s_pinned, "unit": "queries/s", "h2d_bytes_per_step": B * PTS * shipped + B * 8, "d2h_bytes_per_step": B * 24,
+               "ms_per_step": 1e3 * s_pinned, "results_equal_device_leg": bool(same), "h2d_gbs": (B * PTS * shipped) / s_pinned / 1e9,
+               "host_pool_threads": pool, "bytes_per_point_on_the_link": shipped,
+               "input": "pinned host float4 scans (16 B/point); " + ("x, y, z packed to 12 B/point by the library's host threads, double-buffered "
+                        "against the H2D copy" if packs else "DMA straight from the caller's buffer (too few host threads to out-pack the link)")}
         # the input the drop-in really gets: pageable pcl::PointXYZI records (32 bytes); a tail of the run on top of the
         # database the full step left behind (the cut keeps the reference's snapshot schedule: (first - 50) % 10 == 0)
         first = max(n0, (DB_SIZE - 1024 - 50) // 10 * 10 + 50)
@@ -405,7 +410,7 @@ def run_single_gpu(args):
                                                 DB_SIZE, 1491)
     if not args.no_sweep:
         line["online_latency"] = online_latency(m, scans)
-        line["voxel_grid"] = voxel_extra(d_scans.data_ptr(), min(B, 1184))
+        line["voxel_grid"] = voxel_extra(d_scans.data_ptr(), min(B, 1184), scans[0])
         del d_scans, m
         torch.cuda.empty_cache()
         line["db_size_sweep"] = db_size_sweep(torch)
@@ -434,24 +439,43 @@ def online_latency(m, scans, n=96):
     return out
 
 
-def voxel_extra(ptr, n_scans):
+def voxel_extra(ptr, n_scans, first_scan):
     """SURVEY 8(f) rank 2: the caller's pcl::VoxelGrid (leaf 0.5 m) moved in front of the descriptor build on the device
-    (k_build_voxel), on the first n_scans resident scans of the run.  PARITY UNPINNED: PCL is absent here."""
+    (k_build_voxel).  PARITY UNPINNED: PCL is absent here.  Two inputs: (a) the first n_scans resident scans of the
+    run -- an open synthetic scene, ~63k voxels per scan, which forces four key partitions per scan; (b) scans of a denser
+    scene (range capped at 30 m) with the 10-30k voxels per scan that real HDL-64 data gives after a 0.5 m grid (one partition)."""
+    import torch
     from sc_lego_loam_b200.scgpu import SCManager
-    m = SCManager(device=0, capacity_hint=n_scans * 6 + 8)
-    m.set_downsample_leaf(0.5)
-    ms = []
-    for _ in range(5):
-        m.truncate(0)
-        m.append_scans((ptr, n_scans, PTS, 16, 1))
-        ms.append(m.timing()[1])
-    m.close()
-    t = float(np.median(ms[2:]))
+    from sc_lego_loam_b200.synth import ScanGen
     peak, _ = measured_peak()
-    return {"kernel": "k_build_voxel", "leaf_m": 0.5, "scans": n_scans, "ms": t, "scans_per_sec": n_scans / (t * 1e-3),
-            "parity": "unpinned (restated pcl::VoxelGrid; PCL absent)",
-            "roofline": {"bound": "hbm", "achieved": n_scans * PTS * 16 / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": n_scans * PTS * 16 / (t * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": n_scans * PTS * 16}}
+
+    def run(ptr, n, label, one_scan):
+        m = SCManager(device=0, capacity_hint=n * 6 + 8)
+        voxels = len(m.voxel_downsample(one_scan, 0.5)["idx"])
+        m.set_downsample_leaf(0.5)
+        ms = []
+        for _ in range(5):
+            m.truncate(0)
+            m.append_scans((ptr, n, PTS, 16, 1))
+            ms.append(m.timing()[1])
+        m.close()
+        t = float(np.median(ms[2:]))
+        return {"input": label, "voxels_per_scan": voxels, "scans": n, "ms": t, "scans_per_sec": n / (t * 1e-3),
+                "roofline": {"bound": "hbm", "achieved": n * PTS * 16 / (t * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": n * PTS * 16 / (t * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_launch": n * PTS * 16}}
+
+    open_scene = run(ptr, n_scans, "the run's own scans (open scene)", first_scan)
+    gen = ScanGen("hdl64", seed=SEED + 7, n_places=400, max_range=30.0)
+    n2 = min(n_scans, 592)
+    dense = np.empty((n2, PTS, 4), np.float32)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        list(ex.map(lambda j: gen.scan(j, 4, dense[j]), range(n2)))
+    d = torch.from_numpy(dense).cuda()
+    dense_scene = run(d.data_ptr(), n2, "dense scene, range <= 30 m (voxel count of real HDL-64 scans)", dense[0])
+    out = dict(open_scene)
+    out.update({"kernel": "k_build_voxel", "leaf_m": 0.5, "parity": "unpinned (restated pcl::VoxelGrid; PCL absent)", "dense_scene": dense_scene})
+    return out
 
 
 def exhaustive_extra(m, n, peak, qs):
@@ -601,6 +625,9 @@ def run_multi_gpu(args):
     clocks.active = False
     same = all(np.array_equal(res_dev[k], out[k], equal_nan=True) for k in out)
     line = None
+    from sc_lego_loam_b200.scgpu import host_info
+    pool, packs = host_info()
+    shipped = 12 if packs else 16
     if rank == 0:
         clocks.stop()
         peak, peak_src = measured_peak()
@@ -617,9 +644,11 @@ def run_multi_gpu(args):
                                       "NVLink peer memory inside the kernels; two in-kernel flag barriers per step; no NCCL call on the data path",
                        "timing": "CUDA events on the library's streams over K steps enqueued back to back, max over ranks"},
             "wall_ms_per_step": 1e3 * wall_dev / args.steps,
-            "e2e": {"value": total / s_e2e, "unit": "queries/s", "h2d_bytes_per_step": total * PTS * 16 + total * 8,
+            "e2e": {"value": total / s_e2e, "unit": "queries/s", "h2d_bytes_per_step": total * PTS * shipped + total * 8,
                     "d2h_bytes_per_step": total * 24 * G, "ms_per_step": 1e3 * s_e2e, "results_equal_device_leg": bool(same),
-                    "h2d_gbs_aggregate": total * PTS * 16 / s_e2e / 1e9, "input": "pinned host float4 scans, one synchronous collective call per step"},
+                    "h2d_gbs_aggregate": total * PTS * shipped / s_e2e / 1e9, "host_pool_threads_per_rank": pool,
+                    "bytes_per_point_on_the_link": shipped, "host_cores": os.cpu_count(),
+                    "input": "pinned host float4 scans, one synchronous collective call per step"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_build_tma", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic[0] * B if traffic else None, "traffic_source": traffic[1] if traffic else None, "peak_source": peak_src,

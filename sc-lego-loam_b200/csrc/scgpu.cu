@@ -1001,12 +1001,16 @@ int build_from_host(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts
     return fail(SCGPU_E_INVALID, "points must be 4-byte aligned, stride >= 12 and a multiple of 4");
   int dev;
   const bool pinned = is_pinned_or_device(pts, &dev) && !dev;
-  static const bool pack_pinned = getenv("SCGPU_PACK_PINNED") && atoi(getenv("SCGPU_PACK_PINNED")) != 0;
+  // Pinned sources: DMA straight from the caller's buffer costs no host work but ships the padding (16 or 32 bytes per point);
+  // packing first ships 12.  Measured on the B200 host (4,541 x 120k float4 points per step, PCIe at 55.5 GB/s): direct 159 ms,
+  // packed 122 ms with 16 threads (the link rate for 12 B/point) but 159 ms with 8 -- so pack only when this process has the
+  // cores to outrun the link (SCGPU_PACK_PINNED=0/1 overrides; one process per GPU divides the cores, see HostPool).
+  static const bool pack_pinned = getenv("SCGPU_PACK_PINNED") ? atoi(getenv("SCGPU_PACK_PINNED")) != 0 : HostPool::get().threads() >= 12;
   static const bool no_pack = getenv("SCGPU_NO_PACK") && atoi(getenv("SCGPU_NO_PACK")) != 0;
   // the voxel path wants its input as given (it carries no restriction on stride, but keeps the code path of round 1)
   const bool intensity = (h->cfg.flags & SCGPU_FLAG_INTENSITY) != 0;
   if (intensity && stride < 20) return fail(SCGPU_E_INVALID, "the intensity descriptor needs pcl::PointXYZI-like records (stride >= 20 bytes)");
-  const bool pack = !no_pack && (!pinned || pack_pinned) && !(h->voxel_leaf > 0.f);
+  const bool pack = !no_pack && (!pinned || (pack_pinned && n_scans * scan_bytes >= ((size_t)64 << 20))) && !(h->voxel_leaf > 0.f);
   const size_t out_stride = pack ? 12 : stride;
   // staged bytes per scan, padded so that every scan starts 16-byte aligned on the device (TMA)
   const size_t out_scan = h->voxel_leaf > 0.f ? pts_per_scan * out_stride : ((pts_per_scan * out_stride + 15) & ~(size_t)15);
@@ -1835,6 +1839,13 @@ int scgpu_timer_stop(scgpu_handle* h, double* ms) {
   float t = 0;
   CK(cudaEventElapsedTime(&t, h->ev_b0, h->ev_b1));
   *ms = t;
+  return SCGPU_OK;
+}
+
+// Host side of the H2D path: threads of the packing pool and whether pinned batches are packed to 12 bytes per point
+int scgpu_host_info(int* pool_threads, int* packs_pinned) {
+  if (pool_threads) *pool_threads = HostPool::get().threads();
+  if (packs_pinned) *packs_pinned = getenv("SCGPU_PACK_PINNED") ? atoi(getenv("SCGPU_PACK_PINNED")) != 0 : HostPool::get().threads() >= 12;
   return SCGPU_OK;
 }
 

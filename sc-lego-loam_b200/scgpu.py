@@ -66,6 +66,7 @@ _SIGNATURES = {
     "scgpu_replay_results": [_vp, _sz, _vp, _vp, _vp, _vp, _vp],
     "scgpu_default_icp_params": [C.POINTER(IcpParams)],
     "scgpu_verify_loop": [_vp, _vp, _sz, _vp, _sz, _sz, C.POINTER(IcpParams), _vp, _pd, _pi, _pi, _pi],
+    "scgpu_host_info": [_pi, _pi],
     "scgpu_timer_start": [_vp],
     "scgpu_timer_stop": [_vp, _pd],
     "scgpu_peer_partition": [_u64, _sz, _i, _i, C.POINTER(_sz), C.POINTER(_sz)],
@@ -457,6 +458,13 @@ class SCManager:
         n = _sz()
         _check(self.lib.scgpu_record_bytes(self.h, C.byref(n)))
         return n.value
+
+
+def host_info():
+    """(pool_threads, packs_pinned) of the library's H2D packing path."""
+    a, b = C.c_int(), C.c_int()
+    _check(load_library().scgpu_host_info(C.byref(a), C.byref(b)))
+    return a.value, bool(b.value)
 
 
 def peer_partition(first, n_total, G, rank):
