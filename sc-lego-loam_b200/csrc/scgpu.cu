@@ -2646,21 +2646,25 @@ int scgpu_xy2theta(float x, float y, float* out_deg) {
     cudaGetLastError();
     return fail(SCGPU_E_NODEVICE, "no CUDA device: libscgpu has no CPU path");
   }
-  float xyz[3] = {x, y, 0.f}, *dx = nullptr, *dh = nullptr, *dt = nullptr;
-  int* db = nullptr;
-  CK(cudaMalloc(&dx, 12));
-  CK(cudaMalloc(&dh, 4));
-  CK(cudaMalloc(&dt, 4));
-  CK(cudaMalloc(&db, 4));
-  CK(cudaMemcpy(dx, xyz, 12, cudaMemcpyHostToDevice));
+  // one small device allocation per (host thread, device), made on the first call and kept: in / bin / height / theta cells
+  struct Cells {
+    int dev = -1;
+    float* p = nullptr;
+  };
+  static thread_local Cells cells;
+  int dev = 0;
+  CK(cudaGetDevice(&dev));
+  if (cells.dev != dev) {
+    cells.p = nullptr;  // (an allocation on another device is left to the driver's teardown)
+    CK(cudaMalloc(&cells.p, 8 * sizeof(float)));
+    cells.dev = dev;
+  }
+  float xyz[3] = {x, y, 0.f};
+  CK(cudaMemcpy(cells.p, xyz, 12, cudaMemcpyHostToDevice));
   const BinConst bc = make_bin_const(20, 60, 2.0, 80.0, 0);
-  k_probe_bins<<<1, 32>>>(dx, 1, bc, db, dh, dt);
+  k_probe_bins<<<1, 32>>>(cells.p, 1, bc, reinterpret_cast<int*>(cells.p + 4), cells.p + 5, cells.p + 6);
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpy(out_deg, dt, 4, cudaMemcpyDeviceToHost);
-  cudaFree(dx);
-  cudaFree(dh);
-  cudaFree(dt);
-  cudaFree(db);
+  if (e == cudaSuccess) e = cudaMemcpy(out_deg, cells.p + 6, 4, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return fail(SCGPU_E_CUDA, "xy2theta: %s", cudaGetErrorString(e));
   return SCGPU_OK;
 }

@@ -24,8 +24,9 @@ def _check_roofline(r):
     assert "traffic" in r
 
 
-def test_single_gpu_line():
-    d = _line("r1_bench_1gpu.json")
+@pytest.mark.parametrize("name", ["r1_bench_1gpu.json", "r2_bench_1gpu.json"])
+def test_single_gpu_line(name):
+    d = _line(name)
     for k in BASE + ["cpu_baseline"]:
         assert k in d, k
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["higher_is_better"] is True and d["vs_baseline"] is None
@@ -33,12 +34,24 @@ def test_single_gpu_line():
     assert d["gpu_launches"] > 0
     _check_roofline(d["roofline"])
     e = d["e2e"]
-    assert e["h2d_bytes_per_step"] > 8e9 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"] and e["results_equal_device_leg"]
+    assert e["h2d_bytes_per_step"] > 6e9 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"] and e["results_equal_device_leg"]
     c = d["cpu_baseline"]
     assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["sample"] and c["value"] > 0
     assert c.get("loop_ids_and_yaws_equal_gpu", True) is True
     cl = d["clocks"]
     assert cl["sm_mhz"] and cl["sm_max_mhz"] and not set(cl["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+@pytest.mark.parametrize("n", [2, 4, 8])
+def test_round2_multi_gpu_lines_carry_the_other_configs_and_the_reference_check(n):
+    d = _line(f"r2_bench_{n}gpu.json")
+    for k in BASE + ["cpu_baseline", "exhaustive_100k", "config3_40k_k50", "config5_40x120_flipped"]:
+        assert k in d, k
+    assert d["n_gpus"] == n and d["e2e"]["results_equal_device_leg"]
+    assert d["cpu_baseline"]["loop_ids_and_yaws_equal_reference"] is True
+    assert d["exhaustive_100k"]["winners_equal_oracle_on_3000_entry_prefix"] is True
+    assert d["config3_40k_k50"]["first_24_equal_reference"] is True and d["config5_40x120_flipped"]["finds_reversed_revisit"] is True
+    _check_roofline(d["roofline"])
 
 
 @pytest.mark.parametrize("n", [2, 4, 8])
