@@ -147,6 +147,14 @@ struct scgpu_handle {
   size_t last_nq = 0;
   std::vector<uint64_t> last_nsearch;
   uint64_t launches = 0;
+  // "leave room" mode of the binning kernel: its blocks ask for a little more shared memory than they need, so that THREE fit an
+  // SM instead of four and a quarter of every SM (16K registers, ~47 KB of shared memory) stays free for the latency-bound query
+  // kernels of the previous step to run underneath (asynchronous replays).
+  bool build_room = false;
+  // SCGPU_TRACE=1: per-step events of the replay engine (build start / end, query start / end), dumped by scgpu_timer_stop
+  cudaEvent_t tr_ev[16][4] = {};
+  int tr_n = 0;
+  bool trace = false;
   uint64_t mutation = 0, last_mutation = 0;  // candidate dumps are valid only while nothing has changed since the pipeline ran
   DevBuf records2[2];      // record buffers of asynchronous replays (alternating: the next build overlaps this query stage)
   int rec_turn = 0;
@@ -199,6 +207,7 @@ uint64_t local_count(const scgpu_handle* h, uint64_t n_global) {
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+constexpr size_t BUILD_ROOM_SMEM = 57 * 1024 + 512;  // > 227 KB / 4: at most three binning blocks per SM
 constexpr uint64_t PEER_RESULT_CAP = 65536;  // queries per replay batch whose results a shard's slab can hold
 
 // Peer-sharded mode: ONE allocation per shard (so that one cudaIpcMemHandle maps everything the other shards touch) laid out
@@ -443,7 +452,8 @@ int launch_build(scgpu_handle* h, const void* d_pts, size_t n_scans, size_t pts_
         if (q.bc.lh_is_float) k_build_tma<12, true, true><<<grid, 256, sm, st>>>(q);
         else k_build_tma<12, true, false><<<grid, 256, sm, st>>>(q);
       } else {
-        const size_t sm = sk == 16 ? build_tma_smem<16>(h->L.RS) : build_tma_smem<32>(h->L.RS);
+        size_t sm = sk == 16 ? build_tma_smem<16>(h->L.RS) : build_tma_smem<32>(h->L.RS);
+        if (sk == 16 && h->build_room && sm < BUILD_ROOM_SMEM) sm = BUILD_ROOM_SMEM;  // three blocks per SM instead of four: see build_room
         if (sk == 16 && q.bc.lh_is_float) k_build_tma<16, true, true><<<grid, 256, sm, st>>>(q);
         else if (sk == 16) k_build_tma<16, true, false><<<grid, 256, sm, st>>>(q);
         else if (q.bc.lh_is_float) k_build_tma<32, true, true><<<grid, 256, sm, st>>>(q);
@@ -717,7 +727,10 @@ int launch_score_screened(scgpu_handle* h, const void* d_qrec, size_t nq, const 
   cp.pair_shift = h->pair_shift.as<int>();
   // warps per block, staging slots per warp.  One slot: three blocks fit an SM and cover each other's fetch latency
   // (two slots = one block per SM measured slower at K = 50).
-  if (h->exh_cfg == 1) k_cand_screen<20, 60, 3, 1, 10, 1><<<(unsigned)nq, 10 * 32, cand_smem_bytes<20, 60, 3, 10, 1>(), st>>>(cp);
+  static const int cw_env = getenv("SCGPU_CAND_CW") ? atoi(getenv("SCGPU_CAND_CW")) : 0;
+  const bool cw5 = cw_env ? cw_env == 5 : (h->build_room || h->K <= 10);
+  if (h->exh_cfg == 1 && cw5) k_cand_screen<20, 60, 3, 1, 5, 1><<<(unsigned)nq, 5 * 32, cand_smem_bytes<20, 60, 3, 5, 1>(), st>>>(cp);
+  else if (h->exh_cfg == 1) k_cand_screen<20, 60, 3, 1, 10, 1><<<(unsigned)nq, 10 * 32, cand_smem_bytes<20, 60, 3, 10, 1>(), st>>>(cp);
   else k_cand_screen<40, 120, 6, 2, 5, 1><<<(unsigned)nq, 5 * 32, cand_smem_bytes<40, 120, 6, 5, 1>(), st>>>(cp);
   ScoreParams p;
   p.qrecords = static_cast<const unsigned char*>(d_qrec);
@@ -1386,8 +1399,15 @@ int replay_enqueue(std::vector<ReplayShard>& sh, uint64_t first, size_t n_total,
       unsigned char* rec = h->records2[h->rec_turn].as<unsigned char>() + j0 * h->L.rec_bytes;
       const size_t pitch = x.pitch ? x.pitch : P * stride;
       if (c == 0) CK(cudaEventRecord(h->ev_t0, h->stream));
+      if (h->trace && c == 0) {
+        const int k = h->tr_n & 15;
+        for (int e = 0; e < 4; ++e)
+          if (!h->tr_ev[k][e]) CK(cudaEventCreate(&h->tr_ev[k][e]));
+        CK(cudaEventRecord(h->tr_ev[k][0], h->stream));
+      }
       if (nj) RET(build_any(h, static_cast<const unsigned char*>(x.pts) + j0 * pitch, nj, P, stride, location, rec, x.pitch));
       if (c == C - 1) CK(cudaEventRecord(h->ev_t1, h->stream));
+      if (h->trace && c == C - 1) CK(cudaEventRecord(h->tr_ev[h->tr_n & 15][1], h->stream));
       if (c == 0)  // the previous replay's query stage (on every shard) may still be reading what the append overwrites
         for (auto& y : sh) CK(cudaStreamWaitEvent(h->stream, y.h->ev_qdone, 0));
       if (nj) RET(launch_append(h, rec, first + off + j0 * G, G, nj, h->stream, G > 1));
@@ -1401,6 +1421,7 @@ int replay_enqueue(std::vector<ReplayShard>& sh, uint64_t first, size_t n_total,
       const size_t off = shard_off(h), Bx = shard_cnt(off);
       const size_t j0 = std::min(Bx, B * c / C), j1 = std::min(Bx, B * (c + 1) / C), nj = j1 - j0;
       for (auto& y : sh) CK(cudaStreamWaitEvent(h->qstream, y.h->ev_app, 0));
+      if (h->trace && c == 0) CK(cudaEventRecord(h->tr_ev[h->tr_n & 15][2], h->qstream));
       h->n_global = present;
       const uint64_t have = local_count(h, h->n_global);
       if (have > h->n_written) h->n_written = have;
@@ -1422,6 +1443,7 @@ int replay_enqueue(std::vector<ReplayShard>& sh, uint64_t first, size_t n_total,
     if (ipc && G > 1) RET(launch_peer_barrier(h, 1, h->qstream));
     CK(cudaEventRecord(h->ev_qdone, h->qstream));
     CK(cudaEventRecord(h->ev_t2, h->qstream));
+    if (h->trace) CK(cudaEventRecord(h->tr_ev[h->tr_n++ & 15][3], h->qstream));
     h->timing_valid = true;
     h->replay_nq = n_total;
     h->replay_ipc = ipc;
@@ -1647,8 +1669,11 @@ static int create_one(const scgpu_config* cfg, scgpu_handle** out) {
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t1);
   if (e == cudaSuccess) e = cudaEventCreate(&h->ev_t2);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_nl, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<16>(h->L.RS));
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<16>(h->L.RS));
+  const int sm16 = (int)std::max(build_tma_smem<16>(h->L.RS), BUILD_ROOM_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm16);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm16);
+  h->build_room = getenv("SCGPU_BUILD_ROOM") && atoi(getenv("SCGPU_BUILD_ROOM")) != 0;
+  h->trace = getenv("SCGPU_TRACE") && atoi(getenv("SCGPU_TRACE")) != 0;
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<32, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<32>(h->L.RS));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(k_build_tma<12, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)build_tma_smem<12>(h->L.RS));
@@ -1668,6 +1693,8 @@ static int create_one(const scgpu_config* cfg, scgpu_handle** out) {
   }
   if (e == cudaSuccess && h->exh && h->exh_cfg == 1)
     e = cudaFuncSetAttribute(k_cand_screen<20, 60, 3, 1, 10, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem_bytes<20, 60, 3, 10, 1>());
+  if (e == cudaSuccess && h->exh && h->exh_cfg == 1)
+    e = cudaFuncSetAttribute(k_cand_screen<20, 60, 3, 1, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem_bytes<20, 60, 3, 5, 1>());
   if (e == cudaSuccess && h->exh && h->exh_cfg == 2)
     e = cudaFuncSetAttribute(k_cand_screen<40, 120, 6, 2, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cand_smem_bytes<40, 120, 6, 5, 1>());
   if (e == cudaSuccess && smem_f > 48 * 1024) e = cudaFuncSetAttribute(k_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f);
@@ -1724,6 +1751,9 @@ int scgpu_destroy(scgpu_handle* h) {
   if (h->ev_app) cudaEventDestroy(h->ev_app);
   if (h->ev_qdone) cudaEventDestroy(h->ev_qdone);
   if (h->ev_side) cudaEventDestroy(h->ev_side);
+  for (auto& row : h->tr_ev)
+    for (cudaEvent_t e : row)
+      if (e) cudaEventDestroy(e);
   if (h->ev_b0) cudaEventDestroy(h->ev_b0);
   if (h->ev_b1) cudaEventDestroy(h->ev_b1);
   if (h->qstream) cudaStreamDestroy(h->qstream);
@@ -1839,6 +1869,16 @@ int scgpu_timer_stop(scgpu_handle* h, double* ms) {
   float t = 0;
   CK(cudaEventElapsedTime(&t, h->ev_b0, h->ev_b1));
   *ms = t;
+  if (h->trace) {  // timeline of the last (up to 16) steps relative to the stopwatch start
+    const int n = h->tr_n < 16 ? h->tr_n : 16;
+    for (int i = h->tr_n - n; i < h->tr_n; ++i) {
+      float v[4] = {0, 0, 0, 0};
+      for (int e = 0; e < 4; ++e)
+        if (cudaEventElapsedTime(&v[e], h->ev_b0, h->tr_ev[i & 15][e]) != cudaSuccess) cudaGetLastError();
+      fprintf(stderr, "[scgpu trace] step %d: build %.3f .. %.3f ms | query %.3f .. %.3f ms\n", i, v[0], v[1], v[2], v[3]);
+    }
+    h->tr_n = 0;
+  }
   return SCGPU_OK;
 }
 
