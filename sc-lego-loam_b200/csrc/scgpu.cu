@@ -114,10 +114,11 @@ struct scgpu_handle {
   int exh_cfg = 0;  // 1: 20x60 radius 3, 2: 40x120 radius 6, 3: 20x60 full-shift search (tensor-core screening, scgpu_tc.cuh)
   // full-shift search on the tensor cores: hi / lo split of the screening copy, the queries' circulant expansion, TMA maps
   DevBuf tc_e_hi, tc_e_lo, tc_q_hi, tc_q_lo, tc_qaux, tc_shift;
+  DevBuf tc_ev_hi, tc_ev_lo, tc_qv_hi, tc_qv_lo;  // sector keys (windowed search on the tensor cores: alignment GEMM)
   DevBuf icp_src, icp_tgt, icp_state, icp_part;  // loop verification (scgpu_icp.cuh)
   uint64_t tc_rows = 0;    // rows the E buffers (and their tensor maps) were sized for
   uint64_t tc_upto = 0;    // local entries [0, tc_upto) are split
-  CUtensorMap tc_maps[4];  // E_hi, E_lo, Q_hi, Q_lo
+  CUtensorMap tc_maps[8];  // E_hi, E_lo, Q_hi, Q_lo, EV_hi, EV_lo, QV_hi, QV_lo
   bool tc_want_shifts = false;
   float* x_sc_hat = nullptr;
   unsigned char* x_vk = nullptr;  // [cap] ExhVkRec: float sector key + aux
@@ -1118,7 +1119,7 @@ typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D FP32 tensor [rows][TC_K], box = box_rows x TC_BK floats, 128-byte swizzle (what the UMMA shared-memory descriptors expect)
-int tc_make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t box_rows) {
+int tc_make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t box_rows, uint64_t k_extent = TC_K) {
   static TensorMapEncodeFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -1127,8 +1128,8 @@ int tc_make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t box_rows) 
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(SCGPU_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
     encode = reinterpret_cast<TensorMapEncodeFn>(fn);
   }
-  const cuuint64_t dims[2] = {(cuuint64_t)TC_K, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)TC_K * sizeof(float)};
+  const cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)k_extent * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1154,13 +1155,24 @@ int tc_sync(scgpu_handle* h, cudaStream_t st) {
     RET(tc_make_map(&h->tc_maps[1], h->tc_e_lo.p, h->db.cap, TC_M));
     RET(tc_make_map(&h->tc_maps[2], h->tc_q_hi.p, (uint64_t)EXH_MAX_BATCH_TC * TC_S, TC_N));
     RET(tc_make_map(&h->tc_maps[3], h->tc_q_lo.p, (uint64_t)EXH_MAX_BATCH_TC * TC_S, TC_N));
+    h->tc_ev_hi.release();
+    h->tc_ev_lo.release();
+    RET(h->tc_ev_hi.reserve((size_t)h->db.cap * TC_VK * sizeof(float)));
+    RET(h->tc_ev_lo.reserve((size_t)h->db.cap * TC_VK * sizeof(float)));
+    RET(h->tc_qv_hi.reserve((size_t)EXH_MAX_BATCH_TC * TC_S * TC_VK * sizeof(float), true, st));
+    RET(h->tc_qv_lo.reserve((size_t)EXH_MAX_BATCH_TC * TC_S * TC_VK * sizeof(float), true, st));
+    RET(tc_make_map(&h->tc_maps[4], h->tc_ev_hi.p, h->db.cap, TC_M, TC_VK));
+    RET(tc_make_map(&h->tc_maps[5], h->tc_ev_lo.p, h->db.cap, TC_M, TC_VK));
+    RET(tc_make_map(&h->tc_maps[6], h->tc_qv_hi.p, (uint64_t)EXH_MAX_BATCH_TC * TC_S, TC_N, TC_VK));
+    RET(tc_make_map(&h->tc_maps[7], h->tc_qv_lo.p, (uint64_t)EXH_MAX_BATCH_TC * TC_S, TC_N, TC_VK));
     h->tc_rows = h->db.cap;
     h->tc_upto = 0;
   }
   if (h->tc_upto > h->x_upto) h->tc_upto = h->x_upto;
   if (have > h->tc_upto) {
     k_tc_split_db<<<(unsigned)(have - h->tc_upto), 256, 0, st>>>(h->x_sc_hat, h->tc_e_hi.as<float>(), h->tc_e_lo.as<float>(), h->tc_upto);
-    h->launches++;
+    k_tc_split_vk<<<(unsigned)(have - h->tc_upto), 64, 0, st>>>(h->x_vk, h->tc_ev_hi.as<float>(), h->tc_ev_lo.as<float>(), h->tc_upto);
+    h->launches += 2;
     CK(cudaGetLastError());
     h->tc_upto = have;
   }
@@ -1169,6 +1181,41 @@ int tc_sync(scgpu_handle* h, cudaStream_t st) {
 
 constexpr unsigned EXH_CAND_CAP = 65536;   // rescoring list of one batch
 constexpr size_t EXH_MAX_BATCH = 64;       // queries per screening launch
+
+size_t tc_batch_threshold() {  // windowed batches of at least this many queries are screened on the tensor cores (0 = never)
+  static const long v = getenv("SCGPU_EXH_TC_BATCH") ? atol(getenv("SCGPU_EXH_TC_BATCH")) : 8;
+  return v <= 0 ? (size_t)1 << 30 : (size_t)v;
+}
+
+int launch_tc_screen(scgpu_handle* h, size_t nq, uint64_t n_max, uint64_t pitch, const unsigned long long* d_nl, unsigned* d_min, unsigned* d_shift,
+                     int windowed, cudaStream_t st, cudaEvent_t ev0, cudaEvent_t ev1) {
+  k_tc_prep_queries<<<dim3(TC_S, (unsigned)nq), 128, 0, st>>>(h->x_query.as<ExhQuery>(), h->tc_q_hi.as<float>(), h->tc_q_lo.as<float>(),
+                                                              h->tc_qaux.as<TcQueryAux>(), windowed ? h->tc_qv_hi.as<float>() : nullptr,
+                                                              windowed ? h->tc_qv_lo.as<float>() : nullptr);
+  h->launches++;
+  TcParams tp;
+  tp.vk = h->x_vk;
+  tp.qaux = h->tc_qaux.as<TcQueryAux>();
+  tp.n_local = d_nl;
+  tp.nq = (unsigned)nq;
+  tp.n_groups = (unsigned)((nq + TC_QG - 1) / TC_QG);
+  tp.n_tiles = (unsigned)((n_max + TC_M - 1) / TC_M);
+  tp.d32_pitch = pitch;
+  tp.d32 = h->x_d32.as<float>();
+  tp.min_bits = d_min;
+  tp.shift_out = d_shift;
+  tp.windowed = windowed;
+  tp.radius = h->radius;
+  const uint64_t items = (uint64_t)tp.n_groups * tp.n_tiles;
+  const unsigned gx = (unsigned)std::min<uint64_t>(items, (uint64_t)h->sm_count);
+  if (ev0) CK(cudaEventRecord(ev0, st));
+  k_tc_fullshift<<<gx, TC_THREADS, tc_smem_bytes(), st>>>(h->tc_maps[0], h->tc_maps[1], h->tc_maps[2], h->tc_maps[3], h->tc_maps[4], h->tc_maps[5],
+                                                          h->tc_maps[6], h->tc_maps[7], tp);
+  if (ev1) CK(cudaEventRecord(ev1, st));
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
 
 // Screen + rescore for nq (<= EXH_MAX_BATCH) query records on the device; result q (Best: dist, rank = #rescored in the
 // batch, shift, global idx) goes to d_best_out[q].  Everything is enqueued on st; no host synchronisation.
@@ -1245,27 +1292,15 @@ int launch_exhaustive_fast(scgpu_handle* h, const unsigned char* d_qrecs, size_t
             h->x_sc_hat, h->x_vk, h->x_query.as<ExhQuery>(), d_nl, pitch, h->x_d32.as<float>(), d_min, d_shift);
         if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
       } else {
-        k_tc_prep_queries<<<dim3(TC_S, (unsigned)nq), 128, 0, st>>>(h->x_query.as<ExhQuery>(), h->tc_q_hi.as<float>(), h->tc_q_lo.as<float>(),
-                                                                    h->tc_qaux.as<TcQueryAux>());
-        h->launches++;
-        TcParams tp;
-        tp.vk = h->x_vk;
-        tp.qaux = h->tc_qaux.as<TcQueryAux>();
-        tp.n_local = d_nl;
-        tp.nq = (unsigned)nq;
-        tp.n_groups = (unsigned)((nq + TC_QG - 1) / TC_QG);
-        tp.n_tiles = (unsigned)((n_max + TC_M - 1) / TC_M);
-        tp.d32_pitch = pitch;
-        tp.d32 = h->x_d32.as<float>();
-        tp.min_bits = d_min;
-        tp.shift_out = d_shift;
-        const uint64_t items = (uint64_t)tp.n_groups * tp.n_tiles;
-        const unsigned gx = (unsigned)std::min<uint64_t>(items, (uint64_t)h->sm_count);
-        if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
-        k_tc_fullshift<<<gx, TC_THREADS, tc_smem_bytes(), st>>>(h->tc_maps[0], h->tc_maps[1], h->tc_maps[2], h->tc_maps[3], tp);
-        if (ev_screen1) CK(cudaEventRecord(ev_screen1, st));
+        RET(launch_tc_screen(h, nq, n_max, pitch, d_nl, d_min, d_shift, 0, st, ev_screen0, ev_screen1));
         eps = TC_EPS;
       }
+    } else if (h->exh_cfg == 1 && !flipped && nq >= tc_batch_threshold() && h->L.R == TC_R && h->L.S == TC_S) {
+      // batches of the WINDOWED search: the tensor-core kernel computes all 60 shifts plus the alignment (a second small GEMM) and
+      // is still faster than the FFMA2 kernel that computes only the 7 it needs (measured: DESIGN.md section 4)
+      RET(tc_sync(h, st));
+      RET(launch_tc_screen(h, nq, n_max, pitch, d_nl, d_min, nullptr, 1, st, ev_screen0, ev_screen1));
+      eps = TC_EPS;
     } else {
       if (ev_screen0) CK(cudaEventRecord(ev_screen0, st));
       if (h->exh_cfg == 1)
@@ -1686,7 +1721,7 @@ static int create_one(const scgpu_config* cfg, scgpu_handle** out) {
                                                (int)exh_smem_bytes<20, 60, 3, 20>())
                         : cudaFuncSetAttribute(k_exh_screen<40, 120, 6, 1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)exh_smem_bytes<40, 120, 6, 4, 2>());
-  if (e == cudaSuccess && h->exh_cfg == 3) {
+  if (e == cudaSuccess && (h->exh_cfg == 3 || h->exh_cfg == 1)) {
     e = cudaFuncSetAttribute(k_tc_fullshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes());
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(k_fullshift_simt<TC_R, TC_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qtab_bytes<TC_R, TC_S, 15>());
@@ -1771,6 +1806,7 @@ int scgpu_destroy(scgpu_handle* h) {
   }
   DevBuf* xb[] = {&h->x_query, &h->x_d32, &h->x_keys, &h->x_pd,    &h->x_ps,    &h->x_small, &h->x_best,  &h->c_d32,
                   &h->c_list,  &h->c_count, &h->tc_e_hi, &h->tc_e_lo, &h->tc_q_hi, &h->tc_q_lo, &h->tc_qaux, &h->tc_shift,
+                  &h->tc_ev_hi, &h->tc_ev_lo, &h->tc_qv_hi, &h->tc_qv_lo,
                   &h->records2[0], &h->records2[1], &h->res_buf, &h->icp_src, &h->icp_tgt, &h->icp_state, &h->icp_part};
   for (DevBuf* b : xb) b->release();
   for (int i = 0; i < 2; ++i) {

@@ -26,8 +26,12 @@
 //            per K block of 32 floats one stage = E tile 128 x 32 (hi, lo) + Qs tile 240 x 32 (hi, lo) = 92 KB, 2 stages
 //   warp 1   MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::tf32, M = 128 entries, N = 240 = 4 queries x 60
 //            shifts, K = 8 per instruction -> 4 x 3 MMAs per stage; accumulator in TMEM (2 x 256 columns, double-buffered)
-//   warps 2-5 epilogue: tcgen05.ld 32x32b (thread = entry, columns = (query, shift)), n_s from precomputed rotated query masks,
-//            min over s with the reference's smallest-shift tie rule, d32 + per-query running minimum out
+//   warps 2-9 epilogue (two per TMEM lane quarter, two queries each): tcgen05.ld 32x32b (thread = entry, columns = (query, shift)),
+//            n_s from precomputed rotated query masks, min over s with the reference's smallest-shift tie rule, d32 + per-query
+//            running minimum out
+// Windowed mode (batches of the reference's windowed search): two more K blocks per tile carry the sector keys, a second small GEMM
+// into TMEM columns [256, 496) gives the alignment correlations of all S shifts; the epilogue takes the argmax (ambiguous ones: lower
+// bound over both candidates' windows) and the minimum over the 2*radius+1 shifts around it.  One tile in TMEM at a time.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -37,6 +41,7 @@
 
 namespace scgpu {
 
+constexpr float TC_ALIGN_MARGIN = 6.4e-5f;  // relative (to |v1||v2|) gap below which the 3xTF32 alignment is called ambiguous
 constexpr float TC_EPS = 1.0e-4f;  // |d32 - d| bound used for candidate selection on the tensor-core path (observed: < 2e-5)
 
 constexpr int TC_S = 60, TC_R = 20, TC_K = TC_R * TC_S;  // instantiated for the reference's 20 x 60 descriptor
@@ -49,13 +54,15 @@ constexpr int TC_STAGES = 2;
 constexpr int TC_A_BYTES = TC_M * TC_BK * 4;              // 16 KB
 constexpr int TC_B_BYTES = TC_N * TC_BK * 4;              // 30 KB
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;                            // TMA warp, MMA warp, eight epilogue warps
 constexpr int TC_ACC_COLS = 256;                          // TMEM columns per accumulator stage
+constexpr int TC_VK = 64;                                 // sector keys padded to two K blocks (windowed mode: alignment GEMM)
+constexpr int TC_VKBLOCKS = TC_VK / TC_BK;
 
 struct TcQueryAux {  // per query: rotated valid-column masks + flags (epilogue side data)
   unsigned long long qrot[TC_S];  // qrot[s] bit c set <=> query column (c + s) mod S is valid: popc(qrot[s] & vmask_e) = n_s
   unsigned flags;                 // bit 0: rescore everything (non-representable norms)
-  unsigned pad;
+  float v1norm;                   // |sector key| of the query (alignment margin, windowed mode)
 };
 
 constexpr size_t tc_smem_bytes() { return 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + TC_QG * sizeof(TcQueryAux) + 64 * 4 + 256; }
@@ -74,8 +81,19 @@ __global__ void __launch_bounds__(256) k_tc_split_db(const float* sc_hat, float*
   }
 }
 
+// database side, windowed mode: hi / lo split of the float sector keys (pair-interleaved, as stored), padded to TC_VK
+__global__ void __launch_bounds__(64) k_tc_split_vk(const unsigned char* vk, float* hi, float* lo, unsigned long long first) {
+  const unsigned long long e = first + blockIdx.x;
+  const float* v = reinterpret_cast<const float*>(vk + e * sizeof(ExhVkRec<TC_S>));
+  const int i = threadIdx.x;
+  const float x = i < TC_S ? v[i] : 0.f;
+  const float h = tf32_hi(x);
+  hi[e * TC_VK + i] = h;
+  lo[e * TC_VK + i] = x - h;
+}
+
 // query side: the circulant expansion.  Block (s, q): row q*S + s of Qs = query q rotated by s, in the database's k order.
-__global__ void __launch_bounds__(128) k_tc_prep_queries(const ExhQuery* qs, float* qs_hi, float* qs_lo, TcQueryAux* aux) {
+__global__ void __launch_bounds__(128) k_tc_prep_queries(const ExhQuery* qs, float* qs_hi, float* qs_lo, TcQueryAux* aux, float* qv_hi, float* qv_lo) {
   const int s = blockIdx.x, q = blockIdx.y;
   const ExhQuery* Q = qs + q;
   const size_t row = ((size_t)q * TC_S + s) * TC_K;
@@ -89,6 +107,20 @@ __global__ void __launch_bounds__(128) k_tc_prep_queries(const ExhQuery* qs, flo
     qs_hi[row + i] = h;
     qs_lo[row + i] = v - h;
   }
+  if (qv_hi && threadIdx.x < TC_VK) {  // windowed mode: the same expansion of the query's sector key (alignment GEMM, K = 60 -> 64)
+    const int pos = threadIdx.x;
+    float v = 0.f;
+    if (pos < TC_S) {
+      const int c = (pos & 1) ? (pos >> 1) + TC_S / 2 : (pos >> 1);
+      int cq = c + s;
+      if (cq >= TC_S) cq -= TC_S;
+      v = Q->v1[cq];  // corr(s) = sum_c v2[c] * v1[(c + s) mod S]: the shift that minimises |v1 - circshift(v2, s)| (SC.cpp:93-113)
+    }
+    const float h = tf32_hi(v);
+    const size_t o = ((size_t)q * TC_S + s) * TC_VK + pos;
+    qv_hi[o] = h;
+    qv_lo[o] = v - h;
+  }
   if (threadIdx.x == 0) {
     const unsigned long long m = Q->qmask[0];
     const unsigned long long full = (1ull << TC_S) - 1;
@@ -96,7 +128,7 @@ __global__ void __launch_bounds__(128) k_tc_prep_queries(const ExhQuery* qs, flo
     aux[q].qrot[s] = s == 0 ? m : (((m >> s) | (m << (TC_S - s))) & full);
     if (s == 0) {
       aux[q].flags = Q->flags;
-      aux[q].pad = 0;
+      aux[q].v1norm = Q->v1norm;
     }
   }
 }
@@ -156,10 +188,14 @@ struct TcParams {
   float* d32;                         // [nq][d32_pitch]
   unsigned* min_bits;                 // [nq]
   unsigned* shift_out;                // optional [nq][d32_pitch]: argmin shift (tests)
+  int windowed;                       // 1: the reference's windowed search -- a second small GEMM (sector keys, K = 64) gives the alignment,
+  int radius;                         //    the distance is the minimum over the 2*radius+1 shifts around it (SC.cpp:121-144)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_constant__ CUtensorMap map_e_hi, const __grid_constant__ CUtensorMap map_e_lo,
                                                                 const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                                                                const __grid_constant__ CUtensorMap map_ev_hi, const __grid_constant__ CUtensorMap map_ev_lo,
+                                                                const __grid_constant__ CUtensorMap map_qv_hi, const __grid_constant__ CUtensorMap map_qv_lo,
                                                                 const TcParams p) {
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   // carve: [stages][E_hi | E_lo | Q_hi | Q_lo] (each 1024-byte aligned: 16 KB, 16 KB, 30 KB, 30 KB) | query aux | rcp table | barriers
@@ -186,7 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 4);  // one arrival per epilogue warp
+      mbar_init(&acc_empty[a], 8);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -209,14 +245,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
       unsigned it = 0;
       for (unsigned long long w = blockIdx.x; w < n_items; w += gridDim.x) {
         const unsigned g = (unsigned)(w / p.n_tiles), m = (unsigned)(w % p.n_tiles);
-        for (int kb = 0; kb < TC_KBLOCKS; ++kb, ++it) {
+        const int nkb = TC_KBLOCKS + (p.windowed ? TC_VKBLOCKS : 0);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % TC_STAGES;
           if (it >= TC_STAGES) mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
           mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
-          tma_load_2d(stage_ptr(s, 0), &map_e_hi, kb * TC_BK, (int)(m * TC_M), &full[s]);
-          tma_load_2d(stage_ptr(s, 1), &map_e_lo, kb * TC_BK, (int)(m * TC_M), &full[s]);
-          tma_load_2d(stage_ptr(s, 2), &map_q_hi, kb * TC_BK, (int)(g * TC_N), &full[s]);
-          tma_load_2d(stage_ptr(s, 3), &map_q_lo, kb * TC_BK, (int)(g * TC_N), &full[s]);
+          const bool al = kb >= TC_KBLOCKS;  // the last two stages of a windowed tile carry the sector keys
+          const int k0 = (al ? kb - TC_KBLOCKS : kb) * TC_BK;
+          tma_load_2d(stage_ptr(s, 0), al ? &map_ev_hi : &map_e_hi, k0, (int)(m * TC_M), &full[s]);
+          tma_load_2d(stage_ptr(s, 1), al ? &map_ev_lo : &map_e_lo, k0, (int)(m * TC_M), &full[s]);
+          tma_load_2d(stage_ptr(s, 2), al ? &map_qv_hi : &map_q_hi, k0, (int)(g * TC_N), &full[s]);
+          tma_load_2d(stage_ptr(s, 3), al ? &map_qv_lo : &map_q_lo, k0, (int)(g * TC_N), &full[s]);
         }
       }
     }
@@ -226,20 +265,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
       constexpr uint32_t idesc = tc_idesc(TC_M, TC_N);
       unsigned it = 0, tile = 0;
       for (unsigned long long w = blockIdx.x; w < n_items; w += gridDim.x, ++tile) {
-        const int a = tile & 1;
-        if (tile >= 2) mbar_wait(&acc_empty[a], ((tile >> 1) - 1) & 1);  // the epilogue has drained this accumulator
+        // full-shift: two accumulators (256 columns each), the epilogue of tile t overlaps the MMAs of tile t+1.
+        // windowed: ONE tile in TMEM at a time -- columns [0, 240) the per-shift sums, [256, 496) the alignment correlations
+        const int a = p.windowed ? 0 : (tile & 1);
+        if (p.windowed) {
+          if (tile >= 1) mbar_wait(&acc_empty[0], (tile - 1) & 1);
+        } else if (tile >= 2) {
+          mbar_wait(&acc_empty[a], ((tile >> 1) - 1) & 1);  // the epilogue has drained this accumulator
+        }
         tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)a * TC_ACC_COLS;
-        for (int kb = 0; kb < TC_KBLOCKS; ++kb, ++it) {
+        const uint32_t d0 = tmem_base + (uint32_t)a * TC_ACC_COLS;
+        const int nkb = TC_KBLOCKS + (p.windowed ? TC_VKBLOCKS : 0);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % TC_STAGES;
           mbar_wait(&full[s], (it / TC_STAGES) & 1);
           tc_fence_after();
           const uint64_t e_hi = tc_smem_desc(stage_ptr(s, 0)), e_lo = tc_smem_desc(stage_ptr(s, 1));
           const uint64_t q_hi = tc_smem_desc(stage_ptr(s, 2)), q_lo = tc_smem_desc(stage_ptr(s, 3));
+          const bool al = kb >= TC_KBLOCKS;
+          const uint32_t d = al ? d0 + TC_ACC_COLS : d0;
+          const int kfirst = al ? TC_KBLOCKS : 0;
 #pragma unroll
           for (int kk = 0; kk < TC_BK / 8; ++kk) {
             const uint64_t adv = (uint64_t)(kk * 8 * 4) >> 4;  // 32 bytes along K inside the swizzle atom
-            tc_mma_tf32(d, e_hi + adv, q_hi + adv, idesc, (kb | kk) != 0);
+            tc_mma_tf32(d, e_hi + adv, q_hi + adv, idesc, ((kb - kfirst) | kk) != 0);
             tc_mma_tf32(d, e_hi + adv, q_lo + adv, idesc, 1);
             tc_mma_tf32(d, e_lo + adv, q_hi + adv, idesc, 1);
           }
@@ -250,14 +299,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
     }
   } else {
     // ===== epilogue: thread = entry (TMEM lane), columns = (query, shift) =====
-    const int quarter = warp & 3;              // the TMEM lanes this warp may read: 32 * (warp % 4)
+    // eight warps: two per TMEM lane quarter (a warp may read lanes 32 * (warp % 4) .. +31), each taking two of the tile's four queries
+    const int quarter = warp & 3;
+    const int qhalf = (warp - 2) >> 2;         // 0: queries 0, 1 of the group; 1: queries 2, 3
     const int row = quarter * 32 + lane;       // entry within the tile
     unsigned tile = 0;
     unsigned my_min[TC_QG];
     unsigned cur_g = 0xffffffffu;
     for (unsigned long long w = blockIdx.x; w < n_items; w += gridDim.x, ++tile) {
       const unsigned g = (unsigned)(w / p.n_tiles), m = (unsigned)(w % p.n_tiles);
-      const int a = tile & 1;
+      const int a = p.windowed ? 0 : (tile & 1);
       if (g != cur_g) {  // new query group: flush the running minima of the previous one, load the side data of this one
         if (cur_g != 0xffffffffu) {
 #pragma unroll
@@ -266,11 +317,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
             if (lane == 0 && mn != 0x7f800000u && cur_g * TC_QG + q < p.nq) atomicMin(p.min_bits + cur_g * TC_QG + q, mn);
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with the previous group's side data
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone is done with the previous group's side data
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.qaux + (size_t)g * TC_QG);
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_aux);
-        for (int i = threadIdx.x - 64; i < (int)(TC_QG * sizeof(TcQueryAux) / 8); i += 128) dst[i] = src[i];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = threadIdx.x - 64; i < (int)(TC_QG * sizeof(TcQueryAux) / 8); i += 256) dst[i] = src[i];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         cur_g = g;
 #pragma unroll
         for (int q = 0; q < TC_QG; ++q) my_min[q] = 0x7f800000u;
@@ -279,6 +330,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
       const ExhAux* ax = reinterpret_cast<const ExhAux*>(p.vk + e * sizeof(ExhVkRec<TC_S>) + TC_S * sizeof(float));
       unsigned long long vmask = 0;
       unsigned eflags = 0;
+      float vnorm = 0.f;
       unsigned long long nl_max = 0;
 #pragma unroll
       for (int q = 0; q < TC_QG; ++q) {
@@ -289,18 +341,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
       if (e < nl_max) {
         vmask = ax->vmask[0];
         eflags = ax->flags;
+        vnorm = ax->vnorm;
       }
-      mbar_wait(&acc_full[a], (tile >> 1) & 1);
+      const int tpar = p.windowed ? (int)(tile & 1) : (int)((tile >> 1) & 1);
+      mbar_wait(&acc_full[a], tpar);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)a * TC_ACC_COLS;
 #pragma unroll 1
-      for (int q = 0; q < TC_QG; ++q) {
+      for (int q = qhalf * (TC_QG / 2); q < (qhalf + 1) * (TC_QG / 2); ++q) {
         uint32_t v0[32], v1[32];
+        const unsigned qi = g * TC_QG + q;
+        const unsigned long long nl = qi < p.nq ? p.n_local[qi] : 0;
+        // windowed: the alignment first -- argmax over the S correlations (smallest shift on ties), ambiguous when the runner-up is
+        // within the error bound of the best (then the exact kernel decides, as in the SIMT screening)
+        // An alignment whose runner-up is within the error bound is not decided here; instead the distance is taken over the UNION of
+        // the two candidates' windows -- a lower bound of the true windowed distance whichever alignment the reference picks -- and
+        // the entry is kept out of the per-query minimum (which must come from certain values).  A lower bound above the selection
+        // threshold proves the entry cannot win; below it the exact kernel decides.  Three candidates within the bound: flagged.
+        int a_cur = 0, a_2nd = 0;
+        bool amb2 = false, amb3 = false;
+        if (p.windowed) {
+          tc_ld32(tbase + TC_ACC_COLS + q * TC_S, v0);
+          tc_ld32(tbase + TC_ACC_COLS + q * TC_S + 28, v1);
+          tc_ld_wait();
+          float b1 = -3.4e38f, b2 = -3.4e38f, b3 = -3.4e38f;
+#pragma unroll
+          for (int s = 0; s < TC_S; ++s) {
+            const float c = __uint_as_float(s < 32 ? v0[s] : v1[s - 28]);
+            const bool g1 = c > b1;            // strict: the earlier shift keeps a tie
+            const bool g2 = !g1 && c > b2;
+            b3 = fmaxf(b3, g1 ? b2 : (g2 ? b2 : c));
+            a_2nd = g1 ? a_cur : (g2 ? s : a_2nd);
+            b2 = g1 ? b1 : (g2 ? c : b2);
+            a_cur = g1 ? s : a_cur;
+            b1 = g1 ? c : b1;
+          }
+          const float margin = TC_ALIGN_MARGIN * s_aux[q].v1norm * vnorm;
+          amb2 = !((b1 - b2) > margin);
+          amb3 = !((b1 - b3) > margin) || !(b1 == b1);
+        }
         tc_ld32(tbase + q * TC_S, v0);        // shifts 0..31
         tc_ld32(tbase + q * TC_S + 28, v1);   // shifts 28..59
         tc_ld_wait();
-        const unsigned qi = g * TC_QG + q;
-        const unsigned long long nl = qi < p.nq ? p.n_local[qi] : 0;
         float best = __int_as_float(0x7f800000);
         int best_s = 0;
         bool bad = false;
@@ -308,7 +390,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
         for (int s = 0; s < TC_S; ++s) {
           const float sum = __uint_as_float(s < 32 ? v0[s] : v1[s - 28]);
           const int n = __popcll(s_aux[q].qrot[s] & vmask);
-          const float dist = n ? 1.0f - sum * s_rcp[n] : __int_as_float(0x7f800000);
+          float dist = n ? 1.0f - sum * s_rcp[n] : __int_as_float(0x7f800000);
+          if (p.windowed) {  // only the shifts a-radius .. a+radius (mod S) are in the reference's search set (SC.cpp:123-130)
+            int rel = s - a_cur, rel2 = s - a_2nd;
+            rel += rel < 0 ? TC_S : 0;
+            rel2 += rel2 < 0 ? TC_S : 0;
+            const bool in = rel <= p.radius || rel >= TC_S - p.radius || (amb2 && (rel2 <= p.radius || rel2 >= TC_S - p.radius));
+            dist = in ? dist : __int_as_float(0x7f800000);
+          }
           bad |= !(dist == dist);
           if (dist < best) {  // ascending s, strict: the smallest shift keeps a tie (SC.cpp:136-143)
             best = dist;
@@ -317,10 +406,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
         }
         if (e < nl) {
           float out = best < 0.f ? 0.f : best;
-          if (bad || (eflags & 1u) || (s_aux[q].flags & 1u)) out = -1.0f;  // the exact kernel decides
+          if (bad || amb3 || (eflags & 1u) || (s_aux[q].flags & 1u)) out = -1.0f;  // the exact kernel decides
           p.d32[(size_t)qi * p.d32_pitch + e] = out;
           if (p.shift_out) p.shift_out[(size_t)qi * p.d32_pitch + e] = (unsigned)best_s;
-          if (out >= 0.f) my_min[q] = min(my_min[q], __float_as_uint(out));
+          if (out >= 0.f && !amb2) my_min[q] = min(my_min[q], __float_as_uint(out));  // lower bounds do not set the threshold
         }
       }
       tc_fence_before();

@@ -157,3 +157,37 @@ def test_intensity_descriptor_equals_reference_variant():
     assert not np.array_equal(SCManager().makeScancontext(scans[0]), m.makeScancontext(scans[0]))      # it is a different descriptor
     with pytest.raises(ScgpuError):
         m.makeScancontext(xyz[0])                                   # 16-byte points carry no intensity
+
+
+def test_windowed_batches_on_tensor_cores_equal_exact_and_simt():
+    """Batches (>= 8 queries) of the reference's WINDOWED exhaustive search are screened by the tensor-core kernel too (all 60
+    shifts + the sector-key alignment as a second small GEMM, window picked in the epilogue): winners must equal the exact
+    FP64-for-all search and the SIMT screening path (SCGPU_EXH_TC_BATCH=0)."""
+    from sc_lego_loam_b200.scgpu import FLAG_NO_SCREENING, SCManager
+    descs = _db(n=5000, seed=21)
+    n = len(descs)
+    m = SCManager(capacity_hint=n + 8)
+    exact = SCManager(capacity_hint=n + 8, flags=FLAG_NO_SCREENING)
+    m.append_descs(descs)
+    exact.append_descs(descs)
+    qs = [n - 1 - 11 * i for i in range(41)]                  # 41 queries: ten full groups of four and one partial
+    ns = [max(1, q - 50 - 5 * i) for i, q in enumerate(qs)]
+    gd, gs, gi = m.exhaustive_batched(qs, ns)                 # tensor cores (batch >= 8)
+    rescored = m.exhaustive_rescored()
+    for j, (q, nn) in enumerate(zip(qs, ns)):
+        w = exact.exhaustive(q, nn)
+        assert (gd[j], gs[j], gi[j]) == w[:3], (j, q, nn, (gd[j], gs[j], gi[j]), w)
+        assert m.exhaustive(q, nn) == w                       # single queries: the FFMA2 kernel
+    assert rescored < 3000, rescored                          # the 3xTF32 alignment is rarely ambiguous
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import numpy as np\nfrom test_gpu_fullshift import _db\nfrom sc_lego_loam_b200.scgpu import SCManager\n"
+            "descs = _db(n=5000, seed=21); n = len(descs)\nm = SCManager(capacity_hint=n + 8); m.append_descs(descs)\n"
+            "qs = [n - 1 - 11 * i for i in range(41)]; ns = [max(1, q - 50 - 5 * i) for i, q in enumerate(qs)]\n"
+            "d, s, i = m.exhaustive_batched(qs, ns)\nnp.save(sys.argv[1], np.stack([d, s.astype(np.float64), i.astype(np.float64)]))\n") % (ROOT, os.path.join(ROOT, "tests"))
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "simt.npy")
+        r = subprocess.run([sys.executable, "-c", code, out], env=dict(os.environ, SCGPU_EXH_TC_BATCH="0"), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        simt = np.load(out)
+    assert np.array_equal(simt[0], gd) and np.array_equal(simt[1], gs.astype(np.float64)) and np.array_equal(simt[2], gi.astype(np.float64))
