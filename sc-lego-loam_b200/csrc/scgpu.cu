@@ -1368,7 +1368,10 @@ int launch_peer_barrier(scgpu_handle* h, int channel, cudaStream_t st) {
   BarrierCells bc{};
   for (int s = 0; s < h->cfg.shard_count; ++s) bc.cells[s] = h->flags_of[s];
   const unsigned e = ++h->epoch[channel];
-  k_peer_barrier<<<1, 32, 0, st>>>(bc, h->cfg.shard_count, h->cfg.shard_rank, channel, e);
+  // generous bound: ranks reach their first steps seconds apart (allocations, page-ins); $SCGPU_BARRIER_TIMEOUT_MS overrides
+  static const unsigned long long timeout_ns =
+      (getenv("SCGPU_BARRIER_TIMEOUT_MS") ? strtoull(getenv("SCGPU_BARRIER_TIMEOUT_MS"), nullptr, 10) : 20000ull) * 1000000ull;
+  k_peer_barrier<<<1, 32, 0, st>>>(bc, h->cfg.shard_count, h->cfg.shard_rank, channel, e, timeout_ns);
   h->launches++;
   CK(cudaGetLastError());
   return SCGPU_OK;

@@ -1324,13 +1324,13 @@ __global__ void k_finalize(const Best* parts_in, int parts, unsigned nq, const u
 // announcement has arrived in its own block.  cells: [channel][MAX_SHARDS] generations + cell 2*MAX_SHARDS = timeout flag.
 // Everything a shard stored into peer memory before the barrier (ring keys by k_append, results by k_finalize) is
 // ordered before its announcement by the system-scope fence.  Generations only grow; comparison is wrap-safe.
-// The wait is bounded (~2 s of globaltimer): a missing peer turns into an error code, not a hung GPU.
+// The wait is bounded (timeout_ns of globaltimer, 20 s by default): a missing peer turns into an error code, not a hung GPU.
 // Only for shards on DISTINCT devices: kernels that wait on one another must not share a GPU.
 // ------------------------------------------------------------------------------------------------
 struct BarrierCells {
   unsigned* cells[MAX_SHARDS];
 };
-__global__ void k_peer_barrier(BarrierCells peers, int G, int rank, int channel, unsigned epoch) {
+__global__ void k_peer_barrier(BarrierCells peers, int G, int rank, int channel, unsigned epoch, unsigned long long timeout_ns) {
   const int t = threadIdx.x;
   if (t < G) {
     __threadfence_system();
@@ -1344,7 +1344,7 @@ __global__ void k_peer_barrier(BarrierCells peers, int G, int rank, int channel,
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int)(v - epoch) >= 0) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 2000000000ull) {
+      if (t1 - t0 > timeout_ns) {
         peers.cells[rank][2 * MAX_SHARDS] = 1u;
         break;
       }
