@@ -314,8 +314,8 @@ int scgpu_probe_bins(scgpu_handle* h, const float* xyz, size_t n, int32_t* bin, 
  * scgpu_query_batched call: whole call, its k_build launches only, and everything after them. */
 int scgpu_get_timing(scgpu_handle* h, double* ms_total, double* ms_build, double* ms_query);
 /* Host side of the H2D path (no device needed): threads of the packing pool (min(16, cores / LOCAL_WORLD_SIZE), or
- * $SCGPU_HOST_THREADS) and whether pinned batches are packed to 12 bytes per point before they cross PCIe (pool >= 12 threads, or
- * $SCGPU_PACK_PINNED).  Pageable sources are always packed (they are staged through pinned memory anyway). */
+ * $SCGPU_HOST_THREADS) and whether pinned batches are packed to 12 bytes per point before they cross PCIe (a lone process -- LOCAL_WORLD_SIZE 1 -- with a pool of >= 12
+ * threads, or $SCGPU_PACK_PINNED).  Pageable sources are always packed (they are staged through pinned memory anyway). */
 int scgpu_host_info(int* pool_threads, int* packs_pinned);
 /* Device-side stopwatch over a sequence of calls (asynchronous ones included): CUDA events on the handle's own streams --
  * start behind everything enqueued so far, stop behind everything enqueued since; a device-list handle reports its slowest

@@ -899,6 +899,7 @@ class HostPool {
     return p;
   }
   int threads() const { return (int)workers_.size() + 1; }
+  int local_world() const { return local_world_; }
   // fn(i) for i in [0, n); the calling thread takes part; returns when every item is done
   void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
     if (n == 0) return;
@@ -940,6 +941,7 @@ class HostPool {
     if (hw == 0) hw = 4;
     int local_world = 1;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) local_world = atoi(e) > 0 ? atoi(e) : 1;  // one process per GPU: share the cores
+    local_world_ = local_world;
     int n = (int)(hw / (unsigned)local_world);
     if (n > 16) n = 16;
     if (const char* e = getenv("SCGPU_HOST_THREADS")) n = atoi(e);
@@ -983,6 +985,7 @@ class HostPool {
     }
   }
   std::vector<std::thread> workers_;
+  int local_world_ = 1;
   std::mutex mu_;
   std::condition_variable cv_;
   std::shared_ptr<Job> job_;
@@ -1019,7 +1022,10 @@ int build_from_host(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts
   // packing first ships 12.  Measured on the B200 host (4,541 x 120k float4 points per step, PCIe at 55.5 GB/s): direct 159 ms,
   // packed 122 ms with 16 threads (the link rate for 12 B/point) but 159 ms with 8 -- so pack only when this process has the
   // cores to outrun the link (SCGPU_PACK_PINNED=0/1 overrides; one process per GPU divides the cores, see HostPool).
-  static const bool pack_pinned = getenv("SCGPU_PACK_PINNED") ? atoi(getenv("SCGPU_PACK_PINNED")) != 0 : HostPool::get().threads() >= 12;
+  // With several ranks on one host the packers of all ranks share the memory system: 2 ranks x 16 threads packed at 40k keyframes/s
+  // in total where plain DMA from the pinned buffers gives 57k -- so only a lone process packs pinned sources.
+  static const bool pack_pinned = getenv("SCGPU_PACK_PINNED") ? atoi(getenv("SCGPU_PACK_PINNED")) != 0
+                                                               : (HostPool::get().threads() >= 12 && HostPool::get().local_world() == 1);
   static const bool no_pack = getenv("SCGPU_NO_PACK") && atoi(getenv("SCGPU_NO_PACK")) != 0;
   // the voxel path wants its input as given (it carries no restriction on stride, but keeps the code path of round 1)
   const bool intensity = (h->cfg.flags & SCGPU_FLAG_INTENSITY) != 0;
@@ -1924,7 +1930,9 @@ int scgpu_timer_stop(scgpu_handle* h, double* ms) {
 // Host side of the H2D path: threads of the packing pool and whether pinned batches are packed to 12 bytes per point
 int scgpu_host_info(int* pool_threads, int* packs_pinned) {
   if (pool_threads) *pool_threads = HostPool::get().threads();
-  if (packs_pinned) *packs_pinned = getenv("SCGPU_PACK_PINNED") ? atoi(getenv("SCGPU_PACK_PINNED")) != 0 : HostPool::get().threads() >= 12;
+  if (packs_pinned)
+    *packs_pinned = getenv("SCGPU_PACK_PINNED") ? atoi(getenv("SCGPU_PACK_PINNED")) != 0
+                                                 : (HostPool::get().threads() >= 12 && HostPool::get().local_world() == 1);
   return SCGPU_OK;
 }
 
