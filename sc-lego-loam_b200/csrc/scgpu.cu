@@ -296,8 +296,8 @@ int db_reserve(scgpu_handle* h, uint64_t want_local) {
   }
   if (h->db.cap && n) {
     CK(cudaMemcpyAsync(nd.sc, h->db.sc, n * L.RS * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaMemcpy2DAsync(nd.ringT, cap * sizeof(float), h->db.ringT, h->db.cap * sizeof(float), n * sizeof(float), L.R,
-                         cudaMemcpyDeviceToDevice, h->stream));
+    // (the tiled ring-key layout does not depend on the capacity: the stored tiles move as one block)
+    CK(cudaMemcpyAsync(nd.ringT, h->db.ringT, ((n + 31) / 32) * 32 * L.R * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(nd.sector, h->db.sector, n * L.S * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaMemcpyAsync(nd.colnorm, h->db.colnorm, n * L.S * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   }
@@ -633,10 +633,25 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
     return SCGPU_OK;
   }
   dim3 grid(chunks, (unsigned)nq);
-#define SCGPU_TOPK_CASE(SL)                                         \
-  if (warps == 2) k_topk<SL, 2><<<grid, 64, 0, st>>>(p);            \
-  else if (warps == 4) k_topk<SL, 4><<<grid, 128, 0, st>>>(p);      \
-  else k_topk<SL, 8><<<grid, 256, 0, st>>>(p);
+  // software-pipelined key loads for small grids (few resident warps per SM: the L2 latency of the loads is exposed)
+  static const int pipe_env = getenv("SCGPU_TOPK_PIPE") ? atoi(getenv("SCGPU_TOPK_PIPE")) : -1;
+  const bool pipe = pipe_env >= 0 ? pipe_env != 0 : (uint64_t)chunks * nq * warps < (uint64_t)h->sm_count * 32;
+  const int rc = h->L.R == 20 ? 20 : (h->L.R == 40 ? 40 : 0);
+#define SCGPU_TOPK_LAUNCH(SL, W, RC_, PIPE_) k_topk<SL, W, RC_, PIPE_><<<grid, (W) * 32, 0, st>>>(p)
+#define SCGPU_TOPK_RC(SL, W)                                              \
+  if (rc == 20 && pipe) SCGPU_TOPK_LAUNCH(SL, W, 20, true);               \
+  else if (rc == 20) SCGPU_TOPK_LAUNCH(SL, W, 20, false);                 \
+  else if (rc == 40 && pipe) SCGPU_TOPK_LAUNCH(SL, W, 40, true);          \
+  else if (rc == 40) SCGPU_TOPK_LAUNCH(SL, W, 40, false);                 \
+  else SCGPU_TOPK_LAUNCH(SL, W, 0, false);
+#define SCGPU_TOPK_CASE(SL)          \
+  if (warps == 2) {                  \
+    SCGPU_TOPK_RC(SL, 2)             \
+  } else if (warps == 4) {           \
+    SCGPU_TOPK_RC(SL, 4)             \
+  } else {                           \
+    SCGPU_TOPK_RC(SL, 8)             \
+  }
   if (h->slots == 1) {
     SCGPU_TOPK_CASE(1)
   } else if (h->slots == 2) {
@@ -644,6 +659,8 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
   } else {
     SCGPU_TOPK_CASE(4)
   }
+#undef SCGPU_TOPK_RC
+#undef SCGPU_TOPK_LAUNCH
 #undef SCGPU_TOPK_CASE
   h->launches++;
   CK(cudaGetLastError());
@@ -2307,13 +2324,13 @@ int scgpu_get_entry(scgpu_handle* h, uint64_t i, float* sc, float* ring, double*
   if (remote) {
     if (sc) CK(cudaMemcpy(sc, h->peers.sc[owner] + l * h->L.RS, sizeof(float) * h->L.RS, cudaMemcpyDeviceToHost));
     if (ring)
-      CK(cudaMemcpy2D(ring, sizeof(float), h->db.ringT + i, h->db.ring_cap * sizeof(float), sizeof(float), h->L.R, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy2D(ring, sizeof(float), h->db.ringT + ring_at(i, 0, h->L.R), 32 * sizeof(float), sizeof(float), h->L.R, cudaMemcpyDeviceToHost));
     if (sector) CK(cudaMemcpy(sector, h->peers.sector[owner] + l * h->L.S, sizeof(double) * h->L.S, cudaMemcpyDeviceToHost));
     return SCGPU_OK;
   }
   if (sc) CK(cudaMemcpy(sc, h->db.sc + l * h->L.RS, sizeof(float) * h->L.RS, cudaMemcpyDeviceToHost));
   if (ring)
-    CK(cudaMemcpy2D(ring, sizeof(float), h->db.ringT + ring_slot(h->db, i, l), h->db.ring_cap * sizeof(float), sizeof(float), h->L.R,
+    CK(cudaMemcpy2D(ring, sizeof(float), h->db.ringT + ring_at(ring_slot(h->db, i, l), 0, h->L.R), 32 * sizeof(float), sizeof(float), h->L.R,
                     cudaMemcpyDeviceToHost));
   if (sector) CK(cudaMemcpy(sector, h->db.sector + l * h->L.S, sizeof(double) * h->L.S, cudaMemcpyDeviceToHost));
   return SCGPU_OK;

@@ -490,8 +490,8 @@ __global__ void __launch_bounds__(128) k_records_from_sc(const float* sc, Layout
 }
 
 // ------------------------------------------------------------------------------------------------
-// Database (one shard): sc[cap][RS] float | ringT[R][cap] float (dimension-major: coalesced streaming in
-// k_topk) | sector[cap][S] double | colnorm[cap][S] double.  Global entry g lives on shard g % G at g / G.
+// Database (one shard): sc[cap][RS] float | ringT (ring keys, tiled dimension-major: ring_at) | sector[cap][S] double |
+// colnorm[cap][S] double.  Global entry g lives on shard g % G at g / G.
 // ------------------------------------------------------------------------------------------------
 struct Db {
   float* sc;
@@ -509,6 +509,13 @@ struct Db {
 
 __host__ __device__ __forceinline__ unsigned long long ring_slot(const Db& db, unsigned long long g, unsigned long long l) {
   return db.ring_global ? g : l;
+}
+// Ring-key matrix layout: tiles of 32 consecutive slots, dimension-major inside a tile -- element (slot, d) at
+// (slot / 32) * (R * 32) + d * 32 + slot % 32.  A warp that takes 32 consecutive slots reads one aligned 128-byte line per
+// dimension at a CONSTANT offset (d * 128 bytes) from its tile base: no per-dimension address arithmetic in k_topk (the plain
+// dimension-major [R][cap] layout of round 1 cost ~35 integer instructions per key), and the layout does not depend on the capacity.
+__host__ __device__ __forceinline__ size_t ring_at(unsigned long long slot, int d, int R) {
+  return (size_t)(slot >> 5) * (size_t)(R * 32) + (size_t)d * 32 + (size_t)(slot & 31);
 }
 
 // Peer-sharded database: every shard's arrays as seen from THIS device -- its own allocations and the other shards'
@@ -543,7 +550,7 @@ __device__ __forceinline__ bool append_entry(const unsigned char* rec, const Lay
     const float* ring = reinterpret_cast<const float*>(rec + L.off_ring);
     for (int i = threadIdx.x; i < L.R; i += blockDim.x) {
       const float v = ring[i];
-      const size_t o = (size_t)i * db.ring_cap + g;
+      const size_t o = ring_at(g, i, L.R);
       db.ringT[o] = v;
       for (int s = 0; s < push.n; ++s) static_cast<float*>(push.dst[s])[o] = v;
     }
@@ -560,7 +567,7 @@ __device__ __forceinline__ bool append_entry(const unsigned char* rec, const Lay
   const double* sector = reinterpret_cast<const double*>(rec + L.off_sector);
   const double* norm = reinterpret_cast<const double*>(rec + L.off_norm);
   if (!db.ring_global)
-    for (int i = threadIdx.x; i < L.R; i += blockDim.x) db.ringT[(size_t)i * db.cap + l] = ring[i];
+    for (int i = threadIdx.x; i < L.R; i += blockDim.x) db.ringT[ring_at(l, i, L.R)] = ring[i];
   for (int i = threadIdx.x; i < L.S; i += blockDim.x) {
     db.sector[l * L.S + i] = sector[i];
     db.colnorm[l * L.S + i] = norm[i];
@@ -589,7 +596,7 @@ __global__ void __launch_bounds__(128) k_gather(unsigned char* records, Layout L
   unsigned char* rec = records + (size_t)blockIdx.x * L.rec_bytes;
   for (int i = threadIdx.x; i < L.RS; i += blockDim.x) reinterpret_cast<float*>(rec)[i] = sc[l * L.RS + i];
   for (int i = threadIdx.x; i < L.R; i += blockDim.x)
-    reinterpret_cast<float*>(rec + L.off_ring)[i] = db.ringT[(size_t)i * db.ring_cap + ring_slot(db, g, l)];
+    reinterpret_cast<float*>(rec + L.off_ring)[i] = db.ringT[ring_at(ring_slot(db, g, l), i, L.R)];
   for (int i = threadIdx.x; i < L.S; i += blockDim.x) {
     reinterpret_cast<double*>(rec + L.off_sector)[i] = sector[l * L.S + i];
     reinterpret_cast<double*>(rec + L.off_norm)[i] = colnorm[l * L.S + i];
@@ -670,13 +677,14 @@ struct WarpList {
 // RC > 0: compile-time dimension -- the loop unrolls and all RC loads are in flight together (with a run-time bound
 // every group of four loads was a separate round trip to L2); RC = 0: any dimension.
 template <int RC>
-__device__ __forceinline__ float ringkey_dist2(const float* q, const float* ringT, unsigned long long cap, unsigned long long l, int R_rt) {
+__device__ __forceinline__ float ringkey_dist2(const float* q, const float* ringT, unsigned long long l, int R_rt) {
   const int R = RC > 0 ? RC : R_rt;
+  const float* base = ringT + (size_t)(l >> 5) * (size_t)(R * 32) + (size_t)(l & 31);  // element d at base[d * 32] (ring_at)
   float result = 0.f;
   if (RC > 0) {
     float kv[RC > 0 ? RC : 1];
 #pragma unroll
-    for (int d = 0; d < RC; ++d) kv[d] = __ldg(ringT + (size_t)d * cap + l);
+    for (int d = 0; d < RC; ++d) kv[d] = __ldg(base + d * 32);
     int d = 0;
 #pragma unroll
     for (; d + 3 < RC; d += 4) {
@@ -694,15 +702,15 @@ __device__ __forceinline__ float ringkey_dist2(const float* q, const float* ring
   }
   int d = 0;
   for (; d + 3 < R; d += 4) {
-    const float d0 = __fsub_rn(q[d], __ldg(ringT + (size_t)d * cap + l));
-    const float d1 = __fsub_rn(q[d + 1], __ldg(ringT + (size_t)(d + 1) * cap + l));
-    const float d2 = __fsub_rn(q[d + 2], __ldg(ringT + (size_t)(d + 2) * cap + l));
-    const float d3 = __fsub_rn(q[d + 3], __ldg(ringT + (size_t)(d + 3) * cap + l));
+    const float d0 = __fsub_rn(q[d], __ldg(base + d * 32));
+    const float d1 = __fsub_rn(q[d + 1], __ldg(base + (d + 1) * 32));
+    const float d2 = __fsub_rn(q[d + 2], __ldg(base + (d + 2) * 32));
+    const float d3 = __fsub_rn(q[d + 3], __ldg(base + (d + 3) * 32));
     const float t = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
     result = __fadd_rn(result, t);
   }
   for (; d < R; ++d) {
-    const float d0 = __fsub_rn(q[d], __ldg(ringT + (size_t)d * cap + l));
+    const float d0 = __fsub_rn(q[d], __ldg(base + d * 32));
     result = __fadd_rn(result, __fmul_rn(d0, d0));
   }
   return result;
@@ -721,9 +729,63 @@ struct TopkParams {
   unsigned long long* keys_out;        // [nq][K]
 };
 
+template <int RC>
+__device__ __forceinline__ float ringkey_dist2_regs(const float* q, const float (&kv)[RC]) {
+  float result = 0.f;
+  int d = 0;
+#pragma unroll
+  for (; d + 3 < RC; d += 4) {
+    const float d0 = __fsub_rn(q[d], kv[d]), d1 = __fsub_rn(q[d + 1], kv[d + 1]);
+    const float d2 = __fsub_rn(q[d + 2], kv[d + 2]), d3 = __fsub_rn(q[d + 3], kv[d + 3]);
+    const float t = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
+    result = __fadd_rn(result, t);
+  }
+#pragma unroll
+  for (; d < RC; ++d) {
+    const float d0 = __fsub_rn(q[d], kv[d]);
+    result = __fadd_rn(result, __fmul_rn(d0, d0));
+  }
+  return result;
+}
+
+// the streaming loop of k_topk for a compile-time key dimension: keys [first, end) in steps of `step`, two per lane
+template <int SLOTS, int RC>
+__device__ __forceinline__ void topk_stream(WarpList<SLOTS>& list, const float* q, const float* ringT, unsigned long long first, unsigned long long end,
+                                            unsigned step, unsigned long long G, unsigned long long rank, int K) {
+  const int lane = threadIdx.x & 31;
+  float kn[2][RC];
+  auto load = [&](unsigned long long base) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned long long l = base + 32 * u + lane;
+      const float* b = ringT + (size_t)(l >> 5) * (size_t)(RC * 32) + (size_t)(l & 31);
+#pragma unroll
+      for (int d = 0; d < RC; ++d) kn[u][d] = l < end ? __ldg(b + d * 32) : 0.f;
+    }
+  };
+  if (first < end) load(first);
+  for (unsigned long long base = first; base < end; base += step) {
+    float kv[2][RC];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int d = 0; d < RC; ++d) kv[u][d] = kn[u][d];
+    if (base + step < end) load(base + step);  // in flight during the work below
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const unsigned long long l = base + 32 * u + lane;
+      const float d2 = ringkey_dist2_regs<RC>(q, kv[u]);
+      const unsigned long long key = l < end ? (((unsigned long long)__float_as_uint(d2) << 32) | (l * G + rank)) : KEY_NONE;
+      list.offer(key, K);
+    }
+  }
+}
+
 // TOPK_WARPS warps share one (query, chunk).  Every warp's list has a warm-up phase of ~K(1 + ln(n_warp / K)) insertions,
 // so many queries per launch use few warps per query (long streams per warp), few queries use many (latency).
-template <int SLOTS, int TOPK_WARPS>
+// RC: compile-time key dimension (20, 40; 0 = any).  PIPE: software-pipelined key loads (more registers: chosen for small grids,
+// where too few warps are resident to hide the L2 latency of the loads).
+template <int SLOTS, int TOPK_WARPS, int RC, bool PIPE>
 __global__ void __launch_bounds__(TOPK_WARPS * 32) k_topk(const TopkParams p) {
   constexpr int TOPK_THREADS = TOPK_WARPS * 32;
   __shared__ float s_q[64];
@@ -745,21 +807,24 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32) k_topk(const TopkParams p) {
 
   WarpList<SLOTS> list;
   list.init();
-  // two keys per lane per iteration: both keys' loads (2 x R lines from L2) are in flight together, which halves the exposed
-  // latency per key (the kernel is latency-bound: ~15 warps per SM, long-scoreboard stalls on the key loads)
-  auto dist_key = [&](unsigned long long l) {
-    unsigned long long key = KEY_NONE;
-    if (l < end) {
-      const float d2 = R == 20 ? ringkey_dist2<20>(s_q, p.db.ringT, p.db.cap, l, R)
-                               : (R == 40 ? ringkey_dist2<40>(s_q, p.db.ringT, p.db.cap, l, R) : ringkey_dist2<0>(s_q, p.db.ringT, p.db.cap, l, R));
-      key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned long long)(l * p.db.G + p.db.rank);
+  // Two keys per lane per iteration, software-pipelined: the 2 x R loads of the NEXT iteration are issued before the current keys are
+  // scored and offered, so the L2 latency of the key loads (the kernel's top stall: ~15 warps per SM cannot hide it) overlaps the
+  // arithmetic and the list maintenance of the current ones.
+  const unsigned long long G = (unsigned long long)p.db.G, rk = (unsigned long long)p.db.rank;
+  if (PIPE && RC > 0) {
+    topk_stream<SLOTS, (RC > 0 ? RC : 4)>(list, s_q, p.db.ringT, start + (unsigned long long)warp * 64, end, 2 * TOPK_THREADS, G, rk, K);
+  } else {
+    for (unsigned long long base = start + (unsigned long long)warp * 64; base < end; base += 2 * TOPK_THREADS) {
+      unsigned long long k2[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const unsigned long long l = base + 32 * u + lane;
+        k2[u] = KEY_NONE;
+        if (l < end) k2[u] = ((unsigned long long)__float_as_uint(ringkey_dist2<RC>(s_q, p.db.ringT, l, R)) << 32) | (l * G + rk);
+      }
+      list.offer(k2[0], K);
+      list.offer(k2[1], K);
     }
-    return key;
-  };
-  for (unsigned long long base = start + (unsigned long long)warp * 64; base < end; base += 2 * TOPK_THREADS) {
-    const unsigned long long k0 = dist_key(base + lane), k1 = dist_key(base + 32 + lane);
-    list.offer(k0, K);
-    list.offer(k1, K);
   }
   // block merge: warps > 0 publish, warp 0 absorbs
   if (warp > 0) list.store(s_lists + warp * 32 * SLOTS, K);
@@ -805,25 +870,6 @@ __global__ void __launch_bounds__(TOPK_WARPS * 32) k_topk(const TopkParams p) {
 constexpr int TOPK_QT = 8;        // queries per group
 constexpr int TOPK_TILE_WARPS = 4;
 
-template <int RC>
-__device__ __forceinline__ float ringkey_dist2_regs(const float* q, const float (&kv)[RC]) {
-  float result = 0.f;
-  int d = 0;
-#pragma unroll
-  for (; d + 3 < RC; d += 4) {
-    const float d0 = __fsub_rn(q[d], kv[d]), d1 = __fsub_rn(q[d + 1], kv[d + 1]);
-    const float d2 = __fsub_rn(q[d + 2], kv[d + 2]), d3 = __fsub_rn(q[d + 3], kv[d + 3]);
-    const float t = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)), __fmul_rn(d3, d3));
-    result = __fadd_rn(result, t);
-  }
-#pragma unroll
-  for (; d < RC; ++d) {
-    const float d0 = __fsub_rn(q[d], kv[d]);
-    result = __fadd_rn(result, __fmul_rn(d0, d0));
-  }
-  return result;
-}
-
 template <int SLOTS, int RC>
 __global__ void __launch_bounds__(TOPK_TILE_WARPS * 32) k_topk_tile(const TopkParams p, unsigned nq) {
   constexpr int QT = TOPK_QT, TW = TOPK_TILE_WARPS;
@@ -865,18 +911,17 @@ __global__ void __launch_bounds__(TOPK_TILE_WARPS * 32) k_topk_tile(const TopkPa
   }
   float kv[RC], kn[RC];
   const float* col = p.db.ringT;
-  const unsigned long long cap = p.db.cap;
   {
     const unsigned long long l = start + (unsigned long long)warp * 32 + lane;
 #pragma unroll
-    for (int d = 0; d < RC; ++d) kn[d] = l < end ? __ldg(col + (size_t)d * cap + l) : 0.f;
+    for (int d = 0; d < RC; ++d) kn[d] = l < end ? __ldg(col + ring_at(l, d, RC)) : 0.f;
   }
   for (unsigned long long base = start + (unsigned long long)warp * 32; base < end; base += TW * 32) {
 #pragma unroll
     for (int d = 0; d < RC; ++d) kv[d] = kn[d];
     const unsigned long long lcur = base + lane, lnext = lcur + TW * 32;
 #pragma unroll
-    for (int d = 0; d < RC; ++d) kn[d] = lnext < end ? __ldg(col + (size_t)d * cap + lnext) : 0.f;  // in flight during the work below
+    for (int d = 0; d < RC; ++d) kn[d] = lnext < end ? __ldg(col + ring_at(lnext, d, RC)) : 0.f;  // in flight during the work below
     const unsigned long long idx = lcur * p.db.G + p.db.rank;
 #pragma unroll
     for (int q = 0; q < QT; ++q) {
