@@ -250,13 +250,15 @@ def new_out(n):
                 nn_idx=np.empty(n, np.int32), nn_shift=np.empty(n, np.int32))
 
 
-def h2d_probe(torch, device):
+def h2d_probe(torch, device, barrier=None):
     """What the host side can deliver: pinned -> device copy rate of this GPU's link, and one core's memcpy rate."""
     n = 1 << 28
     h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     d = torch.empty(n, dtype=torch.uint8, device=device)
     d.copy_(h, non_blocking=True)
     torch.cuda.synchronize()
+    if barrier is not None:
+        barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(4):
@@ -624,6 +626,10 @@ def run_multi_gpu(args):
     s_e2e = allmax(time.perf_counter() - t0) / args.steps
     clocks.active = False
     same = all(np.array_equal(res_dev[k], out[k], equal_nan=True) for k in out)
+    # what the host can deliver to all GPUs at once: every rank copies 256 MiB pinned -> device four times, simultaneously
+    probe = h2d_probe(torch, f"cuda:{local}", barrier=dist.barrier)
+    agg = torch.tensor([probe["pinned_h2d_gbs"]], dtype=torch.float64, device="cuda")
+    dist.all_reduce(agg, op=dist.ReduceOp.SUM)
     line = None
     from sc_lego_loam_b200.scgpu import host_info
     pool, packs = host_info()
@@ -648,6 +654,8 @@ def run_multi_gpu(args):
                     "d2h_bytes_per_step": total * 24 * G, "ms_per_step": 1e3 * s_e2e, "results_equal_device_leg": bool(same),
                     "h2d_gbs_aggregate": total * PTS * shipped / s_e2e / 1e9, "host_pool_threads_per_rank": pool,
                     "bytes_per_point_on_the_link": shipped, "host_cores": os.cpu_count(),
+                    "host_probe": {"pinned_h2d_gbs_all_ranks_at_once": float(agg.item()), "pinned_h2d_gbs_rank0": probe["pinned_h2d_gbs"],
+                                   "note": "the ceiling of the e2e leg: what this host's memory system and PCIe roots deliver to all GPUs simultaneously"},
                     "input": "pinned host float4 scans, one synchronous collective call per step"},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "k_build_tma", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

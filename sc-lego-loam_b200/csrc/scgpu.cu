@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 #include <float.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -28,6 +29,13 @@
 using namespace scgpu;
 
 namespace {
+
+// NVTX range around a public call (tracing).  Header-only nvtx3: a no-op unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+#define SCGPU_TRACE_CALL() NvtxRange nvtx_range_(__func__)
 
 thread_local char g_err[512] = "";
 
@@ -1962,6 +1970,7 @@ int scgpu_record_bytes(scgpu_handle* h, size_t* out) {
 // ---- reference surface ----------------------------------------------------------------------------
 
 int scgpu_make_sc(scgpu_handle* h, const void* pts, size_t n, size_t stride, double* out_sc) {
+  SCGPU_TRACE_CALL();
   if (!h || !out_sc || (!pts && n)) return fail(SCGPU_E_INVALID, "null argument");
   h = GROUP_FIRST(h);
   CK(cudaSetDevice(h->cfg.device));
@@ -2026,6 +2035,7 @@ static int append_scans_one(scgpu_handle* h, const void* pts, size_t n_scans, si
 }
 
 int scgpu_append_scans_batched(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location) {
+  SCGPU_TRACE_CALL();
   if (!h || (!pts && n_scans && pts_per_scan)) return fail(SCGPU_E_INVALID, "null argument");
   if (n_scans == 0) return SCGPU_OK;
   if (h->is_group) {  // scan i -> shard (size + i) % G, binned on that shard's device; ring keys pushed to every replica
@@ -2150,6 +2160,7 @@ static int group_query_range(scgpu_handle* g, uint64_t first, size_t nq, const u
 }
 
 int scgpu_detect(scgpu_handle* h, int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift) {
+  SCGPU_TRACE_CALL();
   if (!h || !loop_id || !yaw) return fail(SCGPU_E_INVALID, "null argument");
   if (!h->is_group && h->cfg.shard_count != 1)
     return fail(SCGPU_E_INVALID, "scgpu_detect needs the whole database behind the handle (one device, or a device list); use the staged API for shards");
@@ -2197,6 +2208,7 @@ static void replay_shards(scgpu_handle* h, const void* pts, size_t scan_bytes, u
 }
 
 int scgpu_replay_async(scgpu_handle* h, const void* pts, size_t n_scans, size_t pts_per_scan, size_t stride, int location) {
+  SCGPU_TRACE_CALL();
   if (!h || (!pts && n_scans && pts_per_scan)) return fail(SCGPU_E_INVALID, "null argument");
   if (!h->is_group && h->cfg.shard_count != 1)
     return fail(SCGPU_E_INVALID, "scgpu_replay_* needs the whole database behind the handle; shards of other processes use scgpu_peer_replay_async");
@@ -2212,6 +2224,7 @@ int scgpu_replay_async(scgpu_handle* h, const void* pts, size_t n_scans, size_t 
 }
 
 int scgpu_replay_results(scgpu_handle* h, size_t n, int* loop_id, float* yaw, double* nearest_dist, int* nearest_idx, int* nearest_shift) {
+  SCGPU_TRACE_CALL();
   if (!h) return fail(SCGPU_E_INVALID, "null argument");
   std::vector<scgpu_handle*> hs;
   if (h->is_group) hs = h->shards;
@@ -2524,6 +2537,7 @@ int scgpu_exhaustive(scgpu_handle* h, uint64_t q, uint64_t n_search, int flipped
 
 int scgpu_exhaustive_batched(scgpu_handle* h, const uint64_t* q, const uint64_t* n_search, size_t nq, double* best_dist, int* best_shift,
                              int64_t* best_idx) {
+  SCGPU_TRACE_CALL();
   if (!h || ((!q || !n_search || !best_dist || !best_shift || !best_idx) && nq)) return fail(SCGPU_E_INVALID, "null argument");
   std::vector<ExhWin> w;
   RET(exhaustive_any(h, q, n_search, nq, 0, w));
@@ -3086,6 +3100,7 @@ int scgpu_peer_attach(scgpu_handle* h, const void* blobs, int n) {
 }
 
 int scgpu_peer_replay_async(scgpu_handle* h, const void* pts, size_t n_total, size_t pts_per_scan, size_t stride, int location) {
+  SCGPU_TRACE_CALL();
   if (!h || (!pts && n_total && pts_per_scan)) return fail(SCGPU_E_INVALID, "null argument");
   if (!h->peer || h->is_group || !h->attached) return fail(SCGPU_E_INVALID, "needs an attached peer-sharded shard handle");
   if (n_total == 0) return SCGPU_OK;
