@@ -122,11 +122,11 @@ struct scgpu_handle {
   int exh_cfg = 0;  // 1: 20x60 radius 3, 2: 40x120 radius 6, 3: 20x60 full-shift search (tensor-core screening, scgpu_tc.cuh)
   // full-shift search on the tensor cores: hi / lo split of the screening copy, the queries' circulant expansion, TMA maps
   DevBuf tc_e_hi, tc_e_lo, tc_q_hi, tc_q_lo, tc_qaux, tc_shift;
-  DevBuf tc_ev_hi, tc_ev_lo, tc_qv_hi, tc_qv_lo;  // sector keys (windowed search on the tensor cores: alignment GEMM)
+  DevBuf tc_ev_hi, tc_ev_lo, tc_qv_hi, tc_qv_lo, tc_align;  // sector keys (windowed search on the tensor cores: alignment GEMM)
   DevBuf icp_src, icp_tgt, icp_state, icp_part;  // loop verification (scgpu_icp.cuh)
   uint64_t tc_rows = 0;    // rows the E buffers (and their tensor maps) were sized for
   uint64_t tc_upto = 0;    // local entries [0, tc_upto) are split
-  CUtensorMap tc_maps[8];  // E_hi, E_lo, Q_hi, Q_lo, EV_hi, EV_lo, QV_hi, QV_lo
+  CUtensorMap tc_maps[12];  // E_hi, E_lo, Q_hi, Q_lo, EV_hi, EV_lo, QV_hi, QV_lo | the first four again with 64-byte rows (k_tc_fullshift2)
   bool tc_want_shifts = false;
   float* x_sc_hat = nullptr;
   unsigned char* x_vk = nullptr;  // [cap] ExhVkRec: float sector key + aux
@@ -1150,7 +1150,7 @@ typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint3
                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D FP32 tensor [rows][TC_K], box = box_rows x TC_BK floats, 128-byte swizzle (what the UMMA shared-memory descriptors expect)
-int tc_make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t box_rows, uint64_t k_extent = TC_K) {
+int tc_make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t box_rows, uint64_t k_extent = TC_K, uint32_t box_k = TC_BK) {
   static TensorMapEncodeFn encode = nullptr;
   if (!encode) {
     void* fn = nullptr;
@@ -1161,10 +1161,11 @@ int tc_make_map(CUtensorMap* map, void* base, uint64_t rows, uint32_t box_rows, 
   }
   const cuuint64_t dims[2] = {(cuuint64_t)k_extent, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)k_extent * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_k, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            box_k * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SCGPU_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return SCGPU_OK;
 }
@@ -1196,6 +1197,10 @@ int tc_sync(scgpu_handle* h, cudaStream_t st) {
     RET(tc_make_map(&h->tc_maps[5], h->tc_ev_lo.p, h->db.cap, TC_M, TC_VK));
     RET(tc_make_map(&h->tc_maps[6], h->tc_qv_hi.p, (uint64_t)EXH_MAX_BATCH_TC * TC_S, TC_N, TC_VK));
     RET(tc_make_map(&h->tc_maps[7], h->tc_qv_lo.p, (uint64_t)EXH_MAX_BATCH_TC * TC_S, TC_N, TC_VK));
+    RET(tc_make_map(&h->tc_maps[8], h->tc_e_hi.p, h->db.cap, TC2_M, TC_K, TC2_BK));
+    RET(tc_make_map(&h->tc_maps[9], h->tc_e_lo.p, h->db.cap, TC2_M, TC_K, TC2_BK));
+    RET(tc_make_map(&h->tc_maps[10], h->tc_q_hi.p, (uint64_t)EXH_MAX_BATCH_TC * TC_S, TC_N, TC_K, TC2_BK));
+    RET(tc_make_map(&h->tc_maps[11], h->tc_q_lo.p, (uint64_t)EXH_MAX_BATCH_TC * TC_S, TC_N, TC_K, TC2_BK));
     h->tc_rows = h->db.cap;
     h->tc_upto = 0;
   }
@@ -1237,11 +1242,32 @@ int launch_tc_screen(scgpu_handle* h, size_t nq, uint64_t n_max, uint64_t pitch,
   tp.shift_out = d_shift;
   tp.windowed = windowed;
   tp.radius = h->radius;
+  tp.align_out = nullptr;
+  tp.align_in = nullptr;
+  // batches: 256 x 240 tiles (k_tc_fullshift2: 1.48x fewer operand bytes per FLOP); SCGPU_TC_TILE=128 keeps the first kernel.
+  // Windowed batches take two passes then: the alignment GEMM alone (k_tc_fullshift, 128-row tiles), then the big-tile kernel.
+  static const bool big_tile = !(getenv("SCGPU_TC_TILE") && atoi(getenv("SCGPU_TC_TILE")) == 128);
+  const bool use2 = big_tile && nq >= TC_QG;
+  if (ev0) CK(cudaEventRecord(ev0, st));
+  if (use2 && windowed) {
+    RET(h->tc_align.reserve((nq * pitch + 16) * sizeof(unsigned)));
+    TcParams ta = tp;
+    ta.align_out = h->tc_align.as<unsigned>();
+    const uint64_t items_a = (uint64_t)ta.n_groups * ta.n_tiles;
+    k_tc_fullshift<<<(unsigned)std::min<uint64_t>(items_a, (uint64_t)h->sm_count), TC_THREADS, tc_smem_bytes(), st>>>(
+        h->tc_maps[0], h->tc_maps[1], h->tc_maps[2], h->tc_maps[3], h->tc_maps[4], h->tc_maps[5], h->tc_maps[6], h->tc_maps[7], ta);
+    h->launches++;
+    tp.align_in = h->tc_align.as<unsigned>();
+    tp.windowed = 0;
+  }
+  if (use2) tp.n_tiles = (unsigned)((n_max + TC2_M - 1) / TC2_M);
   const uint64_t items = (uint64_t)tp.n_groups * tp.n_tiles;
   const unsigned gx = (unsigned)std::min<uint64_t>(items, (uint64_t)h->sm_count);
-  if (ev0) CK(cudaEventRecord(ev0, st));
-  k_tc_fullshift<<<gx, TC_THREADS, tc_smem_bytes(), st>>>(h->tc_maps[0], h->tc_maps[1], h->tc_maps[2], h->tc_maps[3], h->tc_maps[4], h->tc_maps[5],
-                                                          h->tc_maps[6], h->tc_maps[7], tp);
+  if (use2)
+    k_tc_fullshift2<<<gx, TC_THREADS, tc2_smem_bytes(), st>>>(h->tc_maps[8], h->tc_maps[9], h->tc_maps[10], h->tc_maps[11], tp);
+  else
+    k_tc_fullshift<<<gx, TC_THREADS, tc_smem_bytes(), st>>>(h->tc_maps[0], h->tc_maps[1], h->tc_maps[2], h->tc_maps[3], h->tc_maps[4], h->tc_maps[5],
+                                                            h->tc_maps[6], h->tc_maps[7], tp);
   if (ev1) CK(cudaEventRecord(ev1, st));
   h->launches++;
   CK(cudaGetLastError());
@@ -1757,6 +1783,7 @@ static int create_one(const scgpu_config* cfg, scgpu_handle** out) {
                                                (int)exh_smem_bytes<40, 120, 6, 4, 2>());
   if (e == cudaSuccess && (h->exh_cfg == 3 || h->exh_cfg == 1)) {
     e = cudaFuncSetAttribute(k_tc_fullshift, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_fullshift2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2_smem_bytes());
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(k_fullshift_simt<TC_R, TC_S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qtab_bytes<TC_R, TC_S, 15>());
   }
@@ -1840,7 +1867,7 @@ int scgpu_destroy(scgpu_handle* h) {
   }
   DevBuf* xb[] = {&h->x_query, &h->x_d32, &h->x_keys, &h->x_pd,    &h->x_ps,    &h->x_small, &h->x_best,  &h->c_d32,
                   &h->c_list,  &h->c_count, &h->tc_e_hi, &h->tc_e_lo, &h->tc_q_hi, &h->tc_q_lo, &h->tc_qaux, &h->tc_shift,
-                  &h->tc_ev_hi, &h->tc_ev_lo, &h->tc_qv_hi, &h->tc_qv_lo,
+                  &h->tc_ev_hi, &h->tc_ev_lo, &h->tc_qv_hi, &h->tc_qv_lo, &h->tc_align,
                   &h->records2[0], &h->records2[1], &h->res_buf, &h->icp_src, &h->icp_tgt, &h->icp_state, &h->icp_part};
   for (DevBuf* b : xb) b->release();
   for (int i = 0; i < 2; ++i) {

@@ -190,6 +190,11 @@ struct TcParams {
   unsigned* shift_out;                // optional [nq][d32_pitch]: argmin shift (tests)
   int windowed;                       // 1: the reference's windowed search -- a second small GEMM (sector keys, K = 64) gives the alignment,
   int radius;                         //    the distance is the minimum over the 2*radius+1 shifts around it (SC.cpp:121-144)
+  // two-pass windowed mode (256-row tiles have no TMEM left for the alignment accumulator): k_tc_fullshift runs the alignment GEMM
+  // ALONE and writes, per (query, entry), best shift | runner-up << 8 | ambiguous << 16 | flagged << 17 to align_out;
+  // k_tc_fullshift2 then reads it (align_in) in its epilogue
+  unsigned* align_out;
+  const unsigned* align_in;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_constant__ CUtensorMap map_e_hi, const __grid_constant__ CUtensorMap map_e_lo,
@@ -246,7 +251,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
       for (unsigned long long w = blockIdx.x; w < n_items; w += gridDim.x) {
         const unsigned g = (unsigned)(w / p.n_tiles), m = (unsigned)(w % p.n_tiles);
         const int nkb = TC_KBLOCKS + (p.windowed ? TC_VKBLOCKS : 0);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = p.align_out ? TC_KBLOCKS : 0; kb < nkb; ++kb, ++it) {
           const int s = it % TC_STAGES;
           if (it >= TC_STAGES) mbar_wait(&empty[s], ((it / TC_STAGES) - 1) & 1);
           mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
         tc_fence_after();
         const uint32_t d0 = tmem_base + (uint32_t)a * TC_ACC_COLS;
         const int nkb = TC_KBLOCKS + (p.windowed ? TC_VKBLOCKS : 0);
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
+        for (int kb = p.align_out ? TC_KBLOCKS : 0; kb < nkb; ++kb, ++it) {
           const int s = it % TC_STAGES;
           mbar_wait(&full[s], (it / TC_STAGES) & 1);
           tc_fence_after();
@@ -380,6 +385,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
           amb2 = !((b1 - b2) > margin);
           amb3 = !((b1 - b3) > margin) || !(b1 == b1);
         }
+        if (p.align_out) {  // alignment pass only
+          if (e < nl) p.align_out[(size_t)qi * p.d32_pitch + e] = (unsigned)a_cur | ((unsigned)a_2nd << 8) | (amb2 ? 1u << 16 : 0u) | (amb3 ? 1u << 17 : 0u);
+          continue;
+        }
         tc_ld32(tbase + q * TC_S, v0);        // shifts 0..31
         tc_ld32(tbase + q * TC_S + 28, v1);   // shifts 28..59
         tc_ld_wait();
@@ -415,6 +424,221 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
+    }
+    if (cur_g != 0xffffffffu) {
+#pragma unroll
+      for (int q = 0; q < TC_QG; ++q) {
+        const unsigned mn = __reduce_min_sync(FULL, my_min[q]);
+        if (lane == 0 && mn != 0x7f800000u && cur_g * TC_QG + q < p.nq) atomicMin(p.min_bits + cur_g * TC_QG + q, mn);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- k_tc_fullshift2: the full-shift kernel with a 256 x 240 tile per CTA --------------------------------------------------
+// k_tc_fullshift is bound by operand traffic, not by the tensor pipe (58 % active): every K block moves (128 + 240) rows x hi/lo
+// through shared memory for 128 x 240 x 32 products, and both operands come from L2.  Here one CTA accumulates TWO 128-row halves
+// against the same query tile -- (256 + 240) rows per 256 x 240 products: 1.48x fewer operand bytes per FLOP.  To keep three
+// stages in 227 KB the K block is 16 floats (64-byte rows, 64-byte swizzle): stage = E 256 x 16 (hi, lo) + Qs 240 x 16 (hi, lo)
+// = 62 KB.  The two accumulators take TMEM columns [0, 240) and [256, 496): one tile at a time (the epilogue -- eight warps, one
+// entry x four queries per thread -- is not hidden; ~10 % of a tile's MMA time).  Full-shift mode only.
+constexpr int TC2_M = 256, TC2_BK = 16, TC2_STAGES = 3;
+constexpr int TC2_KBLOCKS = TC_K / TC2_BK;  // 75
+constexpr int TC2_A_BYTES = TC2_M * TC2_BK * 4;  // 16 KB
+constexpr int TC2_B_BYTES = TC_N * TC2_BK * 4;   // 15 KB
+constexpr int TC2_STAGE_BYTES = 2 * TC2_A_BYTES + 2 * TC2_B_BYTES;
+static_assert(TC_K % TC2_BK == 0, "whole K blocks");
+constexpr size_t tc2_smem_bytes() { return 1024 + (size_t)TC2_STAGES * TC2_STAGE_BYTES + TC_QG * sizeof(TcQueryAux) + 64 * 4 + 256; }
+
+// K-major operand tile, 64-byte swizzle: rows of 64 bytes, 8-row atoms of 512 bytes (SBO)
+__device__ __forceinline__ uint64_t tc_smem_desc64(const void* p) {
+  return (uint64_t)((smem_u32(p) >> 4) & 0x3fffu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_tc_fullshift2(const __grid_constant__ CUtensorMap map_e_hi, const __grid_constant__ CUtensorMap map_e_lo,
+                                                                 const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                                                                 const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  auto stage_ptr = [&](int s, int which) {  // which: 0 E_hi, 1 E_lo, 2 Q_hi, 3 Q_lo
+    unsigned char* sp = base + (size_t)s * TC2_STAGE_BYTES;
+    return sp + (which == 0 ? 0 : which == 1 ? TC2_A_BYTES : which == 2 ? 2 * TC2_A_BYTES : 2 * TC2_A_BYTES + TC2_B_BYTES);
+  };
+  TcQueryAux* s_aux = reinterpret_cast<TcQueryAux*>(base + (size_t)TC2_STAGES * TC2_STAGE_BYTES);
+  float* s_rcp = reinterpret_cast<float*>(s_aux + TC_QG);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_rcp + 64);
+  uint64_t* full = bars;                          // [TC2_STAGES]
+  uint64_t* empty = bars + TC2_STAGES;            // [TC2_STAGES]
+  uint64_t* acc_full = bars + 2 * TC2_STAGES;     // [1]
+  uint64_t* acc_empty = acc_full + 1;             // [1]
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC2_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 8);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < 64) s_rcp[threadIdx.x] = threadIdx.x ? 1.0f / (float)threadIdx.x : 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  const unsigned long long n_items = (unsigned long long)p.n_groups * p.n_tiles;  // n_tiles counts 256-entry tiles here
+
+  if (warp == 0) {
+    if (lane == 0) {
+      unsigned it = 0;
+      for (unsigned long long w = blockIdx.x; w < n_items; w += gridDim.x) {
+        const unsigned g = (unsigned)(w / p.n_tiles), m = (unsigned)(w % p.n_tiles);
+        for (int kb = 0; kb < TC2_KBLOCKS; ++kb, ++it) {
+          const int s = it % TC2_STAGES;
+          if (it >= TC2_STAGES) mbar_wait(&empty[s], ((it / TC2_STAGES) - 1) & 1);
+          mbar_arrive_expect_tx(&full[s], TC2_STAGE_BYTES);
+          tma_load_2d(stage_ptr(s, 0), &map_e_hi, kb * TC2_BK, (int)(m * TC2_M), &full[s]);
+          tma_load_2d(stage_ptr(s, 1), &map_e_lo, kb * TC2_BK, (int)(m * TC2_M), &full[s]);
+          tma_load_2d(stage_ptr(s, 2), &map_q_hi, kb * TC2_BK, (int)(g * TC_N), &full[s]);
+          tma_load_2d(stage_ptr(s, 3), &map_q_lo, kb * TC2_BK, (int)(g * TC_N), &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc_idesc(128, TC_N);
+      unsigned it = 0, tile = 0;
+      for (unsigned long long w = blockIdx.x; w < n_items; w += gridDim.x, ++tile) {
+        if (tile >= 1) mbar_wait(acc_empty, (tile - 1) & 1);
+        tc_fence_after();
+        for (int kb = 0; kb < TC2_KBLOCKS; ++kb, ++it) {
+          const int s = it % TC2_STAGES;
+          mbar_wait(&full[s], (it / TC2_STAGES) & 1);
+          tc_fence_after();
+          const uint64_t q_hi = tc_smem_desc64(stage_ptr(s, 2)), q_lo = tc_smem_desc64(stage_ptr(s, 3));
+#pragma unroll
+          for (int mh = 0; mh < 2; ++mh) {  // the two 128-row halves of the entry tile share the query tile
+            const uint64_t e_hi = tc_smem_desc64(stage_ptr(s, 0) + mh * 128 * TC2_BK * 4), e_lo = tc_smem_desc64(stage_ptr(s, 1) + mh * 128 * TC2_BK * 4);
+            const uint32_t d = tmem_base + (uint32_t)mh * TC_ACC_COLS;
+#pragma unroll
+            for (int kk = 0; kk < TC2_BK / 8; ++kk) {
+              const uint64_t adv = (uint64_t)(kk * 8 * 4) >> 4;
+              tc_mma_tf32(d, e_hi + adv, q_hi + adv, idesc, (kb | kk) != 0);
+              tc_mma_tf32(d, e_hi + adv, q_lo + adv, idesc, 1);
+              tc_mma_tf32(d, e_lo + adv, q_hi + adv, idesc, 1);
+            }
+          }
+          tc_commit(&empty[s]);
+        }
+        tc_commit(acc_full);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int mhalf = (warp - 2) >> 2;
+    const int row = mhalf * 128 + quarter * 32 + lane;
+    unsigned tile = 0;
+    unsigned my_min[TC_QG];
+    unsigned cur_g = 0xffffffffu;
+    for (unsigned long long w = blockIdx.x; w < n_items; w += gridDim.x, ++tile) {
+      const unsigned g = (unsigned)(w / p.n_tiles), m = (unsigned)(w % p.n_tiles);
+      if (g != cur_g) {
+        if (cur_g != 0xffffffffu) {
+#pragma unroll
+          for (int q = 0; q < TC_QG; ++q) {
+            const unsigned mn = __reduce_min_sync(FULL, my_min[q]);
+            if (lane == 0 && mn != 0x7f800000u && cur_g * TC_QG + q < p.nq) atomicMin(p.min_bits + cur_g * TC_QG + q, mn);
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(p.qaux + (size_t)g * TC_QG);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_aux);
+        for (int i = threadIdx.x - 64; i < (int)(TC_QG * sizeof(TcQueryAux) / 8); i += 256) dst[i] = src[i];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        cur_g = g;
+#pragma unroll
+        for (int q = 0; q < TC_QG; ++q) my_min[q] = 0x7f800000u;
+      }
+      const unsigned long long e = (unsigned long long)m * TC2_M + row;
+      const ExhAux* ax = reinterpret_cast<const ExhAux*>(p.vk + e * sizeof(ExhVkRec<TC_S>) + TC_S * sizeof(float));
+      unsigned long long vmask = 0;
+      unsigned eflags = 0;
+      unsigned long long nl_max = 0;
+#pragma unroll
+      for (int q = 0; q < TC_QG; ++q) {
+        const unsigned qi = g * TC_QG + q;
+        const unsigned long long nl = qi < p.nq ? p.n_local[qi] : 0;
+        nl_max = nl > nl_max ? nl : nl_max;
+      }
+      if (e < nl_max) {
+        vmask = ax->vmask[0];
+        eflags = ax->flags;
+      }
+      mbar_wait(acc_full, tile & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)mhalf * TC_ACC_COLS;
+#pragma unroll 1
+      for (int q = 0; q < TC_QG; ++q) {
+        uint32_t v0[32], v1[32];
+        tc_ld32(tbase + q * TC_S, v0);
+        tc_ld32(tbase + q * TC_S + 28, v1);
+        tc_ld_wait();
+        const unsigned qi = g * TC_QG + q;
+        const unsigned long long nl = qi < p.nq ? p.n_local[qi] : 0;
+        // windowed search: the alignment of this (query, entry) pair comes from the alignment pass (k_tc_fullshift, align_out)
+        int a_cur = 0, a_2nd = 0;
+        bool amb2 = false, amb3 = false;
+        if (p.align_in && e < nl) {
+          const unsigned ai = p.align_in[(size_t)qi * p.d32_pitch + e];
+          a_cur = (int)(ai & 0xffu);
+          a_2nd = (int)((ai >> 8) & 0xffu);
+          amb2 = (ai >> 16) & 1u;
+          amb3 = (ai >> 17) & 1u;
+        }
+        float best = __int_as_float(0x7f800000);
+        int best_s = 0;
+        bool bad = false;
+#pragma unroll
+        for (int s = 0; s < TC_S; ++s) {
+          const float sum = __uint_as_float(s < 32 ? v0[s] : v1[s - 28]);
+          const int n = __popcll(s_aux[q].qrot[s] & vmask);
+          float dist = n ? 1.0f - sum * s_rcp[n] : __int_as_float(0x7f800000);
+          if (p.align_in) {
+            int rel = s - a_cur, rel2 = s - a_2nd;
+            rel += rel < 0 ? TC_S : 0;
+            rel2 += rel2 < 0 ? TC_S : 0;
+            const bool in = rel <= p.radius || rel >= TC_S - p.radius || (amb2 && (rel2 <= p.radius || rel2 >= TC_S - p.radius));
+            dist = in ? dist : __int_as_float(0x7f800000);
+          }
+          bad |= !(dist == dist);
+          if (dist < best) {
+            best = dist;
+            best_s = s;
+          }
+        }
+        if (e < nl) {
+          float out = best < 0.f ? 0.f : best;
+          if (bad || amb3 || (eflags & 1u) || (s_aux[q].flags & 1u)) out = -1.0f;
+          p.d32[(size_t)qi * p.d32_pitch + e] = out;
+          if (p.shift_out) p.shift_out[(size_t)qi * p.d32_pitch + e] = (unsigned)best_s;
+          if (out >= 0.f && !amb2) my_min[q] = min(my_min[q], __float_as_uint(out));  // lower bounds do not set the threshold
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty);
     }
     if (cur_g != 0xffffffffu) {
 #pragma unroll
