@@ -317,6 +317,12 @@ int scgpu_get_timing(scgpu_handle* h, double* ms_total, double* ms_build, double
  * $SCGPU_HOST_THREADS) and whether pinned batches are packed to 12 bytes per point before they cross PCIe (a lone process -- LOCAL_WORLD_SIZE 1 -- with a pool of >= 12
  * threads, or $SCGPU_PACK_PINNED).  Pageable sources are always packed (they are staged through pinned memory anyway). */
 int scgpu_host_info(int* pool_threads, int* packs_pinned);
+/* Growth of the (non-peer) shard beyond its capacity: the arrays live behind address ranges reserved once
+ * (cuMemAddressReserve) and grow by mapping more physical memory (cuMemCreate / cuMemMap) -- the pointers never change, so
+ * nothing is synchronised or copied and work already enqueued is unaffected.  Where the driver offers no virtual memory
+ * management (or with SCGPU_NO_VMM=1) the shard is reallocated and copied behind a device synchronisation, as in round 1.
+ * Counts of both kinds of growth so far and the current local capacity (any pointer may be null). */
+int scgpu_growth_stats(scgpu_handle* h, unsigned* in_place, unsigned* by_copy, uint64_t* capacity);
 /* Device-side stopwatch over a sequence of calls (asynchronous ones included): CUDA events on the handle's own streams --
  * start behind everything enqueued so far, stop behind everything enqueued since; a device-list handle reports its slowest
  * shard.  scgpu_timer_stop waits for the work to finish. */

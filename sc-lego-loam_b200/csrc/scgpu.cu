@@ -3,6 +3,7 @@
 // kernels or fails.
 #include "scgpu.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <float.h>
 #include <nvtx3/nvToolsExt.h>
@@ -82,6 +83,121 @@ struct DevBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
+// A device array that GROWS IN PLACE: a virtual address range reserved once (cuMemAddressReserve), physical memory mapped
+// behind it chunk by chunk (cuMemCreate / cuMemMap / cuMemSetAccess).  The base pointer never changes, so growing a shard
+// needs no device synchronisation, no copy and no pointer patching in work that is already enqueued (round 1 grew by
+// cudaDeviceSynchronize + cudaMalloc + copy + cudaFree).  The driver entry points come through cudaGetDriverEntryPoint
+// (no -lcuda); if they are missing, or the device cannot do virtual memory management, ok() is false and the caller
+// keeps the copy path.
+struct VmApi {
+  CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*afree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*gran)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
+  static const VmApi& get() {
+    static VmApi api = [] {
+      VmApi a;
+      if (getenv("SCGPU_NO_VMM") && atoi(getenv("SCGPU_NO_VMM")) != 0) return a;
+      auto sym = [](const char* name) -> void* {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return fn;
+      };
+      a.reserve = reinterpret_cast<decltype(a.reserve)>(sym("cuMemAddressReserve"));
+      a.afree = reinterpret_cast<decltype(a.afree)>(sym("cuMemAddressFree"));
+      a.create = reinterpret_cast<decltype(a.create)>(sym("cuMemCreate"));
+      a.release = reinterpret_cast<decltype(a.release)>(sym("cuMemRelease"));
+      a.map = reinterpret_cast<decltype(a.map)>(sym("cuMemMap"));
+      a.unmap = reinterpret_cast<decltype(a.unmap)>(sym("cuMemUnmap"));
+      a.access = reinterpret_cast<decltype(a.access)>(sym("cuMemSetAccess"));
+      a.gran = reinterpret_cast<decltype(a.gran)>(sym("cuMemGetAllocationGranularity"));
+      a.ok = a.reserve && a.afree && a.create && a.release && a.map && a.unmap && a.access && a.gran;
+      cudaGetLastError();
+      return a;
+    }();
+    return api;
+  }
+};
+
+struct VmBuf {
+  CUdeviceptr va = 0;
+  size_t va_bytes = 0, mapped = 0, gran = 0;
+  int device = 0;
+  std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
+  CUmemAllocationProp prop() const {
+    CUmemAllocationProp pr = {};
+    pr.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    pr.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    pr.location.id = device;
+    return pr;
+  }
+  // reserve the address range (once); false = virtual memory management is not usable here
+  bool init(int dev, size_t max_bytes) {
+    const VmApi& a = VmApi::get();
+    if (!a.ok) return false;
+    device = dev;
+    const CUmemAllocationProp pr = prop();
+    if (a.gran(&gran, &pr, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return false;
+    va_bytes = (max_bytes + gran - 1) / gran * gran;
+    if (a.reserve(&va, va_bytes, 0, 0, 0) != CUDA_SUCCESS) {
+      va = 0;
+      return false;
+    }
+    return true;
+  }
+  // make [0, want) usable; what was there stays where it is.  SCGPU_OK, or E_CUDA (out of memory / range exhausted)
+  int grow(size_t want) {
+    if (want <= mapped) return SCGPU_OK;
+    const VmApi& a = VmApi::get();
+    size_t add = (want - mapped + gran - 1) / gran * gran;
+    if (mapped + add > va_bytes) return fail(SCGPU_E_CUDA, "database larger than the reserved address range (%zu bytes)", va_bytes);
+    const CUmemAllocationProp pr = prop();
+    CUmemGenericAllocationHandle hd;
+    CUresult r = a.create(&hd, add, &pr, 0);
+    if (r != CUDA_SUCCESS) return fail(SCGPU_E_CUDA, "cuMemCreate(%zu bytes) failed (%d)", add, (int)r);
+    r = a.map(va + mapped, add, 0, hd, 0);
+    if (r != CUDA_SUCCESS) {
+      a.release(hd);
+      return fail(SCGPU_E_CUDA, "cuMemMap failed (%d)", (int)r);
+    }
+    CUmemAccessDesc ad = {};
+    ad.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    ad.location.id = device;
+    ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    r = a.access(va + mapped, add, &ad, 1);
+    if (r != CUDA_SUCCESS) {
+      a.unmap(va + mapped, add);
+      a.release(hd);
+      return fail(SCGPU_E_CUDA, "cuMemSetAccess failed (%d)", (int)r);
+    }
+    chunks.emplace_back(hd, add);
+    mapped += add;
+    return SCGPU_OK;
+  }
+  void release() {
+    if (!va) return;
+    const VmApi& a = VmApi::get();
+    size_t off = 0;
+    for (auto& c : chunks) {
+      a.unmap(va + off, c.second);
+      a.release(c.first);
+      off += c.second;
+    }
+    chunks.clear();
+    a.afree(va, va_bytes);
+    va = 0;
+    va_bytes = mapped = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(va); }
+};
+
 struct PinBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -128,6 +244,9 @@ struct scgpu_handle {
   uint64_t tc_upto = 0;    // local entries [0, tc_upto) are split
   CUtensorMap tc_maps[12];  // E_hi, E_lo, Q_hi, Q_lo, EV_hi, EV_lo, QV_hi, QV_lo | the first four again with 64-byte rows (k_tc_fullshift2)
   bool tc_want_shifts = false;
+  VmBuf vm[6];            // sc, ring keys, sector keys, column norms, screening copy, screening sector-key records: grown in place
+  int vm_state = 0;       // 0 = not tried yet, 1 = arrays live in vm[], -1 = virtual memory management unavailable: cudaMalloc + copy
+  unsigned n_grow_inplace = 0, n_grow_copy = 0;
   float* x_sc_hat = nullptr;
   unsigned char* x_vk = nullptr;  // [cap] ExhVkRec: float sector key + aux
   DevBuf x_query, x_d32, x_keys, x_pd, x_ps, x_small, x_best;
@@ -277,10 +396,39 @@ int db_reserve(scgpu_handle* h, uint64_t want_local) {
   if (h->peer)
     return fail(SCGPU_E_INVALID, "a peer-sharded database has a fixed capacity (capacity_hint = %llu entries): %llu local slots wanted, %llu there",
                 (unsigned long long)h->cfg.capacity_hint, (unsigned long long)want_local, (unsigned long long)h->db.cap);
-  CK(cudaDeviceSynchronize());  // rare: the shard moves to a larger allocation; nothing may still be reading the old one
   uint64_t cap = h->db.cap ? h->db.cap * 2 : 1024;
   while (cap < want_local) cap *= 2;
   const Layout& L = h->L;
+  // ---- in place: the arrays live behind reserved address ranges; map more physical memory, nothing moves ---------------
+  if (h->vm_state == 0) {
+    const uint64_t max_cap = (uint64_t)1 << 26;  // address space only: 64 Mi keyframes per shard (20 x 60: 322 GB of descriptors)
+    const size_t per[6] = {L.RS * sizeof(float), L.R * sizeof(float), L.S * sizeof(double), L.S * sizeof(double), L.RS * sizeof(float),
+                           exh_vk_bytes(L.S)};
+    bool ok = h->db.cap == 0;
+    for (int a = 0; a < 6 && ok; ++a) ok = h->vm[a].init(h->cfg.device, (max_cap + 64) * per[a]);
+    if (!ok)
+      for (VmBuf& b : h->vm) b.release();
+    h->vm_state = ok ? 1 : -1;
+  }
+  if (h->vm_state == 1) {
+    const size_t want[6] = {cap * L.RS * sizeof(float), cap * L.R * sizeof(float), cap * L.S * sizeof(double), cap * L.S * sizeof(double),
+                            h->exh ? cap * L.RS * sizeof(float) : 0, h->exh ? (cap + 8) * exh_vk_bytes(L.S) : 0};
+    for (int a = 0; a < 6; ++a) RET(h->vm[a].grow(want[a]));
+    h->db.sc = h->vm[0].as<float>();
+    h->db.ringT = h->vm[1].as<float>();
+    h->db.sector = h->vm[2].as<double>();
+    h->db.colnorm = h->vm[3].as<double>();
+    h->x_sc_hat = h->exh ? h->vm[4].as<float>() : nullptr;
+    h->x_vk = h->exh ? h->vm[5].as<unsigned char>() : nullptr;
+    h->db.cap = cap;
+    h->db.ring_cap = cap;
+    h->db.ring_global = 0;
+    h->n_grow_inplace++;
+    return SCGPU_OK;
+  }
+  // ---- fallback: a larger allocation and a copy
+  CK(cudaDeviceSynchronize());  // rare: the shard moves to a larger allocation; nothing may still be reading the old one
+  h->n_grow_copy++;
   Db nd = h->db;
   nd.cap = cap;
   nd.ring_cap = cap;
@@ -1855,6 +2003,8 @@ int scgpu_destroy(scgpu_handle* h) {
   if (h->qstream) cudaStreamDestroy(h->qstream);
   if (h->peer) {
     if (h->slab) cudaFree(h->slab);
+  } else if (h->vm_state == 1) {
+    for (VmBuf& b : h->vm) b.release();
   } else if (h->db.cap) {
     cudaFree(h->db.sc);
     cudaFree(h->db.ringT);
@@ -1985,6 +2135,17 @@ int scgpu_host_info(int* pool_threads, int* packs_pinned) {
   if (packs_pinned)
     *packs_pinned = getenv("SCGPU_PACK_PINNED") ? atoi(getenv("SCGPU_PACK_PINNED")) != 0
                                                  : (HostPool::get().threads() >= 12 && HostPool::get().local_world() == 1);
+  return SCGPU_OK;
+}
+
+// How the shard's arrays have grown so far: in place (more physical memory mapped behind a reserved address range: no
+// synchronisation, no copy) or by reallocation + copy (virtual memory management unavailable, or SCGPU_NO_VMM=1)
+int scgpu_growth_stats(scgpu_handle* h, unsigned* in_place, unsigned* by_copy, uint64_t* capacity) {
+  if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  h = GROUP_FIRST(h);
+  if (in_place) *in_place = h->n_grow_inplace;
+  if (by_copy) *by_copy = h->n_grow_copy;
+  if (capacity) *capacity = h->db.cap;
   return SCGPU_OK;
 }
 

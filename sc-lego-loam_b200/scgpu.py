@@ -67,6 +67,7 @@ _SIGNATURES = {
     "scgpu_default_icp_params": [C.POINTER(IcpParams)],
     "scgpu_verify_loop": [_vp, _vp, _sz, _vp, _sz, _sz, C.POINTER(IcpParams), _vp, _pd, _pi, _pi, _pi],
     "scgpu_host_info": [_pi, _pi],
+    "scgpu_growth_stats": [_vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(_u64)],
     "scgpu_timer_start": [_vp],
     "scgpu_timer_stop": [_vp, _pd],
     "scgpu_peer_partition": [_u64, _sz, _i, _i, C.POINTER(_sz), C.POINTER(_sz)],
@@ -453,6 +454,12 @@ class SCManager:
         bad = np.zeros(5, np.float32)
         _check(self.lib.scgpu_probe_selfcheck(self.h, n, seed, mode, C.byref(mm), C.byref(fb), bad.ctypes.data))
         return mm.value, fb.value, bad
+
+    def growth_stats(self):
+        """(grown in place, grown by copy, local capacity): include/scgpu.h scgpu_growth_stats."""
+        a, b, c = C.c_uint(), C.c_uint(), _u64()
+        _check(self.lib.scgpu_growth_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
 
     def record_bytes(self):
         n = _sz()

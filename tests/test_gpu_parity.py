@@ -376,6 +376,15 @@ def test_exhaustive_screening_equals_exact_and_port_at_scale():
     for qq in (17, 18, 150, 12345):
         f, e = fast.exhaustive(qq, n - 50), exact.exhaustive(qq, n - 50)
         assert f == e, (qq, f, e)
+    # a batch of 64 queries, each with its own n_search (the tensor-core screening path: batches of >= 8), traps included
+    qs = [q, 17, 18, 150, 12345, 4321, 9000] + [n - 2 - 263 * i for i in range(57)]
+    ns = [n - 50, n - 50, n - 50, n - 50, n - 50, 4321, 9001] + [max(1, qq - 50 - 97 * i) for i, qq in enumerate(qs[7:])]
+    gd, gs, gi = fast.exhaustive_batched(qs, ns)
+    assert len(qs) == 64 and fast.exhaustive_rescored() < 64 * 200 + n    # (the all-zero query 17 is rescored against every entry)
+    for j, (qq, nn) in enumerate(zip(qs, ns)):
+        e = exact.exhaustive(qq, nn)
+        same = (gd[j] == e[0] or (np.isnan(gd[j]) and np.isnan(e[0]))) and gs[j] == e[1] and gi[j] == e[2]
+        assert same, (j, qq, nn, (gd[j], gs[j], gi[j]), e)
 
 
 def test_save_load_roundtrip(tmp_path):
@@ -491,3 +500,38 @@ print("tiled-ok")
     env = dict(os.environ, SCGPU_TOPK_TILE=force)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "tiled-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_database_grows_in_place_under_enqueued_work():
+    """A shard that outgrows its capacity maps more physical memory behind the same addresses (include/scgpu.h
+    scgpu_growth_stats): no copy, and an asynchronous replay that is still running keeps reading valid memory.  The run that
+    grows many times must equal the run on a handle that never grows -- results, stored entries, exhaustive search."""
+    from sc_lego_loam_b200.synth import ScanGen
+    p = orc.Params()
+    gen = ScanGen("hdl64", seed=303, n_places=900)
+    n = 3900
+    scans = ScanGen("hdl64", seed=303, n_places=900, n_azim=64).scans(0, 200, 4)      # 4,096 points each
+    descs = gen.descs(0, n)
+    small, big = mgr(p, capacity_hint=0), mgr(p, capacity_hint=n + 800)
+    outs = {}
+    for name, m in (("small", small), ("big", big)):
+        res = []
+        k = 0
+        for c0 in range(0, n, 650):                       # 1024 -> 2048 -> 4096 entries
+            m.append_descs(descs[c0:c0 + 650])
+        m.replay_async(scans[:150])                       # 3,900 -> 4,050 entries
+        k = m.replay_async(scans[50:200])                 # -> 4,200: grows past 4,096 while the first step may still be running
+        res.append(m.replay_results(k))
+        res.append(m.replay(scans[100:160]))
+        res.append({"exh": np.asarray(m.exhaustive(m.size() - 1, m.size() - 60), np.float64)})
+        res.append({"entry": np.asarray(m.get_entry(n // 2)[0])})
+        outs[name] = res
+    for a, b in zip(outs["small"], outs["big"]):
+        assert a.keys() == b.keys()
+        for key in a:
+            assert np.array_equal(np.asarray(a[key]), np.asarray(b[key]), equal_nan=True), key
+    in_place, by_copy, cap = small.growth_stats()
+    assert cap >= small.size() and in_place + by_copy >= 3
+    if os.environ.get("SCGPU_NO_VMM", "0") == "0":
+        assert by_copy == 0 and in_place >= 3, (in_place, by_copy)
+    assert sum(big.growth_stats()[:2]) == 1
