@@ -216,6 +216,35 @@ int scgpu_default_icp_params(scgpu_icp_params* p);
 int scgpu_verify_loop(scgpu_handle* h, const void* src, size_t n_src, const void* tgt, size_t n_tgt, size_t stride_bytes,
                       const scgpu_icp_params* prm, double* T_row_major_16, double* fitness, int* converged, int* iterations,
                       int* accepted);
+/* ---- submap assembly in front of the ICP (mapOptmization.cpp:928-949) ---------------------------------------------------------
+ * The reference builds both ICP inputs from STORED keyframe clouds: each cloud is moved by a 6-DoF key pose with LeGO-LOAM's
+ * transformPointCloud (mapOptmization.cpp:598-627: yaw about z, roll about x, pitch about y, translation; FP32), the clouds are
+ * concatenated, the query side drops points with (int)intensity < 0 (932-939) and the history side goes through a voxel grid
+ * (downSizeFilterHistoryKeyFrames, leaf 0.3 m, 264-268 / 948-949).  scgpu_pose6 = the fields of PointTypePose that function reads.
+ * The transformed coordinates are bit-identical to the reference's (same FP32 operations; cosf / sinf taken on the host);
+ * the voxel grid is k_build_voxel (PARITY UNPINNED, as above).
+ *
+ * scgpu_assemble_submap: clouds[i] (n_points[i] points, `stride` bytes apart, x y z first, intensity at byte `intensity_off`, 0 =
+ * none) moved by poses[i], cloud after cloud (the reference's operator+=); drop_negative_intensity applies 932-939; leaf > 0 applies
+ * the voxel grid to the union.  out_xyzw[i] = {x, y, z, intensity} (leaf = 0) or {centroid x, y, z, number of points} in unspecified
+ * order (leaf > 0); *n_out = points (an error if > cap).
+ *
+ * scgpu_verify_loop_keyframes = mapOptmization.cpp:924-949 + 1053-1078 in one call, nothing returns to the host in between: the
+ * query clouds (corner + surface cloud of the latest keyframe) moved by ONE pose -- that of the matched keyframe -- with negative
+ * intensities dropped when intensity_off != 0; the history clouds (corner + surface clouds of the keyframes around the match) each by
+ * its own pose, then the voxel grid (leaf; 0 = none); then the ICP of scgpu_verify_loop.  n_src_used / n_tgt_used (optional): points
+ * that entered the ICP. */
+typedef struct scgpu_pose6 {
+  float x, y, z, roll, pitch, yaw;
+} scgpu_pose6;
+int scgpu_assemble_submap(scgpu_handle* h, const void* const* clouds, const size_t* n_points, const scgpu_pose6* poses, size_t n_clouds,
+                          size_t stride_bytes, size_t intensity_off, int drop_negative_intensity, float leaf, float* out_xyzw, size_t cap,
+                          size_t* n_out);
+int scgpu_verify_loop_keyframes(scgpu_handle* h, const void* const* src_clouds, const size_t* src_points, size_t n_src_clouds,
+                                const scgpu_pose6* src_pose, const void* const* tgt_clouds, const size_t* tgt_points,
+                                const scgpu_pose6* tgt_poses, size_t n_tgt_clouds, size_t stride_bytes, size_t intensity_off, float leaf,
+                                const scgpu_icp_params* prm, double* T_row_major_16, double* fitness, int* converged, int* iterations,
+                                int* accepted, size_t* n_src_used, size_t* n_tgt_used);
 /* Flat binary save / load of the descriptor database. */
 int scgpu_save(scgpu_handle* h, const char* path);
 int scgpu_load(scgpu_handle* h, const char* path);

@@ -249,6 +249,44 @@ class Icp:
         return dict(T=T.reshape(4, 4), fitness=fit.value, converged=bool(conv.value), iterations=its.value)
 
 
+class Submap:
+    """transformPointCloud(cloud, pose) of the submap assembly (mapOptmization.cpp:598-627).  kind="reference": the reference's
+    own function text compiled from where it lies (oracle/_ref/libsubmapref.so; oracle/Makefile); kind="port": the restatement
+    in oracle/submap_shim.cpp."""
+
+    def __init__(self, kind="port"):
+        path = os.path.join(HERE, "_ref", "libsubmapref.so") if kind == "reference" else os.path.join(HERE, "_build", "libsubmaporacle.so")
+        if not os.path.exists(path):
+            build(ref=kind == "reference")
+        self.L = C.CDLL(path)
+        self.L.submap_transform.argtypes = [_vp, _sz, _sz, _i, _vp, _vp]
+        self.L.submap_keeps.argtypes = [_f]
+        self.L.submap_keeps.restype = _i
+
+    @staticmethod
+    def available(kind):
+        return os.path.exists(os.path.join(HERE, "_ref", "libsubmapref.so")) if kind == "reference" else True
+
+    def transform(self, cloud, pose6, intensity_column=3):
+        cloud = np.ascontiguousarray(cloud, np.float32)
+        pose = np.ascontiguousarray(pose6, np.float32).reshape(6)
+        out = np.empty((cloud.shape[0], 4), np.float32)
+        self.L.submap_transform(cloud.ctypes.data, cloud.shape[0], cloud.shape[1], intensity_column if cloud.shape[1] > intensity_column else -1,
+                                pose.ctypes.data, out.ctypes.data)
+        return out
+
+    def keeps(self, intensity):
+        return np.array([bool(self.L.submap_keeps(float(v))) for v in np.asarray(intensity, np.float32)])
+
+    def assemble(self, clouds, poses, drop_negative_intensity=False, intensity_column=3):
+        """clouds moved by their poses, concatenated (operator+=), optionally filtered as mapOptmization.cpp:932-939."""
+        parts = [self.transform(c, p, intensity_column) for c, p in zip(clouds, poses)]
+        out = np.concatenate(parts) if parts else np.zeros((0, 4), np.float32)
+        if drop_negative_intensity:
+            out = out[self.keeps(out[:, 3])]
+        return out
+
+
 def ref_available(variant="default"):
     return os.path.exists(os.path.join(HERE, "_ref", REF_VARIANTS[variant]))
 

@@ -3151,13 +3151,9 @@ int scgpu_default_icp_params(scgpu_icp_params* p) {
   return SCGPU_OK;
 }
 
-int scgpu_verify_loop(scgpu_handle* h, const void* src, size_t n_src, const void* tgt, size_t n_tgt, size_t stride, const scgpu_icp_params* prm,
-                      double* T16, double* fitness, int* converged, int* iterations, int* accepted) {
-  if (!h || !prm || (!src && n_src) || (!tgt && n_tgt)) return fail(SCGPU_E_INVALID, "null argument");
-  if (stride < 12 || (stride & 3)) return fail(SCGPU_E_INVALID, "stride must be >= 12 and a multiple of 4");
-  if (n_src > 0x7fffffffull || n_tgt > 0x7fffffffull || prm->max_iterations < 1) return fail(SCGPU_E_INVALID, "bad cloud size / iteration cap");
-  h = GROUP_FIRST(h);
-  CK(cudaSetDevice(h->cfg.device));
+// The ICP loop on device-resident clouds (mapOptmization.cpp:1053-1078); everything on the handle's stream.
+static int icp_run_device(scgpu_handle* h, const unsigned char* d_src, size_t n_src, size_t stride_s, const unsigned char* d_tgt, size_t n_tgt,
+                          size_t stride_t, const scgpu_icp_params* prm, double* T16, double* fitness, int* converged, int* iterations, int* accepted) {
   cudaStream_t st = h->stream;
   IcpState s0;
   memset(&s0, 0, sizeof s0);
@@ -3175,12 +3171,8 @@ int scgpu_verify_loop(scgpu_handle* h, const void* src, size_t n_src, const void
   IcpState out = s0;
   if (n_src && n_tgt) {
     const unsigned blocks = (unsigned)((n_src + ICP_BLOCK - 1) / ICP_BLOCK);
-    RET(h->icp_src.reserve(n_src * stride));
-    RET(h->icp_tgt.reserve(n_tgt * stride));
     RET(h->icp_state.reserve(sizeof(IcpState)));
     RET(h->icp_part.reserve((size_t)blocks * sizeof(IcpPartial)));
-    CK(cudaMemcpyAsync(h->icp_src.p, src, n_src * stride, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->icp_tgt.p, tgt, n_tgt * stride, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(h->icp_state.p, &s0, sizeof s0, cudaMemcpyHostToDevice, st));
     IcpCriteria crit;
     crit.max_iterations = prm->max_iterations;
@@ -3192,8 +3184,8 @@ int scgpu_verify_loop(scgpu_handle* h, const void* src, size_t n_src, const void
     const float max_d2 = (float)(md * md);
     IcpState* d_st = h->icp_state.as<IcpState>();
     for (int it = 0; it < prm->max_iterations; ++it) {
-      k_icp_nn<<<blocks, ICP_BLOCK, 0, st>>>(h->icp_src.as<unsigned char>(), (unsigned)n_src, (unsigned)stride, h->icp_tgt.as<unsigned char>(),
-                                             (unsigned)n_tgt, (unsigned)stride, d_st, max_d2, 0, h->icp_part.as<IcpPartial>());
+      k_icp_nn<<<blocks, ICP_BLOCK, 0, st>>>(d_src, (unsigned)n_src, (unsigned)stride_s, d_tgt, (unsigned)n_tgt, (unsigned)stride_t, d_st, max_d2, 0,
+                                             h->icp_part.as<IcpPartial>());
       k_icp_solve<<<1, 32, 0, st>>>(h->icp_part.as<IcpPartial>(), blocks, d_st, crit, 0);
       h->launches += 2;
       if ((it & 7) == 7) {  // peek at the flag now and then so that an early convergence does not cost the full launch list
@@ -3203,8 +3195,8 @@ int scgpu_verify_loop(scgpu_handle* h, const void* src, size_t n_src, const void
         if (done) break;
       }
     }
-    k_icp_nn<<<blocks, ICP_BLOCK, 0, st>>>(h->icp_src.as<unsigned char>(), (unsigned)n_src, (unsigned)stride, h->icp_tgt.as<unsigned char>(),
-                                           (unsigned)n_tgt, (unsigned)stride, d_st, max_d2, 1, h->icp_part.as<IcpPartial>());
+    k_icp_nn<<<blocks, ICP_BLOCK, 0, st>>>(d_src, (unsigned)n_src, (unsigned)stride_s, d_tgt, (unsigned)n_tgt, (unsigned)stride_t, d_st, max_d2, 1,
+                                           h->icp_part.as<IcpPartial>());
     k_icp_solve<<<1, 32, 0, st>>>(h->icp_part.as<IcpPartial>(), blocks, d_st, crit, 1);
     h->launches += 2;
     CK(cudaGetLastError());
@@ -3217,6 +3209,159 @@ int scgpu_verify_loop(scgpu_handle* h, const void* src, size_t n_src, const void
   if (iterations) *iterations = out.iterations;
   if (accepted) *accepted = out.converged && out.fitness <= prm->fitness_threshold;  // mapOpt.cpp:1068
   return SCGPU_OK;
+}
+
+int scgpu_verify_loop(scgpu_handle* h, const void* src, size_t n_src, const void* tgt, size_t n_tgt, size_t stride, const scgpu_icp_params* prm,
+                      double* T16, double* fitness, int* converged, int* iterations, int* accepted) {
+  if (!h || !prm || (!src && n_src) || (!tgt && n_tgt)) return fail(SCGPU_E_INVALID, "null argument");
+  if (stride < 12 || (stride & 3)) return fail(SCGPU_E_INVALID, "stride must be >= 12 and a multiple of 4");
+  if (n_src > 0x7fffffffull || n_tgt > 0x7fffffffull || prm->max_iterations < 1) return fail(SCGPU_E_INVALID, "bad cloud size / iteration cap");
+  h = GROUP_FIRST(h);
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t st = h->stream;
+  if (n_src && n_tgt) {
+    RET(h->icp_src.reserve(n_src * stride));
+    RET(h->icp_tgt.reserve(n_tgt * stride));
+    CK(cudaMemcpyAsync(h->icp_src.p, src, n_src * stride, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->icp_tgt.p, tgt, n_tgt * stride, cudaMemcpyHostToDevice, st));
+  }
+  return icp_run_device(h, h->icp_src.as<unsigned char>(), n_src, stride, h->icp_tgt.as<unsigned char>(), n_tgt, stride, prm, T16, fitness, converged,
+                        iterations, accepted);
+}
+
+// Submap assembly (mapOptmization.cpp:928-949) on the device: the clouds -> staged input -> k_submap_transform[_filtered] -> `out`
+// (float4 x, y, z, intensity; cloud after cloud).  *n_out = points written (known on the host unless `filter`).
+static int submap_to_device(scgpu_handle* h, const void* const* clouds, const size_t* n_points, const scgpu_pose6* poses, size_t n_clouds,
+                            bool one_pose, size_t stride, size_t intensity_off, bool filter, DevBuf& stage, DevBuf& out, size_t* n_out) {
+  cudaStream_t st = h->stream;
+  size_t total = 0;
+  for (size_t i = 0; i < n_clouds; ++i) {
+    if (n_points[i] && !clouds[i]) return fail(SCGPU_E_INVALID, "null cloud");
+    total += n_points[i];
+  }
+  *n_out = 0;
+  if (total == 0) return SCGPU_OK;
+  if (total > 0x7fffffffull) return fail(SCGPU_E_INVALID, "submap too large");
+  std::vector<SubmapCloud> desc(n_clouds);
+  size_t off = 0, pts = 0;
+  for (size_t i = 0; i < n_clouds; ++i) {
+    const scgpu_pose6& ps = poses[one_pose ? 0 : i];
+    SubmapCloud& c = desc[i];
+    c.in_off = off;
+    c.n = (unsigned)n_points[i];
+    c.out_off = (unsigned)pts;
+    c.cy = cosf(ps.yaw), c.sy = sinf(ps.yaw);      // cos(float) / sin(float) of mapOptmization.cpp:611-621 are the float overloads
+    c.cr = cosf(ps.roll), c.sr = sinf(ps.roll);
+    c.cp = cosf(ps.pitch), c.sp = sinf(ps.pitch);
+    c.tx = ps.x, c.ty = ps.y, c.tz = ps.z;
+    off += (n_points[i] * stride + 15) & ~(size_t)15;
+    pts += n_points[i];
+  }
+  RET(stage.reserve(off + n_clouds * sizeof(SubmapCloud) + 64));
+  RET(out.reserve(total * sizeof(float4) + 16));
+  RET(h->x_small.reserve(256));
+  unsigned char* d_in = stage.as<unsigned char>();
+  for (size_t i = 0; i < n_clouds; ++i)
+    if (n_points[i]) CK(cudaMemcpyAsync(d_in + desc[i].in_off, clouds[i], n_points[i] * stride, cudaMemcpyHostToDevice, st));
+  SubmapCloud* d_desc = reinterpret_cast<SubmapCloud*>(d_in + ((off + 15) & ~(size_t)15));
+  CK(cudaMemcpyAsync(d_desc, desc.data(), n_clouds * sizeof(SubmapCloud), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // `desc` (pageable) has been consumed
+  if (!filter) {
+    size_t big = 0;
+    for (size_t i = 0; i < n_clouds; ++i) big = std::max(big, n_points[i]);
+    const unsigned gx = (unsigned)std::min<size_t>((big + 255) / 256, 1024);
+    k_submap_transform<<<dim3(gx ? gx : 1, (unsigned)n_clouds), 256, 0, st>>>(d_in, (unsigned)stride, (unsigned)intensity_off, d_desc, out.as<float4>());
+    *n_out = total;
+  } else {
+    unsigned* d_n = reinterpret_cast<unsigned*>(h->x_small.as<unsigned char>() + 128);
+    k_submap_transform_filtered<<<1, 1024, 0, st>>>(d_in, (unsigned)stride, (unsigned)intensity_off, d_desc, (unsigned)n_clouds, out.as<float4>(), d_n);
+    unsigned n = 0;
+    CK(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_out = n;
+  }
+  h->launches++;
+  CK(cudaGetLastError());
+  return SCGPU_OK;
+}
+
+// voxel grid over device-resident float4 points (the history side, mapOptmization.cpp:948-949); result in h->vox_pts, *n_out voxels
+static int submap_voxel(scgpu_handle* h, const void* d_pts, size_t n, float leaf, size_t* n_out) {
+  cudaStream_t st = h->stream;
+  const unsigned ocap = (unsigned)(n ? n : 1);
+  RET(h->vox_info.reserve(sizeof(VoxInfo)));
+  RET(h->vox_pts.reserve((size_t)ocap * sizeof(float4)));
+  RET(h->vox_idx.reserve((size_t)ocap * sizeof(unsigned)));
+  CK(cudaMemsetAsync(h->vox_info.p, 0, sizeof(VoxInfo), st));
+  VoxInfo vi;
+  memset(&vi, 0, sizeof vi);
+  if (n) {
+    RET(launch_build_voxel(h, d_pts, 1, n, sizeof(float4), leaf, nullptr, h->vox_info.as<VoxInfo>(), h->vox_pts.as<float4>(), h->vox_idx.as<unsigned>(),
+                           ocap, st));
+    CK(cudaMemcpyAsync(&vi, h->vox_info.p, sizeof vi, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  *n_out = vi.n_out;
+  return SCGPU_OK;
+}
+
+static int submap_check(scgpu_handle* h, size_t stride, size_t intensity_off) {
+  if (!h) return fail(SCGPU_E_INVALID, "null argument");
+  if (stride < 12 || (stride & 3)) return fail(SCGPU_E_INVALID, "stride must be >= 12 and a multiple of 4");
+  if (intensity_off && (intensity_off < 12 || intensity_off + 4 > stride || (intensity_off & 3))) return fail(SCGPU_E_INVALID, "intensity offset outside the point record");
+  return SCGPU_OK;
+}
+
+int scgpu_assemble_submap(scgpu_handle* h, const void* const* clouds, const size_t* n_points, const scgpu_pose6* poses, size_t n_clouds,
+                          size_t stride, size_t intensity_off, int drop_negative_intensity, float leaf, float* out_xyzw, size_t cap, size_t* n_out) {
+  RET(submap_check(h, stride, intensity_off));
+  if (!n_out || (n_clouds && (!clouds || !n_points || !poses))) return fail(SCGPU_E_INVALID, "null argument");
+  if (leaf < 0.f || !(leaf < 1e30f)) return fail(SCGPU_E_INVALID, "bad leaf size");
+  h = GROUP_FIRST(h);
+  CK(cudaSetDevice(h->cfg.device));
+  RET(join_replay(h));
+  size_t n = 0;
+  RET(submap_to_device(h, clouds, n_points, poses, n_clouds, false, stride, intensity_off, drop_negative_intensity != 0, h->vox_in, h->icp_tgt, &n));
+  const void* d_res = h->icp_tgt.p;
+  if (leaf > 0.f && n) {
+    RET(submap_voxel(h, h->icp_tgt.p, n, leaf, &n));
+    d_res = h->vox_pts.p;
+  }
+  *n_out = n;
+  if (n > cap) return fail(SCGPU_E_INVALID, "output capacity %zu < %zu points", cap, n);
+  if (n && out_xyzw) {
+    CK(cudaMemcpyAsync(out_xyzw, d_res, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return SCGPU_OK;
+}
+
+int scgpu_verify_loop_keyframes(scgpu_handle* h, const void* const* src_clouds, const size_t* src_points, size_t n_src_clouds, const scgpu_pose6* src_pose,
+                                const void* const* tgt_clouds, const size_t* tgt_points, const scgpu_pose6* tgt_poses, size_t n_tgt_clouds, size_t stride,
+                                size_t intensity_off, float leaf, const scgpu_icp_params* prm, double* T16, double* fitness, int* converged,
+                                int* iterations, int* accepted, size_t* n_src_used, size_t* n_tgt_used) {
+  RET(submap_check(h, stride, intensity_off));
+  if (!prm || prm->max_iterations < 1 || (n_src_clouds && (!src_clouds || !src_points || !src_pose)) ||
+      (n_tgt_clouds && (!tgt_clouds || !tgt_points || !tgt_poses)))
+    return fail(SCGPU_E_INVALID, "null argument");
+  if (leaf < 0.f || !(leaf < 1e30f)) return fail(SCGPU_E_INVALID, "bad leaf size");
+  h = GROUP_FIRST(h);
+  CK(cudaSetDevice(h->cfg.device));
+  RET(join_replay(h));
+  size_t ns = 0, nt = 0;
+  // query side: the latest keyframe's clouds in the frame of the matched keyframe, negative intensities dropped (924-939)
+  RET(submap_to_device(h, src_clouds, src_points, src_pose, n_src_clouds, true, stride, intensity_off, intensity_off != 0, h->vox_in, h->icp_src, &ns));
+  // history side: the keyframes around the match, each by its own pose, then the voxel grid (942-949)
+  RET(submap_to_device(h, tgt_clouds, tgt_points, tgt_poses, n_tgt_clouds, false, stride, intensity_off, false, h->vox_in, h->icp_tgt, &nt));
+  const unsigned char* d_tgt = h->icp_tgt.as<unsigned char>();
+  if (leaf > 0.f && nt) {
+    RET(submap_voxel(h, h->icp_tgt.p, nt, leaf, &nt));
+    d_tgt = h->vox_pts.as<unsigned char>();
+  }
+  if (n_src_used) *n_src_used = ns;
+  if (n_tgt_used) *n_tgt_used = nt;
+  return icp_run_device(h, h->icp_src.as<unsigned char>(), ns, sizeof(float4), d_tgt, nt, sizeof(float4), prm, T16, fitness, converged, iterations,
+                        accepted);
 }
 
 // ---- peer-sharded database, one process per GPU -------------------------------------------------------------------------

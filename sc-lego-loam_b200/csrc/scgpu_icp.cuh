@@ -257,4 +257,85 @@ __global__ void k_icp_solve(const IcpPartial* partials, unsigned n_blocks, IcpSt
   }
 }
 
+
+// ---- submap assembly in front of the ICP (mapOptmization.cpp:928-949) ------------------------------------------------------
+// The reference builds the ICP's two inputs from stored keyframe clouds: every cloud is moved by a 6-DoF key pose with
+// LeGO-LOAM's own transformPointCloud (mapOptmization.cpp:598-627: yaw about z, then roll about x, then pitch about y, then the
+// translation -- all in float), the clouds are concatenated, the query side drops points with (int)intensity < 0 (932-939) and
+// the history side goes through a voxel grid (leaf 0.3 m, 264-268 / 948-949).  k_submap_transform restates the point arithmetic
+// operation by operation in FP32 (the library is built with --fmad=false); the six sines and cosines of a pose are taken on the
+// HOST with the C library's cosf / sinf -- the functions the reference's cos(float) / sin(float) resolve to -- so the
+// transformed coordinates are bit-identical to the reference's.
+struct SubmapCloud {
+  unsigned long long in_off;  // byte offset of the cloud in the staged input
+  unsigned n;                 // points
+  unsigned out_off;           // first output point (unfiltered launches)
+  float cy, sy, cr, sr, cp, sp, tx, ty, tz;
+};
+
+__device__ __forceinline__ float4 submap_point(const SubmapCloud& c, float x, float y, float z, float intensity) {
+  const float x1 = __fsub_rn(__fmul_rn(c.cy, x), __fmul_rn(c.sy, y));  // 611-613
+  const float y1 = __fadd_rn(__fmul_rn(c.sy, x), __fmul_rn(c.cy, y));
+  const float z1 = z;
+  const float x2 = x1;                                                   // 615-617
+  const float y2 = __fsub_rn(__fmul_rn(c.cr, y1), __fmul_rn(c.sr, z1));
+  const float z2 = __fadd_rn(__fmul_rn(c.sr, y1), __fmul_rn(c.cr, z1));
+  float4 o;                                                              // 619-622
+  o.x = __fadd_rn(__fadd_rn(__fmul_rn(c.cp, x2), __fmul_rn(c.sp, z2)), c.tx);
+  o.y = __fadd_rn(y2, c.ty);
+  o.z = __fadd_rn(__fadd_rn(__fmul_rn(-c.sp, x2), __fmul_rn(c.cp, z2)), c.tz);
+  o.w = intensity;
+  return o;
+}
+
+// grid (chunks, clouds): every point of every cloud, order kept (cloud after cloud: the reference's operator+=)
+__global__ void __launch_bounds__(256) k_submap_transform(const unsigned char* in, unsigned stride, unsigned intensity_off, const SubmapCloud* clouds,
+                                                          float4* out) {
+  const SubmapCloud c = clouds[blockIdx.y];
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+    const float* f = reinterpret_cast<const float*>(in + c.in_off + (unsigned long long)i * stride);
+    const float w = intensity_off ? *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(f) + intensity_off) : 0.f;
+    out[c.out_off + i] = submap_point(c, f[0], f[1], f[2], w);
+  }
+}
+
+// one block: the clouds one after the other, points with (int)intensity < 0 dropped, order kept (mapOptmization.cpp:932-939)
+__global__ void __launch_bounds__(1024) k_submap_transform_filtered(const unsigned char* in, unsigned stride, unsigned intensity_off,
+                                                                    const SubmapCloud* clouds, unsigned n_clouds, float4* out, unsigned* n_out) {
+  __shared__ unsigned s_warp[32];
+  __shared__ unsigned s_base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (unsigned ci = 0; ci < n_clouds; ++ci) {
+    const SubmapCloud c = clouds[ci];
+    for (unsigned i0 = 0; i0 < c.n; i0 += blockDim.x) {
+      const unsigned i = i0 + threadIdx.x;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool keep = false;
+      if (i < c.n) {
+        const float* f = reinterpret_cast<const float*>(in + c.in_off + (unsigned long long)i * stride);
+        const float w = intensity_off ? *reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(f) + intensity_off) : 0.f;
+        o = submap_point(c, f[0], f[1], f[2], w);
+        // (int)w >= 0  <=>  -1 < w < 2^31: the cast truncates toward zero; out of range (and NaN) it yields INT_MIN on x86-64
+        keep = !intensity_off || (w > -1.f && w < 2147483648.f);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) s_warp[warp] = __popc(m);
+      __syncthreads();
+      unsigned before = s_base;
+      for (int w2 = 0; w2 < warp; ++w2) before += s_warp[w2];
+      if (keep) out[before + __popc(m & ((1u << lane) - 1u))] = o;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned t = s_base;
+        for (unsigned w2 = 0; w2 < (blockDim.x >> 5); ++w2) t += s_warp[w2];
+        s_base = t;
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) *n_out = s_base;
+}
+
 }  // namespace scgpu

@@ -67,6 +67,9 @@ _SIGNATURES = {
     "scgpu_default_icp_params": [C.POINTER(IcpParams)],
     "scgpu_verify_loop": [_vp, _vp, _sz, _vp, _sz, _sz, C.POINTER(IcpParams), _vp, _pd, _pi, _pi, _pi],
     "scgpu_host_info": [_pi, _pi],
+    "scgpu_assemble_submap": [_vp, _vp, _vp, _vp, _sz, _sz, _sz, _i, C.c_float, _vp, _sz, C.POINTER(_sz)],
+    "scgpu_verify_loop_keyframes": [_vp, _vp, _vp, _sz, _vp, _vp, _vp, _vp, _sz, _sz, _sz, C.c_float, C.POINTER(IcpParams), _vp, _pd, _pi, _pi, _pi,
+                                    C.POINTER(_sz), C.POINTER(_sz)],
     "scgpu_growth_stats": [_vp, C.POINTER(C.c_uint), C.POINTER(C.c_uint), C.POINTER(_u64)],
     "scgpu_timer_start": [_vp],
     "scgpu_timer_stop": [_vp, _pd],
@@ -438,6 +441,58 @@ class SCManager:
         _check(self.lib.scgpu_verify_loop(self.h, sp, sn, tp, tn, ss, C.byref(prm), T.ctypes.data, C.byref(fit), C.byref(conv),
                                           C.byref(its), C.byref(acc)))
         return dict(T=T.reshape(4, 4), fitness=fit.value, converged=bool(conv.value), iterations=its.value, accepted=bool(acc.value))
+
+    @staticmethod
+    def _cloud_list(clouds):
+        """list of (n, k) float32 arrays with one k -> (kept arrays, pointer array, size array, stride bytes)."""
+        arrs = [np.ascontiguousarray(c, np.float32) for c in clouds]
+        k = arrs[0].shape[1] if arrs else 4
+        if any(a.ndim != 2 or a.shape[1] != k for a in arrs):
+            raise ValueError("clouds must be (n, k) arrays with the same k")
+        ptrs = (C.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+        sizes = (_sz * max(1, len(arrs)))(*[a.shape[0] for a in arrs])
+        return arrs, ptrs, sizes, 4 * k
+
+    def assemble_submap(self, clouds, poses, leaf=0.0, drop_negative_intensity=False, intensity_column=3):
+        """mapOptmization.cpp:928-949: clouds[i] moved by poses[i] = (x, y, z, roll, pitch, yaw), concatenated; optional
+        intensity filter (932-939) and voxel grid (948-949).  Returns (n, 4) float32: x, y, z, intensity (or, with leaf > 0,
+        centroid x, y, z and the number of points, in unspecified order)."""
+        arrs, ptrs, sizes, stride = self._cloud_list(clouds)
+        ps = np.ascontiguousarray(np.asarray(poses, np.float32).reshape(-1, 6))
+        if len(ps) != len(arrs):
+            raise ValueError("one pose per cloud")
+        ioff = 4 * intensity_column if arrs and arrs[0].shape[1] > intensity_column else 0
+        cap = max(1, sum(a.shape[0] for a in arrs))
+        out = np.empty((cap, 4), np.float32)
+        n = _sz()
+        _check(self.lib.scgpu_assemble_submap(self.h, ptrs, sizes, ps.ctypes.data, len(arrs), stride, ioff, int(drop_negative_intensity),
+                                              float(leaf), out.ctypes.data, cap, C.byref(n)))
+        return out[:n.value]
+
+    def verify_loop_keyframes(self, src_clouds, src_pose, tgt_clouds, tgt_poses, leaf=0.3, intensity_column=3, seed_axis=-1,
+                              seed_angle=0.0, **overrides):
+        """mapOptmization.cpp:924-949 + 1053-1078 in one call: submap assembly on the device, then the ICP (see verify_loop)."""
+        prm = IcpParams()
+        _check(self.lib.scgpu_default_icp_params(C.byref(prm)))
+        prm.seed_axis, prm.seed_angle = int(seed_axis), float(seed_angle)
+        for k, v in overrides.items():
+            setattr(prm, k, v)
+        sa, sp, ss, stride = self._cloud_list(src_clouds)
+        ta, tp, ts, stride_t = self._cloud_list(tgt_clouds)
+        if stride != stride_t:
+            raise ValueError("query and history clouds must have the same point stride")
+        spose = np.ascontiguousarray(np.asarray(src_pose, np.float32).reshape(6))
+        tposes = np.ascontiguousarray(np.asarray(tgt_poses, np.float32).reshape(-1, 6))
+        if len(tposes) != len(ta):
+            raise ValueError("one pose per history cloud")
+        ioff = 4 * intensity_column if stride > 4 * intensity_column else 0
+        T = np.empty(16, np.float64)
+        fit, conv, its, acc, ns, nt = C.c_double(), C.c_int(), C.c_int(), C.c_int(), _sz(), _sz()
+        _check(self.lib.scgpu_verify_loop_keyframes(self.h, sp, ss, len(sa), spose.ctypes.data, tp, ts, tposes.ctypes.data, len(ta), stride, ioff,
+                                                    float(leaf), C.byref(prm), T.ctypes.data, C.byref(fit), C.byref(conv), C.byref(its),
+                                                    C.byref(acc), C.byref(ns), C.byref(nt)))
+        return dict(T=T.reshape(4, 4), fitness=fit.value, converged=bool(conv.value), iterations=its.value, accepted=bool(acc.value),
+                    n_source=ns.value, n_target=nt.value)
 
     def timer_start(self):
         _check(self.lib.scgpu_timer_start(self.h))
