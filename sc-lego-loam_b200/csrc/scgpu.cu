@@ -791,7 +791,9 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
   dim3 grid(chunks, (unsigned)nq);
   // software-pipelined key loads for small grids (few resident warps per SM: the L2 latency of the loads is exposed)
   static const int pipe_env = getenv("SCGPU_TOPK_PIPE") ? atoi(getenv("SCGPU_TOPK_PIPE")) : -1;
-  const bool pipe = pipe_env >= 0 ? pipe_env != 0 : (uint64_t)chunks * nq * warps < (uint64_t)h->sm_count * 32;
+  // (K <= 32 only: with two or four list slots per lane the pipelined form needs 117-240 registers and loses -- BASELINE config 3,
+  // K = 50 over 40k keys, 64 queries per rank: 545k queries/s without, 439k with, on 2 GPUs)
+  const bool pipe = pipe_env >= 0 ? pipe_env != 0 : (h->slots == 1 && (uint64_t)chunks * nq * warps < (uint64_t)h->sm_count * 32);
   const int rc = h->L.R == 20 ? 20 : (h->L.R == 40 ? 40 : 0);
 #define SCGPU_TOPK_LAUNCH(SL, W, RC_, PIPE_) k_topk<SL, W, RC_, PIPE_><<<grid, (W) * 32, 0, st>>>(p)
 #define SCGPU_TOPK_RC(SL, W)                                              \
