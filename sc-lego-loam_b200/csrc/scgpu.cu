@@ -788,6 +788,26 @@ int launch_topk(scgpu_handle* h, const void* d_qrec, size_t nq, const uint64_t* 
     CK(cudaGetLastError());
     return SCGPU_OK;
   }
+  // batches of hundreds of queries over a few thousand keys with K <= 32: one warp per query, keys staged once per block in
+  // shared memory (k_topk_qs).  SCGPU_TOPK_QS=1/0 forces / forbids it (tests, A/B).
+  {
+    static const int qs_env = getenv("SCGPU_TOPK_QS") ? atoi(getenv("SCGPU_TOPK_QS")) : -1;
+    const bool can = h->slots == 1 && (h->L.R == 20 || h->L.R == 40);
+    const int qpb = nq >= (size_t)h->sm_count * 4 ? 8 : 4;
+    // measured (async replay steps of 568 / 1,135 / 2,270 / 4,541 queries over 4,541 keys): -12 % / -2 % / +3 % / +2 % on the step --
+    // its 42 KB of shared memory keep it from running under the next step's binning, which k_topk does
+    const bool want = qs_env >= 0 ? qs_env != 0 : (nq >= 2048 && n_local <= 65536);
+    if (can && want) {
+      const unsigned blocks = (unsigned)((nq + qpb - 1) / qpb);
+      if (h->L.R == 20 && qpb == 8) k_topk_qs<20, 8><<<blocks, 8 * 32, 0, st>>>(p, (unsigned)nq);
+      else if (h->L.R == 20) k_topk_qs<20, 4><<<blocks, 4 * 32, 0, st>>>(p, (unsigned)nq);
+      else if (qpb == 8) k_topk_qs<40, 8><<<blocks, 8 * 32, 0, st>>>(p, (unsigned)nq);
+      else k_topk_qs<40, 4><<<blocks, 4 * 32, 0, st>>>(p, (unsigned)nq);
+      h->launches++;
+      CK(cudaGetLastError());
+      return SCGPU_OK;
+    }
+  }
   dim3 grid(chunks, (unsigned)nq);
   // software-pipelined key loads for small grids (few resident warps per SM: the L2 latency of the loads is exposed)
   static const int pipe_env = getenv("SCGPU_TOPK_PIPE") ? atoi(getenv("SCGPU_TOPK_PIPE")) : -1;

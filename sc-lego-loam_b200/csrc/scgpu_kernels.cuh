@@ -781,6 +781,84 @@ __device__ __forceinline__ void topk_stream(WarpList<SLOTS>& list, const float* 
   }
 }
 
+// k_topk_qs -- one WARP per query, QPB consecutive queries per block, the ring keys staged ONCE per block in shared memory
+// (cp.async, two stages of 20 KB: the tiled layout makes a run of keys one contiguous span).  Against k_topk for batches of
+// hundreds to thousands of queries over a few thousand keys (the replay of a run): every key leaves L2 once per QPB queries
+// instead of once per query (4,541 queries x ~2,270 visible keys x 80 B = 825 MB of L2 reads per step: the kernel was
+// L2-bound), the distance reads are shared-memory loads (29 cycles instead of an L2 round trip: few resident warps suffice),
+// and a query has ONE list fed by its whole stream (k_topk: two to eight lists per query, each paying its warm-up
+// insertions, plus a merge).  Consecutive queries see almost the same prefix of the database (n_search = index - 50), so a
+// block streams to the largest bound of its queries and every warp stops at its own.  K <= 32.
+template <int RC, int QPB>
+__global__ void __launch_bounds__(QPB * 32) k_topk_qs(const TopkParams p, unsigned nq) {
+  constexpr int TILE = RC == 20 ? 256 : 128;                 // keys per stage
+  constexpr int STAGE_F4 = TILE * RC / 4;                    // float4 per stage
+  __shared__ __align__(16) float s_keys[2][TILE * RC];
+  __shared__ float s_q[QPB][RC];
+  __shared__ unsigned long long s_vis[QPB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, K = p.K;
+  const unsigned q = blockIdx.x * QPB + warp;
+  const unsigned long long G = (unsigned long long)p.db.G, rk = (unsigned long long)p.db.rank;
+  unsigned long long vis = 0;
+  if (q < nq) {
+    const unsigned long long ns = p.n_search[q];
+    if (ns > rk) vis = (ns - 1 - rk) / G + 1;
+    if (vis > p.n_local) vis = p.n_local;
+    const float* qring = reinterpret_cast<const float*>(p.qrecords + (size_t)q * p.L.rec_bytes + p.L.off_ring);
+    if (lane < RC) s_q[warp][lane] = qring[lane];
+    if (RC > 32 && lane + 32 < RC) s_q[warp][lane + 32] = qring[lane + 32];
+  }
+  if (lane == 0) s_vis[warp] = vis;
+  __syncthreads();
+  unsigned long long vmax = 0;
+#pragma unroll
+  for (int w = 0; w < QPB; ++w) vmax = s_vis[w] > vmax ? s_vis[w] : vmax;
+  float qr[RC];
+#pragma unroll
+  for (int d = 0; d < RC; ++d) qr[d] = s_q[warp][d];
+  const unsigned n_tiles = (unsigned)((vmax + TILE - 1) / TILE);
+  const unsigned long long alloc_f4 = p.db.cap * (unsigned long long)RC / 4;  // float4 of the key array (capacities are multiples of 64 keys)
+  const float4* g4 = reinterpret_cast<const float4*>(p.db.ringT);
+  auto stage = [&](unsigned t) {
+    float4* dst = reinterpret_cast<float4*>(s_keys[t & 1]);
+    const unsigned long long base = (unsigned long long)t * STAGE_F4;
+    for (int i = threadIdx.x; i < STAGE_F4; i += QPB * 32)
+      if (base + i < alloc_f4) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + i);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(g4 + base + i) : "memory");
+      }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  WarpList<1> list;
+  list.init();
+  if (n_tiles) stage(0);
+  for (unsigned t = 0; t < n_tiles; ++t) {
+    if (t + 1 < n_tiles) {
+      stage(t + 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // stage t is complete for every thread's copies
+    const unsigned long long base = (unsigned long long)t * TILE;
+    const float* sk = s_keys[t & 1];
+    if (base < vis) {  // (warp-uniform)
+#pragma unroll 2
+      for (int g = 0; g < TILE / 32; ++g) {
+        const unsigned long long l = base + g * 32 + lane;
+        if (base + g * 32 >= vis) break;
+        float kv[RC];
+#pragma unroll
+        for (int d = 0; d < RC; ++d) kv[d] = sk[(g * RC + d) * 32 + lane];
+        const float d2 = ringkey_dist2_regs<RC>(qr, kv);
+        list.offer(l < vis ? (((unsigned long long)__float_as_uint(d2) << 32) | (l * G + rk)) : KEY_NONE, K);
+      }
+    }
+    __syncthreads();  // nobody still reads the stage that the next iteration's copy overwrites
+  }
+  if (q < nq) list.store(p.keys_out + (size_t)q * K, K);
+}
+
 // TOPK_WARPS warps share one (query, chunk).  Every warp's list has a warm-up phase of ~K(1 + ln(n_warp / K)) insertions,
 // so many queries per launch use few warps per query (long streams per warp), few queries use many (latency).
 // RC: compile-time key dimension (20, 40; 0 = any).  PIPE: software-pipelined key loads (more registers: chosen for small grids,

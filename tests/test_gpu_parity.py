@@ -535,3 +535,43 @@ def test_database_grows_in_place_under_enqueued_work():
     if os.environ.get("SCGPU_NO_VMM", "0") == "0":
         assert by_copy == 0 and in_place >= 3, (in_place, by_copy)
     assert sum(big.growth_stats()[:2]) == 1
+
+
+@pytest.mark.parametrize("force", ["1", "0"])
+def test_query_per_warp_topk_kernel_matches_port(force):
+    """k_topk_qs (one warp per query, ring keys staged once per block in shared memory; chosen by itself for batches of
+    hundreds of queries) forced on / off through SCGPU_TOPK_QS in a fresh process: candidate indices and squared distances
+    equal the oracle's brute force bit for bit -- 20x60 and 40x120, ragged last block, queries whose search bound is 0,
+    bounds that end inside / at the edge of a 256-key stage, duplicate keys (index tie-break)."""
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, sys
+sys.path.insert(0, %r)
+from oracle import oracle as orc
+from sc_lego_loam_b200.scgpu import SCManager
+from sc_lego_loam_b200.synth import ScanGen
+for R, S, n, nq in ((20, 60, 1400, 997), (40, 120, 700, 301)):
+    descs = ScanGen("hdl64", seed=14, n_places=500).descs(0, n, R, S)
+    descs[300] = descs[17]; descs[301] = descs[17]          # duplicate ring keys: the lower index wins
+    p = orc.Params(R=R, S=S)
+    port = orc.Port(p)
+    m = SCManager(num_ring=R, num_sector=S, capacity_hint=n + 8)
+    m.append_descs(descs)
+    allkeys = np.stack([port.ringkey(d.astype(np.float64)).astype(np.float32) for d in descs])
+    m.query_batched(n - nq, nq)
+    for q in list(range(0, 60)) + list(range(190, min(330, nq), 3)) + list(range(nq - 40, nq)):
+        qi = n - nq + q
+        ns = max(0, qi + 1 - 50)
+        c = m.candidates(q)
+        assert c["n_tree"] == ns, (q, c["n_tree"], ns)
+        if ns == 0:
+            continue
+        cnt, idx, d2 = port.knn(allkeys[:ns], allkeys[qi])
+        assert np.array_equal(c["cand_d2"].view(np.uint32), d2.view(np.uint32)), (R, q)
+        assert np.array_equal(c["cand_idx"], idx), (R, q)
+print("qs-ok")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SCGPU_TOPK_QS=force)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "qs-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
