@@ -117,20 +117,49 @@ __device__ __forceinline__ void exh_normalise(const float* sc, const double* sec
     s_v2 = 0.f;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < L.S; c += blockDim.x) {
-    const double n = norm[c];
-    const float nf = (float)n, v = (float)sector[c];
-    s_inv[c] = (n == 0.0) ? 0.f : (float)(1.0 / n);
-    vkey32[PAIRED ? pair_pos(c, L.S) : c] = v;
-    if (n != 0.0) atomicOr(&s_mask[c >> 6], 1ull << (c & 63));
-    if (n != 0.0 && !(nf > 1e-30f && nf < 1e30f)) atomicOr(&s_flags, 1u);  // subnormal-ish, inf or NaN norm
-    if (!(fabsf(v) < 1e30f)) atomicOr(&s_flags, 1u);
-    atomicAdd(&s_v2, v * v);
+  {
+    // per column: 1 / norm, valid-column mask, |sector key|^2, "not a clean float" flag -- warp votes and a shuffle sum, one atomic
+    // per warp (a same-address shared-memory atomic per column held the whole block at the barrier below)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    for (int c0 = warp * 32; c0 < L.S; c0 += nwarps * 32) {
+      const int c = c0 + lane;
+      const bool in = c < L.S;
+      const double n = in ? norm[c] : 0.0;
+      const float nf = (float)n, v = in ? (float)sector[c] : 0.f;
+      if (in) {
+        s_inv[c] = (n == 0.0) ? 0.f : (float)(1.0 / n);
+        vkey32[PAIRED ? pair_pos(c, L.S) : c] = v;
+      }
+      const unsigned nz = __ballot_sync(FULL, in && n != 0.0);
+      const bool bad = in && ((n != 0.0 && !(nf > 1e-30f && nf < 1e30f)) || !(fabsf(v) < 1e30f));  // subnormal-ish, inf or NaN
+      const bool any_bad = __any_sync(FULL, bad);
+      float v2 = v * v;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v2 += __shfl_xor_sync(FULL, v2, o);
+      if (lane == 0) {
+        if (nz) atomicOr(&s_mask[c0 >> 6], (unsigned long long)nz << (c0 & 63));
+        if (any_bad) atomicOr(&s_flags, 1u);
+        atomicAdd(&s_v2, v2);
+      }
+    }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < L.RS; i += blockDim.x) {  // ROW-major output: element (r, c) at r*S + c
-    const int r = i / L.S, c = i - r * L.S;
-    sc_hat[PAIRED ? r * L.S + pair_pos(c, L.S) : i] = sc[c * L.R + r] * s_inv[c];
+  // ROW-major output: element (r, c) at r*S + c.  Walk the INPUT (column-major, coalesced loads, four in flight per thread) and
+  // scatter the stores -- the other way round every iteration waited for a strided load.
+  for (int i0 = threadIdx.x; i0 < L.RS; i0 += blockDim.x * 4) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      v[u] = i < L.RS ? sc[i] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * blockDim.x;
+      if (i >= L.RS) break;
+      const int c = i / L.R, r = i - c * L.R;
+      sc_hat[r * L.S + (PAIRED ? pair_pos(c, L.S) : c)] = v[u] * s_inv[c];
+    }
   }
   if (threadIdx.x == 0) {
     vmask[0] = s_mask[0];
@@ -211,15 +240,29 @@ template <int R, int S, int W, class F>
 __device__ __forceinline__ void qtab_fill(float* qtable, F value) {
   constexpr int NP = qtab_pairs(S, W), H = S / 2;
   static_assert(NP <= 2 * S, "a value appears at most twice per half");
-  for (int t = threadIdx.x; t < (R + 1) * S; t += blockDim.x) {
-    const int c = t / (R + 1), r = t - c * (R + 1);
-    const float v = value(r, c);
-    float* row = qtable + r * 2 * NP;
-    const int i1 = c < H ? c + H : c - H;  // pairs whose second half is column c
-    row[2 * c] = v;
-    if (c + S < NP) row[2 * (c + S)] = v;
-    row[2 * i1 + 1] = v;
-    if (i1 + S < NP) row[2 * (i1 + S) + 1] = v;
+  // four values per thread per round: the loads behind value() (global memory: the query record) are all in flight before the
+  // first store (k_cand_screen builds a table per query for ten candidates: one load at a time was a quarter of that kernel)
+  constexpr int U = 4, N = (R + 1) * S;
+  for (int t0 = threadIdx.x; t0 < N; t0 += blockDim.x * U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * blockDim.x;
+      const int c = t / (R + 1), r = t - c * (R + 1);
+      v[u] = t < N ? value(r, c) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int t = t0 + u * blockDim.x;
+      if (t >= N) break;
+      const int c = t / (R + 1), r = t - c * (R + 1);
+      float* row = qtable + r * 2 * NP;
+      const int i1 = c < H ? c + H : c - H;  // pairs whose second half is column c
+      row[2 * c] = v[u];
+      if (c + S < NP) row[2 * (c + S)] = v[u];
+      row[2 * i1 + 1] = v[u];
+      if (i1 + S < NP) row[2 * (i1 + S) + 1] = v[u];
+    }
   }
 }
 
@@ -784,13 +827,25 @@ __global__ void __launch_bounds__(CW * 32) k_cand_screen(const CandScreenParams 
   }
   __syncthreads();
   if (!early) {
-    for (int c = threadIdx.x; c < S; c += blockDim.x) {
-      const double n = qnorm[c];
-      const float nf = (float)n, v = (float)qsector[c];
-      s_inv[c] = (n == 0.0) ? 0.f : (float)(1.0 / n);
-      if (n != 0.0) atomicOr(&s_mask[c >> 6], 1ull << (c & 63));
-      if ((n != 0.0 && !(nf > 1e-30f && nf < 1e30f)) || !(fabsf(v) < 1e30f)) atomicOr(&s_flags, 1u);
-      atomicAdd(&s_v2, v * v);
+    // per column: 1 / norm, valid-column mask, |sector key|^2, "not a clean float" flag -- warp votes and a shuffle sum, then one
+    // atomic per warp (sixty same-address shared-memory atomics per block held every warp at the barrier below)
+    for (int c0 = warp * 32; c0 < S; c0 += CW * 32) {
+      const int c = c0 + lane;
+      const bool in = c < S;
+      const double n = in ? qnorm[c] : 0.0;
+      const float nf = (float)n, v = in ? (float)qsector[c] : 0.f;
+      if (in) s_inv[c] = (n == 0.0) ? 0.f : (float)(1.0 / n);
+      const unsigned nz = __ballot_sync(FULL, in && n != 0.0);
+      const bool bad = in && ((n != 0.0 && !(nf > 1e-30f && nf < 1e30f)) || !(fabsf(v) < 1e30f));
+      const bool any_bad = __any_sync(FULL, bad);
+      float v2 = v * v;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v2 += __shfl_xor_sync(FULL, v2, o);
+      if (lane == 0) {
+        if (nz) atomicOr(&s_mask[c0 >> 6], (unsigned long long)nz << (c0 & 63));
+        if (any_bad) atomicOr(&s_flags, 1u);
+        atomicAdd(&s_v2, v2);
+      }
     }
   }
   __syncthreads();
